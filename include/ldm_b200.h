@@ -1,0 +1,174 @@
+/*
+ * ldm_b200.h -- C ABI of the B200-native latent-DDPM sampling path.
+ *
+ * The reference (ynyeh0221/Oxford-102-Flower-GAN-VAE-latent-diffusion) has no
+ * FFI layer: its boundary for this path is the PyTorch module API of
+ * v2/model_train_test.py.  Each entry point below names the reference method it
+ * stands behind; the Python mirror of those classes (package directory
+ * oxford-102-flower-gan-vae-latent-diffusion_b200/) binds these symbols with
+ * ctypes and nothing else.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every pointer named *_dev is a device pointer on the context's device;
+ *     pointers named *_host are host pointers (pinned memory recommended);
+ *   - all floating point tensors are fp32, row-major, contiguous; all index
+ *     tensors are int64 (the reference's dtypes);
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *     calls are asynchronous on it unless stated otherwise;
+ *   - return value: 0 success; < 0 argument / state validation failure;
+ *     > 0 a cudaError_t / CUresult.  ldm_last_error() holds the message of the
+ *     last failure on the calling thread.  Nothing throws or exits.
+ *   - a context is bound to one device and is not thread-safe; distinct
+ *     contexts are independent.  Multi-GPU = one process and one context per GPU.
+ */
+#ifndef LDM_B200_H_
+#define LDM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDM_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define LDM_API __attribute__((visibility("default")))
+#else
+#define LDM_API
+#endif
+
+#define LDM_MAX_STAGES 8
+
+/* arithmetic of the dense contractions */
+#define LDM_PRECISION_FP32 0 /* fp32 CUDA-core FMA, strict mode (eps within 1e-3 of the reference) */
+#define LDM_PRECISION_BF16 2 /* bf16 operands, fp32 accumulation on tcgen05 tensor cores (2e-2) */
+
+typedef struct ldm_ctx ldm_ctx;
+
+/* ConditionalUNet parameters (v2:501-533), device pointers to the tensors of the
+ * module's state_dict, unchanged layout.  n_stages = len(hidden_dims) - 1. */
+typedef struct ldm_unet_weights {
+  int32_t latent_dim;                 /* v2:502 latent_dim (256) */
+  int32_t time_dim;                   /* v2:503 time_emb_dim (256) */
+  int32_t num_classes;                /* v2:503 (102) */
+  int32_t n_stages;                   /* 4 */
+  int32_t hidden[LDM_MAX_STAGES + 1]; /* v2:502 hidden_dims (256,512,1024,512,256) */
+  int32_t n_t;                        /* rows of `sinusoid` (= n_steps) */
+  /* sinusoid(t) = [sin(t f) | cos(t f)] for t = 0..n_t-1, (n_t, time_dim), built by the host
+   * mirror with the reference's own torch expression (v2:410-414) so it is bit-identical */
+  const float* sinusoid;
+  const float* residual_weight;       /* () v2:533 */
+  const float *time_lin1_w, *time_lin1_b, *time_lin2_w, *time_lin2_b;      /* v2:405-407 */
+  const float* class_embedding;       /* (num_classes, time_dim) v2:424 */
+  const float *class_lin1_w, *class_lin1_b, *class_lin2_w, *class_lin2_b;  /* v2:425-427 */
+  const float *latent_proj_w, *latent_proj_b;                              /* v2:509 */
+  const float* time_proj_w[LDM_MAX_STAGES];   /* time_projections[i] v2:510-512 (i < n_stages used) */
+  const float* time_proj_b[LDM_MAX_STAGES];
+  const float* attn_in_proj_w[LDM_MAX_STAGES]; /* (3d, d) v2:513-516; rows [2d,3d) = V */
+  const float* attn_in_proj_b[LDM_MAX_STAGES];
+  const float* attn_out_w[LDM_MAX_STAGES];
+  const float* attn_out_b[LDM_MAX_STAGES];
+  const float* block_lin_w[LDM_MAX_STAGES];    /* layers[i][0][0] v2:519 */
+  const float* block_lin_b[LDM_MAX_STAGES];
+  const float* block_ln_w[LDM_MAX_STAGES];     /* layers[i][0][1] v2:520 */
+  const float* block_ln_b[LDM_MAX_STAGES];
+  const float* stage_ln_w[LDM_MAX_STAGES];     /* layers[i][1] v2:524 */
+  const float* stage_ln_b[LDM_MAX_STAGES];
+  const float* down_w[LDM_MAX_STAGES];         /* layers[i][2] v2:525 */
+  const float* down_b[LDM_MAX_STAGES];
+  const float *final_time_w, *final_time_b, *final_class_w, *final_class_b; /* v2:528-529 */
+  const float *final_norm_w, *final_norm_b;                                /* v2:530 */
+  const float *final_w, *final_b;                                          /* v2:531 */
+} ldm_unet_weights;
+
+/* ResidualBlock parameters (v2:159-168) */
+typedef struct ldm_resblock_weights {
+  const float *conv1_w, *conv1_b, *ln1_w, *ln1_b; /* (C,C,3,3),(C),(C),(C) */
+  const float *conv2_w, *conv2_b, *ln2_w, *ln2_b;
+  const float *ca_w0, *ca_w2;                     /* (C/8,C,1,1), (C,C/8,1,1) v2:58-61 */
+  const float* sa_w;                              /* (1,2,7,7) v2:72 */
+} ldm_resblock_weights;
+
+/* Decoder parameters (v2:242-278); index 0 -> res3/up3 (512ch), 1 -> res2/up2, 2 -> res1/up1 */
+typedef struct ldm_decoder_weights {
+  int32_t latent_dim; /* 256 */
+  const float *fc0_w, *fc0_b, *fc1_w, *fc1_b; /* Linear(256,512), LayerNorm(512) */
+  const float *fc3_w, *fc3_b, *fc4_w, *fc4_b; /* Linear(512,32768), LayerNorm(32768) */
+  ldm_resblock_weights res[3];
+  const float* up_w[3];  /* ConvTranspose2d weight (Cin, Cin/2, 4, 4) */
+  const float* up_b[3];
+  const float* up_gn_w[3];
+  const float* up_gn_b[3];
+  const float *fin0_w, *fin0_b, *fin_gn_w, *fin_gn_b; /* Conv2d(64,32,3), GroupNorm(8,32) */
+  const float *fin3_w, *fin3_b;                       /* Conv2d(32,3,3) */
+} ldm_decoder_weights;
+
+LDM_API int ldm_version(void);
+LDM_API const char* ldm_last_error(void);
+
+/* One context per (device, caller). precision: LDM_PRECISION_*. */
+LDM_API int ldm_ctx_create(ldm_ctx** out, int device, int precision);
+LDM_API int ldm_ctx_destroy(ldm_ctx* ctx);
+
+/* ConditionalDenoiseDiffusion.__init__ (v2:565-572): the three schedule tables, HOST pointers
+ * (n_steps each).  The per-step update coefficients are derived from them in fp32 with the
+ * reference's own expressions (v2:584-590). Synchronous. */
+LDM_API int ldm_set_schedule(ldm_ctx* ctx, const float* beta_host, const float* alpha_host,
+                     const float* alpha_bar_host, int n_steps);
+
+/* Repack ConditionalUNet weights into kernel layouts and build the per-timestep and per-class
+ * bias tables (hoists v2:537-538,541-545,554-558 out of the loop). Weights are read from the
+ * caller's tensors once; the context keeps its own packed copies. Synchronises the stream. */
+LDM_API int ldm_unet_pack(ldm_ctx* ctx, const ldm_unet_weights* w, void* stream);
+
+/* Class labels of the current batch (argument c of forward / p_sample / sample); NULL = the
+ * c=None branch (v2:538,543,556).  Labels are range-checked on the device; an out-of-range
+ * label makes the next synchronising call fail. */
+LDM_API int ldm_unet_set_classes(ldm_ctx* ctx, const int64_t* c_dev, int batch, void* stream);
+
+/* ConditionalUNet.forward(x, t, c) (v2:535-561), eval mode. t_len is 1 or batch. */
+LDM_API int ldm_unet_forward(ldm_ctx* ctx, const float* x_dev, const int64_t* t_dev, int t_len,
+                     float* eps_out_dev, int batch, void* stream);
+
+/* The posterior update of p_sample alone (v2:584-592) for a given eps:
+ *   x <- (x - (1-alpha_t)/sqrt(1-alpha_bar_t) * eps) / sqrt(alpha_t) [+ sqrt(beta_t) * z if t > 0]
+ * z = noise_dev if non-NULL, else Philox(seed; sample_offset + row, t) generated in-kernel. */
+LDM_API int ldm_ddpm_step(ldm_ctx* ctx, float* x_inout_dev, const float* eps_dev, int t,
+                  const float* noise_dev, uint64_t seed, uint64_t sample_offset, int batch,
+                  void* stream);
+
+/* Standard normals from the in-kernel Philox stream (the x_T draw of v2:595 uses step = n_steps). */
+LDM_API int ldm_randn(ldm_ctx* ctx, float* out_dev, uint64_t seed, uint64_t sample_offset, int step,
+              int batch, int dim, void* stream);
+
+/* ConditionalDenoiseDiffusion.sample / repeated p_sample (v2:580-598): runs timesteps
+ * t_start, t_start-1, ..., t_end (inclusive) on x in place, classes from ldm_unet_set_classes.
+ * noise_dev: NULL (in-kernel Philox) or (t_start - t_end + 1, batch, latent_dim) explicit draws,
+ * slab j used at t = t_start - j (the t = 0 slab is ignored).  use_graph != 0 replays the whole
+ * loop as one CUDA graph (captured and cached per (batch, t_start, t_end, noise mode)). */
+LDM_API int ldm_sample(ldm_ctx* ctx, float* x_inout_dev, int t_start, int t_end, const float* noise_dev,
+               uint64_t seed, uint64_t sample_offset, int batch, int use_graph, void* stream);
+
+/* Repack Decoder weights (v2:242-278). Synchronises the stream. */
+LDM_API int ldm_decoder_pack(ldm_ctx* ctx, const ldm_decoder_weights* w, void* stream);
+
+/* SimpleAutoencoder.decode(z) (v2:355-357, 280-290): (batch, latent_dim) -> (batch,3,64,64) NCHW. */
+LDM_API int ldm_decode(ldm_ctx* ctx, const float* z_dev, float* img_out_dev, int batch, void* stream);
+
+/* generate_class_samples' hot section (v2:865-869) with HOST buffers: copies `c_host`
+ * (batch int64 labels) to the device, draws x_T from Philox(seed; sample_offset..), runs the
+ * full n_steps chain as one graph, decodes, and copies the (batch,3,64,64) images and
+ * (optionally, may be NULL) the final latents back to host memory.  Synchronous on return. */
+LDM_API int ldm_generate_host(ldm_ctx* ctx, const int64_t* c_host, int batch, uint64_t seed,
+                      uint64_t sample_offset, float* img_out_host, float* latents_out_host,
+                      void* stream);
+
+/* Introspection for tests and the benchmark. */
+LDM_API int ldm_kernel_launch_count(ldm_ctx* ctx, uint64_t* out); /* kernels launched (graph nodes count per replay) */
+LDM_API int ldm_get_info(ldm_ctx* ctx, const char* key, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDM_B200_H_ */

@@ -1,0 +1,17 @@
+"""B200-native drop-in for the latent-DDPM sampling path of
+ynyeh0221/Oxford-102-Flower-GAN-VAE-latent-diffusion (v2/model_train_test.py).
+
+The directory name carries hyphens (it is the name the build contract fixes), so import it through the
+shim at the repository root:  `import ldm_b200`.
+"""
+from .engine import default_precision, get_engine, set_default_precision   # noqa: F401
+from .modules import (CALayer, ClassEmbedding, ConditionalDenoiseDiffusion, ConditionalUNet, Decoder, Encoder,  # noqa: F401
+                      LayerNorm2d, ResidualBlock, SimpleAutoencoder, SpatialAttention, Swish, TimeEmbedding,
+                      euclidean_distance_loss, generate_class_samples, init_weights, load_autoencoder_checkpoint)
+from .sharding import generate_sharded, shard_bounds                       # noqa: F401
+from ._lib import LIB_PATH, LdmError                                        # noqa: F401
+
+__all__ = ["ConditionalUNet", "ConditionalDenoiseDiffusion", "SimpleAutoencoder", "Decoder", "Encoder",
+           "TimeEmbedding", "ClassEmbedding", "ResidualBlock", "CALayer", "SpatialAttention", "LayerNorm2d", "Swish",
+           "generate_class_samples", "generate_sharded", "shard_bounds", "init_weights", "load_autoencoder_checkpoint",
+           "get_engine", "set_default_precision", "default_precision", "LdmError", "LIB_PATH"]

@@ -1,0 +1,318 @@
+// Shared declarations of the sm_100a sampling library (not part of the public ABI).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/ldm_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: nothing throws across the ABI
+// ---------------------------------------------------------------------------------------------
+void ldm_set_error(const char* fmt, ...);
+
+#define LDM_CUDA(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      ldm_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return (int)_e;                                                                   \
+    }                                                                                   \
+  } while (0)
+
+#define LDM_CHECK(cond, ...)        \
+  do {                              \
+    if (!(cond)) {                  \
+      ldm_set_error(__VA_ARGS__);   \
+      return -1;                    \
+    }                               \
+  } while (0)
+
+#define LDM_TRY(expr)          \
+  do {                         \
+    int _r = (expr);           \
+    if (_r != 0) return _r;    \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float swishf(float v) { return v / (1.0f + __expf(-v)); }
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + __expf(-v)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---------------------------------------------------------------------------------------------
+// epilogue description shared by the fp32 (CUDA-core) and bf16 (tcgen05) GEMM kernels.
+// Output element (row, col) of  acc = A[row,:] . W[col,:]  is finished as
+//   v = acc + bias[col] + tab_t[tidx(row)*ld_t + col] + tab_c[cls[row]*ld_c + col] + resid[row*ld_r + col]
+//   v = act(v)
+// and then either stored (fp32 and/or bf16 copies) or consumed by the fused DDPM update.
+// ---------------------------------------------------------------------------------------------
+enum { LDM_ACT_NONE = 0, LDM_ACT_SWISH = 1, LDM_ACT_SIGMOID = 2 };
+
+struct Epilogue {
+  const float* bias = nullptr;      // [N]
+  const float* tab_t = nullptr;     // per-timestep table (n_t, ld_t)
+  int ld_t = 0;
+  const int64_t* t_idx = nullptr;   // device timesteps (len t_len) or null -> t_const
+  int t_len = 1;
+  int t_const = 0;
+  int n_t = 1;                      // rows of tab_t (indices are clamped; range is validated upstream)
+  const float* tab_c = nullptr;     // per-class table (n_cls, ld_c)
+  int ld_c = 0;
+  const int32_t* cls = nullptr;     // [M] class of each row (validated copy kept by the context)
+  const float* resid = nullptr;     // fp32 residual
+  int ld_r = 0;
+  int act = LDM_ACT_NONE;
+  float* out_f32 = nullptr;
+  int ld_of = 0;
+  bf16* out_bf16 = nullptr;
+  int ld_ob = 0;
+  // fused DDPM posterior update (v2:584-592): v is eps_theta
+  int ddpm = 0;
+  float* x = nullptr;               // (M, N) fp32 state, updated in place
+  float c2 = 0.f, sqrt_alpha = 1.f, sigma = 0.f;  // (1-a_t)/sqrt(1-abar_t), sqrt(a_t), sqrt(beta_t) (0 at t=0)
+  const float* noise = nullptr;     // explicit (M, N) draws or null -> Philox
+  const unsigned long long* rng = nullptr;  // device {seed, sample_offset}: read at run time so a captured graph replays with new seeds
+  int step = 0;
+};
+
+// ---------------------------------------------------------------------------------------------
+// packed model + context
+// ---------------------------------------------------------------------------------------------
+struct DenseLayer {      // y = x W^T + b, W (N, K) row-major ("K-major")
+  int N = 0, K = 0;
+  float* w32 = nullptr;  // fp32 copy (strict path, and source of the bf16 copy)
+  bf16* w16 = nullptr;   // bf16 copy (tensor-core path)
+  float* b = nullptr;    // fp32 bias [N]
+  CUtensorMap map_w;     // TMA descriptor of w16 (tensor-core path)
+  int bn = 0;            // N tile of the tensor-core kernel for this layer
+};
+
+struct UnetModel {
+  bool packed = false;
+  std::vector<void*> allocs;
+  int latent = 0, tdim = 0, ncls = 0, nst = 0, n_t = 0;
+  int hid[LDM_MAX_STAGES + 1] = {0};
+  int dmax = 0;
+  DenseLayer latent_proj;
+  DenseLayer block[LDM_MAX_STAGES], ov[LDM_MAX_STAGES], down[LDM_MAX_STAGES];
+  DenseLayer fin;                               // K = hid[nst] + latent : [W_f | s W_f], bias (1+s) b_f
+  float *ln_a_w[LDM_MAX_STAGES], *ln_a_b[LDM_MAX_STAGES];  // layers[i][0][1]
+  float *ln_b_w[LDM_MAX_STAGES], *ln_b_b[LDM_MAX_STAGES];  // layers[i][1]
+  float *ln_f_w = nullptr, *ln_f_b = nullptr;
+  float* tab_t[LDM_MAX_STAGES + 1];             // (n_t, hid[i]): time_projections[i](time_emb(t)); [nst] = final_time_proj
+  float* tab_c[LDM_MAX_STAGES + 1];             // (ncls, hid[i]): time_projections[i](class_emb(c)); [nst] = final_class_proj
+  float s_res = 0.f;                            // sigmoid(residual_weight)
+};
+
+struct ConvLayer {       // implicit GEMM: out[pix, co] = sum_{tap, ci} in[pix + off(tap), ci] * w[co][tap*Cin + ci]
+  int Cin = 0, Cout = 0, taps = 0;
+  float* w32 = nullptr;  // (Cout, taps*Cin)
+  bf16* w16 = nullptr;
+  float* b = nullptr;
+  CUtensorMap map_w;
+};
+
+struct ResBlockModel {
+  int C = 0, HW = 0;     // channels, spatial side
+  ConvLayer conv1, conv2;
+  float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+  float *ca_w0, *ca_w2;  // (C/8, C), (C, C/8)
+  float* sa_w;           // (2, 7, 7)
+  float* ca_const;       // bf16 path: sigmoid(W2 swish(W1 ln2_b)) (GAP of an instance-norm output is its beta)
+};
+
+struct DecoderModel {
+  bool packed = false;
+  std::vector<void*> allocs;
+  int latent = 0;
+  DenseLayer fc0, fc3;   // fc3 rows permuted NCHW -> NHWC
+  float *fc1_w, *fc1_b, *fc4_w, *fc4_b;  // fc4 affine permuted likewise
+  ResBlockModel res[3];
+  ConvLayer up[3][4];    // 4 sub-pixel parities (a*2+b), each 4 taps
+  float *up_b[3], *up_gn_w[3], *up_gn_b[3];
+  ConvLayer fin0, fin3;
+  float *fin_gn_w, *fin_gn_b;
+};
+
+struct GraphKey {
+  int batch, t_start, t_end, noise_mode;
+  bool operator<(const GraphKey& o) const {
+    return std::tie(batch, t_start, t_end, noise_mode) < std::tie(o.batch, o.t_start, o.t_end, o.noise_mode);
+  }
+};
+
+struct GraphEntry {
+  cudaGraphExec_t exec = nullptr;
+  cudaGraph_t graph = nullptr;
+  size_t n_nodes = 0;
+  const float* noise = nullptr;   // captured explicit-noise pointer (must match for a replay)
+  bool has_cls = false;           // captured with / without class tables
+};
+
+struct ldm_ctx {
+  int device = 0;
+  int precision = LDM_PRECISION_FP32;
+  int sm_count = 148;
+  std::vector<void*> allocs;      // every device allocation owned by the context
+  // schedule
+  int n_steps = 0;
+  std::vector<float> c2, sqrt_alpha, sigma;
+  // models
+  UnetModel unet;
+  DecoderModel dec;
+  // per-batch state
+  int cap = 0;                    // rows the activation workspace holds
+  int batch_cls = -1;             // batch of the last set_classes (-1: none)
+  bool has_cls = false;
+  int32_t* cls = nullptr;         // [cap]
+  int* dev_flags = nullptr;       // [0] out-of-range label / timestep seen
+  // denoiser workspace (fp32 master copies + operand copies in the GEMM operand type)
+  float *h = nullptr, *u = nullptr, *h2 = nullptr;   // (cap, dmax) fp32
+  void *h_op = nullptr, *n_op = nullptr, *h3_op = nullptr;  // operand-typed (fp32 or bf16)
+  void* af_op[2] = {nullptr, nullptr};  // [LN_f(h) | x] operand of the final GEMM, double-buffered across steps
+  float* x_state = nullptr;       // (cap, latent) fp32 chain state the captured graph works on
+  unsigned long long* rng_dev = nullptr;  // {seed, sample_offset}
+  cudaStream_t cap_stream = nullptr;      // capture-only stream (the caller may be on the legacy stream)
+  std::vector<void*> ws_allocs;   // workspace allocations (freed on regrow)
+  // decoder workspace
+  int dec_cap = 0;
+  std::vector<void*> dec_allocs;
+  void *d_a = nullptr, *d_b = nullptr, *d_c = nullptr;  // ping-pong activation buffers (operand-typed, NHWC)
+  float *d_f0 = nullptr, *d_f1 = nullptr;               // fp32 scratch (raw conv outputs, fc rows)
+  float *d_stats = nullptr, *d_gap = nullptr, *d_ca = nullptr, *d_map = nullptr;
+  float* z_tmp = nullptr;
+  // generate_host staging
+  int64_t* c_stage = nullptr;     // device staging of the labels copied from the host
+  float* img_stage = nullptr;     // device images before the copy back
+  int host_cap = 0;
+  std::vector<void*> stage_allocs;
+  // graphs
+  std::map<GraphKey, GraphEntry> graphs;
+  // TMA descriptors over the workspace (tensor-core path), rebuilt when the workspace regrows
+  std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> act_maps;
+  // accounting
+  unsigned long long launches = 0;
+  bool capturing = false;
+  int use_pdl = 0;
+};
+
+// memory helpers (api.cu)
+int ldm_alloc(ldm_ctx* ctx, std::vector<void*>& pool, void** out, size_t bytes);
+template <typename T>
+static inline int ldm_alloc_t(ldm_ctx* ctx, std::vector<void*>& pool, T** out, size_t count) {
+  return ldm_alloc(ctx, pool, (void**)out, count * sizeof(T));
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel launchers (one .cu each); all return 0 or an error code and count launches in ctx
+// ---------------------------------------------------------------------------------------------
+// fp32 CUDA-core GEMM  C = epi(A (M,K; lda) . W (N,K)^T)
+int launch_gemm_f32(ldm_ctx* ctx, const float* A, int lda, const float* W, int M, int N, int K,
+                    const Epilogue& epi, cudaStream_t st);
+
+// implicit-GEMM convolution over NHWC fp32 activations (strict path)
+struct ConvGeom {
+  int B, H, W;            // input batch and spatial size
+  int Cin, Cout;
+  int taps;
+  int dy[9], dx[9];       // input offset of each tap
+  int up;                 // 1: plain conv (output H x W); 2: sub-pixel of a stride-2 transposed conv
+  int pa, pb;             // sub-pixel parity (output pixel (2i+pa, 2j+pb)) when up == 2
+  int nchw_out;           // 1: write (B, Cout, H, W) fp32 instead of NHWC
+  int act;
+};
+int launch_conv_f32(ldm_ctx* ctx, const float* in, const float* w, const float* bias, float* out,
+                    const ConvGeom& g, cudaStream_t st);
+
+// rowwise / normalisation kernels
+template <typename TOP>
+int launch_stage_mid(ldm_ctx* ctx, const float* u, const float* h, const float* ga, const float* ba,
+                     const float* gb, const float* bb, float* h2, TOP* n_op, int ld_op, int M, int d,
+                     cudaStream_t st);
+template <typename TOP>
+int launch_row_ln(ldm_ctx* ctx, const float* in, int ld_in, const float* g, const float* b, int act,
+                  TOP* out, int ld_out, int M, int d, cudaStream_t st);
+template <typename TOP>
+int launch_load_x(ldm_ctx* ctx, const float* x, TOP* dst, int ld_dst, int M, int d, cudaStream_t st);
+int launch_set_classes(ldm_ctx* ctx, const int64_t* c, int32_t* out, int M, int ncls, int* flags,
+                       cudaStream_t st);
+int launch_check_t(ldm_ctx* ctx, const int64_t* t, int n, int n_t, int* flags, cudaStream_t st);
+int launch_ddpm_update(ldm_ctx* ctx, float* x, const float* eps, float c2, float sqrt_alpha, float sigma,
+                       const float* noise, unsigned long long seed, unsigned long long sample_offset,
+                       int step, int M, int d, cudaStream_t st);
+int launch_set_rng(ldm_ctx* ctx, unsigned long long* rng, unsigned long long seed, unsigned long long sample_offset,
+                   cudaStream_t st);
+int launch_randn(ldm_ctx* ctx, float* out, unsigned long long seed, unsigned long long sample_offset,
+                 int step, int M, int d, cudaStream_t st);
+
+// pack-time helpers (fp64 accumulation, run once)
+int launch_pack_matmul_nn(ldm_ctx* ctx, const float* A, const float* B, float* C, int M, int N, int K,
+                          cudaStream_t st);  // C(M,N) = A(M,K) B(K,N)
+int launch_pack_matvec(ldm_ctx* ctx, const float* A, const float* x, const float* add, float* y, int M,
+                       int K, cudaStream_t st);  // y = A x + add
+int launch_pack_final(ldm_ctx* ctx, const float* wf, const float* bf, const float* rw, float* wcat,
+                      float* bcat, float* s_out, int N, int K, cudaStream_t st);
+int launch_to_bf16(ldm_ctx* ctx, const float* in, bf16* out, size_t n, cudaStream_t st);
+int launch_permute_rows(ldm_ctx* ctx, const float* in, float* out, int C, int P, int K, cudaStream_t st);
+int launch_pack_conv(ldm_ctx* ctx, const float* w, float* out, int Cout, int Cin, int KH, int KW,
+                     cudaStream_t st);
+int launch_pack_convT(ldm_ctx* ctx, const float* w, float* out, int Cin, int Cout, int pa, int pb,
+                      cudaStream_t st);
+int launch_ca_const(ldm_ctx* ctx, const float* beta, const float* w0, const float* w2, float* out, int C,
+                    cudaStream_t st);
+
+// decoder normalisation / gating kernels (activation type T = float or bf16, NHWC)
+template <typename T>
+int launch_inorm_stats(ldm_ctx* ctx, const T* x, float* stats, int B, int HW, int C, int group,
+                       cudaStream_t st);  // stats[(n*G+g)*2] = mean, rstd over HW x group channels
+template <typename T>
+int launch_norm_apply(ldm_ctx* ctx, const T* x, const float* stats, const float* gamma, const float* beta,
+                      T* out, int B, int HW, int C, int group, int act, cudaStream_t st);
+template <typename T>
+int launch_gap_norm(ldm_ctx* ctx, const T* x, const float* stats, const float* gamma, const float* beta,
+                    float* gap, int B, int HW, int C, cudaStream_t st);
+int launch_ca_mlp(ldm_ctx* ctx, const float* gap, const float* w0, const float* w2, float* ca, int B, int C,
+                  cudaStream_t st);
+template <typename T>
+int launch_sa_map(ldm_ctx* ctx, const T* x, const float* stats, const float* gamma, const float* beta,
+                  const float* ca, int ca_stride, float* map, int B, int HW, int C, cudaStream_t st);
+template <typename T>
+int launch_sa_apply(ldm_ctx* ctx, const T* x, const float* stats, const float* gamma, const float* beta,
+                    const float* ca, int ca_stride, const float* map, const float* sa_w, const T* resid,
+                    T* out, int B, int H, int C, cudaStream_t st);
+
+// tensor-core path (gemm_tc.cu)
+int tc_init(ldm_ctx* ctx);
+int tc_make_weight_map(ldm_ctx* ctx, const bf16* w, int N, int K, int bn, CUtensorMap* out);
+int launch_gemm_tc(ldm_ctx* ctx, const bf16* A, int lda, int M, const DenseLayer& L, const Epilogue& epi,
+                   cudaStream_t st);

@@ -1,0 +1,204 @@
+// VAE decoder pass (Decoder.forward v2:280-290) over NHWC activations: weight repacking and the kernel
+// sequence.  Convolutions are implicit GEMMs (rows = pixels, K = taps x Cin); ConvTranspose2d(4,2,1) is
+// four sub-pixel 2x2-tap convolutions; LayerNorm2d / GroupNorm / CALayer / SpatialAttention are the
+// memory-bound kernels of decoder_norm.cu.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kDecChunk = 256;   // samples per pass: bounds the activation workspace (3 x 256 MiB fp32)
+
+int own(ldm_ctx* ctx, std::vector<void*>& pool, const float* src, size_t n, float** out, cudaStream_t st) {
+  LDM_CHECK(src != nullptr, "ldm_decoder_pack: null weight pointer");
+  LDM_TRY(ldm_alloc_t(ctx, pool, out, n));
+  LDM_CUDA(cudaMemcpyAsync(*out, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int pack_conv3(ldm_ctx* ctx, std::vector<void*>& pool, ConvLayer& L, const float* w, const float* b, int Cout, int Cin,
+               cudaStream_t st) {
+  LDM_CHECK(w && b, "ldm_decoder_pack: conv weights missing");
+  L.Cin = Cin; L.Cout = Cout; L.taps = 9;
+  LDM_TRY(ldm_alloc_t(ctx, pool, &L.w32, (size_t)Cout * 9 * Cin));
+  LDM_TRY(launch_pack_conv(ctx, w, L.w32, Cout, Cin, 3, 3, st));
+  LDM_TRY(own(ctx, pool, b, Cout, &L.b, st));
+  return 0;
+}
+
+void conv3_geom(ConvGeom& g, int B, int H, int Cin, int Cout) {
+  g = ConvGeom();
+  g.B = B; g.H = H; g.W = H; g.Cin = Cin; g.Cout = Cout; g.taps = 9; g.up = 1;
+  for (int t = 0; t < 9; ++t) { g.dy[t] = t / 3 - 1; g.dx[t] = t % 3 - 1; }
+}
+
+// sub-pixel (pa, pb) of ConvTranspose2d(4, 2, 1): tap j in {0,1} per axis reads input offset 0 / (-1 or +1)
+void convT_geom(ConvGeom& g, int B, int H, int Cin, int Cout, int pa, int pb) {
+  g = ConvGeom();
+  g.B = B; g.H = H; g.W = H; g.Cin = Cin; g.Cout = Cout; g.taps = 4; g.up = 2; g.pa = pa; g.pb = pb;
+  for (int t = 0; t < 4; ++t) {
+    const int jy = t >> 1, jx = t & 1;
+    g.dy[t] = jy == 0 ? 0 : (pa == 0 ? -1 : 1);
+    g.dx[t] = jx == 0 ? 0 : (pb == 0 ? -1 : 1);
+  }
+}
+
+int ensure_dec_workspace(ldm_ctx* ctx, int B) {
+  if (B <= ctx->dec_cap) return 0;
+  cudaDeviceSynchronize();
+  for (void* p : ctx->dec_allocs) cudaFree(p);
+  ctx->dec_allocs.clear();
+  auto& P = ctx->dec_allocs;
+  const size_t act = (size_t)B * 64 * 64 * 64;   // largest activation: up1 output (B, 64, 64, 64)
+  LDM_TRY(ldm_alloc(ctx, P, &ctx->d_a, act * sizeof(float)));
+  LDM_TRY(ldm_alloc(ctx, P, &ctx->d_b, act * sizeof(float)));
+  LDM_TRY(ldm_alloc(ctx, P, &ctx->d_c, act * sizeof(float)));
+  LDM_TRY(ldm_alloc_t(ctx, P, &ctx->d_f0, (size_t)B * 512));
+  LDM_TRY(ldm_alloc_t(ctx, P, &ctx->d_f1, (size_t)B * 512));
+  LDM_TRY(ldm_alloc_t(ctx, P, &ctx->d_stats, (size_t)B * 512 * 2));
+  LDM_TRY(ldm_alloc_t(ctx, P, &ctx->d_gap, (size_t)B * 512));
+  LDM_TRY(ldm_alloc_t(ctx, P, &ctx->d_ca, (size_t)B * 512));
+  LDM_TRY(ldm_alloc_t(ctx, P, &ctx->d_map, (size_t)B * 1024 * 2));
+  ctx->dec_cap = B;
+  return 0;
+}
+
+// ResidualBlock.forward (v2:170-178): x in `X`, result in `OUT`, scratch `Y` (raw conv outputs)
+int res_block_f32(ldm_ctx* ctx, const ResBlockModel& R, int B, const float* X, float* Y, float* OUT, cudaStream_t st) {
+  const int C = R.C, H = R.HW, P = H * H;
+  ConvGeom g;
+  conv3_geom(g, B, H, C, C);
+  LDM_TRY(launch_conv_f32(ctx, X, R.conv1.w32, R.conv1.b, Y, g, st));                                   // conv1
+  LDM_TRY(launch_inorm_stats<float>(ctx, Y, ctx->d_stats, B, P, C, 1, st));                              // ln1 statistics
+  LDM_TRY(launch_norm_apply<float>(ctx, Y, ctx->d_stats, R.ln1_w, R.ln1_b, OUT, B, P, C, 1, LDM_ACT_SWISH, st));  // swish(ln1(.))
+  LDM_TRY(launch_conv_f32(ctx, OUT, R.conv2.w32, R.conv2.b, Y, g, st));                                  // conv2
+  LDM_TRY(launch_inorm_stats<float>(ctx, Y, ctx->d_stats, B, P, C, 1, st));                              // ln2 statistics
+  LDM_TRY(launch_gap_norm<float>(ctx, Y, ctx->d_stats, R.ln2_w, R.ln2_b, ctx->d_gap, B, P, C, st));      // CALayer avg_pool
+  LDM_TRY(launch_ca_mlp(ctx, ctx->d_gap, R.ca_w0, R.ca_w2, ctx->d_ca, B, C, st));                        // CALayer conv_du
+  LDM_TRY(launch_sa_map<float>(ctx, Y, ctx->d_stats, R.ln2_w, R.ln2_b, ctx->d_ca, C, ctx->d_map, B, P, C, st));
+  LDM_TRY(launch_sa_apply<float>(ctx, Y, ctx->d_stats, R.ln2_w, R.ln2_b, ctx->d_ca, C, ctx->d_map, R.sa_w, X, OUT, B, H, C, st));
+  return 0;
+}
+
+// up block (v2:255-271): ConvTranspose2d -> GroupNorm (8 channels per group) -> Swish
+int up_block_f32(ldm_ctx* ctx, const DecoderModel& D, int idx, int B, int H, int Cin, const float* X, float* Y, float* OUT,
+                 cudaStream_t st) {
+  const int Cout = Cin / 2;
+  for (int pa = 0; pa < 2; ++pa)
+    for (int pb = 0; pb < 2; ++pb) {
+      ConvGeom g;
+      convT_geom(g, B, H, Cin, Cout, pa, pb);
+      LDM_TRY(launch_conv_f32(ctx, X, D.up[idx][pa * 2 + pb].w32, D.up_b[idx], Y, g, st));
+    }
+  const int P = 4 * H * H;
+  LDM_TRY(launch_inorm_stats<float>(ctx, Y, ctx->d_stats, B, P, Cout, 8, st));
+  LDM_TRY(launch_norm_apply<float>(ctx, Y, ctx->d_stats, D.up_gn_w[idx], D.up_gn_b[idx], OUT, B, P, Cout, 8, LDM_ACT_SWISH, st));
+  return 0;
+}
+
+int decode_chunk_f32(ldm_ctx* ctx, const float* z, float* img, int B, cudaStream_t st) {
+  DecoderModel& D = ctx->dec;
+  float *A = (float*)ctx->d_a, *Bf = (float*)ctx->d_b, *C = (float*)ctx->d_c;
+  {  // Decoder.fc (v2:246-253); fc.3 rows were permuted so the result is already NHWC (B, 8, 8, 512)
+    Epilogue e; e.bias = D.fc0.b; e.out_f32 = ctx->d_f0; e.ld_of = 512;
+    LDM_TRY(launch_gemm_f32(ctx, z, D.latent, D.fc0.w32, B, 512, D.latent, e, st));
+    LDM_TRY(launch_row_ln<float>(ctx, ctx->d_f0, 512, D.fc1_w, D.fc1_b, LDM_ACT_SWISH, ctx->d_f1, 512, B, 512, st));
+    Epilogue e2; e2.bias = D.fc3.b; e2.out_f32 = Bf; e2.ld_of = 32768;
+    LDM_TRY(launch_gemm_f32(ctx, ctx->d_f1, 512, D.fc3.w32, B, 32768, 512, e2, st));
+    LDM_TRY(launch_row_ln<float>(ctx, Bf, 32768, D.fc4_w, D.fc4_b, LDM_ACT_SWISH, A, 32768, B, 32768, st));
+  }
+  // x in A.  res -> C (scratch Bf), up -> A (scratch Bf)
+  LDM_TRY(res_block_f32(ctx, D.res[0], B, A, Bf, C, st));
+  LDM_TRY(up_block_f32(ctx, D, 0, B, 8, 512, C, Bf, A, st));
+  LDM_TRY(res_block_f32(ctx, D.res[1], B, A, Bf, C, st));
+  LDM_TRY(up_block_f32(ctx, D, 1, B, 16, 256, C, Bf, A, st));
+  LDM_TRY(res_block_f32(ctx, D.res[2], B, A, Bf, C, st));
+  LDM_TRY(up_block_f32(ctx, D, 2, B, 32, 128, C, Bf, A, st));
+  // final_conv (v2:272-278): conv 64->32, GroupNorm(8, 32), Swish, conv 32->3, Sigmoid; output NCHW
+  ConvGeom g;
+  conv3_geom(g, B, 64, 64, 32);
+  LDM_TRY(launch_conv_f32(ctx, A, D.fin0.w32, D.fin0.b, Bf, g, st));
+  LDM_TRY(launch_inorm_stats<float>(ctx, Bf, ctx->d_stats, B, 4096, 32, 4, st));
+  LDM_TRY(launch_norm_apply<float>(ctx, Bf, ctx->d_stats, D.fin_gn_w, D.fin_gn_b, C, B, 4096, 32, 4, LDM_ACT_SWISH, st));
+  conv3_geom(g, B, 64, 32, 3);
+  g.nchw_out = 1;
+  g.act = LDM_ACT_SIGMOID;
+  LDM_TRY(launch_conv_f32(ctx, C, D.fin3.w32, D.fin3.b, img, g, st));
+  return 0;
+}
+
+}  // namespace
+
+int decoder_pack_impl(ldm_ctx* ctx, const ldm_decoder_weights* w, cudaStream_t st) {
+  DecoderModel& D = ctx->dec;
+  LDM_CHECK(w->latent_dim > 0 && w->latent_dim % 16 == 0, "ldm_decoder_pack: latent_dim must be a positive multiple of 16");
+  cudaDeviceSynchronize();
+  for (void* p : D.allocs) cudaFree(p);
+  D = DecoderModel();
+  D.latent = w->latent_dim;
+  auto& P = D.allocs;
+  // fc
+  D.fc0.N = 512; D.fc0.K = D.latent;
+  LDM_TRY(own(ctx, P, w->fc0_w, (size_t)512 * D.latent, &D.fc0.w32, st));
+  LDM_TRY(own(ctx, P, w->fc0_b, 512, &D.fc0.b, st));
+  LDM_TRY(own(ctx, P, w->fc1_w, 512, &D.fc1_w, st));
+  LDM_TRY(own(ctx, P, w->fc1_b, 512, &D.fc1_b, st));
+  // fc.3 produces view(B, 512, 8, 8) (v2:282): flat index c*64 + p.  Permute its rows (and fc.4's affine, a
+  // LayerNorm over the whole row, so statistics are unchanged) to p*512 + c: the output is NHWC directly.
+  LDM_CHECK(w->fc3_w && w->fc3_b && w->fc4_w && w->fc4_b, "ldm_decoder_pack: fc weights missing");
+  D.fc3.N = 32768; D.fc3.K = 512;
+  LDM_TRY(ldm_alloc_t(ctx, P, &D.fc3.w32, (size_t)32768 * 512));
+  LDM_TRY(ldm_alloc_t(ctx, P, &D.fc3.b, 32768));
+  LDM_TRY(ldm_alloc_t(ctx, P, &D.fc4_w, 32768));
+  LDM_TRY(ldm_alloc_t(ctx, P, &D.fc4_b, 32768));
+  LDM_TRY(launch_permute_rows(ctx, w->fc3_w, D.fc3.w32, 512, 64, 512, st));
+  LDM_TRY(launch_permute_rows(ctx, w->fc3_b, D.fc3.b, 512, 64, 1, st));
+  LDM_TRY(launch_permute_rows(ctx, w->fc4_w, D.fc4_w, 512, 64, 1, st));
+  LDM_TRY(launch_permute_rows(ctx, w->fc4_b, D.fc4_b, 512, 64, 1, st));
+  const int chans[3] = {512, 256, 128}, sides[3] = {8, 16, 32};
+  for (int i = 0; i < 3; ++i) {
+    const int C = chans[i];
+    const ldm_resblock_weights& r = w->res[i];
+    ResBlockModel& R = D.res[i];
+    R.C = C; R.HW = sides[i];
+    LDM_TRY(pack_conv3(ctx, P, R.conv1, r.conv1_w, r.conv1_b, C, C, st));
+    LDM_TRY(pack_conv3(ctx, P, R.conv2, r.conv2_w, r.conv2_b, C, C, st));
+    LDM_TRY(own(ctx, P, r.ln1_w, C, &R.ln1_w, st));
+    LDM_TRY(own(ctx, P, r.ln1_b, C, &R.ln1_b, st));
+    LDM_TRY(own(ctx, P, r.ln2_w, C, &R.ln2_w, st));
+    LDM_TRY(own(ctx, P, r.ln2_b, C, &R.ln2_b, st));
+    LDM_TRY(own(ctx, P, r.ca_w0, (size_t)(C / 8) * C, &R.ca_w0, st));
+    LDM_TRY(own(ctx, P, r.ca_w2, (size_t)C * (C / 8), &R.ca_w2, st));
+    LDM_TRY(own(ctx, P, r.sa_w, 98, &R.sa_w, st));
+    LDM_TRY(ldm_alloc_t(ctx, P, &R.ca_const, (size_t)C));
+    LDM_TRY(launch_ca_const(ctx, R.ln2_b, R.ca_w0, R.ca_w2, R.ca_const, C, st));
+    // ConvTranspose2d(C, C/2, 4, 2, 1) -> four 2x2-tap sub-pixel kernels
+    LDM_CHECK(w->up_w[i] && w->up_b[i] && w->up_gn_w[i] && w->up_gn_b[i], "ldm_decoder_pack: up-block weights missing");
+    for (int pa = 0; pa < 2; ++pa)
+      for (int pb = 0; pb < 2; ++pb) {
+        ConvLayer& L = D.up[i][pa * 2 + pb];
+        L.Cin = C; L.Cout = C / 2; L.taps = 4;
+        LDM_TRY(ldm_alloc_t(ctx, P, &L.w32, (size_t)(C / 2) * 4 * C));
+        LDM_TRY(launch_pack_convT(ctx, w->up_w[i], L.w32, C, C / 2, pa, pb, st));
+      }
+    LDM_TRY(own(ctx, P, w->up_b[i], C / 2, &D.up_b[i], st));
+    LDM_TRY(own(ctx, P, w->up_gn_w[i], C / 2, &D.up_gn_w[i], st));
+    LDM_TRY(own(ctx, P, w->up_gn_b[i], C / 2, &D.up_gn_b[i], st));
+  }
+  LDM_TRY(pack_conv3(ctx, P, D.fin0, w->fin0_w, w->fin0_b, 32, 64, st));
+  LDM_TRY(own(ctx, P, w->fin_gn_w, 32, &D.fin_gn_w, st));
+  LDM_TRY(own(ctx, P, w->fin_gn_b, 32, &D.fin_gn_b, st));
+  LDM_TRY(pack_conv3(ctx, P, D.fin3, w->fin3_w, w->fin3_b, 3, 32, st));
+  LDM_CUDA(cudaStreamSynchronize(st));
+  D.packed = true;
+  return 0;
+}
+
+int decoder_run_impl(ldm_ctx* ctx, const float* z, float* img, int B, cudaStream_t st) {
+  const int chunk = B < kDecChunk ? B : kDecChunk;
+  LDM_TRY(ensure_dec_workspace(ctx, chunk));
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nb = B - b0 < chunk ? B - b0 : chunk;
+    LDM_TRY(decode_chunk_f32(ctx, z + (size_t)b0 * ctx->dec.latent, img + (size_t)b0 * 3 * 64 * 64, nb, st));
+  }
+  return 0;
+}

@@ -1,0 +1,133 @@
+// One-time weight repacking (runs inside ldm_unet_pack / ldm_decoder_pack, never in the sampling loop).
+// Folds that change operation order accumulate in fp64 so they stay below fp32 rounding:
+//   W_ov = W_out . W_v,  b_ov = W_out . b_v + b_out     (the L=1 attention of v2:550-551 is out_proj(V(.)))
+//   [W_f | s W_f], (1+s) b_f                            (v2:560-561: final(h) + s final(x), s = sigmoid(residual_weight))
+#include "common.cuh"
+
+namespace {
+
+__global__ void matmul_nn_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                                 int M, int N, int K) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y;
+  if (n >= N || m >= M) return;
+  double s = 0.0;
+  for (int k = 0; k < K; ++k) s += (double)A[(size_t)m * K + k] * (double)B[(size_t)k * N + n];
+  C[(size_t)m * N + n] = (float)s;
+}
+
+__global__ void matvec_kernel(const float* __restrict__ A, const float* __restrict__ x, const float* __restrict__ add,
+                              float* __restrict__ y, int M, int K) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  double s = add ? (double)add[m] : 0.0;
+  for (int k = 0; k < K; ++k) s += (double)A[(size_t)m * K + k] * (double)x[k];
+  y[m] = (float)s;
+}
+
+__global__ void pack_final_kernel(const float* __restrict__ wf, const float* __restrict__ bf_, const float* __restrict__ rw,
+                                  float* __restrict__ wcat, float* __restrict__ bcat, float* __restrict__ s_out, int N,
+                                  int K) {
+  const float s = 1.0f / (1.0f + expf(-rw[0]));
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) s_out[0] = s;
+  if (i < N) bcat[i] = (1.0f + s) * bf_[i];
+  if (i >= N * K) return;
+  const int n = i / K, k = i - n * K;
+  const float w = wf[i];
+  wcat[(size_t)n * 2 * K + k] = w;
+  wcat[(size_t)n * 2 * K + K + k] = s * w;
+}
+
+__global__ void to_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+
+// out[(p*C + c)*K + k] = in[(c*P + p)*K + k]: rows in NCHW-flat order (c*P + p) to NHWC-flat order (p*C + c)
+__global__ void permute_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int P, int K) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)C * P * K) return;
+  const int k = (int)(i % K);
+  const size_t r = i / K;
+  const int c = (int)(r % C), p = (int)(r / C);
+  out[i] = in[((size_t)c * P + p) * K + k];
+}
+
+// Conv2d weight (Cout, Cin, KH, KW) -> (Cout, (ky*KW + kx)*Cin + ci)
+__global__ void pack_conv_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int KH, int KW) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)Cout * Cin * KH * KW) return;
+  const int ci = (int)(i % Cin);
+  size_t r = i / Cin;
+  const int tap = (int)(r % (KH * KW)), co = (int)(r / (KH * KW));
+  const int ky = tap / KW, kx = tap - ky * KW;
+  out[i] = w[(((size_t)co * Cin + ci) * KH + ky) * KW + kx];
+}
+
+// ConvTranspose2d(k=4, s=2, p=1) weight (Cin, Cout, 4, 4) -> the 2x2-tap kernel of output parity (pa, pb):
+// out[2i+pa] += in[i + d] * w[k] with k = pa + 1 - 2 d  =>  pa=0: (d=0,k=1), (d=-1,k=3); pa=1: (d=0,k=2), (d=+1,k=0)
+__device__ __forceinline__ int convT_k(int parity, int j) { return j == 0 ? (parity == 0 ? 1 : 2) : (parity == 0 ? 3 : 0); }
+__global__ void pack_convT_kernel(const float* __restrict__ w, float* __restrict__ out, int Cin, int Cout, int pa, int pb) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)Cout * 4 * Cin) return;
+  const int ci = (int)(i % Cin);
+  size_t r = i / Cin;
+  const int tap = (int)(r % 4), co = (int)(r / 4);
+  const int ky = convT_k(pa, tap >> 1), kx = convT_k(pb, tap & 1);
+  out[i] = w[(((size_t)ci * Cout + co) * 4 + ky) * 4 + kx];
+}
+
+}  // namespace
+
+#define LDM_LAUNCHED(ctx)         \
+  do {                            \
+    (ctx)->launches++;            \
+    LDM_CUDA(cudaGetLastError()); \
+  } while (0)
+
+int launch_pack_matmul_nn(ldm_ctx* ctx, const float* A, const float* B, float* C, int M, int N, int K, cudaStream_t st) {
+  matmul_nn_kernel<<<dim3(ceil_div(N, 128), M), 128, 0, st>>>(A, B, C, M, N, K);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+int launch_pack_matvec(ldm_ctx* ctx, const float* A, const float* x, const float* add, float* y, int M, int K,
+                       cudaStream_t st) {
+  matvec_kernel<<<ceil_div(M, 128), 128, 0, st>>>(A, x, add, y, M, K);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+int launch_pack_final(ldm_ctx* ctx, const float* wf, const float* bf_, const float* rw, float* wcat, float* bcat,
+                      float* s_out, int N, int K, cudaStream_t st) {
+  pack_final_kernel<<<ceil_div(N * K, 256), 256, 0, st>>>(wf, bf_, rw, wcat, bcat, s_out, N, K);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+int launch_to_bf16(ldm_ctx* ctx, const float* in, bf16* out, size_t n, cudaStream_t st) {
+  to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+int launch_permute_rows(ldm_ctx* ctx, const float* in, float* out, int C, int P, int K, cudaStream_t st) {
+  const size_t n = (size_t)C * P * K;
+  permute_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, C, P, K);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+int launch_pack_conv(ldm_ctx* ctx, const float* w, float* out, int Cout, int Cin, int KH, int KW, cudaStream_t st) {
+  const size_t n = (size_t)Cout * Cin * KH * KW;
+  pack_conv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, out, Cout, Cin, KH, KW);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+int launch_pack_convT(ldm_ctx* ctx, const float* w, float* out, int Cin, int Cout, int pa, int pb, cudaStream_t st) {
+  const size_t n = (size_t)Cout * 4 * Cin;
+  pack_convT_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, out, Cin, Cout, pa, pb);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+int launch_ca_const(ldm_ctx* ctx, const float* beta, const float* w0, const float* w2, float* out, int C,
+                    cudaStream_t st) {
+  // The spatial mean of an instance-normalised map is exactly its beta, so CALayer's pooled input
+  // (v2:65 on ln2's output) is sample-independent: evaluate conv_du once on beta.
+  return launch_ca_mlp(ctx, beta, w0, w2, out, 1, C, st);
+}

@@ -1,0 +1,317 @@
+// Memory-bound row kernels of the denoiser step: LayerNorm + Swish + residual (v2:546-549,559),
+// operand staging, label validation, the stand-alone DDPM update (v2:584-592) and Philox draws.
+// One warp owns one row: the row lives in registers, statistics are warp-shuffle reductions,
+// global accesses are 128-bit and coalesced.
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace {
+
+constexpr int kWarpsPerCta = 4;
+
+template <typename TOP> struct Pack4;
+template <> struct Pack4<float> {
+  static __device__ __forceinline__ void store(float* p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+  }
+};
+template <> struct Pack4<bf16> {
+  static __device__ __forceinline__ void store(bf16* p, float a, float b, float c, float d) {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a, b), p1 = __floats2bfloat162_rn(c, d);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&p0);
+    pk.y = *reinterpret_cast<uint32_t*>(&p1);
+    *reinterpret_cast<uint2*>(p) = pk;
+  }
+};
+
+// mean and 1/sqrt(var + eps) of a row held as NV4 float4 per lane (biased variance, two-pass)
+template <int NV4>
+__device__ __forceinline__ void row_stats(const float4 (&v)[NV4], int d, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV4; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  mean = warp_sum(s) / (float)d;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV4; ++j) {
+    float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, e = v[j].w - mean;
+    q += (a * a + b * b) + (c * c + e * e);
+  }
+  rstd = 1.0f / sqrtf(warp_sum(q) / (float)d + 1e-5f);
+}
+
+// h2 = swish(LN_a(u)) + h ; n = LN_b(h2)           (v2:546-549)
+template <int NV4, typename TOP>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+stage_mid_kernel(const float* __restrict__ u, const float* __restrict__ h, const float* __restrict__ ga,
+                 const float* __restrict__ ba, const float* __restrict__ gb, const float* __restrict__ bb,
+                 float* __restrict__ h2, TOP* __restrict__ n_op, int ld_op, int M, int d) {
+  const int row = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float4 v[NV4];
+  const float4* up = reinterpret_cast<const float4*>(u + (size_t)row * d);
+#pragma unroll
+  for (int j = 0; j < NV4; ++j) v[j] = up[j * 32 + lane];
+  float mean, rstd;
+  row_stats<NV4>(v, d, mean, rstd);
+  const float4* hp = reinterpret_cast<const float4*>(h + (size_t)row * d);
+  float4* h2p = reinterpret_cast<float4*>(h2 + (size_t)row * d);
+#pragma unroll
+  for (int j = 0; j < NV4; ++j) {
+    const int q = j * 32 + lane;
+    float4 g = reinterpret_cast<const float4*>(ga)[q], b = reinterpret_cast<const float4*>(ba)[q], r = hp[q];
+    v[j].x = swishf((v[j].x - mean) * rstd * g.x + b.x) + r.x;
+    v[j].y = swishf((v[j].y - mean) * rstd * g.y + b.y) + r.y;
+    v[j].z = swishf((v[j].z - mean) * rstd * g.z + b.z) + r.z;
+    v[j].w = swishf((v[j].w - mean) * rstd * g.w + b.w) + r.w;
+    h2p[q] = v[j];
+  }
+  row_stats<NV4>(v, d, mean, rstd);
+#pragma unroll
+  for (int j = 0; j < NV4; ++j) {
+    const int q = j * 32 + lane;
+    float4 g = reinterpret_cast<const float4*>(gb)[q], b = reinterpret_cast<const float4*>(bb)[q];
+    Pack4<TOP>::store(n_op + (size_t)row * ld_op + q * 4, (v[j].x - mean) * rstd * g.x + b.x,
+                      (v[j].y - mean) * rstd * g.y + b.y, (v[j].z - mean) * rstd * g.z + b.z,
+                      (v[j].w - mean) * rstd * g.w + b.w);
+  }
+}
+
+// out = act(LN(in))   (v2:559 final_norm; also Decoder.fc LayerNorm(512), v2:247)
+template <int NV4, typename TOP>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+row_ln_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ g_, const float* __restrict__ b_,
+              int act, TOP* __restrict__ out, int ld_out, int M, int d) {
+  const int row = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float4 v[NV4];
+  const float4* ip = reinterpret_cast<const float4*>(in + (size_t)row * ld_in);
+#pragma unroll
+  for (int j = 0; j < NV4; ++j) v[j] = ip[j * 32 + lane];
+  float mean, rstd;
+  row_stats<NV4>(v, d, mean, rstd);
+#pragma unroll
+  for (int j = 0; j < NV4; ++j) {
+    const int q = j * 32 + lane;
+    float4 g = reinterpret_cast<const float4*>(g_)[q], b = reinterpret_cast<const float4*>(b_)[q];
+    float o0 = (v[j].x - mean) * rstd * g.x + b.x, o1 = (v[j].y - mean) * rstd * g.y + b.y;
+    float o2 = (v[j].z - mean) * rstd * g.z + b.z, o3 = (v[j].w - mean) * rstd * g.w + b.w;
+    if (act == LDM_ACT_SWISH) { o0 = swishf(o0); o1 = swishf(o1); o2 = swishf(o2); o3 = swishf(o3); }
+    Pack4<TOP>::store(out + (size_t)row * ld_out + q * 4, o0, o1, o2, o3);
+  }
+}
+
+// LayerNorm over a long row (Decoder.fc LayerNorm(32768), v2:251): one CTA per row, three passes
+// over an L2-resident row (sum; centred sum of squares; write).
+template <typename TOP>
+__global__ void __launch_bounds__(256)
+row_ln_big_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ g_, const float* __restrict__ b_,
+                  int act, TOP* __restrict__ out, int ld_out, int d) {
+  __shared__ float red[8];
+  __shared__ float bc;
+  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const float4* ip = reinterpret_cast<const float4*>(in + (size_t)row * ld_in);
+  const int n4 = d >> 2;
+  float s = 0.f;
+  for (int q = tid; q < n4; q += 256) { float4 v = ip[q]; s += (v.x + v.y) + (v.z + v.w); }
+  s = warp_sum(s);
+  if (lane == 0) red[wid] = s;
+  __syncthreads();
+  if (tid == 0) { float t = 0.f; for (int i = 0; i < 8; ++i) t += red[i]; bc = t / (float)d; }
+  __syncthreads();
+  const float mean = bc;
+  float qq = 0.f;
+  for (int q = tid; q < n4; q += 256) {
+    float4 v = ip[q];
+    float a = v.x - mean, b = v.y - mean, c = v.z - mean, e = v.w - mean;
+    qq += (a * a + b * b) + (c * c + e * e);
+  }
+  qq = warp_sum(qq);
+  __syncthreads();
+  if (lane == 0) red[wid] = qq;
+  __syncthreads();
+  if (tid == 0) { float t = 0.f; for (int i = 0; i < 8; ++i) t += red[i]; bc = 1.0f / sqrtf(t / (float)d + 1e-5f); }
+  __syncthreads();
+  const float rstd = bc;
+  for (int q = tid; q < n4; q += 256) {
+    float4 v = ip[q], g = reinterpret_cast<const float4*>(g_)[q], b = reinterpret_cast<const float4*>(b_)[q];
+    float o0 = (v.x - mean) * rstd * g.x + b.x, o1 = (v.y - mean) * rstd * g.y + b.y;
+    float o2 = (v.z - mean) * rstd * g.z + b.z, o3 = (v.w - mean) * rstd * g.w + b.w;
+    if (act == LDM_ACT_SWISH) { o0 = swishf(o0); o1 = swishf(o1); o2 = swishf(o2); o3 = swishf(o3); }
+    Pack4<TOP>::store(out + (size_t)row * ld_out + q * 4, o0, o1, o2, o3);
+  }
+}
+
+template <typename TOP>
+__global__ void load_x_kernel(const float* __restrict__ x, TOP* __restrict__ dst, int ld_dst, int M, int d4) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * d4) return;
+  const int row = i / d4, q = i - row * d4;
+  float4 v = reinterpret_cast<const float4*>(x)[i];
+  Pack4<TOP>::store(dst + (size_t)row * ld_dst + q * 4, v.x, v.y, v.z, v.w);
+}
+
+__global__ void set_classes_kernel(const int64_t* __restrict__ c, int32_t* __restrict__ out, int M, int ncls,
+                                   int* __restrict__ flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  long long v = c[i];
+  if (v < 0 || v >= ncls) { atomicOr(flags, 1); v = v < 0 ? 0 : ncls - 1; }
+  out[i] = (int32_t)v;
+}
+
+__global__ void check_t_kernel(const int64_t* __restrict__ t, int n, int n_t, int* __restrict__ flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long v = t[i];
+  if (v < 0 || v >= n_t) atomicOr(flags, 2);
+}
+
+__global__ void ddpm_update_kernel(float* __restrict__ x, const float* __restrict__ eps, float c2, float sqrt_alpha,
+                                   float sigma, const float* __restrict__ noise, unsigned long long seed,
+                                   unsigned long long sample_offset, int step, int M, int d4) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * d4) return;
+  const int row = i / d4, q = i - row * d4;
+  float4 xv = reinterpret_cast<float4*>(x)[i];
+  float4 e = reinterpret_cast<const float4*>(eps)[i];
+  float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (sigma > 0.0f) {
+    if (noise) z = reinterpret_cast<const float4*>(noise)[i];
+    else z = philox_normal4(seed, sample_offset + (unsigned long long)row, (uint32_t)step, (uint32_t)q);
+  }
+  xv.x = ddpm_update_one(xv.x, e.x, c2, sqrt_alpha, sigma, z.x);
+  xv.y = ddpm_update_one(xv.y, e.y, c2, sqrt_alpha, sigma, z.y);
+  xv.z = ddpm_update_one(xv.z, e.z, c2, sqrt_alpha, sigma, z.z);
+  xv.w = ddpm_update_one(xv.w, e.w, c2, sqrt_alpha, sigma, z.w);
+  reinterpret_cast<float4*>(x)[i] = xv;
+}
+
+__global__ void randn_kernel(float* __restrict__ out, unsigned long long seed, unsigned long long sample_offset,
+                             int step, int M, int d4) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * d4) return;
+  const int row = i / d4, q = i - row * d4;
+  reinterpret_cast<float4*>(out)[i] =
+      philox_normal4(seed, sample_offset + (unsigned long long)row, (uint32_t)step, (uint32_t)q);
+}
+
+__global__ void set_rng_kernel(unsigned long long* rng, unsigned long long seed, unsigned long long off) {
+  rng[0] = seed;
+  rng[1] = off;
+}
+
+template <typename F>
+int dispatch_nv4(int d, F&& f) {
+  switch (d / 128) {
+    case 1: return f(std::integral_constant<int, 1>());
+    case 2: return f(std::integral_constant<int, 2>());
+    case 3: return f(std::integral_constant<int, 3>());
+    case 4: return f(std::integral_constant<int, 4>());
+    case 5: return f(std::integral_constant<int, 5>());
+    case 6: return f(std::integral_constant<int, 6>());
+    case 7: return f(std::integral_constant<int, 7>());
+    case 8: return f(std::integral_constant<int, 8>());
+  }
+  return -1;
+}
+
+}  // namespace
+
+#define LDM_LAUNCHED(ctx)                      \
+  do {                                         \
+    (ctx)->launches++;                         \
+    LDM_CUDA(cudaGetLastError());              \
+  } while (0)
+
+template <typename TOP>
+int launch_stage_mid(ldm_ctx* ctx, const float* u, const float* h, const float* ga, const float* ba,
+                     const float* gb, const float* bb, float* h2, TOP* n_op, int ld_op, int M, int d,
+                     cudaStream_t st) {
+  LDM_CHECK(d % 128 == 0 && d >= 128 && d <= 1024, "stage_mid: hidden dim %d must be a multiple of 128 in [128,1024]", d);
+  dim3 grid(ceil_div(M, kWarpsPerCta)), block(kWarpsPerCta * 32);
+  dispatch_nv4(d, [&](auto nv) {
+    stage_mid_kernel<decltype(nv)::value, TOP><<<grid, block, 0, st>>>(u, h, ga, ba, gb, bb, h2, n_op, ld_op, M, d);
+    return 0;
+  });
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+template int launch_stage_mid<float>(ldm_ctx*, const float*, const float*, const float*, const float*, const float*,
+                                     const float*, float*, float*, int, int, int, cudaStream_t);
+template int launch_stage_mid<bf16>(ldm_ctx*, const float*, const float*, const float*, const float*, const float*,
+                                    const float*, float*, bf16*, int, int, int, cudaStream_t);
+
+template <typename TOP>
+int launch_row_ln(ldm_ctx* ctx, const float* in, int ld_in, const float* g, const float* b, int act, TOP* out,
+                  int ld_out, int M, int d, cudaStream_t st) {
+  LDM_CHECK(d % 4 == 0 && ld_in % 4 == 0 && ld_out % 4 == 0, "row_ln: dims must be multiples of 4");
+  if (d % 128 == 0 && d <= 1024) {
+    dim3 grid(ceil_div(M, kWarpsPerCta)), block(kWarpsPerCta * 32);
+    dispatch_nv4(d, [&](auto nv) {
+      row_ln_kernel<decltype(nv)::value, TOP><<<grid, block, 0, st>>>(in, ld_in, g, b, act, out, ld_out, M, d);
+      return 0;
+    });
+  } else {
+    row_ln_big_kernel<TOP><<<M, 256, 0, st>>>(in, ld_in, g, b, act, out, ld_out, d);
+  }
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+template int launch_row_ln<float>(ldm_ctx*, const float*, int, const float*, const float*, int, float*, int, int, int,
+                                  cudaStream_t);
+template int launch_row_ln<bf16>(ldm_ctx*, const float*, int, const float*, const float*, int, bf16*, int, int, int,
+                                 cudaStream_t);
+
+template <typename TOP>
+int launch_load_x(ldm_ctx* ctx, const float* x, TOP* dst, int ld_dst, int M, int d, cudaStream_t st) {
+  LDM_CHECK(d % 4 == 0, "load_x: dim must be a multiple of 4");
+  const int n = M * (d / 4);
+  load_x_kernel<TOP><<<ceil_div(n, 256), 256, 0, st>>>(x, dst, ld_dst, M, d / 4);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+template int launch_load_x<float>(ldm_ctx*, const float*, float*, int, int, int, cudaStream_t);
+template int launch_load_x<bf16>(ldm_ctx*, const float*, bf16*, int, int, int, cudaStream_t);
+
+int launch_set_classes(ldm_ctx* ctx, const int64_t* c, int32_t* out, int M, int ncls, int* flags, cudaStream_t st) {
+  set_classes_kernel<<<ceil_div(M, 256), 256, 0, st>>>(c, out, M, ncls, flags);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+
+int launch_check_t(ldm_ctx* ctx, const int64_t* t, int n, int n_t, int* flags, cudaStream_t st) {
+  check_t_kernel<<<ceil_div(n, 256), 256, 0, st>>>(t, n, n_t, flags);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+
+int launch_ddpm_update(ldm_ctx* ctx, float* x, const float* eps, float c2, float sqrt_alpha, float sigma,
+                       const float* noise, unsigned long long seed, unsigned long long sample_offset, int step,
+                       int M, int d, cudaStream_t st) {
+  LDM_CHECK(d % 4 == 0, "ddpm_update: dim must be a multiple of 4");
+  const int n = M * (d / 4);
+  ddpm_update_kernel<<<ceil_div(n, 256), 256, 0, st>>>(x, eps, c2, sqrt_alpha, sigma, noise, seed, sample_offset,
+                                                       step, M, d / 4);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+
+int launch_randn(ldm_ctx* ctx, float* out, unsigned long long seed, unsigned long long sample_offset, int step,
+                 int M, int d, cudaStream_t st) {
+  LDM_CHECK(d % 4 == 0, "randn: dim must be a multiple of 4");
+  const int n = M * (d / 4);
+  randn_kernel<<<ceil_div(n, 256), 256, 0, st>>>(out, seed, sample_offset, step, M, d / 4);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+
+int launch_set_rng(ldm_ctx* ctx, unsigned long long* rng, unsigned long long seed, unsigned long long sample_offset,
+                   cudaStream_t st) {
+  set_rng_kernel<<<1, 1, 0, st>>>(rng, seed, sample_offset);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}

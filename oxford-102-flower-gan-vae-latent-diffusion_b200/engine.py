@@ -1,0 +1,244 @@
+"""Per-(device, precision) handle on an ldm_ctx: packs module weights into it and issues the calls.
+
+PyTorch is used here for device memory and streams only; all arithmetic of the hot path happens inside
+libldm_b200.so.  One denoiser and one decoder are resident per engine; packing is redone when a
+different module, or a module whose parameters changed (tensor._version / data_ptr), is used."""
+import ctypes
+import os
+import threading
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+_engines = {}
+_lock = threading.Lock()
+_default_precision = None
+
+
+def default_precision():
+    """'bf16' (tcgen05 tensor cores, eps within 2e-2) unless LDM_B200_PRECISION=fp32 or set_default_precision()."""
+    if _default_precision is not None:
+        return _default_precision
+    p = os.environ.get("LDM_B200_PRECISION", "bf16").lower()
+    if p not in _lib.PRECISION:
+        raise ValueError("LDM_B200_PRECISION must be one of %s" % sorted(_lib.PRECISION))
+    return p
+
+
+def set_default_precision(p):
+    global _default_precision
+    if p is not None and p not in _lib.PRECISION:
+        raise ValueError("precision must be one of %s" % sorted(_lib.PRECISION))
+    _default_precision = p
+
+
+def _dev_index(device):
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("the B200 sampling path runs on CUDA devices only (got %s); there is no CPU fallback" % device)
+    return device.index if device.index is not None else torch.cuda.current_device()
+
+
+def get_engine(device, precision=None):
+    precision = precision or default_precision()
+    key = (_dev_index(device), precision)
+    with _lock:
+        eng = _engines.get(key)
+        if eng is None:
+            eng = _engines[key] = Engine(key[0], precision)
+    return eng
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _f32(t, device):
+    """fp32 contiguous view/copy of a parameter on `device` (kept alive by the caller during packing)."""
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def _state_key(module, extra=()):
+    ps = list(module.parameters())
+    return (id(module), tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps)) + tuple(extra)
+
+
+class Engine:
+    def __init__(self, device_index, precision):
+        self.device = torch.device("cuda", device_index)
+        self.precision = precision
+        self.ctx = ctypes.c_void_p()
+        check(lib().ldm_ctx_create(ctypes.byref(self.ctx), device_index, _lib.PRECISION[precision]), "ldm_ctx_create")
+        self._unet_key = None
+        self._dec_key = None
+        self._sched_key = None
+        self._cls_key = None
+
+    def __del__(self):
+        try:
+            if self.ctx:
+                lib().ldm_ctx_destroy(self.ctx)
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def info(self, key):
+        out = ctypes.c_double()
+        check(lib().ldm_get_info(self.ctx, key.encode(), ctypes.byref(out)), "ldm_get_info")
+        return out.value
+
+    def launches(self):
+        out = ctypes.c_uint64()
+        check(lib().ldm_kernel_launch_count(self.ctx, ctypes.byref(out)), "ldm_kernel_launch_count")
+        return out.value
+
+    def check_device_flags(self, num_classes=None):
+        """Raise like the reference's nn.Embedding / tensor indexing would on a bad index."""
+        f = int(self.info("device_flags"))
+        if f & 1:
+            raise IndexError("class label out of range [0, %s)" % (num_classes if num_classes is not None else "num_classes"))
+        if f & 2:
+            raise IndexError("timestep out of range of the time-embedding table")
+        e = int(self.info("tc_error"))
+        if e:
+            raise _lib.LdmError("tensor-core kernel barrier timeout (code %d, block %d)" % (e >> 16, e & 0xFFFF))
+
+    # ------------------------------------------------------------------ schedule
+    def set_schedule(self, beta, alpha, alpha_bar):
+        b, a, ab = (t.detach().to("cpu", torch.float32).contiguous() for t in (beta, alpha, alpha_bar))
+        key = (b.numpy().tobytes(), a.numpy().tobytes(), ab.numpy().tobytes())
+        if key == self._sched_key:
+            return
+        check(lib().ldm_set_schedule(self.ctx, _ptr(b), _ptr(a), _ptr(ab), b.numel()), "ldm_set_schedule")
+        self._sched_key = key
+
+    # ------------------------------------------------------------------ denoiser
+    def pack_unet(self, m, n_t):
+        key = _state_key(m, (n_t,))
+        if key == self._unet_key:
+            return
+        dev, keep = self.device, []
+        def P(t):
+            v = _f32(t, dev); keep.append(v); return v.data_ptr()
+        w = _lib.UnetWeights()
+        hidden = list(m.hidden_dims)
+        nst = len(hidden) - 1
+        if nst > _lib.MAX_STAGES:
+            raise ValueError("at most %d stages are supported" % _lib.MAX_STAGES)
+        w.latent_dim, w.time_dim, w.num_classes, w.n_stages, w.n_t = m.latent_dim, m.time_emb_dim, m.num_classes, nst, n_t
+        for i, d in enumerate(hidden):
+            w.hidden[i] = d
+        w.sinusoid = P(m.time_emb.sinusoid_table(n_t))
+        w.residual_weight = P(m.residual_weight.reshape(1))
+        w.time_lin1_w, w.time_lin1_b = P(m.time_emb.lin1.weight), P(m.time_emb.lin1.bias)
+        w.time_lin2_w, w.time_lin2_b = P(m.time_emb.lin2.weight), P(m.time_emb.lin2.bias)
+        w.class_embedding = P(m.class_emb.embedding.weight)
+        w.class_lin1_w, w.class_lin1_b = P(m.class_emb.lin1.weight), P(m.class_emb.lin1.bias)
+        w.class_lin2_w, w.class_lin2_b = P(m.class_emb.lin2.weight), P(m.class_emb.lin2.bias)
+        w.latent_proj_w, w.latent_proj_b = P(m.latent_proj.weight), P(m.latent_proj.bias)
+        for i in range(nst):
+            w.time_proj_w[i], w.time_proj_b[i] = P(m.time_projections[i].weight), P(m.time_projections[i].bias)
+            att = m.attention_layers[i]
+            w.attn_in_proj_w[i], w.attn_in_proj_b[i] = P(att.in_proj_weight), P(att.in_proj_bias)
+            w.attn_out_w[i], w.attn_out_b[i] = P(att.out_proj.weight), P(att.out_proj.bias)
+            block, ln, down = m.layers[i]
+            w.block_lin_w[i], w.block_lin_b[i] = P(block[0].weight), P(block[0].bias)
+            w.block_ln_w[i], w.block_ln_b[i] = P(block[1].weight), P(block[1].bias)
+            w.stage_ln_w[i], w.stage_ln_b[i] = P(ln.weight), P(ln.bias)
+            w.down_w[i], w.down_b[i] = P(down.weight), P(down.bias)
+        w.final_time_w, w.final_time_b = P(m.final_time_proj.weight), P(m.final_time_proj.bias)
+        w.final_class_w, w.final_class_b = P(m.final_class_proj.weight), P(m.final_class_proj.bias)
+        w.final_norm_w, w.final_norm_b = P(m.final_norm.weight), P(m.final_norm.bias)
+        w.final_w, w.final_b = P(m.final.weight), P(m.final.bias)
+        check(lib().ldm_unet_pack(self.ctx, ctypes.byref(w), self.stream()), "ldm_unet_pack")
+        self._unet_key = key
+        self._cls_key = None
+
+    def set_classes(self, c, batch):
+        if c is None:
+            check(lib().ldm_unet_set_classes(self.ctx, None, batch, self.stream()), "ldm_unet_set_classes")
+            return None
+        c = c.detach().to(device=self.device, dtype=torch.int64).contiguous()
+        if c.dim() != 1 or c.numel() != batch:
+            raise ValueError("class tensor must have shape (%d,), got %s" % (batch, tuple(c.shape)))
+        check(lib().ldm_unet_set_classes(self.ctx, _ptr(c), batch, self.stream()), "ldm_unet_set_classes")
+        return c
+
+    def unet_forward(self, x, t, c):
+        x = x.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        B = x.shape[0]
+        t = t.detach().to(device=self.device, dtype=torch.int64).contiguous().reshape(-1)
+        if t.numel() not in (1, B):
+            raise ValueError("t must have 1 or %d entries, got %d" % (B, t.numel()))
+        keep = self.set_classes(c, B)
+        out = torch.empty_like(x)
+        check(lib().ldm_unet_forward(self.ctx, _ptr(x), _ptr(t), t.numel(), _ptr(out), B, self.stream()), "ldm_unet_forward")
+        del keep
+        return out
+
+    def ddpm_step(self, x, eps, t, noise=None, seed=0, sample_offset=0):
+        check(lib().ldm_ddpm_step(self.ctx, _ptr(x), _ptr(eps), int(t), _ptr(noise) if noise is not None else None,
+                                  seed, sample_offset, x.shape[0], self.stream()), "ldm_ddpm_step")
+        return x
+
+    def randn(self, batch, dim, seed, sample_offset, step):
+        out = torch.empty(batch, dim, device=self.device, dtype=torch.float32)
+        check(lib().ldm_randn(self.ctx, _ptr(out), seed, sample_offset, int(step), batch, dim, self.stream()), "ldm_randn")
+        return out
+
+    def sample(self, x, t_start, t_end, c, noise=None, seed=0, sample_offset=0, use_graph=True):
+        """In-place chain on x (B, latent) for t = t_start .. t_end."""
+        B = x.shape[0]
+        keep = self.set_classes(c, B)
+        if noise is not None:
+            noise = noise.detach().to(device=self.device, dtype=torch.float32).contiguous()
+            if noise.shape != (t_start - t_end + 1, B, x.shape[1]):
+                raise ValueError("noise must have shape (%d, %d, %d)" % (t_start - t_end + 1, B, x.shape[1]))
+        check(lib().ldm_sample(self.ctx, _ptr(x), int(t_start), int(t_end), _ptr(noise) if noise is not None else None,
+                               seed, sample_offset, B, 1 if use_graph else 0, self.stream()), "ldm_sample")
+        del keep
+        return x
+
+    # ------------------------------------------------------------------ decoder
+    def pack_decoder(self, dec):
+        key = _state_key(dec)
+        if key == self._dec_key:
+            return
+        dev, keep = self.device, []
+        def P(t):
+            v = _f32(t, dev); keep.append(v); return v.data_ptr()
+        w = _lib.DecoderWeights()
+        w.latent_dim = dec.latent_dim
+        w.fc0_w, w.fc0_b, w.fc1_w, w.fc1_b = P(dec.fc[0].weight), P(dec.fc[0].bias), P(dec.fc[1].weight), P(dec.fc[1].bias)
+        w.fc3_w, w.fc3_b, w.fc4_w, w.fc4_b = P(dec.fc[3].weight), P(dec.fc[3].bias), P(dec.fc[4].weight), P(dec.fc[4].bias)
+        for i, (res, up) in enumerate(((dec.res3, dec.up3), (dec.res2, dec.up2), (dec.res1, dec.up1))):
+            r = w.res[i]
+            r.conv1_w, r.conv1_b, r.ln1_w, r.ln1_b = P(res.conv1.weight), P(res.conv1.bias), P(res.ln1.weight), P(res.ln1.bias)
+            r.conv2_w, r.conv2_b, r.ln2_w, r.ln2_b = P(res.conv2.weight), P(res.conv2.bias), P(res.ln2.weight), P(res.ln2.bias)
+            r.ca_w0, r.ca_w2, r.sa_w = P(res.ca.conv_du[0].weight), P(res.ca.conv_du[2].weight), P(res.sa.conv.weight)
+            w.up_w[i], w.up_b[i], w.up_gn_w[i], w.up_gn_b[i] = P(up[0].weight), P(up[0].bias), P(up[1].weight), P(up[1].bias)
+        fc = dec.final_conv
+        w.fin0_w, w.fin0_b, w.fin_gn_w, w.fin_gn_b = P(fc[0].weight), P(fc[0].bias), P(fc[1].weight), P(fc[1].bias)
+        w.fin3_w, w.fin3_b = P(fc[3].weight), P(fc[3].bias)
+        check(lib().ldm_decoder_pack(self.ctx, ctypes.byref(w), self.stream()), "ldm_decoder_pack")
+        self._dec_key = key
+
+    def decode(self, z):
+        z = z.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        out = torch.empty(z.shape[0], 3, 64, 64, device=self.device, dtype=torch.float32)
+        check(lib().ldm_decode(self.ctx, _ptr(z), _ptr(out), z.shape[0], self.stream()), "ldm_decode")
+        return out
+
+    def generate_host(self, c_host, img_host, latents_host=None, seed=0, sample_offset=0):
+        """Host buffers in, host buffers out (pinned recommended): labels -> images, one call."""
+        B = img_host.shape[0]
+        cp = _ptr(c_host) if c_host is not None else None
+        lp = _ptr(latents_host) if latents_host is not None else None
+        check(lib().ldm_generate_host(self.ctx, cp, B, seed, sample_offset, _ptr(img_host), lp, self.stream()),
+              "ldm_generate_host")
+        return img_host

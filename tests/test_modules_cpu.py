@@ -1,0 +1,80 @@
+"""Host-side mirror of the reference's module API: state_dict layout, loud failures, bit-exact host tables."""
+import numpy as np
+import pytest
+import torch
+
+import ldm_b200
+from oracle import restate as R, weights
+from tests._util import UNET_SEED
+
+
+def test_state_dict_layout_is_the_references():
+    u, ae = ldm_b200.ConditionalUNet(), ldm_b200.SimpleAutoencoder()
+    assert [(k, tuple(v.shape)) for k, v in u.state_dict().items()] == [(k, tuple(s)) for k, s, _ in weights.unet_spec()]
+    assert [(k, tuple(v.shape)) for k, v in ae.state_dict().items()] == [(k, tuple(s)) for k, s, _ in weights.autoencoder_spec()]
+    assert sum(p.numel() for p in u.parameters()) == 11131137
+    assert sum(p.numel() for p in ae.parameters()) == 69218997
+    assert sum(p.numel() for p in ae.decoder.parameters()) == 26066217
+    u.load_state_dict(weights.make_unet_state(UNET_SEED, "perturbed"), strict=True)
+    ae.load_state_dict(weights.make_autoencoder_state(1, "init"), strict=True)
+
+
+def test_checkpoint_loader_accepts_both_reference_formats():
+    ae = ldm_b200.SimpleAutoencoder()
+    sd = weights.make_autoencoder_state(2, "perturbed")
+    ldm_b200.load_autoencoder_checkpoint(ae, {"autoencoder": sd, "discriminator": {}})      # v2:1179-1191
+    assert torch.equal(ae.decoder.fc[0].weight, sd["decoder.fc.0.weight"])
+    ae2 = ldm_b200.SimpleAutoencoder()
+    ldm_b200.load_autoencoder_checkpoint(ae2, sd)                                            # v2:1326
+    assert torch.equal(ae2.decoder.fc[3].bias, sd["decoder.fc.3.bias"])
+
+
+def test_schedule_and_sinusoid_tables_are_bit_exact(golden):
+    g = golden("init")
+    u = ldm_b200.ConditionalUNet().eval()
+    d = ldm_b200.ConditionalDenoiseDiffusion(u, 1000, None)
+    assert d.n_steps == 1000 and d.eps_model is u and d.device is None
+    assert np.array_equal(d.beta.numpy(), g["beta"])
+    assert np.array_equal(d.alpha.numpy(), g["alpha"])
+    assert np.array_equal(d.alpha_bar.numpy(), g["alpha_bar"])
+    tab = u.time_emb.sinusoid_table(1000)
+    assert torch.equal(tab, R.sinusoid(torch.arange(1000)))
+    assert torch.equal(tab[[0, 17, 999]], R.sinusoid(torch.tensor([0, 17, 999])))   # row t IS the reference's value for t
+
+
+def test_q_sample_matches_restatement():
+    u = ldm_b200.ConditionalUNet().eval()
+    d = ldm_b200.ConditionalDenoiseDiffusion(u, 1000, None)
+    g = torch.Generator().manual_seed(0)
+    x0, eps = torch.randn(3, 256, generator=g), torch.randn(3, 256, generator=g)
+    t = torch.tensor([0, 500, 999])
+    assert torch.equal(d.q_sample(x0, t, eps), R.q_sample(R.schedule(1000), x0, t, eps))
+
+
+def test_cpu_tensors_and_training_mode_fail_loudly():
+    u = ldm_b200.ConditionalUNet()
+    x, t = torch.zeros(2, 256), torch.tensor([5])
+    with pytest.raises(RuntimeError, match="eval"):
+        u(x, t)                                      # training mode
+    u.eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        u(x, t)                                      # no CPU fallback
+    d = ldm_b200.ConditionalDenoiseDiffusion(u, 1000, None)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        d.sample((2, 256), "cpu")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ldm_b200.SimpleAutoencoder().eval().decode(torch.zeros(1, 256))
+    with pytest.raises(IndexError):
+        d.p_sample(x, 1000)
+    with pytest.raises(ValueError):
+        d.p_sample(x, torch.tensor([1, 2]))
+
+
+def test_product_package_never_imports_the_oracle():
+    import os
+    pkg = os.path.dirname(ldm_b200.LIB_PATH)
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "oracle." not in src.replace("oracle/", ""), f
