@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: samples/s of (1000-step class-conditional DDPM in latent space + VAE decode).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--precision bf16|fp32]
+
+One "step" = one pass of the hot path over one batch: x_T draw, the 1000-step reverse loop (one CUDA-graph
+launch) and the decoder, for `--batch` samples per GPU (default 256 = BASELINE.json configs[1]).  Under
+torchrun (N > 1) every rank runs its own shard (weak scaling: 256 samples per GPU, 2048 in total at N = 8 =
+configs[2]) with no per-step communication; the decoded images are all-gathered once per step with NCCL and
+the time is the max over ranks.  Prints ONE JSON line (rank 0).
+
+--impl reference times the reference algorithm on the host CPU cores: the oracle port (oracle/restate.py, pinned
+bit-for-bit to the reference in the build container) because /root/reference does not travel to the GPU box.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic work per unit
+FLOP_DENOISER_PER_SAMPLE_STEP = 12_845_056          # algorithmically necessary (6 422 528 MAC)
+FLOP_DECODE_PER_SAMPLE = 2_809_570_560
+N_STEPS = 1000
+LATENT = 256
+IMG_BYTES = 3 * 64 * 64 * 4
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
+                "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm on host cores (oracle port), bounded sample
+# ------------------------------------------------------------------------------------------------------
+def cpu_sample_rate(batch, denoise_steps, decode_rows, threads=None):
+    """samples/s of the reference path on the CPU, extrapolated from `denoise_steps` of the 1000 reverse steps at the
+    full batch and a decode of `decode_rows` samples (both scale linearly: the loop is 1000 identical steps, the
+    decoder is per-sample)."""
+    import torch
+    from oracle import philox, restate as R, weights
+    torch.set_grad_enabled(False)
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd_u = weights.make_unet_state(42, "init")
+    sd_a = weights.make_decoder_state(43, "init")
+    sched = R.schedule(N_STEPS)
+    c = torch.arange(batch) % 102
+    x = torch.from_numpy(philox.normal_rows(1234, 0, batch, N_STEPS))
+    R.p_sample(sd_u, sched, x, N_STEPS - 1, c, literal_attention=True)          # warm-up (thread pool, MKL plans)
+    t0 = time.perf_counter()
+    for t in range(N_STEPS - 1, N_STEPS - 1 - denoise_steps, -1):
+        # the reference AS EXECUTED: full multi_head_attention_forward, embeddings recomputed every step, randn_like
+        x = R.p_sample(sd_u, sched, x, t, c, literal_attention=True)
+    t_loop = (time.perf_counter() - t0) / denoise_steps * N_STEPS
+    z = x[:decode_rows]
+    t0 = time.perf_counter()
+    R.decode(sd_a, z)
+    t_dec = (time.perf_counter() - t0) / decode_rows * batch
+    return batch / (t_loop + t_dec), {"loop_s_extrapolated": t_loop, "decode_s_extrapolated": t_dec, "threads": torch.get_num_threads()}
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    batch = args.batch
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, info = cpu_sample_rate(batch, denoise_steps=20, decode_rows=8)
+        if i >= args.warmup:
+            vals.append(v)
+    value = sum(vals) / len(vals)
+    sample = "per step: batch %d, 20 of the 1000 reverse steps + decode of 8 samples, extrapolated linearly" % batch
+    line = {
+        "impl": "reference", "metric": "samples/s (1000-step DDPM + VAE decode)", "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * batch / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "v2 latent U-Net 1000-step sampling + VAE decode, batch %d, host CPU" % batch,
+                   "batch_per_gpu": batch, "n_steps": N_STEPS},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": info["threads"], "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import ldm_b200
+    from oracle import weights   # deterministic synthetic weights only (the oracle's arithmetic is not used on this arm)
+
+    torch.set_grad_enabled(False)
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    B, K, W = args.batch, args.steps, args.warmup
+    prec = args.precision
+
+    # random-init weights of the named architecture (ConditionalUNet + init_weights, SimpleAutoencoder())
+    unet = ldm_b200.ConditionalUNet(precision=prec)
+    unet.load_state_dict(weights.make_unet_state(42, "init"), strict=True)
+    unet = unet.to(dev).eval()
+    ae = ldm_b200.SimpleAutoencoder(precision=prec)
+    ae.load_state_dict(weights.make_autoencoder_state(43, "init"), strict=True)
+    ae = ae.to(dev).eval()
+    diffusion = ldm_b200.ConditionalDenoiseDiffusion(unet, N_STEPS, dev)
+    eng = unet.engine(dev, N_STEPS)
+    eng.set_schedule(*diffusion._host_schedule)
+    eng.pack_decoder(ae.decoder)
+
+    total = B * world
+    lo = rank * B
+    classes = (torch.arange(total) % 102)
+    c_dev = classes[lo:lo + B].to(dev)
+    gathered = torch.empty(total, 3, 64, 64, device=dev) if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    def step(i):
+        x0 = diffusion.sample((B, LATENT), dev, c_dev, seed=1234 + i, sample_offset=lo)
+        img = ae.decode(x0)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, img)
+        return img
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        step(i)
+    barrier()
+    eng.check_device_flags()
+
+    # ---- device-timed region: K steps, L2 flushed between iterations (flush outside the event pairs)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(K)]
+    sampler = ClockSampler(local_rank)
+    launches0 = eng.launches()
+    barrier()
+    sampler.start()
+    for i in range(K):
+        flush.zero_()
+        s, m, e = ev[i]
+        s.record()
+        x0 = diffusion.sample((B, LATENT), dev, c_dev, seed=99 + i, sample_offset=lo)
+        m.record()
+        img = ae.decode(x0)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, img)
+        e.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = eng.launches() - launches0
+    t_loop_ms = sum(s.elapsed_time(m) for s, m, e in ev)
+    t_total_ms = sum(s.elapsed_time(e) for s, m, e in ev)
+    assert torch.isfinite(img).all()
+
+    # ---- end to end through the host-buffer entry point: pinned labels in, pinned images out, every step
+    c_host = classes[lo:lo + B].clone().pin_memory()
+    img_host = torch.empty(B, 3, 64, 64).pin_memory()
+    eng.generate_host(c_host, img_host, None, seed=5, sample_offset=lo)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        eng.generate_host(c_host, img_host, None, seed=500 + i, sample_offset=lo)   # synchronous: returns with the images on the host
+    barrier()
+    t_e2e = time.perf_counter() - t0
+
+    if world > 1:
+        t = torch.tensor([t_total_ms, t_loop_ms, t_e2e * 1000.0], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_total_ms, t_loop_ms, t_e2e = float(t[0]), float(t[1]), float(t[2]) / 1000.0
+
+    if rank != 0:
+        return
+    pk = peaks()
+    value = total * K / (t_total_ms / 1000.0)
+    loop_flops = FLOP_DENOISER_PER_SAMPLE_STEP * B * N_STEPS                      # per graph launch, per GPU
+    loop_s = t_loop_ms / 1000.0 / K
+    achieved = loop_flops / loop_s / 1e12
+    dec_s = (t_total_ms - t_loop_ms) / 1000.0 / K
+    line = {
+        "metric": "samples/s (1000-step DDPM + VAE decode)", "value": value, "unit": "samples/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_total_ms / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if prec == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": "v2 latent U-Net 1000-step sampling + VAE decode, batch %d per GPU%s" %
+                               (B, "" if world == 1 else ", %d total, final NCCL all-gather of images" % total),
+                   "batch_per_gpu": B, "global_batch": total, "n_steps": N_STEPS, "precision": prec,
+                   "l2": "flushed (256 MiB write) between timed iterations", "weights": "random-init (seeded), eval mode"},
+        "e2e": {"value": total * K / t_e2e, "unit": "samples/s", "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": B * IMG_BYTES},
+        "gpu_launches": int(launches),
+        "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
+        "roofline": {"bound": "tensor", "kernel": "sampling loop (one CUDA-graph launch = 1000 steps x %d kernels)" % int(eng.info("launches_per_step")),
+                     "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
+                     "traffic": None, "peak_source": pk["src"], "ms_per_launch": loop_s * 1000.0,
+                     "algorithmic_flop_per_launch": loop_flops},
+        "decode": {"ms": dec_s * 1000.0, "tflops": FLOP_DECODE_PER_SAMPLE * B / dec_s / 1e12 if dec_s > 0 else None},
+    }
+    if world == 1 and not args.no_cpu:
+        v, info = cpu_sample_rate(B, denoise_steps=100, decode_rows=32)
+        line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": info["threads"], "kind": "port",
+                                "sample": "batch %d: 100 of the 1000 reverse steps + decode of 32 samples, extrapolated linearly" % B}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="samples per GPU per step")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -67,10 +67,15 @@ def _ln(x, sd, name):
     return F.layer_norm(x, (x.shape[-1],), sd[name + ".weight"], sd[name + ".bias"], 1e-5)
 
 
-def unet_forward(sd, x, t, c=None, n_stages=4, v1=False):
+def unet_forward(sd, x, t, c=None, n_stages=4, v1=False, literal_attention=False):
     """ConditionalUNet.forward v2:535-561, eval mode (Dropout v2:521 is the
     identity).  The L=1 attention (v2:550-552) is softmax over ONE key, i.e.
-    out_proj(V(h_norm)) with V = in_proj rows [2d:3d]."""
+    out_proj(V(h_norm)) with V = in_proj rows [2d:3d].
+    literal_attention=True runs torch's multi_head_attention_forward exactly as
+    nn.MultiheadAttention.forward does for the reference's call (need_weights
+    defaults to True, so the fused fast path is not taken): same result, and
+    the reference's real CPU cost (full 3d in_proj, bmm, softmax) -- used when
+    the oracle is TIMED as the CPU baseline."""
     residual = x
     te = time_embedding(sd, t)                                   # v2:537
     ce = class_embedding(sd, c) if c is not None else None       # v2:538
@@ -87,8 +92,16 @@ def unet_forward(sd, x, t, c=None, n_stages=4, v1=False):
         d = n.shape[-1]
         wv = sd[f"attention_layers.{i}.in_proj_weight"][2 * d:3 * d]
         bv = sd[f"attention_layers.{i}.in_proj_bias"][2 * d:3 * d]
-        a = F.linear(F.linear(n, wv, bv), sd[f"attention_layers.{i}.out_proj.weight"],
-                     sd[f"attention_layers.{i}.out_proj.bias"])  # v2:550-551
+        if literal_attention:
+            q = n.unsqueeze(0)                                   # v2:550: (L=1, N=B, E)
+            a, _ = F.multi_head_attention_forward(
+                q, q, q, d, 8, sd[f"attention_layers.{i}.in_proj_weight"], sd[f"attention_layers.{i}.in_proj_bias"],
+                None, None, False, 0.3, sd[f"attention_layers.{i}.out_proj.weight"],
+                sd[f"attention_layers.{i}.out_proj.bias"], training=False, need_weights=True)
+            a = a.squeeze(0)
+        else:
+            a = F.linear(F.linear(n, wv, bv), sd[f"attention_layers.{i}.out_proj.weight"],
+                         sd[f"attention_layers.{i}.out_proj.bias"])  # v2:550-551
         h = h + a                                                # v2:552
         h = F.linear(h, sd[f"layers.{i}.2.weight"], sd[f"layers.{i}.2.bias"])  # v2:553
     h = h + F.linear(te, sd["final_time_proj.weight"], sd["final_time_proj.bias"])      # v2:554-555
@@ -104,13 +117,13 @@ def unet_forward(sd, x, t, c=None, n_stages=4, v1=False):
 # --------------------------------------------------------------------------
 # DDPM reverse process (a2, a3)
 # --------------------------------------------------------------------------
-def p_sample(sd, sched, xt, t, c=None, noise=None):
+def p_sample(sd, sched, xt, t, c=None, noise=None, literal_attention=False):
     """ConditionalDenoiseDiffusion.p_sample v2:580-592.  `t` is a python int
     or an int64 tensor of shape (1,); `noise` replaces randn_like (v2:589)."""
     beta, alpha, alpha_bar = sched
     if not isinstance(t, torch.Tensor):
         t = torch.tensor([t])
-    eps_theta = unet_forward(sd, xt, t, c)
+    eps_theta = unet_forward(sd, xt, t, c, literal_attention=literal_attention)
     alpha_t = alpha[t].reshape(-1, 1)
     alpha_bar_t = alpha_bar[t].reshape(-1, 1)
     mean = (xt - ((1 - alpha_t) / torch.sqrt(1 - alpha_bar_t)) * eps_theta) / torch.sqrt(alpha_t)

@@ -1,0 +1,229 @@
+"""Parity of the sm_100a path with the oracle: through the module mirror, i.e. through the C ABI.
+Tolerances are north_star's: eps per step max|d|/max|ref| <= 1e-3 (fp32 mode) / 2e-2 (bf16 mode); final latents
+relative L2; indexing bit-exact.  Reference outputs come from tests/golden (made by the reference itself) and,
+for other sizes, from the CPU restatement (pinned to the reference by tests/test_oracle_*.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import philox, restate as R, weights
+from tests._util import (AE_SEED, EPS_TOL, IMAGE_TOL, LATENT_TOL, NOISE_SEED, T, UNET_SEED, chain_noise,
+                         make_autoencoder, make_unet)
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+DEV = "cuda"
+PRECISIONS = ["fp32", "bf16"]
+
+
+@pytest.fixture(scope="module", params=PRECISIONS)
+def precision(request):
+    return request.param
+
+
+def _diffusion(unet):
+    import ldm_b200
+    return ldm_b200.ConditionalDenoiseDiffusion(unet, 1000, torch.device(DEV))
+
+
+# ----------------------------------------------------------------------------- noise stream + update (a3)
+def test_philox_kernel_matches_spec():
+    import ldm_b200
+    eng = ldm_b200.get_engine(DEV, "fp32")
+    for seed, off, step, B in ((1234, 0, 1000, 4), (2 ** 40 + 3, 2 ** 33 + 5, 17, 64), (7, 123456, 0, 257)):
+        z = eng.randn(B, 256, seed, off, step).cpu().numpy()
+        want = philox.normal_rows(seed, off, B, step)
+        assert np.abs(z - want).max() < 2e-5, (seed, off, step)
+    # sharding invariance is exact: rows are keyed by the global sample index
+    a = eng.randn(8, 256, 9, 100, 3)
+    b = torch.cat([eng.randn(3, 256, 9, 100, 3), eng.randn(5, 256, 9, 103, 3)])
+    assert torch.equal(a, b)
+
+
+def test_ddpm_update_is_bit_exact_with_the_reference_expression(golden):
+    import ldm_b200
+    eng = ldm_b200.get_engine(DEV, "fp32")
+    sched = R.schedule(1000)
+    eng.set_schedule(*sched)
+    g = torch.Generator().manual_seed(0)
+    for t in (999, 500, 1, 0):
+        x = torch.randn(37, 256, generator=g) * 50
+        eps = torch.randn(37, 256, generator=g) * 7
+        nz = torch.randn(37, 256, generator=g)
+        want = R.ddpm_update(sched, x, eps, t, nz)
+        got = eng.ddpm_step(x.to(DEV).clone(), eps.to(DEV), t, noise=nz.to(DEV)).cpu()
+        assert torch.equal(got, want), t       # same fp32 operations in the same order: bit-equal
+    # in-kernel Philox noise == explicit spec noise up to the libm difference of the normals
+    x = torch.randn(16, 256, generator=g)
+    eps = torch.randn(16, 256, generator=g)
+    got = eng.ddpm_step(x.to(DEV).clone(), eps.to(DEV), 300, noise=None, seed=5, sample_offset=40).cpu()
+    want = R.ddpm_update(sched, x, eps, 300, T(philox.normal_rows(5, 40, 16, 300)))
+    assert float((got - want).abs().max()) < 1e-5
+
+
+# ----------------------------------------------------------------------------- denoiser forward (a4-a10)
+def test_unet_forward_against_reference_goldens(golden, style, precision):
+    g = golden(style)
+    u = make_unet(style, precision)
+    x, c = T(g["fwd_x"]).to(DEV), T(g["fwd_c"]).to(DEV)
+    tol = EPS_TOL[precision]
+    for t in (999, 500, 1, 0):
+        eps = u(x, torch.tensor([t], device=DEV), c).cpu()
+        assert R.max_rel(eps, g["fwd_eps_t%d" % t]) < tol, (t, R.max_rel(eps, g["fwd_eps_t%d" % t]))
+    eps = u(x, T(g["fwd_tb"]).to(DEV), c).cpu()                       # per-sample timesteps (training-style call, v2:606)
+    assert R.max_rel(eps, g["fwd_eps_tb"]) < tol
+    eps = u(x, torch.tensor([500], device=DEV), None).cpu()           # c=None branch (v2:538,543,556)
+    assert R.max_rel(eps, g["fwd_eps_noclass_t500"]) < tol
+
+
+def test_unet_forward_ragged_batches_against_restatement(precision):
+    sd = weights.make_unet_state(UNET_SEED, "perturbed")
+    u = make_unet("perturbed", precision)
+    for B in (1, 3, 130, 256):
+        g = torch.Generator().manual_seed(B)
+        x = torch.randn(B, 256, generator=g) * 4
+        c = torch.randint(0, 102, (B,), generator=g)
+        t = torch.randint(0, 1000, (B,), generator=g)
+        want = R.unet_forward(sd, x, t, c)
+        got = u(x.to(DEV), t.to(DEV), c.to(DEV)).cpu()
+        assert R.max_rel(got, want) < EPS_TOL[precision], (B, R.max_rel(got, want))
+
+
+def test_timestep_and_class_indexing_is_bit_exact(precision):
+    """Row i of a batched call with per-row t / c equals the same row computed with that t / c alone:
+    the table gathers pick exactly the right rows (values compared with torch.equal)."""
+    u = make_unet("perturbed", precision)
+    g = torch.Generator().manual_seed(11)
+    B = 12
+    x = (torch.randn(B, 256, generator=g) * 2).to(DEV)
+    t = torch.tensor([0, 1, 2, 999, 998, 500, 17, 17, 250, 750, 3, 64], device=DEV)
+    c = torch.tensor([0, 101, 50, 1, 100, 7, 7, 8, 33, 66, 99, 2], device=DEV)
+    full = u(x, t, c)
+    for i in range(B):
+        one = u(x, t[i:i + 1], c[i:i + 1].expand(B).contiguous())
+        assert torch.equal(one[i], full[i]), i
+    with pytest.raises(IndexError):
+        u(x, t, torch.full((B,), 102, device=DEV))
+    with pytest.raises(IndexError):
+        u(x, torch.tensor([1000], device=DEV), c)
+
+
+# ----------------------------------------------------------------------------- p_sample / sample (a2, a3)
+def test_p_sample_against_reference_goldens(golden, style, precision):
+    g = golden(style)
+    u = make_unet(style, precision)
+    d = _diffusion(u)
+    x, c = T(g["fwd_x"]).to(DEV), T(g["fwd_c"]).to(DEV)
+    tol = EPS_TOL[precision] * 2
+    got = d.p_sample(x, 500, c, noise=T(g["ps_noise"]).to(DEV)).cpu()
+    assert R.max_rel(got, g["ps_t500"]) < tol
+    got = d.p_sample(x, torch.tensor([0], device=DEV), c).cpu()       # tensor t as visualize_denoising_steps passes it
+    assert R.max_rel(got, g["ps_t0"]) < tol
+    assert x.data_ptr() != got.data_ptr() and torch.equal(x.cpu(), T(g["fwd_x"]))   # input not modified
+
+
+def test_full_chain_against_reference_goldens(golden, style, precision):
+    """BASELINE config 1 on the GPU: B = 4, 1000 steps, the reference's noise replayed."""
+    g = golden(style)
+    u = make_unet(style, precision)
+    d = _diffusion(u)
+    c = T(g["chain_c"]).to(DEV)
+    noise = torch.from_numpy(chain_noise(NOISE_SEED, 0, 4, 999)).to(DEV)
+    x0 = d.sample((4, 256), DEV, c, x_T=T(g["chain_xT"]).to(DEV), noise=noise).cpu()
+    err = R.rel_l2(x0, g["chain_x0"])
+    assert err < LATENT_TOL[precision], err
+    # the captured graph and the plain launch sequence are the same kernels: bit-equal
+    x0b = d.sample((4, 256), DEV, c, x_T=T(g["chain_xT"]).to(DEV), noise=noise, use_graph=False).cpu()
+    assert torch.equal(x0, x0b)
+    # in-kernel Philox (seed, global offset 0) reproduces the replayed-noise run up to libm ulps in the normals
+    x0c = d.sample((4, 256), DEV, c, seed=NOISE_SEED, sample_offset=0).cpu()
+    assert R.rel_l2(x0c, x0) < 1e-3
+    assert np.abs(x0c.numpy()).max() > 100          # random-init chains blow up in magnitude: relative metrics only
+
+
+def test_partial_chain_and_intermediate_states(golden, precision):
+    g = golden("perturbed")
+    u = make_unet("perturbed", precision)
+    d = _diffusion(u)
+    eng = u.engine(DEV, 1000)
+    eng.set_schedule(*d._host_schedule)
+    c = T(g["chain_c"]).to(DEV)
+    x = T(g["partial_x_start"]).to(DEV).clone()
+    eng.sample(x, 120, 0, c, noise=torch.from_numpy(chain_noise(NOISE_SEED + 3, 0, 4, 120)).to(DEV))
+    assert R.rel_l2(x.cpu(), g["partial_x0"]) < LATENT_TOL[precision]
+    # first 100 steps of the full chain against the reference's recorded state after t = 900
+    x = T(g["chain_xT"]).to(DEV).clone()
+    eng.sample(x, 999, 900, c, noise=torch.from_numpy(chain_noise(NOISE_SEED, 0, 4, 999, 900)).to(DEV))
+    assert R.rel_l2(x.cpu(), g["chain_x_after_t900"]) < LATENT_TOL[precision]
+
+
+def test_sharding_invariance_is_exact(precision):
+    """Rows [lo, hi) sampled alone with sample_offset = lo equal the same rows of the full batch, bit for bit."""
+    u = make_unet("init", precision)
+    d = _diffusion(u)
+    c = (torch.arange(24) * 5 % 102).to(DEV)
+    full = d.sample((24, 256), DEV, c, seed=77, sample_offset=1000)
+    for lo, hi in ((0, 8), (8, 17), (17, 24)):
+        part = d.sample((hi - lo, 256), DEV, c[lo:hi].contiguous(), seed=77, sample_offset=1000 + lo)
+        assert torch.equal(part, full[lo:hi]), (lo, hi)
+
+
+# ----------------------------------------------------------------------------- decoder (a11-a15)
+def test_decode_against_reference_goldens(golden, style, precision):
+    g = golden(style)
+    ae = make_autoencoder(style, precision)
+    img = ae.decode(T(g["dec_z"]).to(DEV)).cpu()
+    assert img.shape == (2, 3, 64, 64) and img.dtype == torch.float32
+    err = float((img - T(g["dec_img"])).abs().max())
+    assert err < IMAGE_TOL[precision], err
+    img = ae.decode(T(g["chain_x0"]).to(DEV)).cpu()          # the exploded-magnitude chain latents
+    err = float((img - T(g["dec_img_chain"])).abs().max())
+    assert err < IMAGE_TOL[precision] * 2, err
+
+
+def test_decode_batches_and_determinism(precision):
+    sd = weights.make_autoencoder_state(AE_SEED, "perturbed")
+    ae = make_autoencoder("perturbed", precision)
+    z = torch.from_numpy(philox.normal_rows(3, 0, 5, 0))
+    want = R.decode(sd, z)
+    got = ae.decode(z.to(DEV))
+    assert float((got.cpu() - want).abs().max()) < IMAGE_TOL[precision]
+    assert torch.equal(got, ae.decode(z.to(DEV)))
+    assert torch.equal(got[1:3], ae.decode(z[1:3].to(DEV)))   # per-sample norms only: rows are independent
+    assert float(got.min()) > 0 and float(got.max()) < 1
+
+
+# ----------------------------------------------------------------------------- host-buffer entry + full size
+def test_generate_host_end_to_end(precision):
+    u = make_unet("init", precision)
+    ae = make_autoencoder("init", precision)
+    d = _diffusion(u)
+    eng = u.engine(DEV, 1000)
+    eng.set_schedule(*d._host_schedule)
+    eng.pack_decoder(ae.decoder)
+    B = 6
+    c = (torch.arange(B) * 17 % 102).pin_memory()
+    img = torch.empty(B, 3, 64, 64).pin_memory()
+    lat = torch.empty(B, 256).pin_memory()
+    eng.generate_host(c, img, lat, seed=21, sample_offset=0)
+    x0 = d.sample((B, 256), DEV, c.to(DEV), seed=21, sample_offset=0)
+    assert torch.equal(lat, x0.cpu())
+    assert torch.equal(img, ae.decode(x0).cpu())
+    assert float(img.min()) >= 0 and float(img.max()) <= 1 and torch.isfinite(img).all()
+
+
+def test_full_size_batch_properties():
+    """BASELINE config 2 size (B = 256, bf16): properties that need no CPU run of 1000 steps at this size:
+    determinism, finiteness, image range, and agreement of rows with a B = 4 sub-run (sharding invariance)."""
+    u = make_unet("init", "bf16")
+    ae = make_autoencoder("init", "bf16")
+    d = _diffusion(u)
+    c = (torch.arange(256) % 102).to(DEV)
+    x0 = d.sample((256, 256), DEV, c, seed=1234, sample_offset=0)
+    assert torch.isfinite(x0).all()
+    assert torch.equal(x0, d.sample((256, 256), DEV, c, seed=1234, sample_offset=0))
+    sub = d.sample((4, 256), DEV, c[128:132].contiguous(), seed=1234, sample_offset=128)
+    assert torch.equal(sub, x0[128:132])
+    img = ae.decode(x0)
+    assert img.shape == (256, 3, 64, 64) and torch.isfinite(img).all()
+    assert float(img.min()) >= 0 and float(img.max()) <= 1
