@@ -168,6 +168,12 @@ LDM_API int ldm_generate_host(ldm_ctx* ctx, const int64_t* c_host, int batch, ui
 LDM_API int ldm_kernel_launch_count(ldm_ctx* ctx, uint64_t* out); /* kernels launched (graph nodes count per replay) */
 LDM_API int ldm_get_info(ldm_ctx* ctx, const char* key, double* out);
 
+/* Profiling aid for the persistent loop kernel: ldm_debug_chain_trace(ctx, step, NULL, 0) arms a per-CTA clock64()
+ * timeline of reverse step `step` of the next ldm_sample (cluster 0 only; step < 0 switches it off);
+ * ldm_debug_chain_trace(ctx, 0, out_host, n >= 16*64) synchronises and copies the stamps out: row = rank of the
+ * CTA in its cluster, entries = stamps in program order (0 = unused). */
+LDM_API int ldm_debug_chain_trace(ldm_ctx* ctx, int step, long long* out_host, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,7 @@ PROTOTYPES = {
     "ldm_generate_host": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, _vp, _vp, _vp]),
     "ldm_kernel_launch_count": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64)]),
     "ldm_get_info": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]),
+    "ldm_debug_chain_trace": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int]),
 }
 
 _lib = None

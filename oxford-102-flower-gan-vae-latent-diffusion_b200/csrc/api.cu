@@ -99,6 +99,14 @@ extern "C" LDM_API int ldm_ctx_create(ldm_ctx** out, int device, int precision) 
   if (r == 0) r = (int)cudaMemset(ctx->dev_flags, 0, 4 * sizeof(int));
   if (r == 0) r = (int)cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking);
   if (r == 0 && precision == LDM_PRECISION_BF16) r = tc_init(ctx);
+  if (r == 0) r = ldm_alloc_t(ctx, ctx->allocs, &ctx->chain_err, 2);
+  if (r == 0) r = (int)cudaMemset(ctx->chain_err, 0, 2 * sizeof(int));
+  if (r == 0 && precision == LDM_PRECISION_BF16) {
+    // the persistent cluster kernel is the bf16 denoiser; LDM_CHAIN=0 selects the one-kernel-per-layer sequence
+    const char* ch = getenv("LDM_CHAIN");
+    ctx->use_chain = ch ? atoi(ch) : 0;   // TODO(round 1): default on once it beats the graph path
+    if (ctx->use_chain && chain_init(ctx) != 0) ctx->use_chain = 0;   // ldm_last_error() keeps the reason; ldm_get_info("chain") reports 0
+  }
   const char* pdl = getenv("LDM_PDL");
   ctx->use_pdl = pdl ? atoi(pdl) : 0;
   if (r != 0) {
@@ -121,6 +129,9 @@ extern "C" LDM_API int ldm_ctx_destroy(ldm_ctx* ctx) {
   free_pool(ctx->unet.allocs);
   free_pool(ctx->dec.allocs);
   free_pool(ctx->stage_allocs);
+  free_pool(ctx->chain.allocs);
+  if (ctx->coef_dev) cudaFree(ctx->coef_dev);
+  if (ctx->chain_trace) cudaFree(ctx->chain_trace);
   if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
   delete ctx;
   return 0;
@@ -142,6 +153,15 @@ extern "C" LDM_API int ldm_set_schedule(ldm_ctx* ctx, const float* beta, const f
     ctx->sigma[t] = t > 0 ? sqrtf(beta[t]) : 0.0f;   // v2:588: no noise at t = 0
   }
   drop_graphs(ctx);
+  {  // device copy for the persistent chain kernel: (c2, sqrt_alpha, sigma, 0) per timestep
+    LDM_CUDA(cudaSetDevice(ctx->device));
+    LDM_CUDA(cudaDeviceSynchronize());
+    if (ctx->coef_dev) { cudaFree(ctx->coef_dev); ctx->coef_dev = nullptr; }
+    std::vector<float4> h(n_steps);
+    for (int t = 0; t < n_steps; ++t) h[t] = make_float4(ctx->c2[t], ctx->sqrt_alpha[t], ctx->sigma[t], 0.f);
+    LDM_CUDA(cudaMalloc((void**)&ctx->coef_dev, sizeof(float4) * n_steps));
+    LDM_CUDA(cudaMemcpy(ctx->coef_dev, h.data(), sizeof(float4) * n_steps, cudaMemcpyHostToDevice));
+  }
   return 0;
 }
 
@@ -258,6 +278,7 @@ extern "C" LDM_API int ldm_unet_pack(ldm_ctx* ctx, const ldm_unet_weights* w, vo
   cudaError_t e = cudaStreamSynchronize(st);
   free_pool(tmp);
   LDM_CUDA(e);
+  if (ctx->use_chain) LDM_TRY(chain_pack(ctx, st));
   U.packed = true;
   return 0;
 }
@@ -287,6 +308,8 @@ static int ensure_workspace(ldm_ctx* ctx, int B) {
   else ctx->h_op = ctx->h;      // strict path: the fp32 master copy is the operand
   LDM_TRY(ldm_alloc(ctx, P, &ctx->af_op[0], naf * op));
   LDM_TRY(ldm_alloc(ctx, P, &ctx->af_op[1], naf * op));
+  if (ctx->use_chain)
+    for (int j = 0; j < U.nst; ++j) LDM_TRY(ldm_alloc_t(ctx, P, &ctx->opbuf[j], (size_t)cap * 2 * U.hid[j]));
   LDM_TRY(ldm_alloc_t(ctx, P, &ctx->x_state, (size_t)cap * U.latent));
   LDM_TRY(ldm_alloc_t(ctx, P, &ctx->cls, (size_t)cap));
   // zero everything once: rows beyond the batch are read by full 128-row TMA boxes
@@ -430,6 +453,7 @@ extern "C" LDM_API int ldm_unet_forward(ldm_ctx* ctx, const float* x_dev, const 
   StepMode md; md.t_idx = t_dev; md.t_len = t_len; md.eps_out = eps_out_dev;
   if (ctx->precision == LDM_PRECISION_BF16) {
     LDM_TRY(stage_x<bf16>(ctx, x_dev, batch, 0, st));
+    if (ctx->use_chain) return launch_chain(ctx, batch, 1, 0, 0, t_dev, t_len, nullptr, eps_out_dev, nullptr, st);
     return denoise<bf16>(ctx, batch, 0, md, st);
   }
   LDM_TRY(stage_x<float>(ctx, x_dev, batch, 0, st));
@@ -460,6 +484,8 @@ extern "C" LDM_API int ldm_randn(ldm_ctx* ctx, float* out, uint64_t seed, uint64
 static int run_chain(ldm_ctx* ctx, int B, int t_start, int t_end, const float* noise, cudaStream_t st) {
   // x lives in ctx->x_state; its operand copy must already be staged in af_op[0]
   const size_t slab = (size_t)B * ctx->unet.latent;
+  if (ctx->precision == LDM_PRECISION_BF16 && ctx->use_chain)   // the whole loop is one persistent kernel
+    return launch_chain(ctx, B, t_start - t_end + 1, t_start, 1, nullptr, 1, ctx->x_state, nullptr, noise, st);
   for (int t = t_start, j = 0; t >= t_end; --t, ++j) {
     StepMode md; md.sample = 1; md.t = t; md.x = ctx->x_state;
     md.noise = noise ? noise + (size_t)j * slab : nullptr;
@@ -584,6 +610,29 @@ extern "C" LDM_API int ldm_kernel_launch_count(ldm_ctx* ctx, uint64_t* out) {
   return 0;
 }
 
+extern "C" LDM_API int ldm_debug_chain_trace(ldm_ctx* ctx, int step, long long* out_host, int n) {
+  LDM_CHECK(ctx, "ldm_debug_chain_trace: null context");
+  LDM_CUDA(cudaSetDevice(ctx->device));
+  const int total = LDM_CHAIN_CLUSTER * 64;
+  if (out_host) {   // read back (and keep tracing)
+    LDM_CHECK(ctx->chain_trace && n >= total, "ldm_debug_chain_trace: tracing is off or the buffer is shorter than %d", total);
+    LDM_CUDA(cudaDeviceSynchronize());
+    LDM_CUDA(cudaMemcpy(out_host, ctx->chain_trace, sizeof(long long) * total, cudaMemcpyDeviceToHost));
+    return 0;
+  }
+  if (step < 0) {   // off
+    ctx->chain_trace_step = 0;
+    if (ctx->chain_trace) { LDM_CUDA(cudaDeviceSynchronize()); cudaFree(ctx->chain_trace); ctx->chain_trace = nullptr; }
+    drop_graphs(ctx);
+    return 0;
+  }
+  if (!ctx->chain_trace) LDM_CUDA(cudaMalloc((void**)&ctx->chain_trace, sizeof(long long) * total));
+  LDM_CUDA(cudaMemset(ctx->chain_trace, 0, sizeof(long long) * total));
+  ctx->chain_trace_step = step;
+  drop_graphs(ctx);
+  return 0;
+}
+
 extern "C" LDM_API int ldm_get_info(ldm_ctx* ctx, const char* key, double* out) {
   LDM_CHECK(ctx && key && out, "ldm_get_info: bad arguments");
   if (!strcmp(key, "precision")) { *out = ctx->precision; return 0; }
@@ -591,7 +640,11 @@ extern "C" LDM_API int ldm_get_info(ldm_ctx* ctx, const char* key, double* out) 
   if (!strcmp(key, "n_steps")) { *out = ctx->n_steps; return 0; }
   if (!strcmp(key, "graphs")) { *out = (double)ctx->graphs.size(); return 0; }
   if (!strcmp(key, "residual_gate")) { *out = ctx->unet.s_res; return 0; }
+  if (!strcmp(key, "chain")) { *out = ctx->use_chain; return 0; }
+  if (!strcmp(key, "chain_max_clusters")) { *out = ctx->chain_max_clusters; return 0; }
+  if (!strcmp(key, "chain_peak_bytes_per_step")) { *out = ctx->chain.peak_bytes_per_step; return 0; }
   if (!strcmp(key, "launches_per_step")) {
+    if (ctx->use_chain) { *out = 0.0; return 0; }                // the loop is one launch
     *out = ctx->unet.packed ? 3.0 + 4.0 * ctx->unet.nst : 0.0;   // G0, (G1, R1, G2, G3) x stages, R_f, G_f
     return 0;
   }
@@ -605,6 +658,11 @@ extern "C" LDM_API int ldm_get_info(ldm_ctx* ctx, const char* key, double* out) 
   if (!strcmp(key, "tc_error")) {       // barrier timeout record of the tensor-core kernels (0 = none)
     int f = 0;
     if (ctx->precision == LDM_PRECISION_BF16) { LDM_TRY(tc_error_flag(&f)); if (f) tc_error_reset(); }
+    if (!f) {
+      int ce[2] = {0, 0};
+      LDM_CUDA(cudaMemcpy(ce, ctx->chain_err, sizeof(ce), cudaMemcpyDeviceToHost));
+      if (ce[0]) { f = (ce[0] << 16) | (ce[1] & 0xFFFF); LDM_CUDA(cudaMemset(ctx->chain_err, 0, sizeof(ce))); }
+    }
     *out = f;
     return 0;
   }

@@ -134,6 +134,30 @@ struct UnetModel {
   float s_res = 0.f;                            // sigmoid(residual_weight)
 };
 
+// ---------------------------------------------------------------------------------------------
+// persistent cluster kernel of the reverse chain (chain.cu): folded per-phase weights in tile order
+// ---------------------------------------------------------------------------------------------
+#define LDM_CHAIN_CLUSTER 16      // CTAs per cluster (non-portable size; one cluster per GPC on B200)
+#define LDM_CHAIN_ROWS 32         // batch rows a cluster carries through the whole chain
+#define LDM_CHAIN_MAX_K 2048      // longest reduction of a phase (2 x widest hidden layer)
+#define LDM_CHAIN_MAX_PHASES (LDM_MAX_STAGES + 2)
+enum { LDM_PH_STAGE = 0, LDM_PH_FINAL_LN = 1, LDM_PH_EPS = 2 };
+
+struct ChainPhaseHost {
+  int type = 0, K = 0, tiles = 0, first = 0, d = 0, rows = 0;
+  bf16* w = nullptr;              // (rows, K) bf16, 128-row tiles
+  float *bias = nullptr, *tab_t = nullptr, *tab_c = nullptr;
+  CUtensorMap map;
+};
+
+struct ChainModel {
+  bool ready = false;
+  int n_phases = 0;
+  ChainPhaseHost ph[LDM_CHAIN_MAX_PHASES];
+  double peak_bytes_per_step = 0;  // L2 -> SM bytes of the busiest CTA of a cluster per reverse step
+  std::vector<void*> allocs;
+};
+
 struct ConvLayer {       // implicit GEMM: out[pix, co] = sum_{tap, ci} in[pix + off(tap), ci] * w[co][tap*Cin + ci]
   int Cin = 0, Cout = 0, taps = 0;
   float* w32 = nullptr;  // (Cout, taps*Cin)
@@ -189,6 +213,7 @@ struct ldm_ctx {
   std::vector<float> c2, sqrt_alpha, sigma;
   // models
   UnetModel unet;
+  ChainModel chain;
   DecoderModel dec;
   // per-batch state
   int cap = 0;                    // rows the activation workspace holds
@@ -223,6 +248,14 @@ struct ldm_ctx {
   // accounting
   unsigned long long launches = 0;
   bool capturing = false;
+  // persistent chain kernel (bf16 path)
+  int use_chain = 0;              // 1: chain.cu runs the denoiser; 0: one kernel per layer (gemm_tc.cu + rowwise.cu)
+  int chain_max_clusters = 0;     // co-resident clusters the device offers
+  bf16* opbuf[LDM_MAX_STAGES] = {nullptr};   // (cap, 2 hid[j]): [h2 | n] operand written by stage phase j
+  float4* coef_dev = nullptr;     // [n_steps] (c2, sqrt_alpha, sigma, 0)
+  int* chain_err = nullptr;       // [2] first barrier timeout of the chain kernel: code, block
+  long long* chain_trace = nullptr;   // [16][64] clock stamps (ldm_debug_chain_trace), null = off
+  int chain_trace_step = 0;
   int use_pdl = 0;
 };
 
@@ -310,6 +343,12 @@ template <typename T>
 int launch_sa_apply(ldm_ctx* ctx, const T* x, const float* stats, const float* gamma, const float* beta,
                     const float* ca, int ca_stride, const float* map, const float* sa_w, const T* resid,
                     T* out, int B, int H, int C, cudaStream_t st);
+
+// persistent chain kernel (chain.cu)
+int chain_init(ldm_ctx* ctx);
+int chain_pack(ldm_ctx* ctx, cudaStream_t st);
+int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const int64_t* t_idx, int t_len, float* x,
+                 float* eps_out, const float* noise, cudaStream_t st);
 
 // tensor-core path (gemm_tc.cu)
 int tc_init(ldm_ctx* ctx);

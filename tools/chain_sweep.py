@@ -1,0 +1,61 @@
+"""Time the persistent chain kernel alone for several batch sizes (clusters) and step counts.
+    python tools/chain_sweep.py [--steps 200] [--batches 32,64,128,256]"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import ldm_b200
+from oracle import weights
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--steps", type=int, default=200)
+ap.add_argument("--batches", default="32,64,128,256")
+ap.add_argument("--reps", type=int, default=3)
+a = ap.parse_args()
+torch.set_grad_enabled(False)
+dev = torch.device("cuda", 0)
+u = ldm_b200.ConditionalUNet(precision="bf16")
+u.load_state_dict(weights.make_unet_state(42, "init"))
+u = u.to(dev).eval()
+d = ldm_b200.ConditionalDenoiseDiffusion(u, 1000, dev)
+eng = u.engine(dev, 1000)
+eng.set_schedule(*d._host_schedule)
+print("chain", eng.info("chain"), "max co-resident clusters", eng.info("chain_max_clusters"),
+      "peak bytes/step/CTA", eng.info("chain_peak_bytes_per_step"))
+for B in [int(b) for b in a.batches.split(",")]:
+    c = (torch.arange(B) % 102).to(dev)
+    x = eng.randn(B, 256, 1, 0, 1000)
+    eng.sample(x, 999, 1000 - a.steps, c, seed=3, use_graph=False)
+    torch.cuda.synchronize()
+    best = 1e9
+    for rep in range(a.reps):
+        x = eng.randn(B, 256, 1, 0, 1000)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        eng.sample(x, 999, 1000 - a.steps, c, seed=3, use_graph=False)
+        e.record()
+        torch.cuda.synchronize()
+        best = min(best, s.elapsed_time(e))
+    eng.check_device_flags()
+    print("B %4d  steps %d  %.3f ms  -> %.2f us/step  finite %s" % (B, a.steps, best, best * 1e3 / a.steps, bool(torch.isfinite(x).all())))
+
+# ---- per-CTA timeline of one reverse step (cluster 0)
+import ctypes
+import numpy as np
+from ldm_b200 import _lib
+L = _lib.lib()
+B = 32
+c = (torch.arange(B) % 102).to(dev)
+x = eng.randn(B, 256, 1, 0, 1000)
+_lib.check(L.ldm_debug_chain_trace(eng.ctx, 20, None, 0))
+eng.sample(x, 999, 1000 - 40, c, seed=3, use_graph=False)
+buf = np.zeros((16, 64), dtype=np.int64)
+_lib.check(L.ldm_debug_chain_trace(eng.ctx, 0, buf.ctypes.data_as(ctypes.c_void_p), buf.size))
+_lib.check(L.ldm_debug_chain_trace(eng.ctx, -1, None, 0))
+for r in range(16):
+    row = buf[r][buf[r] != 0]
+    if len(row) > 1:
+        print("rank %2d  n=%2d  total %7d cyc | deltas:" % (r, len(row), row[-1] - row[0]), " ".join(str(int(v)) for v in np.diff(row)))
