@@ -12,6 +12,7 @@
 
 int tc_error_flag(int* out);
 int tc_error_reset();
+int conv_tc_error_flag(int* out);
 int tc_pick_bn(int M, int N);
 int decoder_pack_impl(ldm_ctx* ctx, const ldm_decoder_weights* w, cudaStream_t st);
 int decoder_run_impl(ldm_ctx* ctx, const float* z, float* img, int B, cudaStream_t st);
@@ -658,6 +659,7 @@ extern "C" LDM_API int ldm_get_info(ldm_ctx* ctx, const char* key, double* out) 
   if (!strcmp(key, "tc_error")) {       // barrier timeout record of the tensor-core kernels (0 = none)
     int f = 0;
     if (ctx->precision == LDM_PRECISION_BF16) { LDM_TRY(tc_error_flag(&f)); if (f) tc_error_reset(); }
+    if (!f && ctx->precision == LDM_PRECISION_BF16) LDM_TRY(conv_tc_error_flag(&f));
     if (!f) {
       int ce[2] = {0, 0};
       LDM_CUDA(cudaMemcpy(ce, ctx->chain_err, sizeof(ce), cudaMemcpyDeviceToHost));

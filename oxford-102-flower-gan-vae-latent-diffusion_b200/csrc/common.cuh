@@ -236,6 +236,7 @@ struct ldm_ctx {
   float *d_f0 = nullptr, *d_f1 = nullptr;               // fp32 scratch (raw conv outputs, fc rows)
   float *d_stats = nullptr, *d_gap = nullptr, *d_ca = nullptr, *d_map = nullptr;
   float* z_tmp = nullptr;
+  bf16 *d_zb = nullptr, *d_h1b = nullptr;               // bf16 operands of Decoder.fc (tensor-core path)
   // generate_host staging
   int64_t* c_stage = nullptr;     // device staging of the labels copied from the host
   float* img_stage = nullptr;     // device images before the copy back

@@ -4,6 +4,13 @@
 // memory-bound kernels of decoder_norm.cu.
 #include "common.cuh"
 
+int tc_pick_bn(int M, int N);
+int conv_tc_pick_bn(int Cout);
+int launch_conv_tc(ldm_ctx* ctx, const bf16* in, const ConvLayer& L, const float* bias, bf16* out, int B, int H, int W,
+                   int up, cudaStream_t st);
+int launch_conv_out3(ldm_ctx* ctx, const bf16* in, const float* w, const float* bias, float* out, int B, int H, int W,
+                     cudaStream_t st);
+
 namespace {
 
 constexpr int kDecChunk = 256;   // samples per pass: bounds the activation workspace (3 x 256 MiB fp32)
@@ -58,6 +65,9 @@ int ensure_dec_workspace(ldm_ctx* ctx, int B) {
   LDM_TRY(ldm_alloc_t(ctx, P, &ctx->d_gap, (size_t)B * 512));
   LDM_TRY(ldm_alloc_t(ctx, P, &ctx->d_ca, (size_t)B * 512));
   LDM_TRY(ldm_alloc_t(ctx, P, &ctx->d_map, (size_t)B * 1024 * 2));
+  LDM_TRY(ldm_alloc_t(ctx, P, &ctx->d_zb, (size_t)B * 256 + 64));
+  LDM_TRY(ldm_alloc_t(ctx, P, &ctx->d_h1b, (size_t)B * 512));
+  ctx->act_maps.clear();   // descriptors over the old workspace are stale
   ctx->dec_cap = B;
   return 0;
 }
@@ -126,6 +136,72 @@ int decode_chunk_f32(ldm_ctx* ctx, const float* z, float* img, int B, cudaStream
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// bf16 tensor-core pass: activations NHWC bf16, every convolution on tcgen05 (conv_tc.cu), statistics in fp32
+// ---------------------------------------------------------------------------------------------------------------
+int res_block_bf16(ldm_ctx* ctx, const ResBlockModel& R, int B, const bf16* X, bf16* Y, bf16* OUT, cudaStream_t st) {
+  const int C = R.C, H = R.HW, P = H * H;
+  LDM_TRY(launch_conv_tc(ctx, X, R.conv1, R.conv1.b, Y, B, H, H, 1, st));                                         // conv1
+  LDM_TRY(launch_inorm_stats<bf16>(ctx, Y, ctx->d_stats, B, P, C, 1, st));                                        // ln1 statistics
+  LDM_TRY(launch_norm_apply<bf16>(ctx, Y, ctx->d_stats, R.ln1_w, R.ln1_b, OUT, B, P, C, 1, LDM_ACT_SWISH, st));   // swish(ln1(.))
+  LDM_TRY(launch_conv_tc(ctx, OUT, R.conv2, R.conv2.b, Y, B, H, H, 1, st));                                       // conv2
+  LDM_TRY(launch_inorm_stats<bf16>(ctx, Y, ctx->d_stats, B, P, C, 1, st));                                        // ln2 statistics
+  // CALayer (v2:64-67): the average pool of an instance-normalised map is its beta, so the channel gate is a
+  // per-channel constant computed at pack time (ca_const); stride 0 = the same gate for every sample
+  LDM_TRY(launch_sa_map<bf16>(ctx, Y, ctx->d_stats, R.ln2_w, R.ln2_b, R.ca_const, 0, ctx->d_map, B, P, C, st));
+  LDM_TRY(launch_sa_apply<bf16>(ctx, Y, ctx->d_stats, R.ln2_w, R.ln2_b, R.ca_const, 0, ctx->d_map, R.sa_w, X, OUT, B, H, C, st));
+  return 0;
+}
+
+int up_block_bf16(ldm_ctx* ctx, const DecoderModel& D, int idx, int B, int H, int Cin, const bf16* X, bf16* Y, bf16* OUT,
+                  cudaStream_t st) {
+  const int Cout = Cin / 2, P = 4 * H * H;
+  LDM_TRY(launch_conv_tc(ctx, X, D.up[idx][0], D.up_b[idx], Y, B, H, H, 2, st));   // four sub-pixel parities, one launch
+  LDM_TRY(launch_inorm_stats<bf16>(ctx, Y, ctx->d_stats, B, P, Cout, 8, st));
+  LDM_TRY(launch_norm_apply<bf16>(ctx, Y, ctx->d_stats, D.up_gn_w[idx], D.up_gn_b[idx], OUT, B, P, Cout, 8, LDM_ACT_SWISH, st));
+  return 0;
+}
+
+int decode_chunk_bf16(ldm_ctx* ctx, const float* z, float* img, int B, cudaStream_t st) {
+  DecoderModel& D = ctx->dec;
+  bf16 *A = (bf16*)ctx->d_a, *Bf = (bf16*)ctx->d_b, *C = (bf16*)ctx->d_c;
+  {  // Decoder.fc (v2:246-253) on the tensor cores; LayerNorm statistics over the fp32 accumulators
+    LDM_TRY(launch_load_x<bf16>(ctx, z, ctx->d_zb, D.latent, B, D.latent, st));
+    Epilogue e; e.bias = D.fc0.b; e.out_f32 = ctx->d_f0; e.ld_of = 512;
+    LDM_TRY(launch_gemm_tc(ctx, ctx->d_zb, D.latent, B, D.fc0, e, st));
+    LDM_TRY(launch_row_ln<bf16>(ctx, ctx->d_f0, 512, D.fc1_w, D.fc1_b, LDM_ACT_SWISH, ctx->d_h1b, 512, B, 512, st));
+    Epilogue e2; e2.bias = D.fc3.b; e2.out_f32 = (float*)ctx->d_b; e2.ld_of = 32768;
+    LDM_TRY(launch_gemm_tc(ctx, ctx->d_h1b, 512, B, D.fc3, e2, st));
+    LDM_TRY(launch_row_ln<bf16>(ctx, (const float*)ctx->d_b, 32768, D.fc4_w, D.fc4_b, LDM_ACT_SWISH, A, 32768, B, 32768, st));
+  }
+  LDM_TRY(res_block_bf16(ctx, D.res[0], B, A, Bf, C, st));
+  LDM_TRY(up_block_bf16(ctx, D, 0, B, 8, 512, C, Bf, A, st));
+  LDM_TRY(res_block_bf16(ctx, D.res[1], B, A, Bf, C, st));
+  LDM_TRY(up_block_bf16(ctx, D, 1, B, 16, 256, C, Bf, A, st));
+  LDM_TRY(res_block_bf16(ctx, D.res[2], B, A, Bf, C, st));
+  LDM_TRY(up_block_bf16(ctx, D, 2, B, 32, 128, C, Bf, A, st));
+  // final_conv (v2:272-278)
+  LDM_TRY(launch_conv_tc(ctx, A, D.fin0, D.fin0.b, Bf, B, 64, 64, 1, st));
+  LDM_TRY(launch_inorm_stats<bf16>(ctx, Bf, ctx->d_stats, B, 4096, 32, 4, st));
+  LDM_TRY(launch_norm_apply<bf16>(ctx, Bf, ctx->d_stats, D.fin_gn_w, D.fin_gn_b, C, B, 4096, 32, 4, LDM_ACT_SWISH, st));
+  LDM_TRY(launch_conv_out3(ctx, C, D.fin3.w32, D.fin3.b, img, B, 64, 64, st));
+  return 0;
+}
+
+// bf16 copies + TMA descriptors of the decoder weights (tensor-core path)
+int dense_bf16(ldm_ctx* ctx, std::vector<void*>& pool, DenseLayer& L, int M_hint, cudaStream_t st) {
+  LDM_TRY(ldm_alloc_t(ctx, pool, &L.w16, (size_t)L.N * L.K));
+  LDM_TRY(launch_to_bf16(ctx, L.w32, L.w16, (size_t)L.N * L.K, st));
+  L.bn = tc_pick_bn(M_hint, L.N);
+  return tc_make_weight_map(ctx, L.w16, L.N, L.K, L.bn, &L.map_w);
+}
+int conv_bf16(ldm_ctx* ctx, std::vector<void*>& pool, ConvLayer& L, cudaStream_t st) {
+  const size_t n = (size_t)L.Cout * L.taps * L.Cin;
+  LDM_TRY(ldm_alloc_t(ctx, pool, &L.w16, n));
+  LDM_TRY(launch_to_bf16(ctx, L.w32, L.w16, n, st));
+  return tc_make_weight_map(ctx, L.w16, L.Cout, L.taps * L.Cin, conv_tc_pick_bn(L.Cout), &L.map_w);
+}
+
 }  // namespace
 
 int decoder_pack_impl(ldm_ctx* ctx, const ldm_decoder_weights* w, cudaStream_t st) {
@@ -188,6 +264,22 @@ int decoder_pack_impl(ldm_ctx* ctx, const ldm_decoder_weights* w, cudaStream_t s
   LDM_TRY(own(ctx, P, w->fin_gn_w, 32, &D.fin_gn_w, st));
   LDM_TRY(own(ctx, P, w->fin_gn_b, 32, &D.fin_gn_b, st));
   LDM_TRY(pack_conv3(ctx, P, D.fin3, w->fin3_w, w->fin3_b, 3, 32, st));
+  if (ctx->precision == LDM_PRECISION_BF16) {
+    LDM_CHECK(D.latent % 64 == 0, "ldm_decoder_pack: the tensor-core path needs latent_dim %% 64 == 0");
+    LDM_TRY(dense_bf16(ctx, P, D.fc0, 256, st));
+    LDM_TRY(dense_bf16(ctx, P, D.fc3, 256, st));
+    for (int i = 0; i < 3; ++i) {
+      LDM_TRY(conv_bf16(ctx, P, D.res[i].conv1, st));
+      LDM_TRY(conv_bf16(ctx, P, D.res[i].conv2, st));
+      // the four sub-pixel kernels stacked along the output-channel axis: rows [z*Cout, (z+1)*Cout) = parity z
+      ConvLayer& U0 = D.up[i][0];
+      const size_t per = (size_t)U0.Cout * 4 * U0.Cin;
+      LDM_TRY(ldm_alloc_t(ctx, P, &U0.w16, 4 * per));
+      for (int z = 0; z < 4; ++z) LDM_TRY(launch_to_bf16(ctx, D.up[i][z].w32, U0.w16 + (size_t)z * per, per, st));
+      LDM_TRY(tc_make_weight_map(ctx, U0.w16, 4 * U0.Cout, 4 * U0.Cin, conv_tc_pick_bn(U0.Cout), &U0.map_w));
+    }
+    LDM_TRY(conv_bf16(ctx, P, D.fin0, st));
+  }
   LDM_CUDA(cudaStreamSynchronize(st));
   D.packed = true;
   return 0;
@@ -198,7 +290,10 @@ int decoder_run_impl(ldm_ctx* ctx, const float* z, float* img, int B, cudaStream
   LDM_TRY(ensure_dec_workspace(ctx, chunk));
   for (int b0 = 0; b0 < B; b0 += chunk) {
     const int nb = B - b0 < chunk ? B - b0 : chunk;
-    LDM_TRY(decode_chunk_f32(ctx, z + (size_t)b0 * ctx->dec.latent, img + (size_t)b0 * 3 * 64 * 64, nb, st));
+    const float* zc = z + (size_t)b0 * ctx->dec.latent;
+    float* ic = img + (size_t)b0 * 3 * 64 * 64;
+    if (ctx->precision == LDM_PRECISION_BF16) LDM_TRY(decode_chunk_bf16(ctx, zc, ic, nb, st));
+    else LDM_TRY(decode_chunk_f32(ctx, zc, ic, nb, st));
   }
   return 0;
 }
