@@ -614,7 +614,7 @@ extern "C" LDM_API int ldm_kernel_launch_count(ldm_ctx* ctx, uint64_t* out) {
 extern "C" LDM_API int ldm_debug_chain_trace(ldm_ctx* ctx, int step, long long* out_host, int n) {
   LDM_CHECK(ctx, "ldm_debug_chain_trace: null context");
   LDM_CUDA(cudaSetDevice(ctx->device));
-  const int total = LDM_CHAIN_CLUSTER * 64;
+  const int total = LDM_CHAIN_CLUSTER * 2 * 64;
   if (out_host) {   // read back (and keep tracing)
     LDM_CHECK(ctx->chain_trace && n >= total, "ldm_debug_chain_trace: tracing is off or the buffer is shorter than %d", total);
     LDM_CUDA(cudaDeviceSynchronize());

@@ -34,18 +34,28 @@
 namespace {
 
 constexpr int CS = LDM_CHAIN_CLUSTER;   // CTAs per cluster
-constexpr int BNB = LDM_CHAIN_ROWS;     // batch rows per cluster
 constexpr int BK = 64;
-constexpr int kStages = 5;
-constexpr int kThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kCtlThreads = 128;        // warp 0: weight TMA, warp 1: operand TMA, warp 2: TMEM + MMA, warp 3: spare
 constexpr uint32_t kWBytes = 128 * BK * 2;               // one weight k-block: 16 KiB
-constexpr uint32_t kActKbBytes = BNB * BK * 2;           // one operand k-block: 4 KiB
-constexpr int kMaxK = LDM_CHAIN_MAX_K;
-constexpr uint32_t kActBytes = (uint32_t)BNB * kMaxK * 2;  // 128 KiB
-constexpr int kSlots = 32;                               // partial-statistics slots per buffer
-constexpr uint32_t kSlotBytes = 2u * kSlots * BNB * sizeof(float2);   // two buffers: 16 KiB
-constexpr size_t kSmemBytes = 1024 + kActBytes + (size_t)kStages * kWBytes + kSlotBytes;
+constexpr int kSlots = 32;                               // partial-statistics slots per buffer (32 features each)
+constexpr int kMaxStagesRing = 8;
+constexpr int kAccCols = 64;                             // TMEM columns reserved for the accumulator
+constexpr int kTmemCols = 512;
+constexpr int kMaxXMaps = LDM_MAX_STAGES + 2;
+
+// per-variant geometry: NW epilogue warps per TMEM lane quadrant, 16 batch rows each
+template <int NW> struct Geo {
+  static constexpr int NB = 16 * NW;                                   // batch rows per cluster
+  static constexpr int kEpiThreads = 128 * NW;
+  static constexpr int kThreads = kCtlThreads + kEpiThreads;
+  static constexpr uint32_t kXBytes = NB * BK * 2;                     // one operand k-block
+  static constexpr uint32_t kStageBytes = kWBytes + kXBytes;           // multiple of 1024
+  static constexpr uint32_t kYsmBytes = NB * 64 * sizeof(float);
+  static constexpr uint32_t kSlotBytes = 2u * kSlots * NB * sizeof(float2);
+  static constexpr int kStages = (int)((225u * 1024u - kYsmBytes - kSlotBytes) / kStageBytes) < kMaxStagesRing
+                                     ? (int)((225u * 1024u - kYsmBytes - kSlotBytes) / kStageBytes) : kMaxStagesRing;
+  static constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + kYsmBytes + kSlotBytes;
+};
 
 struct ChainPhase {
   int type;            // LDM_PH_*
@@ -54,21 +64,25 @@ struct ChainPhase {
   int first;           // cluster rank of the CTA that owns tile 0 (tile i -> rank first + i)
   int d;               // LayerNorm width (stage: d_j; final-LN / eps: latent)
   int rows;            // tiles * 128: leading dimension of the tables
+  int xmap;            // index of the operand's tensor map (+ 1 on odd steps when xmap_alt)
+  int xmap_alt;        // 1: the operand alternates between xmap and xmap + 1 with the step parity ([LN_f(h) | x])
+  int xcol;            // first column of the operand inside that buffer
+  int cadd_col;        // TMEM column of this phase's per-sample additive term (-1: none)
   const float* bias;   // [rows]       tile order
   const float* tab_t;  // [n_t, rows]  tile order (null: none)
   const float* tab_c;  // [ncls, rows] tile order (null: none)
   const float *ga, *ba, *gb, *bb;   // LayerNorm affine parameters, natural feature order
-  const bf16* in;      // operand of this phase (B, ld_in); null -> af[step parity] (+ in_off)
-  int ld_in, in_off;
   bf16* out;           // operand this phase produces (stage phases)
   int ld_out;
 };
 
 struct ChainParams {
   CUtensorMap wmap[LDM_CHAIN_MAX_PHASES];
+  CUtensorMap xmaps[kMaxXMaps];   // [0], [1]: af[0], af[1]; [2 + j]: opbuf[j]
   ChainPhase ph[LDM_CHAIN_MAX_PHASES];
   int n_phases;
-  int B;
+  int B;                      // rows of the whole batch (leading dimension of `noise` slabs)
+  int row_begin, row_end;     // rows this launch works on
   int n_iter;                 // reverse steps (sample) or 1 (forward)
   int t_start;                // sample: step `it` runs timestep t_start - it
   int sample;                 // 1: fused posterior update on x; 0: write eps_out
@@ -85,7 +99,7 @@ struct ChainParams {
   bf16* af[2];                // (B, ld_af): [LN_f(h) | x] operand of the last phase, double-buffered over steps
   int ld_af;
   int* err;                   // [2]: first failure code, detail
-  long long* trace;           // profiling aid: [CS][64] clock64 stamps of cluster 0 in step trace_step (null: off)
+  long long* trace;           // profiling aid: [CS][2][64] clock64 stamps of cluster 0 in step trace_step (null: off); [0]: an h-warp thread, [1]: a u-warp thread
   int trace_step;
 };
 
@@ -98,11 +112,13 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
 __device__ __forceinline__ void remote_arrive(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ void remote_st_f2(uint32_t cluster_addr, float a, float b) {
-  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
-}
 __device__ __forceinline__ void remote_st_u32(uint32_t cluster_addr, uint32_t v) {
   asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+// 8-byte store into a peer's shared memory that signals the peer's mbarrier (complete_tx of 8 bytes) when it lands
+__device__ __forceinline__ void st_async_f2(uint32_t cluster_addr, float a, float b, uint32_t cluster_bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+               ::"r"(cluster_addr), "f"(a), "f"(b), "r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ bool try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -118,12 +134,40 @@ __device__ __forceinline__ bool try_wait_cluster(uint64_t* bar, uint32_t parity)
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// 32 lanes x 16 consecutive fp32 columns, thread i <-> lane (base + i)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+      "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+      "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+      "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+      "r"(__float_as_uint(v[15]))
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// two 16-column loads in flight, one wait
+__device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float (&a)[16], float (&b)[16]) {
+  uint32_t r[16], s[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(ta));
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]), "=r"(s[8]),
+        "=r"(s[9]), "=r"(s[10]), "=r"(s[11]), "=r"(s[12]), "=r"(s[13]), "=r"(s[14]), "=r"(s[15])
+      : "r"(tb));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(s[i]); }
+}
 
 // Every wait in this kernel is bounded and abortable: the first timeout raises the abort flag of all CTAs of the
-// cluster, after which every wait returns at once and the kernel drains to its end (no hung GPU).  The epilogue
-// warps share named barriers, so they never leave individually: they finish the step on whatever data they have
-// and take ONE uniform decision per step (end of the step loop body).
+// cluster, after which every wait returns at once and the kernel drains to its end (no hung GPU).
 struct Waiter {
   volatile int* abort_flag;   // this CTA's flag (shared memory)
   int* err;
@@ -134,24 +178,26 @@ struct Waiter {
     for (uint32_t r = 0; r < (uint32_t)CS; ++r) remote_st_u32(mapa_u32(a, r), 1u);
   }
   __device__ __forceinline__ bool wait(uint64_t* bar, uint32_t parity, int code) const {
+    if (tc::mbar_try_wait(bar, parity)) return true;
     if (aborted()) return false;
-    for (uint32_t it = 0; it < (1u << 19); ++it) {
+    for (uint32_t it = 0; it < (1u << 21); ++it) {
       if (tc::mbar_try_wait(bar, parity)) return true;
-      if (it > 32) {
+      if (it > 256) {
         if (aborted()) return false;
-        __nanosleep(it > 2048 ? 128 : 20);
+        __nanosleep(it > 8192 ? 128 : 20);
       }
     }
     fail(code);
     return false;
   }
   __device__ __forceinline__ bool wait_cluster(uint64_t* bar, uint32_t parity, int code) const {
+    if (try_wait_cluster(bar, parity)) return true;
     if (aborted()) return false;
-    for (uint32_t it = 0; it < (1u << 19); ++it) {
+    for (uint32_t it = 0; it < (1u << 21); ++it) {
       if (try_wait_cluster(bar, parity)) return true;
-      if (it > 32) {
+      if (it > 256) {
         if (aborted()) return false;
-        __nanosleep(it > 2048 ? 128 : 20);
+        __nanosleep(it > 8192 ? 128 : 20);
       }
     }
     fail(code);
@@ -159,132 +205,95 @@ struct Waiter {
   }
 };
 
-// 32 lanes x 32 consecutive fp32 accumulator columns
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+// Transposed warp reduction of 16 values per lane: on return EVERY lane holds the 32-lane total of element (lane >> 1).
+// 16 shuffles instead of 16 x 5.
+__device__ __forceinline__ float tsum16(float (&a)[16], int lane) {
+  {
+    const bool up = (lane & 16) != 0;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// Transposed warp reduction: every lane holds 32 values (one per batch row j); on return lane j holds the sum over
-// the 32 lanes of value j.  31 shuffles instead of 32 x 5.
-__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
-#pragma unroll
-  for (int n = 16; n >= 1; n >>= 1) {
-    const bool upper = (lane & n) != 0;
-#pragma unroll
-    for (int i = 0; i < n; ++i) {
-      const float send = upper ? v[i] : v[i + n];
-      const float keep = upper ? v[i + n] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, n);
+    for (int i = 0; i < 8; ++i) {
+      const float send = up ? a[i] : a[i + 8], keep = up ? a[i + 8] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
     }
   }
-  return v[0];
+  {
+    const bool up = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? a[i] : a[i + 4], keep = up ? a[i + 4] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = (lane & 4) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? a[i] : a[i + 2], keep = up ? a[i + 2] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool up = (lane & 2) != 0;
+    const float send = up ? a[0] : a[1], keep = up ? a[1] : a[0];
+    a[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  return a[0] + __shfl_xor_sync(0xffffffffu, a[0], 1);
 }
 
-// (sum, sum of squares) over this warp's 32 features for each of the 32 rows -> lane j: (mean, M2) of row j
-__device__ __forceinline__ float2 warp_row_stats(const float (&v)[32], int lane) {
-  float a[32], b[32];
+// (mean, M2) over this warp's 32 features of batch row (lane >> 1)
+__device__ __forceinline__ float2 warp_row_stats16(const float (&v)[16], int lane) {
+  float a[16], b[16];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) { a[j] = v[j]; b[j] = v[j] * v[j]; }
-  const float s1 = warp_transpose_sum(a, lane);
-  const float s2 = warp_transpose_sum(b, lane);
+  for (int j = 0; j < 16; ++j) { a[j] = v[j]; b[j] = v[j] * v[j]; }
+  const float s1 = tsum16(a, lane);
+  const float s2 = tsum16(b, lane);
   const float m = s1 * (1.0f / 32.0f);
   return make_float2(m, fmaxf(s2 - s1 * m, 0.0f));
 }
 
-// publish this warp's partial statistics (lane j = row j) into slot `slot` of buffer `buf` of ranks [first, first+n)
-__device__ __forceinline__ void publish_stats(float2* slots, int buf, int slot, int lane, float2 st, int first, int n) {
-  const uint32_t local = tc::smem_u32(slots + ((size_t)buf * kSlots + slot) * BNB + lane);
-  for (int r = 0; r < n; ++r) remote_st_f2(mapa_u32(local, (uint32_t)(first + r)), st.x, st.y);
-}
-
-// merge `n` partials of 32 features each (Chan et al.): lane j -> (mean, rstd) of row j over d = 32 n features
-__device__ __forceinline__ float2 combine_stats(const float2* slots, int buf, int n, int lane) {
-  const float2* p = slots + (size_t)buf * kSlots * BNB + lane;
-  float msum = 0.f, m2 = 0.f;
-  for (int k = 0; k < n; ++k) msum += p[(size_t)k * BNB].x;
-  const float mean = msum / (float)n;
-  for (int k = 0; k < n; ++k) {
-    const float2 s = p[(size_t)k * BNB];
-    const float dm = s.x - mean;
-    m2 += s.y + 32.0f * dm * dm;
-  }
-  const float var = m2 / (32.0f * (float)n);
-  return make_float2(mean, 1.0f / sqrtf(var + 1e-5f));
-}
-
-// global (B, ld) bf16 rows [row0, row0+32) x K  ->  shared K-major operand, k-blocks of 64 elements, 128-byte swizzle
-__device__ __forceinline__ void load_operand(uint8_t* act_s, const bf16* __restrict__ in, int ld, int K, int row0, int B,
-                                             int et) {
-  const int cpr = K >> 3;                 // 16-byte chunks per row
-  const int total = BNB * cpr;
-  for (int base = 0; base < total; base += kEpiThreads * 8) {
-    uint4 buf[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int idx = base + u * kEpiThreads + et;
-      buf[u] = make_uint4(0u, 0u, 0u, 0u);
-      if (idx < total) {
-        const int r = idx / cpr, kc = idx - r * cpr;
-        if (row0 + r < B) buf[u] = __ldcg(reinterpret_cast<const uint4*>(in + (size_t)(row0 + r) * ld + (size_t)kc * 8));
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int idx = base + u * kEpiThreads + et;
-      if (idx < total) {
-        const int r = idx / cpr, kc = idx - r * cpr;
-        const uint32_t off = (uint32_t)(kc >> 3) * kActKbBytes + (uint32_t)r * 128u + (uint32_t)(((kc & 7) ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(act_s + off) = buf[u];
-      }
-    }
-  }
-}
-
+__device__ __forceinline__ float swish_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 __device__ __forceinline__ int clamp_t(long long t, int n_t) { return (int)(t < 0 ? 0 : (t >= n_t ? n_t - 1 : t)); }
 
-__global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constant__ ChainParams P) {
+template <int NW>
+__global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __grid_constant__ ChainParams P) {
+  using G = Geo<NW>;
+  constexpr int NB = G::NB;
+  constexpr int S = G::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* act_s = smem;
-  uint8_t* ring = smem + kActBytes;
-  float2* slots = reinterpret_cast<float2*>(ring + (size_t)kStages * kWBytes);
-  float* ysm = reinterpret_cast<float*>(act_s);     // [32 rows][64 features]: aliases the operand once the MMAs are done
-  __shared__ __align__(8) uint64_t full_bar[kStages];
-  __shared__ __align__(8) uint64_t empty_bar[kStages];
-  __shared__ __align__(8) uint64_t act_full_bar, tmem_full_bar, xbar;
+  uint8_t* ring = smem;
+  float* ysm = reinterpret_cast<float*>(ring + (size_t)S * G::kStageBytes);          // [NB rows][64 features]
+  float2* slots = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(ysm) + G::kYsmBytes);   // [2][kSlots][NB]
+  __shared__ __align__(8) uint64_t full_bar[kMaxStagesRing];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStagesRing];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t obar[2];   // phase hand-over: 16 remote arrives (one per CTA) + the local operand producer
+  __shared__ __align__(8) uint64_t sbar[2];   // LayerNorm statistics: transaction barrier fed by the peers' st.async
   __shared__ uint32_t tmem_slot;
-  __shared__ int abort_flag, abort_decision;
+  __shared__ int abort_flag;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = blockIdx.x;                 // gridDim.x == CS: rank in cluster
-  const int row0 = blockIdx.y * BNB;           // first batch row of this cluster
+  const int row0 = P.row_begin + blockIdx.y * NB;   // first batch row of this cluster
   const Waiter W{&abort_flag, P.err};
+  const int NP = P.n_phases;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      tc::mbar_init(&full_bar[s], 1);
+    for (int s = 0; s < S; ++s) {
+      tc::mbar_init(&full_bar[s], 2);          // weight producer + operand producer (each arrive.expect_tx)
       tc::mbar_init(&empty_bar[s], 1);
     }
-    tc::mbar_init(&act_full_bar, kEpiThreads);
     tc::mbar_init(&tmem_full_bar, 1);
-    tc::mbar_init(&xbar, CS);
+    tc::mbar_init(&obar[0], CS + 1);
+    tc::mbar_init(&obar[1], CS + 1);
+    tc::mbar_init(&sbar[0], 1);
+    tc::mbar_init(&sbar[1], 1);
     abort_flag = 0;
     tc::fence_barrier_init();
-    for (int p = 0; p < P.n_phases; ++p) tc::prefetch_tmap(&P.wmap[p]);
+    for (int p = 0; p < NP; ++p) tc::prefetch_tmap(&P.wmap[p]);
+    for (int p = 0; p < kMaxXMaps; ++p) tc::prefetch_tmap(&P.xmaps[p]);
   }
-  if (warp == 1) tc::tmem_alloc<32>(&tmem_slot);
+  if (warp == 2) tc::tmem_alloc<kTmemCols>(&tmem_slot);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -292,44 +301,71 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
   cluster_sync_all();   // every CTA's barriers exist before any remote arrive / store
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ weight-tile producer
+    // ------------------------------------------------------------------ weight-tile producer (runs ahead of the phases)
     if (lane == 0) {
       uint32_t n = 0;
       bool ok = true;
       for (int it = 0; it < P.n_iter && ok; ++it) {
-        for (int p = 0; p < P.n_phases && ok; ++p) {
+        for (int p = 0; p < NP && ok; ++p) {
           const int tile = rank - P.ph[p].first;
           if (tile < 0 || tile >= P.ph[p].tiles) continue;
           const int nkb = P.ph[p].K / BK;
           for (int kb = 0; kb < nkb; ++kb, ++n) {
-            const uint32_t s = n % kStages, par = (n / kStages) & 1u;
+            const uint32_t s = n % S, par = (n / S) & 1u;
             if (!W.wait(&empty_bar[s], par ^ 1u, 1)) { ok = false; break; }
             tc::mbar_arrive_expect_tx(&full_bar[s], kWBytes);
-            tc::tma_load_2d(ring + (size_t)s * kWBytes, &P.wmap[p], &full_bar[s], kb * BK, tile * 128);
+            tc::tma_load_2d(ring + (size_t)s * G::kStageBytes, &P.wmap[p], &full_bar[s], kb * BK, tile * 128);
           }
         }
       }
     }
   } else if (warp == 1) {
+    // ------------------------------------------------------------------ operand producer: waits for the phase hand-over
+    if (lane == 0) {
+      uint32_t n = 0, gp = 0;
+      bool ok = true;
+      tc::mbar_arrive(&obar[0]);   // this thread's share of hand-overs 0 and 1
+      tc::mbar_arrive(&obar[1]);
+      for (int it = 0; it < P.n_iter && ok; ++it) {
+        for (int p = 0; p < NP && ok; ++p, ++gp) {
+          if (gp > 0) {
+            const uint32_t f = gp - 1;   // hand-over that publishes this phase's operand
+            if (!W.wait_cluster(&obar[f & 1u], (f >> 1) & 1u, 2)) { ok = false; break; }
+            tc::mbar_arrive(&obar[f & 1u]);   // share of hand-over f + 2 (same barrier, next phase)
+            fence_proxy_async_all();          // peers' generic-proxy global writes -> visible to the TMA (async proxy) reads below
+          }
+          const ChainPhase& ph = P.ph[p];
+          const int tile = rank - ph.first;
+          if (tile < 0 || tile >= ph.tiles) continue;
+          const CUtensorMap* xm = &P.xmaps[ph.xmap + (ph.xmap_alt ? (it & 1) : 0)];
+          const int nkb = ph.K / BK;
+          for (int kb = 0; kb < nkb; ++kb, ++n) {
+            const uint32_t s = n % S, par = (n / S) & 1u;
+            if (!W.wait(&empty_bar[s], par ^ 1u, 3)) { ok = false; break; }
+            tc::mbar_arrive_expect_tx(&full_bar[s], G::kXBytes);
+            tc::tma_load_2d(ring + (size_t)s * G::kStageBytes + kWBytes, xm, &full_bar[s], ph.xcol + kb * BK, row0);
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc_bf16(128, BNB);
-      uint32_t n = 0, an = 0;
+      constexpr uint32_t idesc = tc::make_idesc_bf16(128, NB);
+      uint32_t n = 0;
       bool ok = true;
       for (int it = 0; it < P.n_iter && ok; ++it) {
-        for (int p = 0; p < P.n_phases && ok; ++p) {
+        for (int p = 0; p < NP && ok; ++p) {
           const int tile = rank - P.ph[p].first;
           if (tile < 0 || tile >= P.ph[p].tiles) continue;
-          if (!W.wait(&act_full_bar, an & 1u, 2)) { ok = false; break; }
-          ++an;
-          tc::fence_after_sync();
           const int nkb = P.ph[p].K / BK;
           for (int kb = 0; kb < nkb; ++kb, ++n) {
-            const uint32_t s = n % kStages, par = (n / kStages) & 1u;
-            if (!W.wait(&full_bar[s], par, 3)) { ok = false; break; }
+            const uint32_t s = n % S, par = (n / S) & 1u;
+            if (!W.wait(&full_bar[s], par, 4)) { ok = false; break; }
             tc::fence_after_sync();
-            const uint64_t dw = tc::make_desc_sw128(tc::smem_u32(ring + (size_t)s * kWBytes));
-            const uint64_t dx = tc::make_desc_sw128(tc::smem_u32(act_s + (size_t)kb * kActKbBytes));
+            const uint32_t base = tc::smem_u32(ring + (size_t)s * G::kStageBytes);
+            const uint64_t dw = tc::make_desc_sw128(base);
+            const uint64_t dx = tc::make_desc_sw128(base + kWBytes);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
               tc::umma_bf16(tmem_base, dw + (uint64_t)(2 * k), dx + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
@@ -339,69 +375,163 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
         }
       }
     }
-  } else {
-    // ------------------------------------------------------------------ operand copy + epilogue + rendezvous
-    const int et = threadIdx.x - 64;          // 0..127
-    const int q = warp & 3;                   // TMEM lane quadrant of this warp
-    const int lrow = q * 32 + lane;           // row of the 128-row weight tile this thread finishes
-    const uint32_t xbar_local = tc::smem_u32(&xbar);
-    uint32_t xpar = 0, tpar = 0;
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue + statistics exchange + hand-over
+    const int et = threadIdx.x - kCtlThreads;   // 0 .. 128 NW - 1
+    const int q = warp & 3;                     // TMEM lane quadrant of this warp
+    const int g = (warp - 4) >> 2;              // batch-row group: rows [16 g, 16 g + 16) of the cluster
+    const int lrow = q * 32 + lane;             // row of the 128-row weight tile this thread finishes
+    const int s0 = 16 * g;
+    const int srow = s0 + (lane >> 1);          // batch row (in cluster) this lane owns in the statistics exchange
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t sbar_local[2] = {tc::smem_u32(&sbar[0]), tc::smem_u32(&sbar[1])};
+    const uint32_t obar_local[2] = {tc::smem_u32(&obar[0]), tc::smem_u32(&obar[1])};
+    uint32_t tpar = 0;            // parity of tmem_full_bar
+    uint32_t sidx = 0;            // statistics exchanges so far (same count in every CTA)
+    uint32_t sph[2] = {0, 0};     // completed phases of sbar[b] in THIS CTA
+    uint32_t oidx = 0;            // hand-overs so far
     int tr_n = 0;
     bool tr_on = false;
     auto stamp = [&]() {
-      if (tr_on && tr_n < 64) P.trace[rank * 64 + tr_n++] = clock64();
+      if (tr_on && tr_n < 64) P.trace[(rank * 2 + (et == 0 ? 0 : 1)) * 64 + tr_n++] = clock64();
+    };
+    auto epi_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(G::kEpiThreads) : "memory"); };
+
+    // publish (mean, M2) of batch row `srow` over this warp's 32 features into slot `part` of buffer `buf` of every
+    // CTA that owns a tile of the phase; the two lanes that hold the same row split the destinations
+    auto publish = [&](uint32_t buf, int part, float2 st, int first, int ntiles) {
+      const uint32_t slot = tc::smem_u32(slots + ((size_t)buf * kSlots + part) * NB + srow);
+      for (int k = lane & 1; k < ntiles; k += 2)
+        st_async_f2(mapa_u32(slot, (uint32_t)(first + k)), st.x, st.y, mapa_u32(sbar_local[buf], (uint32_t)(first + k)));
+    };
+    // wait until all `nparts` partials of all NB rows have landed in buffer `buf`
+    auto exchange_wait = [&](uint32_t buf, int nparts, int code) {
+      if (et == 0) tc::mbar_arrive_expect_tx(&sbar[buf], (uint32_t)nparts * NB * (uint32_t)sizeof(float2));
+      W.wait_cluster(&sbar[buf], sph[buf] & 1u, code);
+      sph[buf]++;
+    };
+    // merge `nparts` partials of 32 features each (Chan et al.): (mean, rstd) of row `srow` over d = 32 nparts features
+    auto combine = [&](uint32_t buf, int nparts) -> float2 {
+      const float2* p = slots + ((size_t)buf * kSlots + (lane & 1)) * NB + srow;
+      const int half = nparts >> 1;             // partials this lane merges (the pair of lanes that own the row split them)
+      const float inv_n = 1.0f / (float)nparts;
+      float2 s[kSlots / 2];
+#pragma unroll
+      for (int k = 0; k < kSlots / 2; ++k) s[k] = k < half ? p[(size_t)(2 * k) * NB] : make_float2(0.f, 0.f);
+      float msum = 0.f;
+#pragma unroll
+      for (int k = 0; k < kSlots / 2; ++k) msum += s[k].x;
+      msum += __shfl_xor_sync(0xffffffffu, msum, 1);
+      const float mean = msum * inv_n;
+      float m2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < kSlots / 2; ++k) {
+        const float dm = s[k].x - mean;
+        m2 += k < half ? s[k].y + 32.0f * dm * dm : 0.f;
+      }
+      m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
+      const float var = m2 * inv_n * (1.0f / 32.0f);
+      return make_float2(mean, rsqrtf(var + 1e-5f));
     };
 
-    auto rendezvous = [&](int code) {
-      epi_bar_sync();                         // this CTA's epilogue threads are done writing
-      if (et < CS) remote_arrive(mapa_u32(xbar_local, (uint32_t)et));
-      W.wait_cluster(&xbar, xpar, code);
-      xpar ^= 1u;
-      stamp();
-    };
+    // ---- per-sample additive terms (class tables; per-sample timesteps of forward()) live in TMEM for the whole chain
+    {
+      const bool per_row_t = !P.sample && P.t_len != 1;
+      for (int p = 0; p < NP; ++p) {
+        const ChainPhase& ph = P.ph[p];
+        const int tile = rank - ph.first;
+        if (tile < 0 || tile >= ph.tiles || ph.cadd_col < 0) continue;
+        const int grow = tile * 128 + lrow;
+        float c[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int r = row0 + s0 + j;
+          float a = 0.f;
+          if (r < P.row_end) {
+            if (ph.tab_c && P.cls) a += __ldg(ph.tab_c + (size_t)P.cls[r] * ph.rows + grow);
+            if (ph.tab_t && per_row_t) a += __ldg(ph.tab_t + (size_t)clamp_t(P.t_idx[r], P.n_t) * ph.rows + grow);
+          }
+          c[j] = a;
+        }
+        tmem_st16(lane_taddr + (uint32_t)(ph.cadd_col + s0), c);
+      }
+      tc::fence_before_sync();
+    }
+
+    // ---- the chain state of the rows / features this thread finishes in the eps phase stays in registers
+    float xr[16];
+    const ChainPhase& phe = P.ph[NP - 1];
+    const int etile = rank - phe.first;
+    const bool eps_owner = etile >= 0 && etile < phe.tiles;
+    const int ef = etile * 128 + lrow;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int r = row0 + s0 + j;
+      xr[j] = (eps_owner && P.sample && r < P.row_end) ? P.x[(size_t)r * P.latent + ef] : 0.f;
+    }
 
     for (int it = 0; it < P.n_iter; ++it) {
       const int par = it & 1;
-      tr_on = P.trace != nullptr && blockIdx.y == 0 && it == P.trace_step && et == 0;
+      tr_on = P.trace != nullptr && blockIdx.y == 0 && it == P.trace_step && (et == 0 || et == 64);
       stamp();
       const int t_uni = P.sample ? P.t_start - it : (P.t_len == 1 ? clamp_t(P.t_idx[0], P.n_t) : -1);
-      for (int p = 0; p < P.n_phases; ++p) {
+      for (int p = 0; p < NP; ++p) {
         const ChainPhase& ph = P.ph[p];
         const int tile = rank - ph.first;
         const bool active = tile >= 0 && tile < ph.tiles;
-        float v[32];
+        const int grow = tile * 128 + lrow;
+        float v[16];
+        float z[16];
         if (active) {
-          const bf16* in = ph.in ? ph.in : P.af[par] + ph.in_off;
-          load_operand(act_s, in, ph.ld_in, ph.K, row0, P.B, et);
-          tc::fence_proxy_async();            // generic-proxy writes -> visible to the tensor core (async proxy)
-          tc::mbar_arrive(&act_full_bar);
-          stamp();
-          // additive terms of this thread's weight row while the MMAs run
-          const int grow = tile * 128 + lrow;
-          float add[32];
-          {
-            const float b = ph.bias ? ph.bias[grow] : 0.f;
-            const float tt = (ph.tab_t && t_uni >= 0) ? ph.tab_t[(size_t)t_uni * ph.rows + grow] : 0.f;
+          // everything that does not depend on the accumulator is fetched before the waits
+          float tt = ph.bias ? __ldg(ph.bias + grow) : 0.f;
+          if (ph.tab_t && t_uni >= 0) tt += __ldg(ph.tab_t + (size_t)t_uni * ph.rows + grow);
+          if (ph.type == LDM_PH_EPS && P.sample) {
+            // noise of this step: independent of eps, generated while the tensor core works
+            const int t = P.t_start - it;
+            const float sigma = P.coef[t].z;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float a = b + tt;
-              const int r = row0 + j;
-              if (r < P.B) {
-                if (ph.tab_t && t_uni < 0) a += ph.tab_t[(size_t)clamp_t(P.t_idx[r], P.n_t) * ph.rows + grow];
-                if (ph.tab_c && P.cls) a += ph.tab_c[(size_t)P.cls[r] * ph.rows + grow];
+            for (int j = 0; j < 16; ++j) z[j] = 0.f;
+            if (sigma > 0.0f) {
+              if (P.noise) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int r = row0 + s0 + j;
+                  if (r < P.row_end) z[j] = P.noise[((size_t)it * P.B + r) * P.latent + grow];
+                }
+              } else {
+                // the 4 lanes that share a Philox quad split the rows between them, then trade components
+                const unsigned long long seed = P.rng[0], off = P.rng[1] + (unsigned long long)(row0 + s0);
+                const int sub = lane & 3, base = lane & ~3;
+#pragma unroll
+                for (int gq = 0; gq < 4; ++gq) {
+                  const float4 z4 = philox_normal4(seed, off + (unsigned long long)(4 * gq + sub), (uint32_t)t, (uint32_t)(grow >> 2));
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float gx = __shfl_sync(0xffffffffu, z4.x, base + i), gy = __shfl_sync(0xffffffffu, z4.y, base + i);
+                    const float gz = __shfl_sync(0xffffffffu, z4.z, base + i), gw = __shfl_sync(0xffffffffu, z4.w, base + i);
+                    z[4 * gq + i] = sub == 0 ? gx : (sub == 1 ? gy : (sub == 2 ? gz : gw));
+                  }
+                }
               }
-              add[j] = a;
             }
           }
           stamp();
-          W.wait(&tmem_full_bar, tpar, 4);
-          stamp();
+          W.wait(&tmem_full_bar, tpar, 5);
           tpar ^= 1u;
+          stamp();
           tc::fence_after_sync();
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16), v);
-          tc::fence_before_sync();            // ordered before the next phase's MMAs through act_full_bar
+          if (ph.cadd_col >= 0) {
+            float c[16];
+            tmem_ld16x2(lane_taddr + (uint32_t)s0, lane_taddr + (uint32_t)(ph.cadd_col + s0), v, c);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += add[j];
+            for (int j = 0; j < 16; ++j) v[j] += c[j] + tt;
+          } else {
+            tc::tmem_ld16(lane_taddr + (uint32_t)s0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += tt;
+          }
+          tc::fence_before_sync();            // ordered before the next phase's MMAs through the hand-over
         }
 
         if (ph.type == LDM_PH_STAGE) {
@@ -410,116 +540,117 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
           const int fl = (q & 1) * 32 + lane;       // feature inside the 64-feature slice
           const int f = tile * 64 + fl;
           const int nparts = ph.tiles * 2;
-          if (active && is_u) publish_stats(slots, 0, tile * 2 + (q & 1), lane, warp_row_stats(v, lane), ph.first, ph.tiles);
-          rendezvous(5);
+          const uint32_t b0 = sidx & 1u, b1 = b0 ^ 1u;
+          sidx += 2;
           if (active) {
+            const float ga = is_u ? __ldg(ph.ga + f) : __ldg(ph.gb + f);
+            const float be = is_u ? __ldg(ph.ba + f) : __ldg(ph.bb + f);
+            if (is_u) publish(b0, tile * 2 + (q & 1), warp_row_stats16(v, lane), ph.first, ph.tiles);
+            stamp();
+            exchange_wait(b0, nparts, 6);
+            stamp();
             if (is_u) {   // y = swish(LN_a(u))                                            (v2:520-522)
-              const float2 st = combine_stats(slots, 0, nparts, lane);
-              const float g = ph.ga[f], b = ph.ba[f];
+              const float2 st = combine(b0, nparts);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float m = __shfl_sync(0xffffffffu, st.x, j), r = __shfl_sync(0xffffffffu, st.y, j);
-                ysm[j * 64 + fl] = swishf((v[j] - m) * r * g + b);
+              for (int j = 0; j < 16; ++j) {
+                const float m = __shfl_sync(0xffffffffu, st.x, 2 * j), r = __shfl_sync(0xffffffffu, st.y, 2 * j);
+                ysm[(s0 + j) * 64 + fl] = swish_fast((v[j] - m) * r * ga + be);
               }
             }
-            epi_bar_sync();
+            stamp();
+            epi_bar();
+            stamp();
             if (!is_u) {  // h2 = y + h                                                    (v2:547)
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += ysm[j * 64 + fl];
-              publish_stats(slots, 1, tile * 2 + (q & 1), lane, warp_row_stats(v, lane), ph.first, ph.tiles);
+              for (int j = 0; j < 16; ++j) v[j] += ysm[(s0 + j) * 64 + fl];
+              publish(b1, tile * 2 + (q & 1), warp_row_stats16(v, lane), ph.first, ph.tiles);
             }
-          }
-          rendezvous(6);
-          if (active && !is_u) {   // n = LN_b(h2); operand of the next phase is [h2 | n]    (v2:548-553)
-            const float2 st = combine_stats(slots, 1, nparts, lane);
-            const float g = ph.gb[f], b = ph.bb[f];
+            stamp();
+            exchange_wait(b1, nparts, 7);
+            stamp();
+            if (!is_u) {   // n = LN_b(h2); operand of the next phase is [h2 | n]          (v2:548-553)
+              const float2 st = combine(b1, nparts);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float m = __shfl_sync(0xffffffffu, st.x, j), r = __shfl_sync(0xffffffffu, st.y, j);
-              if (row0 + j < P.B) {
-                bf16* o = ph.out + (size_t)(row0 + j) * ph.ld_out;
-                o[f] = __float2bfloat16_rn(v[j]);
-                o[ph.d + f] = __float2bfloat16_rn((v[j] - m) * r * g + b);
+              for (int j = 0; j < 16; ++j) {
+                const float m = __shfl_sync(0xffffffffu, st.x, 2 * j), r = __shfl_sync(0xffffffffu, st.y, 2 * j);
+                const int row = row0 + s0 + j;
+                if (row < P.row_end) {
+                  bf16* o = ph.out + (size_t)row * ph.ld_out;
+                  o[f] = __float2bfloat16_rn(v[j]);
+                  o[ph.d + f] = __float2bfloat16_rn((v[j] - m) * r * ga + be);
+                }
               }
             }
           }
-          rendezvous(7);
         } else if (ph.type == LDM_PH_FINAL_LN) {
-          const int f = tile * 128 + lrow;
-          if (active) publish_stats(slots, 0, tile * 4 + q, lane, warp_row_stats(v, lane), ph.first, ph.tiles);
-          rendezvous(8);
+          const int f = grow;
+          const int nparts = ph.tiles * 4;
+          const uint32_t b0 = sidx & 1u;
+          sidx += 1;
           if (active) {   // LN_f(h + T_f[t] + C_f[c])                                     (v2:554-559)
-            const float2 st = combine_stats(slots, 0, ph.tiles * 4, lane);
-            const float g = ph.ga[f], b = ph.ba[f];
+            const float ga = __ldg(ph.ga + f), be = __ldg(ph.ba + f);
+            publish(b0, tile * 4 + q, warp_row_stats16(v, lane), ph.first, ph.tiles);
+            exchange_wait(b0, nparts, 8);
+            stamp();
+            const float2 st = combine(b0, nparts);
             bf16* o = P.af[par] + f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float m = __shfl_sync(0xffffffffu, st.x, j), r = __shfl_sync(0xffffffffu, st.y, j);
-              if (row0 + j < P.B) o[(size_t)(row0 + j) * P.ld_af] = __float2bfloat16_rn((v[j] - m) * r * g + b);
+            for (int j = 0; j < 16; ++j) {
+              const float m = __shfl_sync(0xffffffffu, st.x, 2 * j), r = __shfl_sync(0xffffffffu, st.y, 2 * j);
+              const int row = row0 + s0 + j;
+              if (row < P.row_end) o[(size_t)row * P.ld_af] = __float2bfloat16_rn((v[j] - m) * r * ga + be);
             }
           }
-          rendezvous(9);
         } else {   // LDM_PH_EPS: v is eps_theta                                           (v2:560-561)
           if (active) {
-            const int f = tile * 128 + lrow;
+            const int f = grow;
             if (!P.sample) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (row0 + j < P.B) P.eps_out[(size_t)(row0 + j) * P.latent + f] = v[j];
-            } else {
-              const int t = P.t_start - it;
-              const float4 cf = P.coef[t];
-              float z[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) z[j] = 0.f;
-              if (cf.z > 0.0f) {
-                if (P.noise) {
-#pragma unroll
-                  for (int j = 0; j < 32; ++j)
-                    if (row0 + j < P.B) z[j] = P.noise[((size_t)it * P.B + row0 + j) * P.latent + f];
-                } else {
-                  // the 4 lanes that share a Philox quad split the rows between them, then trade components
-                  const unsigned long long seed = P.rng[0], off = P.rng[1] + (unsigned long long)row0;
-                  const int sub = lane & 3, base = lane & ~3;
-#pragma unroll
-                  for (int g = 0; g < 8; ++g) {
-                    const float4 z4 = philox_normal4(seed, off + (unsigned long long)(4 * g + sub), (uint32_t)t, (uint32_t)(f >> 2));
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                      const float gx = __shfl_sync(0xffffffffu, z4.x, base + i), gy = __shfl_sync(0xffffffffu, z4.y, base + i);
-                      const float gz = __shfl_sync(0xffffffffu, z4.z, base + i), gw = __shfl_sync(0xffffffffu, z4.w, base + i);
-                      z[4 * g + i] = sub == 0 ? gx : (sub == 1 ? gy : (sub == 2 ? gz : gw));
-                    }
-                  }
-                }
+              for (int j = 0; j < 16; ++j) {
+                const int row = row0 + s0 + j;
+                if (row < P.row_end) P.eps_out[(size_t)row * P.latent + f] = v[j];
               }
+            } else {
+              const float4 cf = P.coef[P.t_start - it];
               bf16* o = P.af[par ^ 1] + P.latent + f;   // x operand of the NEXT step
+              const bool last = it + 1 == P.n_iter;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (row0 + j < P.B) {
-                  float* xp = P.x + (size_t)(row0 + j) * P.latent + f;
-                  const float xn = ddpm_update_one(*xp, v[j], cf.x, cf.y, cf.z, z[j]);
-                  *xp = xn;
-                  o[(size_t)(row0 + j) * P.ld_af] = __float2bfloat16_rn(xn);
+              for (int j = 0; j < 16; ++j) {
+                const int row = row0 + s0 + j;
+                const float xn = ddpm_update_one(xr[j], v[j], cf.x, cf.y, cf.z, z[j]);
+                xr[j] = xn;
+                if (row < P.row_end) {
+                  o[(size_t)row * P.ld_af] = __float2bfloat16_rn(xn);
+                  if (last) P.x[(size_t)row * P.latent + f] = xn;
                 }
               }
             }
           }
-          rendezvous(10);
         }
+
+        // ---- hand-over: this CTA's share of the phase is in global memory; tell every CTA of the cluster, then wait
+        //      for all of them (the operand producer waits on the same barrier and starts the next phase's loads)
+        stamp();
+        fence_proxy_async_all();
+        stamp();
+        epi_bar();
+        stamp();
+        {
+          const uint32_t ob = oidx & 1u, opar = (oidx >> 1) & 1u;
+          if (et < CS) remote_arrive(mapa_u32(obar_local[ob], (uint32_t)et));
+          stamp();
+          W.wait_cluster(&obar[ob], opar, 9);
+          oidx++;
+        }
+        stamp();
       }
-      // uniform abort decision for the 128 epilogue threads
-      epi_bar_sync();
-      if (et == 0) abort_decision = abort_flag;
-      epi_bar_sync();
-      if (abort_decision) break;
     }
   }
 
   tc::fence_before_sync();
   __syncthreads();
   cluster_sync_all();   // nobody leaves while a peer may still address its shared memory
-  if (warp == 1) tc::tmem_dealloc<32>(tmem_base);
+  if (warp == 2) tc::tmem_dealloc<kTmemCols>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------- pack kernels
@@ -595,20 +726,15 @@ int copy2d(ldm_ctx* ctx, const float* src, int lds, float* dst, int ldd, int row
 
 bool g_chain_attr_set = false;
 
-}  // namespace
-
-// Can a 16-CTA cluster of this kernel be scheduled on this device?  (called once per context)
-int chain_init(ldm_ctx* ctx) {
-  LDM_TRY(tc_init(ctx));
-  if (!g_chain_attr_set) {
-    LDM_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    LDM_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    g_chain_attr_set = true;
-  }
+template <int NW>
+int chain_occupancy(int* out) {
+  using G = Geo<NW>;
+  LDM_CUDA(cudaFuncSetAttribute(chain_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::kSmemBytes));
+  LDM_CUDA(cudaFuncSetAttribute(chain_kernel<NW>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CS, 1);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.blockDim = dim3(G::kThreads);
+  cfg.dynamicSmemBytes = G::kSmemBytes;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CS;
@@ -617,9 +743,49 @@ int chain_init(ldm_ctx* ctx) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  LDM_CUDA(cudaOccupancyMaxActiveClusters(&n, chain_kernel, &cfg));
-  LDM_CHECK(n >= 1, "the device cannot co-schedule a cluster of %d CTAs with %zu bytes of shared memory each", CS, kSmemBytes);
-  ctx->chain_max_clusters = n;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&n, chain_kernel<NW>, &cfg);
+  if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+  *out = n;
+  return 0;
+}
+
+int g_chain_clusters[5] = {0, 0, 0, 0, 0};   // co-resident clusters per variant NW (index)
+
+template <int NW>
+int launch_variant(const ChainParams& P, int nclusters, cudaStream_t st) {
+  using G = Geo<NW>;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CS, nclusters);
+  cfg.blockDim = dim3(G::kThreads);
+  cfg.dynamicSmemBytes = G::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LDM_CUDA(cudaLaunchKernelEx(&cfg, chain_kernel<NW>, P));
+  return 0;
+}
+
+}  // namespace
+
+int tc_make_act_map(const void* base, int rows, int cols, int ld, int box_rows, CUtensorMap* out);
+
+// Can 16-CTA clusters of this kernel be scheduled on this device?  (called once per context)
+int chain_init(ldm_ctx* ctx) {
+  LDM_TRY(tc_init(ctx));
+  if (!g_chain_attr_set) {
+    LDM_TRY(chain_occupancy<2>(&g_chain_clusters[2]));
+    LDM_TRY(chain_occupancy<3>(&g_chain_clusters[3]));
+    LDM_TRY(chain_occupancy<4>(&g_chain_clusters[4]));
+    g_chain_attr_set = true;
+  }
+  LDM_CHECK(g_chain_clusters[2] >= 1 || g_chain_clusters[3] >= 1,
+            "the device cannot co-schedule a cluster of %d CTAs with %zu bytes of shared memory each", CS, Geo<3>::kSmemBytes);
+  ctx->chain_max_clusters = g_chain_clusters[3] > 0 ? g_chain_clusters[3] : g_chain_clusters[2];
   return 0;
 }
 
@@ -631,9 +797,9 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
   C = ChainModel();
   const int nst = U.nst, L = U.latent;
   LDM_CHECK(nst + 2 <= LDM_CHAIN_MAX_PHASES, "chain: too many stages");
-  LDM_CHECK(L % 128 == 0 && 2 * L <= kMaxK && L / 128 * 4 <= kSlots, "chain: latent_dim %d unsupported", L);
+  LDM_CHECK(L % 128 == 0 && L / 128 * 4 <= kSlots, "chain: latent_dim %d unsupported", L);
   for (int i = 0; i < nst; ++i)
-    LDM_CHECK(U.hid[i] % 64 == 0 && U.hid[i] / 64 <= CS && 2 * U.hid[i] <= kMaxK, "chain: hidden dim %d unsupported", U.hid[i]);
+    LDM_CHECK(U.hid[i] % 64 == 0 && U.hid[i] / 64 <= CS && U.hid[i] / 64 * 2 <= kSlots, "chain: hidden dim %d unsupported", U.hid[i]);
   auto& PA = C.allocs;
   std::vector<void*> tmp;
   auto free_tmp = [&]() { for (void* p : tmp) cudaFree(p); tmp.clear(); };
@@ -689,7 +855,7 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
         Gn = U.fin.w32; bn = U.fin.b;
         H.type = LDM_PH_EPS;
       }
-      LDM_CHECK(rows % 128 == 0 && K % BK == 0 && K <= kMaxK && rows / 128 <= CS, "chain: phase %d shape (%d x %d) unsupported", j, rows, K);
+      LDM_CHECK(rows % 128 == 0 && K % BK == 0 && rows / 128 <= CS, "chain: phase %d shape (%d x %d) unsupported", j, rows, K);
       H.K = K; H.rows = rows; H.tiles = rows / 128; H.d = d;
       LDM_TRY(ldm_alloc_t(ctx, PA, &H.w, (size_t)rows * K));
       LDM_TRY(ldm_alloc_t(ctx, PA, &H.bias, (size_t)rows));
@@ -724,7 +890,7 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
     double load[CS] = {0};
     int order[LDM_CHAIN_MAX_PHASES];
     for (int j = 0; j < C.n_phases; ++j) order[j] = j;
-    auto bytes = [&](int j) { return (double)C.ph[j].K * 256.0 + (double)C.ph[j].K * BNB * 2.0; };   // weight tile + operand
+    auto bytes = [&](int j) { return (double)C.ph[j].K * 256.0 + (double)C.ph[j].K * 48 * 2.0; };   // weight tile + operand
     for (int a = 0; a < C.n_phases; ++a)
       for (int b = a + 1; b < C.n_phases; ++b)
         if (bytes(order[b]) * C.ph[order[b]].tiles > bytes(order[a]) * C.ph[order[a]].tiles) { int t = order[a]; order[a] = order[b]; order[b] = t; }
@@ -747,6 +913,18 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
   return 0;
 }
 
+// Batch rows per cluster for a batch of B rows: the variant with the fewest waves of co-resident clusters, then the
+// fewest rows per cluster (shortest epilogue).
+static int chain_pick_nw(int B) {
+  int best = 0, best_waves = 1 << 30;
+  for (int nw = 2; nw <= 4; ++nw) {
+    if (g_chain_clusters[nw] < 1) continue;
+    const int waves = ceil_div(ceil_div(B, 16 * nw), g_chain_clusters[nw]);
+    if (waves < best_waves) { best_waves = waves; best = nw; }
+  }
+  return best;
+}
+
 // Run `n_iter` reverse steps (sample = 1) or one forward evaluation (sample = 0) for `B` rows.
 // The bf16 operand copy of x must already sit in ctx->af_op[0] (columns [latent, 2 latent)).
 int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const int64_t* t_idx, int t_len, float* x,
@@ -755,24 +933,39 @@ int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const
   ChainModel& C = ctx->chain;
   LDM_CHECK(C.ready, "chain: weights not packed");
   LDM_CHECK(!sample || ctx->coef_dev != nullptr, "chain: schedule not set");
+  const int nw = chain_pick_nw(B);
+  LDM_CHECK(nw >= 2, "chain: no cluster variant fits this device");
+  const int NB = 16 * nw;
   ChainParams P;
   memset(&P, 0, sizeof(P));
   const int nst = U.nst, L = U.latent;
+  LDM_CHECK(kAccCols + C.n_phases * NB <= kTmemCols, "chain: %d phases x %d rows exceed the TMEM columns", C.n_phases, NB);
+  LDM_CHECK(nst + 2 <= kMaxXMaps, "chain: too many stages");
+  // operand descriptors: rows beyond the batch are zero-filled by the TMA unit
+  LDM_TRY(tc_make_act_map(ctx->af_op[0], B, 2 * L, 2 * L, NB, &P.xmaps[0]));
+  LDM_TRY(tc_make_act_map(ctx->af_op[1], B, 2 * L, 2 * L, NB, &P.xmaps[1]));
+  for (int j = 0; j < nst; ++j) LDM_TRY(tc_make_act_map(ctx->opbuf[j], B, 2 * U.hid[j], 2 * U.hid[j], NB, &P.xmaps[2 + j]));
+  for (int j = nst; j < kMaxXMaps - 2; ++j) P.xmaps[2 + j] = P.xmaps[0];
+  int cadd = kAccCols;
   for (int j = 0; j < C.n_phases; ++j) {
     const ChainPhaseHost& H = C.ph[j];
     ChainPhase& D = P.ph[j];
     P.wmap[j] = H.map;
     D.type = H.type; D.K = H.K; D.tiles = H.tiles; D.first = H.first; D.d = H.d; D.rows = H.rows;
     D.bias = H.bias; D.tab_t = H.tab_t; D.tab_c = ctx->has_cls ? H.tab_c : nullptr;
+    D.cadd_col = -1;
+    if (H.tab_t) { D.cadd_col = cadd; cadd += NB; }
     if (j < nst) { D.ga = U.ln_a_w[j]; D.ba = U.ln_a_b[j]; D.gb = U.ln_b_w[j]; D.bb = U.ln_b_b[j]; }
     else if (j == nst) { D.ga = U.ln_f_w; D.ba = U.ln_f_b; }
-    if (j == 0) { D.in = nullptr; D.in_off = L; D.ld_in = 2 * L; }
-    else if (j <= nst) { D.in = ctx->opbuf[j - 1]; D.ld_in = 2 * U.hid[j - 1]; D.in_off = 0; }
-    else { D.in = nullptr; D.in_off = 0; D.ld_in = 2 * L; }
+    if (j == 0) { D.xmap = 0; D.xmap_alt = 1; D.xcol = L; }
+    else if (j <= nst) { D.xmap = 2 + (j - 1); D.xmap_alt = 0; D.xcol = 0; }
+    else { D.xmap = 0; D.xmap_alt = 1; D.xcol = 0; }
     if (j < nst) { D.out = ctx->opbuf[j]; D.ld_out = 2 * U.hid[j]; }
   }
+  for (int j = C.n_phases; j < LDM_CHAIN_MAX_PHASES; ++j) P.wmap[j] = C.ph[0].map;
   P.n_phases = C.n_phases;
-  P.B = B; P.n_iter = n_iter; P.t_start = t_start; P.sample = sample; P.latent = L; P.n_t = U.n_t;
+  P.B = B; P.row_begin = 0; P.row_end = B;
+  P.n_iter = n_iter; P.t_start = t_start; P.sample = sample; P.latent = L; P.n_t = U.n_t;
   P.t_idx = t_idx; P.t_len = t_len;
   P.cls = ctx->has_cls ? ctx->cls : nullptr;
   P.x = x; P.eps_out = eps_out; P.noise = noise; P.rng = ctx->rng_dev;
@@ -781,20 +974,12 @@ int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const
   P.err = ctx->chain_err;
   P.trace = ctx->chain_trace;
   P.trace_step = ctx->chain_trace_step;
-
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(CS, ceil_div(B, BNB));
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = kSmemBytes;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  LDM_CUDA(cudaLaunchKernelEx(&cfg, chain_kernel, P));
+  const int nclusters = ceil_div(B, NB);
+  int rc = -1;
+  if (nw == 2) rc = launch_variant<2>(P, nclusters, st);
+  else if (nw == 3) rc = launch_variant<3>(P, nclusters, st);
+  else rc = launch_variant<4>(P, nclusters, st);
+  LDM_TRY(rc);
   ctx->launches++;
   return 0;
 }

@@ -207,3 +207,9 @@ int tc_error_reset() {
   LDM_CUDA(cudaMemcpyToSymbol(g_tc_error, &z, sizeof(int)));
   return 0;
 }
+
+// 2-D bf16 activation (rows, cols) with row pitch ld, box (box_rows, 64 columns), 128-byte swizzle; rows read past
+// `rows` are zero-filled
+int tc_make_act_map(const void* base, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+  return make_map_2d(base, rows, cols, ld, box_rows, out);
+}

@@ -47,15 +47,16 @@ import ctypes
 import numpy as np
 from ldm_b200 import _lib
 L = _lib.lib()
-B = 32
+B = 48
 c = (torch.arange(B) % 102).to(dev)
 x = eng.randn(B, 256, 1, 0, 1000)
 _lib.check(L.ldm_debug_chain_trace(eng.ctx, 20, None, 0))
 eng.sample(x, 999, 1000 - 40, c, seed=3, use_graph=False)
-buf = np.zeros((16, 64), dtype=np.int64)
+buf = np.zeros((16, 2, 64), dtype=np.int64)
 _lib.check(L.ldm_debug_chain_trace(eng.ctx, 0, buf.ctypes.data_as(ctypes.c_void_p), buf.size))
 _lib.check(L.ldm_debug_chain_trace(eng.ctx, -1, None, 0))
 for r in range(16):
-    row = buf[r][buf[r] != 0]
-    if len(row) > 1:
-        print("rank %2d  n=%2d  total %7d cyc | deltas:" % (r, len(row), row[-1] - row[0]), " ".join(str(int(v)) for v in np.diff(row)))
+    for w in range(2):
+        row = buf[r][w][buf[r][w] != 0]
+        if len(row) > 1:
+            print("rank %2d %s n=%2d  total %7d cyc | deltas:" % (r, "hu"[w], len(row), row[-1] - row[0]), " ".join(str(int(v)) for v in np.diff(row)))
