@@ -144,7 +144,7 @@ def run_reference_arm(args, rank):
 # ------------------------------------------------------------------------------------------------------
 def loop_kernel_name(eng):
     if int(eng.info("chain")):
-        return "chain_kernel: the whole 1000-step loop is ONE persistent launch (16-CTA clusters x 32 samples, tcgen05 + TMA)"
+        return "chain_kernel: the whole 1000-step loop is ONE persistent launch (16-CTA clusters x 48 samples, tcgen05 + TMA + DSMEM)"
     return "sampling loop (one CUDA-graph launch = 1000 steps x %d kernels)" % int(eng.info("launches_per_step"))
 
 

@@ -105,7 +105,7 @@ extern "C" LDM_API int ldm_ctx_create(ldm_ctx** out, int device, int precision) 
   if (r == 0 && precision == LDM_PRECISION_BF16) {
     // the persistent cluster kernel is the bf16 denoiser; LDM_CHAIN=0 selects the one-kernel-per-layer sequence
     const char* ch = getenv("LDM_CHAIN");
-    ctx->use_chain = ch ? atoi(ch) : 0;   // TODO(round 1): default on once it beats the graph path
+    ctx->use_chain = ch ? atoi(ch) : 1;
     if (ctx->use_chain && chain_init(ctx) != 0) ctx->use_chain = 0;   // ldm_last_error() keeps the reason; ldm_get_info("chain") reports 0
   }
   const char* pdl = getenv("LDM_PDL");

@@ -25,6 +25,7 @@
 //   warp 0    : TMA producer of weight tiles (all steps, all phases of this CTA, 5-stage ring)
 //   warp 1    : TMEM allocator + tcgen05.mma issuer
 //   warps 2-5 : operand copy, epilogue (tables, LayerNorm, Swish, residual, DDPM update), cluster rendezvous
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -37,8 +38,8 @@ constexpr int CS = LDM_CHAIN_CLUSTER;   // CTAs per cluster
 constexpr int BK = 64;
 constexpr int kCtlThreads = 128;        // warp 0: weight TMA, warp 1: operand TMA, warp 2: TMEM + MMA, warp 3: spare
 constexpr uint32_t kWBytes = 128 * BK * 2;               // one weight k-block: 16 KiB
-constexpr int kSlots = 32;                               // partial-statistics slots per buffer (32 features each)
-constexpr int kMaxStagesRing = 8;
+constexpr int kSlots = CS;                               // partial-statistics slots per buffer: one per tile of a phase
+constexpr int kMaxStagesRing = 10;
 constexpr int kAccCols = 64;                             // TMEM columns reserved for the accumulator
 constexpr int kTmemCols = 512;
 constexpr int kMaxXMaps = LDM_MAX_STAGES + 2;
@@ -50,11 +51,13 @@ template <int NW> struct Geo {
   static constexpr int kThreads = kCtlThreads + kEpiThreads;
   static constexpr uint32_t kXBytes = NB * BK * 2;                     // one operand k-block
   static constexpr uint32_t kStageBytes = kWBytes + kXBytes;           // multiple of 1024
-  static constexpr uint32_t kYsmBytes = NB * 64 * sizeof(float);
   static constexpr uint32_t kSlotBytes = 2u * kSlots * NB * sizeof(float2);
-  static constexpr int kStages = (int)((225u * 1024u - kYsmBytes - kSlotBytes) / kStageBytes) < kMaxStagesRing
-                                     ? (int)((225u * 1024u - kYsmBytes - kSlotBytes) / kStageBytes) : kMaxStagesRing;
-  static constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + kYsmBytes + kSlotBytes;
+  static constexpr uint32_t kGstatBytes = 2u * NW * 4u * 16u * sizeof(float2);   // per-warp partials of a row group, double-buffered
+  static constexpr uint32_t kRowStatBytes = 4u * NW * 16u * sizeof(float2);      // (mean, rstd) of 16 rows per epilogue warp
+  static constexpr uint32_t kAuxBytes = kSlotBytes + kGstatBytes + kRowStatBytes;
+  static constexpr int kStages = (int)((225u * 1024u - kAuxBytes) / kStageBytes) < kMaxStagesRing
+                                     ? (int)((225u * 1024u - kAuxBytes) / kStageBytes) : kMaxStagesRing;
+  static constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + kAuxBytes;
 };
 
 struct ChainPhase {
@@ -98,6 +101,8 @@ struct ChainParams {
   const float4* coef;         // [n_steps]: (c2, sqrt_alpha, sigma, 0)
   bf16* af[2];                // (B, ld_af): [LN_f(h) | x] operand of the last phase, double-buffered over steps
   int ld_af;
+  int writer_fence;           // 1: every writer thread issues fence.proxy.async before the hand-over; 0: the operand producer does
+  int z_col;                  // TMEM column where the eps owners park the step's noise
   int* err;                   // [2]: first failure code, detail
   long long* trace;           // profiling aid: [CS][2][64] clock64 stamps of cluster 0 in step trace_step (null: off); [0]: an h-warp thread, [1]: a u-warp thread
   int trace_step;
@@ -135,6 +140,7 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // 32 lanes x 16 consecutive fp32 columns, thread i <-> lane (base + i)
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
@@ -240,6 +246,43 @@ __device__ __forceinline__ float tsum16(float (&a)[16], int lane) {
   return a[0] + __shfl_xor_sync(0xffffffffu, a[0], 1);
 }
 
+// Transposed reduction of 8 values per lane inside each 16-lane half of the warp: on return every lane holds the
+// 16-lane total of element ((lane >> 1) & 7) of its half.  8 shuffles.
+__device__ __forceinline__ float tsum8_half(float (&a)[8], int lane) {
+  {
+    const bool up = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? a[i] : a[i + 4], keep = up ? a[i + 4] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = (lane & 4) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? a[i] : a[i + 2], keep = up ? a[i + 2] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool up = (lane & 2) != 0;
+    const float send = up ? a[0] : a[1], keep = up ? a[1] : a[0];
+    a[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  return a[0] + __shfl_xor_sync(0xffffffffu, a[0], 1);
+}
+// (mean, M2) over the 16 features of this half-warp, of the half's row ((lane >> 1) & 7)
+__device__ __forceinline__ float2 half_row_stats8(const float (&v)[8], int lane) {
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a[j] = v[j]; b[j] = v[j] * v[j]; }
+  const float s1 = tsum8_half(a, lane);
+  const float s2 = tsum8_half(b, lane);
+  const float m = s1 * (1.0f / 16.0f);
+  return make_float2(m, fmaxf(s2 - s1 * m, 0.0f));
+}
+
 // (mean, M2) over this warp's 32 features of batch row (lane >> 1)
 __device__ __forceinline__ float2 warp_row_stats16(const float (&v)[16], int lane) {
   float a[16], b[16];
@@ -262,8 +305,9 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem;
-  float* ysm = reinterpret_cast<float*>(ring + (size_t)S * G::kStageBytes);          // [NB rows][64 features]
-  float2* slots = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(ysm) + G::kYsmBytes);   // [2][kSlots][NB]
+  float2* slots = reinterpret_cast<float2*>(ring + (size_t)S * G::kStageBytes);                          // [2][kSlots][NB]
+  float2* gstat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(slots) + G::kSlotBytes);          // [2][NW][4 warps][16 rows]
+  float2* rowstat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(gstat) + G::kGstatBytes);       // [4 NW warps][16 rows]
   __shared__ __align__(8) uint64_t full_bar[kMaxStagesRing];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStagesRing];
   __shared__ __align__(8) uint64_t tmem_full_bar;
@@ -332,7 +376,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
             const uint32_t f = gp - 1;   // hand-over that publishes this phase's operand
             if (!W.wait_cluster(&obar[f & 1u], (f >> 1) & 1u, 2)) { ok = false; break; }
             tc::mbar_arrive(&obar[f & 1u]);   // share of hand-over f + 2 (same barrier, next phase)
-            fence_proxy_async_all();          // peers' generic-proxy global writes -> visible to the TMA (async proxy) reads below
+            if (!P.writer_fence) fence_proxy_async_global();   // peers' generic-proxy global writes (released above) -> async-proxy reads below
           }
           const ChainPhase& ph = P.ph[p];
           const int tile = rank - ph.first;
@@ -396,24 +440,38 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
       if (tr_on && tr_n < 64) P.trace[(rank * 2 + (et == 0 ? 0 : 1)) * 64 + tr_n++] = clock64();
     };
     auto epi_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(G::kEpiThreads) : "memory"); };
+    auto group_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory"); };   // the 4 warps of row group g
 
-    // publish (mean, M2) of batch row `srow` over this warp's 32 features into slot `part` of buffer `buf` of every
-    // CTA that owns a tile of the phase; the two lanes that hold the same row split the destinations
-    auto publish = [&](uint32_t buf, int part, float2 st, int first, int ntiles) {
-      const uint32_t slot = tc::smem_u32(slots + ((size_t)buf * kSlots + part) * NB + srow);
-      for (int k = lane & 1; k < ntiles; k += 2)
-        st_async_f2(mapa_u32(slot, (uint32_t)(first + k)), st.x, st.y, mapa_u32(sbar_local[buf], (uint32_t)(first + k)));
+    // Statistics exchange, sender side.  Lane l holds (mean, M2) of group row (l >> 1) over `cnt` features of this
+    // warp.  The 4 warps of the row group merge their partials (Chan et al.) in shared memory, then every thread
+    // sends the merged (mean, M2) of one row over 4 cnt features to 1/8 of the CTAs that own a tile of the phase:
+    // an 8-byte st.async that also signals the receiver's transaction barrier.
+    const int tg = q * 32 + lane;                 // thread index inside the row group
+    const int xrow = tg >> 3, xds = tg & 7;       // row / destination slice this thread publishes
+    auto publish = [&](uint32_t buf, int tile, float2 st, float cnt, int first, int ntiles) {
+      float2* gs = gstat + ((size_t)buf * NW + g) * 64;
+      if ((lane & 1) == 0) gs[q * 16 + (lane >> 1)] = st;
+      group_bar();
+      const float2 p0 = gs[xrow], p1 = gs[16 + xrow], p2 = gs[32 + xrow], p3 = gs[48 + xrow];
+      const float mean = 0.25f * ((p0.x + p1.x) + (p2.x + p3.x));
+      const float d0 = p0.x - mean, d1 = p1.x - mean, d2 = p2.x - mean, d3 = p3.x - mean;
+      const float m2 = ((p0.y + p1.y) + (p2.y + p3.y)) + cnt * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
+      const uint32_t slot = tc::smem_u32(slots + ((size_t)buf * kSlots + tile) * NB + s0 + xrow);
+      for (int k = xds; k < ntiles; k += 8)
+        st_async_f2(mapa_u32(slot, (uint32_t)(first + k)), mean, m2, mapa_u32(sbar_local[buf], (uint32_t)(first + k)));
     };
-    // wait until all `nparts` partials of all NB rows have landed in buffer `buf`
+    // wait until the partials of all `nparts` tiles for all NB rows have landed in buffer `buf`
     auto exchange_wait = [&](uint32_t buf, int nparts, int code) {
       if (et == 0) tc::mbar_arrive_expect_tx(&sbar[buf], (uint32_t)nparts * NB * (uint32_t)sizeof(float2));
-      W.wait_cluster(&sbar[buf], sph[buf] & 1u, code);
+      W.wait(&sbar[buf], sph[buf] & 1u, code);
       sph[buf]++;
     };
-    // merge `nparts` partials of 32 features each (Chan et al.): (mean, rstd) of row `srow` over d = 32 nparts features
-    auto combine = [&](uint32_t buf, int nparts) -> float2 {
+    // receiver side: merge the `nparts` per-tile partials (`cnt` features each) into (mean, rstd) of the warp's 16
+    // rows, left in shared memory (rs[row], broadcast reads).  Lane l merges half of the partials of row (l >> 1).
+    float2* rs = rowstat + (size_t)(warp - 4) * 16;
+    auto combine = [&](uint32_t buf, int nparts, float cnt) {
       const float2* p = slots + ((size_t)buf * kSlots + (lane & 1)) * NB + srow;
-      const int half = nparts >> 1;             // partials this lane merges (the pair of lanes that own the row split them)
+      const int half = (nparts + 1 - (lane & 1)) >> 1;   // partials lane & 1, lane & 1 + 2, ...
       const float inv_n = 1.0f / (float)nparts;
       float2 s[kSlots / 2];
 #pragma unroll
@@ -427,11 +485,13 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
 #pragma unroll
       for (int k = 0; k < kSlots / 2; ++k) {
         const float dm = s[k].x - mean;
-        m2 += k < half ? s[k].y + 32.0f * dm * dm : 0.f;
+        m2 += k < half ? s[k].y + cnt * dm * dm : 0.f;
       }
       m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
-      const float var = m2 * inv_n * (1.0f / 32.0f);
-      return make_float2(mean, rsqrtf(var + 1e-5f));
+      const float var = m2 * inv_n / cnt;
+      __syncwarp();
+      if ((lane & 1) == 0) rs[lane >> 1] = make_float2(mean, rsqrtf(var + 1e-5f));
+      __syncwarp();
     };
 
     // ---- per-sample additive terms (class tables; per-sample timesteps of forward()) live in TMEM for the whole chain
@@ -475,47 +535,49 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
       tr_on = P.trace != nullptr && blockIdx.y == 0 && it == P.trace_step && (et == 0 || et == 64);
       stamp();
       const int t_uni = P.sample ? P.t_start - it : (P.t_len == 1 ? clamp_t(P.t_idx[0], P.n_t) : -1);
+      if (eps_owner && P.sample) {
+        // noise of this step (v2:589): independent of eps, generated while this CTA has no tile to finish and parked
+        // in spare TMEM columns until the eps phase
+        const int t = P.t_start - it;
+        const float sigma = P.coef[t].z;
+        float z[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) z[j] = 0.f;
+        if (sigma > 0.0f) {
+          if (P.noise) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int r = row0 + s0 + j;
+              if (r < P.row_end) z[j] = P.noise[((size_t)it * P.B + r) * P.latent + ef];
+            }
+          } else {
+            // the 4 lanes that share a Philox quad split the rows between them, then trade components
+            const unsigned long long seed = P.rng[0], off = P.rng[1] + (unsigned long long)(row0 + s0);
+            const int sub = lane & 3, base = lane & ~3;
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) {
+              const float4 z4 = philox_normal4(seed, off + (unsigned long long)(4 * gq + sub), (uint32_t)t, (uint32_t)(ef >> 2));
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float gx = __shfl_sync(0xffffffffu, z4.x, base + i), gy = __shfl_sync(0xffffffffu, z4.y, base + i);
+                const float gz = __shfl_sync(0xffffffffu, z4.z, base + i), gw = __shfl_sync(0xffffffffu, z4.w, base + i);
+                z[4 * gq + i] = sub == 0 ? gx : (sub == 1 ? gy : (sub == 2 ? gz : gw));
+              }
+            }
+          }
+        }
+        tmem_st16(lane_taddr + (uint32_t)(P.z_col + s0), z);
+      }
       for (int p = 0; p < NP; ++p) {
         const ChainPhase& ph = P.ph[p];
         const int tile = rank - ph.first;
         const bool active = tile >= 0 && tile < ph.tiles;
         const int grow = tile * 128 + lrow;
-        float v[16];
-        float z[16];
+        float v[16], zz[16];
         if (active) {
           // everything that does not depend on the accumulator is fetched before the waits
           float tt = ph.bias ? __ldg(ph.bias + grow) : 0.f;
           if (ph.tab_t && t_uni >= 0) tt += __ldg(ph.tab_t + (size_t)t_uni * ph.rows + grow);
-          if (ph.type == LDM_PH_EPS && P.sample) {
-            // noise of this step: independent of eps, generated while the tensor core works
-            const int t = P.t_start - it;
-            const float sigma = P.coef[t].z;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) z[j] = 0.f;
-            if (sigma > 0.0f) {
-              if (P.noise) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int r = row0 + s0 + j;
-                  if (r < P.row_end) z[j] = P.noise[((size_t)it * P.B + r) * P.latent + grow];
-                }
-              } else {
-                // the 4 lanes that share a Philox quad split the rows between them, then trade components
-                const unsigned long long seed = P.rng[0], off = P.rng[1] + (unsigned long long)(row0 + s0);
-                const int sub = lane & 3, base = lane & ~3;
-#pragma unroll
-                for (int gq = 0; gq < 4; ++gq) {
-                  const float4 z4 = philox_normal4(seed, off + (unsigned long long)(4 * gq + sub), (uint32_t)t, (uint32_t)(grow >> 2));
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    const float gx = __shfl_sync(0xffffffffu, z4.x, base + i), gy = __shfl_sync(0xffffffffu, z4.y, base + i);
-                    const float gz = __shfl_sync(0xffffffffu, z4.z, base + i), gw = __shfl_sync(0xffffffffu, z4.w, base + i);
-                    z[4 * gq + i] = sub == 0 ? gx : (sub == 1 ? gy : (sub == 2 ? gz : gw));
-                  }
-                }
-              }
-            }
-          }
           stamp();
           W.wait(&tmem_full_bar, tpar, 5);
           tpar ^= 1u;
@@ -526,6 +588,10 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
             tmem_ld16x2(lane_taddr + (uint32_t)s0, lane_taddr + (uint32_t)(ph.cadd_col + s0), v, c);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] += c[j] + tt;
+          } else if (ph.type == LDM_PH_EPS && P.sample) {
+            tmem_ld16x2(lane_taddr + (uint32_t)s0, lane_taddr + (uint32_t)(P.z_col + s0), v, zz);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += tt;
           } else {
             tc::tmem_ld16(lane_taddr + (uint32_t)s0, v);
 #pragma unroll
@@ -535,70 +601,69 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
         }
 
         if (ph.type == LDM_PH_STAGE) {
-          // lanes 0..63 of the tile: h features; lanes 64..127: u = Linear_b(h) of the SAME features
-          const bool is_u = q >= 2;
-          const int fl = (q & 1) * 32 + lane;       // feature inside the 64-feature slice
-          const int f = tile * 64 + fl;
-          const int nparts = ph.tiles * 2;
+          // Tile rows: quadrant q holds 16 h features in lanes 0..15 and u = Linear_b(h) of the SAME 16 features in lanes
+          // 16..31.  The two halves trade 8 rows, after which every lane owns feature f for 8 rows, h AND u: the whole
+          // LayerNorm / Swish / residual chain of v2:546-553 runs in registers on all 32 lanes.
+          const int f = tile * 64 + q * 16 + (lane & 15);
+          const int hr = (lane >> 4) * 8;             // first of this lane's 8 rows inside the row group
+          const int nparts = ph.tiles;
           const uint32_t b0 = sidx & 1u, b1 = b0 ^ 1u;
           sidx += 2;
           if (active) {
-            const float ga = is_u ? __ldg(ph.ga + f) : __ldg(ph.gb + f);
-            const float be = is_u ? __ldg(ph.ba + f) : __ldg(ph.bb + f);
-            if (is_u) publish(b0, tile * 2 + (q & 1), warp_row_stats16(v, lane), ph.first, ph.tiles);
+            const float ga = __ldg(ph.ga + f), ba = __ldg(ph.ba + f), gb = __ldg(ph.gb + f), bb = __ldg(ph.bb + f);
+            float h[8], u[8];
+            {
+              const bool lo = lane < 16;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float recv = __shfl_xor_sync(0xffffffffu, lo ? v[8 + i] : v[i], 16);
+                h[i] = lo ? v[i] : recv;
+                u[i] = lo ? recv : v[8 + i];
+              }
+            }
+            publish(b0, tile, half_row_stats8(u, lane), 16.0f, ph.first, ph.tiles);
             stamp();
             exchange_wait(b0, nparts, 6);
             stamp();
-            if (is_u) {   // y = swish(LN_a(u))                                            (v2:520-522)
-              const float2 st = combine(b0, nparts);
+            combine(b0, nparts, 64.0f);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float m = __shfl_sync(0xffffffffu, st.x, 2 * j), r = __shfl_sync(0xffffffffu, st.y, 2 * j);
-                ysm[(s0 + j) * 64 + fl] = swish_fast((v[j] - m) * r * ga + be);
-              }
+            for (int i = 0; i < 8; ++i) {   // h2 = swish(LN_a(u)) + h                       (v2:520-522, 547)
+              const float2 mr = rs[hr + i];
+              h[i] += swish_fast((u[i] - mr.x) * mr.y * ga + ba);
             }
-            stamp();
-            epi_bar();
-            stamp();
-            if (!is_u) {  // h2 = y + h                                                    (v2:547)
+            publish(b1, tile, half_row_stats8(h, lane), 16.0f, ph.first, ph.tiles);
+            // the h2 half of the next operand does not depend on the statistics: store it while they travel
+            bf16* o = ph.out + (size_t)(row0 + s0 + hr) * ph.ld_out + f;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] += ysm[(s0 + j) * 64 + fl];
-              publish(b1, tile * 2 + (q & 1), warp_row_stats16(v, lane), ph.first, ph.tiles);
-            }
+            for (int i = 0; i < 8; ++i)
+              if (row0 + s0 + hr + i < P.row_end) o[(size_t)i * ph.ld_out] = __float2bfloat16_rn(h[i]);
             stamp();
             exchange_wait(b1, nparts, 7);
             stamp();
-            if (!is_u) {   // n = LN_b(h2); operand of the next phase is [h2 | n]          (v2:548-553)
-              const float2 st = combine(b1, nparts);
+            combine(b1, nparts, 64.0f);
+            o += ph.d;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float m = __shfl_sync(0xffffffffu, st.x, 2 * j), r = __shfl_sync(0xffffffffu, st.y, 2 * j);
-                const int row = row0 + s0 + j;
-                if (row < P.row_end) {
-                  bf16* o = ph.out + (size_t)row * ph.ld_out;
-                  o[f] = __float2bfloat16_rn(v[j]);
-                  o[ph.d + f] = __float2bfloat16_rn((v[j] - m) * r * ga + be);
-                }
-              }
+            for (int i = 0; i < 8; ++i) {   // n = LN_b(h2); operand of the next phase is [h2 | n]   (v2:548-553)
+              const float2 mr = rs[hr + i];
+              if (row0 + s0 + hr + i < P.row_end) o[(size_t)i * ph.ld_out] = __float2bfloat16_rn((h[i] - mr.x) * mr.y * gb + bb);
             }
           }
         } else if (ph.type == LDM_PH_FINAL_LN) {
           const int f = grow;
-          const int nparts = ph.tiles * 4;
+          const int nparts = ph.tiles;
           const uint32_t b0 = sidx & 1u;
           sidx += 1;
           if (active) {   // LN_f(h + T_f[t] + C_f[c])                                     (v2:554-559)
             const float ga = __ldg(ph.ga + f), be = __ldg(ph.ba + f);
-            publish(b0, tile * 4 + q, warp_row_stats16(v, lane), ph.first, ph.tiles);
+            publish(b0, tile, warp_row_stats16(v, lane), 32.0f, ph.first, ph.tiles);
             exchange_wait(b0, nparts, 8);
             stamp();
-            const float2 st = combine(b0, nparts);
-            bf16* o = P.af[par] + f;
+            combine(b0, nparts, 128.0f);
+            bf16* o = P.af[par] + (size_t)(row0 + s0) * P.ld_af + f;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const float m = __shfl_sync(0xffffffffu, st.x, 2 * j), r = __shfl_sync(0xffffffffu, st.y, 2 * j);
-              const int row = row0 + s0 + j;
-              if (row < P.row_end) o[(size_t)row * P.ld_af] = __float2bfloat16_rn((v[j] - m) * r * ga + be);
+              const float2 mr = rs[j];
+              if (row0 + s0 + j < P.row_end) o[(size_t)j * P.ld_af] = __float2bfloat16_rn((v[j] - mr.x) * mr.y * ga + be);
             }
           }
         } else {   // LDM_PH_EPS: v is eps_theta                                           (v2:560-561)
@@ -617,7 +682,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const int row = row0 + s0 + j;
-                const float xn = ddpm_update_one(xr[j], v[j], cf.x, cf.y, cf.z, z[j]);
+                const float xn = ddpm_update_one(xr[j], v[j], cf.x, cf.y, cf.z, zz[j]);
                 xr[j] = xn;
                 if (row < P.row_end) {
                   o[(size_t)row * P.ld_af] = __float2bfloat16_rn(xn);
@@ -631,7 +696,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
         // ---- hand-over: this CTA's share of the phase is in global memory; tell every CTA of the cluster, then wait
         //      for all of them (the operand producer waits on the same barrier and starts the next phase's loads)
         stamp();
-        fence_proxy_async_all();
+        if (P.writer_fence) fence_proxy_async_all();
         stamp();
         epi_bar();
         stamp();
@@ -639,7 +704,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
           const uint32_t ob = oidx & 1u, opar = (oidx >> 1) & 1u;
           if (et < CS) remote_arrive(mapa_u32(obar_local[ob], (uint32_t)et));
           stamp();
-          W.wait_cluster(&obar[ob], opar, 9);
+          W.wait(&obar[ob], opar, 9);
           oidx++;
         }
         stamp();
@@ -680,11 +745,11 @@ __global__ void pack_copy2d_kernel(const float* __restrict__ src, int lds, float
   const int r = (int)(i / cols), c = (int)(i % cols);
   dst[(size_t)r * ldd + c] = src[(size_t)r * lds + c];
 }
-// natural row order [h_0..h_{d-1} | u_0..u_{d-1}] -> tile order (tile s: h[64s..64s+63] | u[64s..64s+63]); half = 0: identity
+// natural row order [h_0..h_{d-1} | u_0..u_{d-1}] -> tile order (tile s, quadrant q: h[64s+16q ..+15] | u[64s+16q ..+15]); stage = 0: identity
 __device__ __forceinline__ int tile_src_row(int rt, int d, int stage) {
   if (!stage) return rt;
-  const int s = rt >> 7, l = rt & 127;
-  return l < 64 ? s * 64 + l : d + s * 64 + (l - 64);
+  const int s = rt >> 7, l = rt & 127, q = l >> 5, w = l & 31;   // quadrant q: 16 h rows, then the 16 u rows of the same features
+  return w < 16 ? s * 64 + q * 16 + w : d + s * 64 + q * 16 + (w - 16);
 }
 __global__ void pack_rows_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int rows, int K, int d, int stage) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -797,9 +862,9 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
   C = ChainModel();
   const int nst = U.nst, L = U.latent;
   LDM_CHECK(nst + 2 <= LDM_CHAIN_MAX_PHASES, "chain: too many stages");
-  LDM_CHECK(L % 128 == 0 && L / 128 * 4 <= kSlots, "chain: latent_dim %d unsupported", L);
+  LDM_CHECK(L % 128 == 0 && L / 128 <= kSlots, "chain: latent_dim %d unsupported", L);
   for (int i = 0; i < nst; ++i)
-    LDM_CHECK(U.hid[i] % 64 == 0 && U.hid[i] / 64 <= CS && U.hid[i] / 64 * 2 <= kSlots, "chain: hidden dim %d unsupported", U.hid[i]);
+    LDM_CHECK(U.hid[i] % 64 == 0 && U.hid[i] / 64 <= CS && U.hid[i] / 64 <= kSlots, "chain: hidden dim %d unsupported", U.hid[i]);
   auto& PA = C.allocs;
   std::vector<void*> tmp;
   auto free_tmp = [&]() { for (void* p : tmp) cudaFree(p); tmp.clear(); };
@@ -939,7 +1004,7 @@ int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const
   ChainParams P;
   memset(&P, 0, sizeof(P));
   const int nst = U.nst, L = U.latent;
-  LDM_CHECK(kAccCols + C.n_phases * NB <= kTmemCols, "chain: %d phases x %d rows exceed the TMEM columns", C.n_phases, NB);
+  LDM_CHECK(kAccCols + (C.n_phases + 1) * NB <= kTmemCols + NB, "chain: %d phases x %d rows exceed the TMEM columns", C.n_phases, NB);
   LDM_CHECK(nst + 2 <= kMaxXMaps, "chain: too many stages");
   // operand descriptors: rows beyond the batch are zero-filled by the TMA unit
   LDM_TRY(tc_make_act_map(ctx->af_op[0], B, 2 * L, 2 * L, NB, &P.xmaps[0]));
@@ -963,6 +1028,9 @@ int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const
     if (j < nst) { D.out = ctx->opbuf[j]; D.ld_out = 2 * U.hid[j]; }
   }
   for (int j = C.n_phases; j < LDM_CHAIN_MAX_PHASES; ++j) P.wmap[j] = C.ph[0].map;
+  P.z_col = cadd;
+  { const char* wf = getenv("LDM_CHAIN_WRITER_FENCE"); P.writer_fence = wf ? atoi(wf) : 0; }
+  LDM_CHECK(cadd + NB <= kTmemCols, "chain: TMEM columns exhausted (%d phases x %d rows)", C.n_phases, NB);
   P.n_phases = C.n_phases;
   P.B = B; P.row_begin = 0; P.row_end = B;
   P.n_iter = n_iter; P.t_start = t_start; P.sample = sample; P.latent = L; P.n_t = U.n_t;
