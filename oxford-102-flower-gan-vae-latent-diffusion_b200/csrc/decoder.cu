@@ -8,6 +8,14 @@ int tc_pick_bn(int M, int N);
 int conv_tc_pick_bn(int Cout);
 int launch_conv_tc(ldm_ctx* ctx, const bf16* in, const ConvLayer& L, const float* bias, bf16* out, int B, int H, int W,
                    int up, cudaStream_t st);
+int launch_norm_coef_bf16(ldm_ctx* ctx, const bf16* x, const float* gamma, const float* beta, float2* coef, int B, int HW,
+                          int C, int group, cudaStream_t st);
+int launch_coef_apply_bf16(ldm_ctx* ctx, const bf16* x, const float2* coef, bf16* out, int B, int HW, int C, int act,
+                           cudaStream_t st);
+int launch_sa_map_bf16(ldm_ctx* ctx, const bf16* x, const float2* coef, const float* ca, float* map, int B, int HW, int C,
+                       cudaStream_t st);
+int launch_sa_apply_bf16(ldm_ctx* ctx, const bf16* x, const float2* coef, const float* ca, const float* map,
+                         const float* sa_w, const bf16* resid, bf16* out, int B, int H, int C, cudaStream_t st);
 int launch_conv_out3(ldm_ctx* ctx, const bf16* in, const float* w, const float* bias, float* out, int B, int H, int W,
                      cudaStream_t st);
 
@@ -141,15 +149,16 @@ int decode_chunk_f32(ldm_ctx* ctx, const float* z, float* img, int B, cudaStream
 // ---------------------------------------------------------------------------------------------------------------
 int res_block_bf16(ldm_ctx* ctx, const ResBlockModel& R, int B, const bf16* X, bf16* Y, bf16* OUT, cudaStream_t st) {
   const int C = R.C, H = R.HW, P = H * H;
-  LDM_TRY(launch_conv_tc(ctx, X, R.conv1, R.conv1.b, Y, B, H, H, 1, st));                                         // conv1
-  LDM_TRY(launch_inorm_stats<bf16>(ctx, Y, ctx->d_stats, B, P, C, 1, st));                                        // ln1 statistics
-  LDM_TRY(launch_norm_apply<bf16>(ctx, Y, ctx->d_stats, R.ln1_w, R.ln1_b, OUT, B, P, C, 1, LDM_ACT_SWISH, st));   // swish(ln1(.))
-  LDM_TRY(launch_conv_tc(ctx, OUT, R.conv2, R.conv2.b, Y, B, H, H, 1, st));                                       // conv2
-  LDM_TRY(launch_inorm_stats<bf16>(ctx, Y, ctx->d_stats, B, P, C, 1, st));                                        // ln2 statistics
+  float2* coef = reinterpret_cast<float2*>(ctx->d_stats);
+  LDM_TRY(launch_conv_tc(ctx, X, R.conv1, R.conv1.b, Y, B, H, H, 1, st));                              // conv1
+  LDM_TRY(launch_norm_coef_bf16(ctx, Y, R.ln1_w, R.ln1_b, coef, B, P, C, 1, st));                       // ln1 as (scale, shift)
+  LDM_TRY(launch_coef_apply_bf16(ctx, Y, coef, OUT, B, P, C, LDM_ACT_SWISH, st));                       // swish(ln1(.))
+  LDM_TRY(launch_conv_tc(ctx, OUT, R.conv2, R.conv2.b, Y, B, H, H, 1, st));                             // conv2
+  LDM_TRY(launch_norm_coef_bf16(ctx, Y, R.ln2_w, R.ln2_b, coef, B, P, C, 1, st));                       // ln2 as (scale, shift)
   // CALayer (v2:64-67): the average pool of an instance-normalised map is its beta, so the channel gate is a
-  // per-channel constant computed at pack time (ca_const); stride 0 = the same gate for every sample
-  LDM_TRY(launch_sa_map<bf16>(ctx, Y, ctx->d_stats, R.ln2_w, R.ln2_b, R.ca_const, 0, ctx->d_map, B, P, C, st));
-  LDM_TRY(launch_sa_apply<bf16>(ctx, Y, ctx->d_stats, R.ln2_w, R.ln2_b, R.ca_const, 0, ctx->d_map, R.sa_w, X, OUT, B, H, C, st));
+  // per-channel constant computed at pack time (ca_const), the same for every sample
+  LDM_TRY(launch_sa_map_bf16(ctx, Y, coef, R.ca_const, ctx->d_map, B, P, C, st));
+  LDM_TRY(launch_sa_apply_bf16(ctx, Y, coef, R.ca_const, ctx->d_map, R.sa_w, X, OUT, B, H, C, st));
   return 0;
 }
 
@@ -157,8 +166,9 @@ int up_block_bf16(ldm_ctx* ctx, const DecoderModel& D, int idx, int B, int H, in
                   cudaStream_t st) {
   const int Cout = Cin / 2, P = 4 * H * H;
   LDM_TRY(launch_conv_tc(ctx, X, D.up[idx][0], D.up_b[idx], Y, B, H, H, 2, st));   // four sub-pixel parities, one launch
-  LDM_TRY(launch_inorm_stats<bf16>(ctx, Y, ctx->d_stats, B, P, Cout, 8, st));
-  LDM_TRY(launch_norm_apply<bf16>(ctx, Y, ctx->d_stats, D.up_gn_w[idx], D.up_gn_b[idx], OUT, B, P, Cout, 8, LDM_ACT_SWISH, st));
+  float2* coef = reinterpret_cast<float2*>(ctx->d_stats);
+  LDM_TRY(launch_norm_coef_bf16(ctx, Y, D.up_gn_w[idx], D.up_gn_b[idx], coef, B, P, Cout, 8, st));
+  LDM_TRY(launch_coef_apply_bf16(ctx, Y, coef, OUT, B, P, Cout, LDM_ACT_SWISH, st));
   return 0;
 }
 

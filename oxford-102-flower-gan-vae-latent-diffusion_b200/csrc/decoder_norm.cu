@@ -173,6 +173,174 @@ sa_apply_kernel(const T* __restrict__ x, const float* __restrict__ stats, const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// bf16 fast path: 16-byte (8-channel) accesses, one pass statistics, (scale, shift) precomputed per (sample, channel)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+    f[2 * e] = __low2float(h2);
+    f[2 * e + 1] = __high2float(h2);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+    w[e] = *reinterpret_cast<uint32_t*>(&h2);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// One CTA per (sample, 64-channel block): threads = 8 channel-octets x 32 pixel lanes.  Writes, per channel,
+// scale = rstd * gamma and shift = beta - mean * scale of its normalisation group (cg channels x HW pixels; cg | 8),
+// so that the consumers apply LayerNorm2d / GroupNorm as one FMA.  Sums are centred on the first pixel of the
+// channel to keep the single pass free of cancellation.
+__global__ void __launch_bounds__(256)
+norm_coef_bf16_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      float2* __restrict__ coef, int HW, int C, int cg) {
+  __shared__ float s1[32][65], s2[32][65];
+  const int n = blockIdx.y, c0 = blockIdx.x * 64, oct = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const bf16* base = x + (size_t)n * HW * C + c0 + oct * 8;
+  float piv[8], a[8], b[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(base)), piv);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { a[e] = 0.f; b[e] = 0.f; }
+  for (int p = pl; p < HW; p += 32) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(base + (size_t)p * C)), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const float d = f[e] - piv[e]; a[e] += d; b[e] += d * d; }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { s1[pl][oct * 8 + e] = a[e]; s2[pl][oct * 8 + e] = b[e]; }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int c = threadIdx.x;
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) { t1 += s1[i][c]; t2 += s2[i][c]; }
+    // per-channel (mean, M2), then merge the cg channels of the group (Chan et al.)
+    const float inv = 1.0f / (float)HW;
+    const float pv = __bfloat162float(x[(size_t)n * HW * C + c0 + c]);
+    const float dm = t1 * inv;
+    float mean = pv + dm, m2 = fmaxf(t2 - t1 * dm, 0.f);
+    s1[0][c] = mean; s2[0][c] = m2;
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int c = threadIdx.x, g0 = (c / cg) * cg;
+    float gm = 0.f;
+    for (int i = 0; i < cg; ++i) gm += s1[0][g0 + i];
+    gm /= (float)cg;
+    float gq = 0.f;
+    for (int i = 0; i < cg; ++i) { const float d = s1[0][g0 + i] - gm; gq += s2[0][g0 + i] + (float)HW * d * d; }
+    const float rstd = rsqrtf(gq / ((float)HW * (float)cg) + 1e-5f);
+    const float sc = rstd * gamma[c0 + c];
+    coef[(size_t)n * C + c0 + c] = make_float2(sc, beta[c0 + c] - gm * sc);
+  }
+}
+
+// out = act(x * scale + shift), 8 channels per thread
+__global__ void __launch_bounds__(256)
+coef_apply_bf16_kernel(const bf16* __restrict__ x, const float2* __restrict__ coef, bf16* __restrict__ out, int HWC8, int C8,
+                       int act, size_t total8) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int n = (int)(i / HWC8), c8 = (int)(i % C8);
+  float f[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), f);
+  const float4* cf = reinterpret_cast<const float4*>(coef + (size_t)n * C8 * 8 + c8 * 8);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float4 k = __ldg(cf + e);   // (scale, shift) of two channels
+    float v0 = f[2 * e] * k.x + k.y, v1 = f[2 * e + 1] * k.z + k.w;
+    if (act == LDM_ACT_SWISH) { v0 = swishf(v0); v1 = swishf(v1); }
+    f[2 * e] = v0; f[2 * e + 1] = v1;
+  }
+  reinterpret_cast<uint4*>(out)[i] = pack8(f);
+}
+
+// SpatialAttention input (v2:76-78): per pixel, mean and max over channels of z = ca[c] * (x * scale + shift).
+// C/8 lanes per pixel (C = 128: 16 lanes, two pixels per warp; C >= 256: a whole warp, several octets per lane).
+__global__ void __launch_bounds__(256)
+sa_map_bf16_kernel(const bf16* __restrict__ x, const float2* __restrict__ coef, const float* __restrict__ ca,
+                   float* __restrict__ map, int HW, int C, int npix) {
+  const int lpp = C >= 256 ? 32 : C / 8;                 // lanes per pixel
+  const int ppw = 32 / lpp;                              // pixels per warp
+  const int lane = threadIdx.x & 31, wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int pix = wid * ppw + lane / lpp, sub = lane % lpp;
+  float s = 0.f, m = -INFINITY;
+  if (pix < npix) {
+    const int n = pix / HW;
+    const bf16* row = x + (size_t)pix * C;
+    const float2* cf = coef + (size_t)n * C;
+    for (int c = sub * 8; c < C; c += lpp * 8) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(row + c)), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float2 k = __ldg(cf + c + e);
+        const float z = __ldg(ca + c + e) * (f[e] * k.x + k.y);
+        s += z;
+        m = fmaxf(m, z);
+      }
+    }
+  }
+  for (int o = lpp >> 1; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  }
+  if (pix < npix && sub == 0) {
+    map[(size_t)pix * 2 + 0] = s / (float)C;
+    map[(size_t)pix * 2 + 1] = m;
+  }
+}
+
+// out = swish(z * sigmoid(conv7x7(map)) + resid)   (v2:79-81 then v2:176-177), same lane layout as sa_map
+__global__ void __launch_bounds__(256)
+sa_apply_bf16_kernel(const bf16* __restrict__ x, const float2* __restrict__ coef, const float* __restrict__ ca,
+                     const float* __restrict__ map, const float* __restrict__ sa_w, const bf16* __restrict__ resid,
+                     bf16* __restrict__ out, int H, int C, int npix) {
+  const int lpp = C >= 256 ? 32 : C / 8;
+  const int ppw = 32 / lpp;
+  const int lane = threadIdx.x & 31, wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int pix = wid * ppw + lane / lpp, sub = lane % lpp;
+  const int HW = H * H;
+  const bool ok = pix < npix;
+  const int n = ok ? pix / HW : 0, rem = ok ? pix - n * HW : 0, y = rem / H, xx = rem - y * H;
+  float a = 0.f;
+  if (ok) {
+    for (int t = sub; t < 98; t += lpp) {
+      const int ch = t / 49, k = t - ch * 49, ky = k / 7, kx = k - ky * 7;
+      const int yy = y + ky - 3, xq = xx + kx - 3;
+      if (yy >= 0 && yy < H && xq >= 0 && xq < H) a += __ldg(sa_w + t) * __ldg(map + ((size_t)n * HW + yy * H + xq) * 2 + ch);
+    }
+  }
+  for (int o = lpp >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (!ok) return;
+  const float gate = sigmoidf_(a);
+  const bf16* row = x + (size_t)pix * C;
+  const bf16* rr = resid + (size_t)pix * C;
+  bf16* orow = out + (size_t)pix * C;
+  const float2* cf = coef + (size_t)n * C;
+  for (int c = sub * 8; c < C; c += lpp * 8) {
+    float f[8], r[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(row + c)), f);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(rr + c)), r);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float2 k = __ldg(cf + c + e);
+      const float z = __ldg(ca + c + e) * (f[e] * k.x + k.y);
+      f[e] = swishf(z * gate + r[e]);
+    }
+    *reinterpret_cast<uint4*>(orow + c) = pack8(f);
+  }
+}
+
 }  // namespace
 
 #define LDM_LAUNCHED(ctx)         \
@@ -224,6 +392,42 @@ int launch_sa_apply(ldm_ctx* ctx, const T* x, const float* stats, const float* g
                     int H, int C, cudaStream_t st) {
   const int npix = B * H * H;
   sa_apply_kernel<T><<<ceil_div(npix, 8), 256, 0, st>>>(x, stats, gamma, beta, ca, ca_stride, map, sa_w, resid, out, H, C, npix);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+
+
+// ---- bf16 fast path launchers
+int launch_norm_coef_bf16(ldm_ctx* ctx, const bf16* x, const float* gamma, const float* beta, float2* coef, int B, int HW,
+                          int C, int group, cudaStream_t st) {
+  LDM_CHECK(C % 64 == 0 || C == 32, "norm_coef: C must be 32 or a multiple of 64 (C=%d)", C);
+  LDM_CHECK(group == 1 || group == 2 || group == 4 || group == 8, "norm_coef: group size %d unsupported", group);
+  LDM_CHECK(C % 64 == 0, "norm_coef: C %% 64 == 0 required on the vector path (C=%d)", C);
+  norm_coef_bf16_kernel<<<dim3(C / 64, B), 256, 0, st>>>(x, gamma, beta, coef, HW, C, group);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+int launch_coef_apply_bf16(ldm_ctx* ctx, const bf16* x, const float2* coef, bf16* out, int B, int HW, int C, int act,
+                           cudaStream_t st) {
+  const size_t total8 = (size_t)B * HW * C / 8;
+  coef_apply_bf16_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(x, coef, out, HW * C / 8, C / 8, act, total8);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+int launch_sa_map_bf16(ldm_ctx* ctx, const bf16* x, const float2* coef, const float* ca, float* map, int B, int HW, int C,
+                       cudaStream_t st) {
+  LDM_CHECK(C % 64 == 0, "sa_map: C %% 64 == 0 required");
+  const int npix = B * HW, lpp = C >= 256 ? 32 : C / 8, ppw = 32 / lpp;
+  const int warps = ceil_div(npix, ppw);
+  sa_map_bf16_kernel<<<ceil_div(warps, 8), 256, 0, st>>>(x, coef, ca, map, HW, C, npix);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+int launch_sa_apply_bf16(ldm_ctx* ctx, const bf16* x, const float2* coef, const float* ca, const float* map,
+                         const float* sa_w, const bf16* resid, bf16* out, int B, int H, int C, cudaStream_t st) {
+  const int npix = B * H * H, lpp = C >= 256 ? 32 : C / 8, ppw = 32 / lpp;
+  const int warps = ceil_div(npix, ppw);
+  sa_apply_bf16_kernel<<<ceil_div(warps, 8), 256, 0, st>>>(x, coef, ca, map, sa_w, resid, out, H, C, npix);
   LDM_LAUNCHED(ctx);
   return 0;
 }
