@@ -25,6 +25,7 @@
 //   warp 0    : TMA producer of weight tiles (all steps, all phases of this CTA, 5-stage ring)
 //   warp 1    : TMEM allocator + tcgen05.mma issuer
 //   warps 2-5 : operand copy, epilogue (tables, LayerNorm, Swish, residual, DDPM update), cluster rendezvous
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -54,7 +55,8 @@ template <int NW> struct Geo {
   static constexpr uint32_t kSlotBytes = 2u * kSlots * NB * sizeof(float2);
   static constexpr uint32_t kGstatBytes = 2u * NW * 4u * 16u * sizeof(float2);   // per-warp partials of a row group, double-buffered
   static constexpr uint32_t kRowStatBytes = 4u * NW * 16u * sizeof(float2);      // (mean, rstd) of 16 rows per epilogue warp
-  static constexpr uint32_t kAuxBytes = kSlotBytes + kGstatBytes + kRowStatBytes;
+  static constexpr uint32_t kPbufBytes = 128u * NB * sizeof(float);               // split-K partner's partial accumulator
+  static constexpr uint32_t kAuxBytes = kSlotBytes + kGstatBytes + kRowStatBytes + kPbufBytes;
   static constexpr int kStages = (int)((225u * 1024u - kAuxBytes) / kStageBytes) < kMaxStagesRing
                                      ? (int)((225u * 1024u - kAuxBytes) / kStageBytes) : kMaxStagesRing;
   static constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + kAuxBytes;
@@ -64,7 +66,8 @@ struct ChainPhase {
   int type;            // LDM_PH_*
   int K;               // reduction length, multiple of 64
   int tiles;           // 128-row weight tiles
-  int first;           // cluster rank of the CTA that owns tile 0 (tile i -> rank first + i)
+  int first;           // cluster rank of the CTA that owns unit 0; unit = tile * ks + k-part -> rank first + unit
+  int ks;              // split of the reduction: 1, or 2 (the odd unit sends its partial accumulator to the even one)
   int d;               // LayerNorm width (stage: d_j; final-LN / eps: latent)
   int rows;            // tiles * 128: leading dimension of the tables
   int xmap;            // index of the operand's tensor map (+ 1 on odd steps when xmap_alt)
@@ -124,6 +127,10 @@ __device__ __forceinline__ void remote_st_u32(uint32_t cluster_addr, uint32_t v)
 __device__ __forceinline__ void st_async_f2(uint32_t cluster_addr, float a, float b, uint32_t cluster_bar) {
   asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
                ::"r"(cluster_addr), "f"(a), "f"(b), "r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void st_async_f4(uint32_t cluster_addr, float a, float b, float c, float d, uint32_t cluster_bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(cluster_addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ bool try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -297,6 +304,18 @@ __device__ __forceinline__ float2 warp_row_stats16(const float (&v)[16], int lan
 __device__ __forceinline__ float swish_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 __device__ __forceinline__ int clamp_t(long long t, int n_t) { return (int)(t < 0 ? 0 : (t >= n_t ? n_t - 1 : t)); }
 
+// work unit of cluster rank `rank` in a phase: tile, k-part and k-block range; false: no unit
+struct Unit { int tile, kp, kb0, nk; };
+__device__ __forceinline__ bool unit_of(const ChainPhase& ph, int rank, Unit& u) {
+  const int un = rank - ph.first;
+  if (un < 0 || un >= ph.tiles * ph.ks) return false;
+  u.tile = un / ph.ks;
+  u.kp = un - u.tile * ph.ks;
+  u.nk = ph.K / BK / ph.ks;
+  u.kb0 = u.kp * u.nk;
+  return true;
+}
+
 template <int NW>
 __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __grid_constant__ ChainParams P) {
   using G = Geo<NW>;
@@ -308,11 +327,13 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
   float2* slots = reinterpret_cast<float2*>(ring + (size_t)S * G::kStageBytes);                          // [2][kSlots][NB]
   float2* gstat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(slots) + G::kSlotBytes);          // [2][NW][4 warps][16 rows]
   float2* rowstat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(gstat) + G::kGstatBytes);       // [4 NW warps][16 rows]
+  float4* pbuf = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(rowstat) + G::kRowStatBytes);      // [NW][4 chunks][128 rows] x 4 columns
   __shared__ __align__(8) uint64_t full_bar[kMaxStagesRing];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStagesRing];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ __align__(8) uint64_t obar[2];   // phase hand-over: 16 remote arrives (one per CTA) + the local operand producer
   __shared__ __align__(8) uint64_t sbar[2];   // LayerNorm statistics: transaction barrier fed by the peers' st.async
+  __shared__ __align__(8) uint64_t pbar;      // split-K: the partner's partial accumulator has landed in pbuf
   __shared__ uint32_t tmem_slot;
   __shared__ int abort_flag;
 
@@ -332,6 +353,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
     tc::mbar_init(&obar[1], CS + 1);
     tc::mbar_init(&sbar[0], 1);
     tc::mbar_init(&sbar[1], 1);
+    tc::mbar_init(&pbar, 1);
     abort_flag = 0;
     tc::fence_barrier_init();
     for (int p = 0; p < NP; ++p) tc::prefetch_tmap(&P.wmap[p]);
@@ -351,14 +373,13 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
       bool ok = true;
       for (int it = 0; it < P.n_iter && ok; ++it) {
         for (int p = 0; p < NP && ok; ++p) {
-          const int tile = rank - P.ph[p].first;
-          if (tile < 0 || tile >= P.ph[p].tiles) continue;
-          const int nkb = P.ph[p].K / BK;
-          for (int kb = 0; kb < nkb; ++kb, ++n) {
+          Unit un;
+          if (!unit_of(P.ph[p], rank, un)) continue;
+          for (int kb = un.kb0; kb < un.kb0 + un.nk; ++kb, ++n) {
             const uint32_t s = n % S, par = (n / S) & 1u;
             if (!W.wait(&empty_bar[s], par ^ 1u, 1)) { ok = false; break; }
             tc::mbar_arrive_expect_tx(&full_bar[s], kWBytes);
-            tc::tma_load_2d(ring + (size_t)s * G::kStageBytes, &P.wmap[p], &full_bar[s], kb * BK, tile * 128);
+            tc::tma_load_2d(ring + (size_t)s * G::kStageBytes, &P.wmap[p], &full_bar[s], kb * BK, un.tile * 128);
           }
         }
       }
@@ -379,11 +400,10 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
             if (!P.writer_fence) fence_proxy_async_global();   // peers' generic-proxy global writes (released above) -> async-proxy reads below
           }
           const ChainPhase& ph = P.ph[p];
-          const int tile = rank - ph.first;
-          if (tile < 0 || tile >= ph.tiles) continue;
+          Unit un;
+          if (!unit_of(ph, rank, un)) continue;
           const CUtensorMap* xm = &P.xmaps[ph.xmap + (ph.xmap_alt ? (it & 1) : 0)];
-          const int nkb = ph.K / BK;
-          for (int kb = 0; kb < nkb; ++kb, ++n) {
+          for (int kb = un.kb0; kb < un.kb0 + un.nk; ++kb, ++n) {
             const uint32_t s = n % S, par = (n / S) & 1u;
             if (!W.wait(&empty_bar[s], par ^ 1u, 3)) { ok = false; break; }
             tc::mbar_arrive_expect_tx(&full_bar[s], G::kXBytes);
@@ -400,10 +420,9 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
       bool ok = true;
       for (int it = 0; it < P.n_iter && ok; ++it) {
         for (int p = 0; p < NP && ok; ++p) {
-          const int tile = rank - P.ph[p].first;
-          if (tile < 0 || tile >= P.ph[p].tiles) continue;
-          const int nkb = P.ph[p].K / BK;
-          for (int kb = 0; kb < nkb; ++kb, ++n) {
+          Unit un;
+          if (!unit_of(P.ph[p], rank, un)) continue;
+          for (int kb = 0; kb < un.nk; ++kb, ++n) {
             const uint32_t s = n % S, par = (n / S) & 1u;
             if (!W.wait(&full_bar[s], par, 4)) { ok = false; break; }
             tc::fence_after_sync();
@@ -431,6 +450,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
     const uint32_t sbar_local[2] = {tc::smem_u32(&sbar[0]), tc::smem_u32(&sbar[1])};
     const uint32_t obar_local[2] = {tc::smem_u32(&obar[0]), tc::smem_u32(&obar[1])};
     uint32_t tpar = 0;            // parity of tmem_full_bar
+    uint32_t ppar = 0;            // parity of pbar
     uint32_t sidx = 0;            // statistics exchanges so far (same count in every CTA)
     uint32_t sph[2] = {0, 0};     // completed phases of sbar[b] in THIS CTA
     uint32_t oidx = 0;            // hand-overs so far
@@ -448,7 +468,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
     // an 8-byte st.async that also signals the receiver's transaction barrier.
     const int tg = q * 32 + lane;                 // thread index inside the row group
     const int xrow = tg >> 3, xds = tg & 7;       // row / destination slice this thread publishes
-    auto publish = [&](uint32_t buf, int tile, float2 st, float cnt, int first, int ntiles) {
+    auto publish = [&](uint32_t buf, int tile, float2 st, float cnt, int first, int ntiles, int ks) {
       float2* gs = gstat + ((size_t)buf * NW + g) * 64;
       if ((lane & 1) == 0) gs[q * 16 + (lane >> 1)] = st;
       group_bar();
@@ -458,7 +478,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
       const float m2 = ((p0.y + p1.y) + (p2.y + p3.y)) + cnt * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
       const uint32_t slot = tc::smem_u32(slots + ((size_t)buf * kSlots + tile) * NB + s0 + xrow);
       for (int k = xds; k < ntiles; k += 8)
-        st_async_f2(mapa_u32(slot, (uint32_t)(first + k)), mean, m2, mapa_u32(sbar_local[buf], (uint32_t)(first + k)));
+        st_async_f2(mapa_u32(slot, (uint32_t)(first + k * ks)), mean, m2, mapa_u32(sbar_local[buf], (uint32_t)(first + k * ks)));
     };
     // wait until the partials of all `nparts` tiles for all NB rows have landed in buffer `buf`
     auto exchange_wait = [&](uint32_t buf, int nparts, int code) {
@@ -499,9 +519,9 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
       const bool per_row_t = !P.sample && P.t_len != 1;
       for (int p = 0; p < NP; ++p) {
         const ChainPhase& ph = P.ph[p];
-        const int tile = rank - ph.first;
-        if (tile < 0 || tile >= ph.tiles || ph.cadd_col < 0) continue;
-        const int grow = tile * 128 + lrow;
+        Unit un;
+        if (!unit_of(ph, rank, un) || un.kp != 0 || ph.cadd_col < 0) continue;
+        const int grow = un.tile * 128 + lrow;
         float c[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -521,8 +541,9 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
     // ---- the chain state of the rows / features this thread finishes in the eps phase stays in registers
     float xr[16];
     const ChainPhase& phe = P.ph[NP - 1];
-    const int etile = rank - phe.first;
-    const bool eps_owner = etile >= 0 && etile < phe.tiles;
+    Unit eun;
+    const bool eps_owner = unit_of(phe, rank, eun) && eun.kp == 0;
+    const int etile = eps_owner ? eun.tile : 0;
     const int ef = etile * 128 + lrow;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -570,9 +591,26 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
       }
       for (int p = 0; p < NP; ++p) {
         const ChainPhase& ph = P.ph[p];
-        const int tile = rank - ph.first;
-        const bool active = tile >= 0 && tile < ph.tiles;
+        Unit un;
+        const bool has_unit = unit_of(ph, rank, un);
+        const bool active = has_unit && un.kp == 0;       // owns the tile: finishes it
+        const bool partner = has_unit && un.kp != 0;      // split-K helper: ships its partial accumulator to the owner
+        const int tile = has_unit ? un.tile : 0;
         const int grow = tile * 128 + lrow;
+        if (partner) {
+          W.wait(&tmem_full_bar, tpar, 5);
+          tpar ^= 1u;
+          tc::fence_after_sync();
+          float pv[16];
+          tc::tmem_ld16(lane_taddr + (uint32_t)s0, pv);
+          tc::fence_before_sync();
+          const uint32_t owner = (uint32_t)(ph.first + tile * ph.ks);
+          const uint32_t dst = mapa_u32(tc::smem_u32(pbuf + (size_t)(g * 4) * 128 + lrow), owner);
+          const uint32_t dbar = mapa_u32(tc::smem_u32(&pbar), owner);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            st_async_f4(dst + (uint32_t)(c * 128 * sizeof(float4)), pv[4 * c], pv[4 * c + 1], pv[4 * c + 2], pv[4 * c + 3], dbar);
+        }
         float v[16], zz[16];
         if (active) {
           // everything that does not depend on the accumulator is fetched before the waits
@@ -598,6 +636,17 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
             for (int j = 0; j < 16; ++j) v[j] += tt;
           }
           tc::fence_before_sync();            // ordered before the next phase's MMAs through the hand-over
+          if (ph.ks > 1) {   // add the partner's half of the reduction
+            if (et == 0) tc::mbar_arrive_expect_tx(&pbar, G::kPbufBytes);
+            W.wait(&pbar, ppar, 10);
+            ppar ^= 1u;
+            const float4* pp = pbuf + (size_t)(g * 4) * 128 + lrow;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 a = pp[c * 128];
+              v[4 * c] += a.x; v[4 * c + 1] += a.y; v[4 * c + 2] += a.z; v[4 * c + 3] += a.w;
+            }
+          }
         }
 
         if (ph.type == LDM_PH_STAGE) {
@@ -621,7 +670,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
                 u[i] = lo ? recv : v[8 + i];
               }
             }
-            publish(b0, tile, half_row_stats8(u, lane), 16.0f, ph.first, ph.tiles);
+            publish(b0, tile, half_row_stats8(u, lane), 16.0f, ph.first, ph.tiles, ph.ks);
             stamp();
             exchange_wait(b0, nparts, 6);
             stamp();
@@ -631,7 +680,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
               const float2 mr = rs[hr + i];
               h[i] += swish_fast((u[i] - mr.x) * mr.y * ga + ba);
             }
-            publish(b1, tile, half_row_stats8(h, lane), 16.0f, ph.first, ph.tiles);
+            publish(b1, tile, half_row_stats8(h, lane), 16.0f, ph.first, ph.tiles, ph.ks);
             // the h2 half of the next operand does not depend on the statistics: store it while they travel
             bf16* o = ph.out + (size_t)(row0 + s0 + hr) * ph.ld_out + f;
 #pragma unroll
@@ -655,7 +704,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
           sidx += 1;
           if (active) {   // LN_f(h + T_f[t] + C_f[c])                                     (v2:554-559)
             const float ga = __ldg(ph.ga + f), be = __ldg(ph.ba + f);
-            publish(b0, tile, warp_row_stats16(v, lane), 32.0f, ph.first, ph.tiles);
+            publish(b0, tile, warp_row_stats16(v, lane), 32.0f, ph.first, ph.tiles, ph.ks);
             exchange_wait(b0, nparts, 8);
             stamp();
             combine(b0, nparts, 128.0f);
@@ -922,6 +971,7 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
       }
       LDM_CHECK(rows % 128 == 0 && K % BK == 0 && rows / 128 <= CS, "chain: phase %d shape (%d x %d) unsupported", j, rows, K);
       H.K = K; H.rows = rows; H.tiles = rows / 128; H.d = d;
+      H.ks = (K >= 1024 && H.tiles * 2 <= CS && (K / BK) % 2 == 0 && !getenv("LDM_CHAIN_NO_SPLITK")) ? 2 : 1;
       LDM_TRY(ldm_alloc_t(ctx, PA, &H.w, (size_t)rows * K));
       LDM_TRY(ldm_alloc_t(ctx, PA, &H.bias, (size_t)rows));
       {
@@ -955,25 +1005,37 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
     double load[CS] = {0};
     int order[LDM_CHAIN_MAX_PHASES];
     for (int j = 0; j < C.n_phases; ++j) order[j] = j;
-    auto bytes = [&](int j) { return (double)C.ph[j].K * 256.0 + (double)C.ph[j].K * 48 * 2.0; };   // weight tile + operand
+    auto bytes = [&](int j) { return ((double)C.ph[j].K * 256.0 + (double)C.ph[j].K * 48 * 2.0) / C.ph[j].ks; };   // weight tile + operand of one unit
+    auto units = [&](int j) { return C.ph[j].tiles * C.ph[j].ks; };
     for (int a = 0; a < C.n_phases; ++a)
       for (int b = a + 1; b < C.n_phases; ++b)
-        if (bytes(order[b]) * C.ph[order[b]].tiles > bytes(order[a]) * C.ph[order[a]].tiles) { int t = order[a]; order[a] = order[b]; order[b] = t; }
+        if (bytes(order[b]) * units(order[b]) > bytes(order[a]) * units(order[a])) { int t = order[a]; order[a] = order[b]; order[b] = t; }
     for (int a = 0; a < C.n_phases; ++a) {
       ChainPhaseHost& H = C.ph[order[a]];
       int best = 0;
       double best_peak = 1e300, best_sum = 1e300;
-      for (int f = 0; f + H.tiles <= CS; ++f) {
+      const int nu = H.tiles * H.ks;
+      // the CTAs that finish the eps phase also generate the step's noise at the top of the step, while phase 0 runs:
+      // keep them off the CTAs that own a phase-0 tile (phase 0 is placed before the eps phase: it is heavier)
+      const bool avoid0 = order[a] == C.n_phases - 1;
+      const int p0a = C.ph[0].first, p0b = C.ph[0].first + C.ph[0].tiles * C.ph[0].ks;
+      for (int pass = 0; pass < 2 && best_peak > 1e299; ++pass)
+      for (int f = 0; f + nu <= CS; ++f) {
+        if (pass == 0 && avoid0 && f < p0b && f + nu > p0a) continue;
         double peak = 0, sum = 0;
-        for (int r = f; r < f + H.tiles; ++r) { peak = load[r] > peak ? load[r] : peak; sum += load[r]; }
+        for (int r = f; r < f + nu; ++r) { peak = load[r] > peak ? load[r] : peak; sum += load[r]; }
         if (peak < best_peak - 1e-9 || (peak < best_peak + 1e-9 && sum < best_sum)) { best_peak = peak; best_sum = sum; best = f; }
       }
       H.first = best;
-      for (int r = best; r < best + H.tiles; ++r) load[r] += bytes(order[a]);
+      for (int r = best; r < best + nu; ++r) load[r] += bytes(order[a]);
     }
     C.peak_bytes_per_step = 0;
     for (int r = 0; r < CS; ++r) C.peak_bytes_per_step = load[r] > C.peak_bytes_per_step ? load[r] : C.peak_bytes_per_step;
   }
+  if (getenv("LDM_CHAIN_DEBUG"))
+    for (int j = 0; j < C.n_phases; ++j)
+      fprintf(stderr, "chain phase %d: type %d rows %d K %d tiles %d ks %d first %d\n", j, C.ph[j].type, C.ph[j].rows, C.ph[j].K,
+              C.ph[j].tiles, C.ph[j].ks, C.ph[j].first);
   C.ready = true;
   return 0;
 }
@@ -1016,7 +1078,7 @@ int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const
     const ChainPhaseHost& H = C.ph[j];
     ChainPhase& D = P.ph[j];
     P.wmap[j] = H.map;
-    D.type = H.type; D.K = H.K; D.tiles = H.tiles; D.first = H.first; D.d = H.d; D.rows = H.rows;
+    D.type = H.type; D.K = H.K; D.tiles = H.tiles; D.first = H.first; D.ks = H.ks; D.d = H.d; D.rows = H.rows;
     D.bias = H.bias; D.tab_t = H.tab_t; D.tab_c = ctx->has_cls ? H.tab_c : nullptr;
     D.cadd_col = -1;
     if (H.tab_t) { D.cadd_col = cadd; cadd += NB; }

@@ -144,7 +144,7 @@ struct UnetModel {
 enum { LDM_PH_STAGE = 0, LDM_PH_FINAL_LN = 1, LDM_PH_EPS = 2 };
 
 struct ChainPhaseHost {
-  int type = 0, K = 0, tiles = 0, first = 0, d = 0, rows = 0;
+  int type = 0, K = 0, tiles = 0, first = 0, ks = 1, d = 0, rows = 0;
   bf16* w = nullptr;              // (rows, K) bf16, 128-row tiles
   float *bias = nullptr, *tab_t = nullptr, *tab_c = nullptr;
   CUtensorMap map;
