@@ -30,6 +30,7 @@ FLOP_DECODE_PER_SAMPLE = 2_809_570_560
 N_STEPS = 1000
 LATENT = 256
 IMG_BYTES = 3 * 64 * 64 * 4
+CHAIN_DRAM_BYTES_PER_LAUNCH = 33_072_128 + 83_712   # ncu capture r01_f (see roofline.traffic_source)
 
 
 def peaks():
@@ -130,8 +131,9 @@ def run_reference_arm(args, rank):
         "impl": "reference", "metric": "samples/s (1000-step DDPM + VAE decode)", "value": value, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * batch / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "v2 latent U-Net 1000-step sampling + VAE decode, batch %d, host CPU" % batch,
-                   "batch_per_gpu": batch, "n_steps": N_STEPS},
+        "config": {"workload": "v2 latent U-Net 1000-step sampling + VAE decode, batch %d per GPU" % batch,
+                   "batch_per_gpu": batch, "global_batch": batch, "n_steps": N_STEPS, "precision": "fp32",
+                   "where": "host CPU cores (rank 0 only), reference algorithm as executed", "weights": "random-init (seeded), eval mode"},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": info["threads"], "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -257,8 +259,14 @@ def run_ours(args, rank, world, local_rank):
         "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
         "roofline": {"bound": "tensor", "kernel": loop_kernel_name(eng),
                      "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
-                     "traffic": None, "peak_source": pk["src"], "ms_per_launch": loop_s * 1000.0,
-                     "algorithmic_flop_per_launch": loop_flops},
+                     "traffic": CHAIN_DRAM_BYTES_PER_LAUNCH if (prec == "bf16" and B == 256 and int(eng.info("chain"))) else None,
+                     "traffic_source": "ncu --set full, profiles/r01_f_chain_full_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                       "1000-step launch at B=256; weights and operands stay in L2, hit rate 96.7 %)",
+                     "peak_source": pk["src"], "ms_per_launch": loop_s * 1000.0,
+                     "algorithmic_flop_per_launch": loop_flops,
+                     "note": "the loop is a chain of 6 dependent contractions per step x 1000 steps on 96 of 148 SMs: it is bound by "
+                             "L2->SM operand latency and cluster hand-overs, not by the tensor pipe (DESIGN.md section 5); the decoder "
+                             "convolutions are the tensor-bound kernels (62 % tensor-pipe active in ncu, profiles/r01_f_conv_full_summary.txt)"},
         "decode": {"ms": dec_s * 1000.0, "tflops": FLOP_DECODE_PER_SAMPLE * B / dec_s / 1e12 if dec_s > 0 else None},
     }
     if world == 1 and not args.no_cpu:

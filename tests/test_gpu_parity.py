@@ -227,3 +227,42 @@ def test_full_size_batch_properties():
     img = ae.decode(x0)
     assert img.shape == (256, 3, 64, 64) and torch.isfinite(img).all()
     assert float(img.min()) >= 0 and float(img.max()) <= 1
+
+
+# ----------------------------------------------------------------------------- the other bf16 denoiser path
+def test_per_layer_graph_path_bf16_in_a_fresh_process():
+    """bf16 runs the persistent chain kernel by default; LDM_CHAIN=0 selects the one-kernel-per-layer CUDA graph
+    (gemm_tc.cu + rowwise.cu).  The switch is read when the context is created, so the second path is checked in
+    a fresh interpreter: eps against the reference goldens and 30 chain steps against the CPU restatement."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import numpy as np, torch
+from oracle import restate as R, weights
+from tests._util import EPS_TOL, LATENT_TOL, T, chain_noise, make_unet
+import ldm_b200
+torch.set_grad_enabled(False)
+g = np.load("tests/golden/v2_perturbed.npz")
+u = make_unet("perturbed", "bf16")
+eng = u.engine("cuda", 1000)
+assert int(eng.info("chain")) == 0
+x, c = T(g["fwd_x"]).cuda(), T(g["fwd_c"]).cuda()
+eps = u(x, torch.tensor([500], device="cuda"), c).cpu()
+assert R.max_rel(eps, T(g["fwd_eps_t500"])) < EPS_TOL["bf16"]
+d = ldm_b200.ConditionalDenoiseDiffusion(u, 1000, torch.device("cuda"))
+sd = weights.make_unet_state(42, "perturbed")
+noise = chain_noise(5, 0, 4, 29)
+xT = T(g["chain_xT"])
+want, _ = R.sample(sd, R.schedule(1000), xT, T(g["chain_c"]), noise_fn=lambda t: torch.from_numpy(noise[29 - t]), t_start=29)
+xs = xT.cuda().clone()
+eng.set_schedule(*d._host_schedule)
+eng.sample(xs, 29, 0, T(g["chain_c"]).cuda(), noise=torch.from_numpy(noise).cuda())
+assert R.rel_l2(xs.cpu(), want) < LATENT_TOL["bf16"]
+eng.check_device_flags()
+print("per-layer path ok")
+"""
+    env = dict(os.environ, LDM_CHAIN="0", PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "per-layer path ok" in r.stdout, r.stdout + r.stderr
