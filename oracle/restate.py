@@ -67,7 +67,7 @@ def _ln(x, sd, name):
     return F.layer_norm(x, (x.shape[-1],), sd[name + ".weight"], sd[name + ".bias"], 1e-5)
 
 
-def unet_forward(sd, x, t, c=None, n_stages=4, v1=False, literal_attention=False):
+def unet_forward(sd, x, t, c=None, n_stages=None, v1=False, literal_attention=False):
     """ConditionalUNet.forward v2:535-561, eval mode (Dropout v2:521 is the
     identity).  The L=1 attention (v2:550-552) is softmax over ONE key, i.e.
     out_proj(V(h_norm)) with V = in_proj rows [2d:3d].
@@ -76,6 +76,8 @@ def unet_forward(sd, x, t, c=None, n_stages=4, v1=False, literal_attention=False
     defaults to True, so the fused fast path is not taken): same result, and
     the reference's real CPU cost (full 3d in_proj, bmm, softmax) -- used when
     the oracle is TIMED as the CPU baseline."""
+    if n_stages is None:   # len(hidden_dims) - 1 (v2:517): one layers.{i} entry per stage
+        n_stages = sum(1 for k in sd if k.startswith("layers.") and k.endswith(".2.weight"))
     residual = x
     te = time_embedding(sd, t)                                   # v2:537
     ce = class_embedding(sd, c) if c is not None else None       # v2:538

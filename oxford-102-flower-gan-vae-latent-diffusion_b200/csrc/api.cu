@@ -105,8 +105,9 @@ extern "C" LDM_API int ldm_ctx_create(ldm_ctx** out, int device, int precision) 
   if (r == 0 && precision == LDM_PRECISION_BF16) {
     // the persistent cluster kernel is the bf16 denoiser; LDM_CHAIN=0 selects the one-kernel-per-layer sequence
     const char* ch = getenv("LDM_CHAIN");
-    ctx->use_chain = ch ? atoi(ch) : 1;
-    if (ctx->use_chain && chain_init(ctx) != 0) ctx->use_chain = 0;   // ldm_last_error() keeps the reason; ldm_get_info("chain") reports 0
+    ctx->chain_enabled = ch ? atoi(ch) : 1;
+    if (ctx->chain_enabled && chain_init(ctx) != 0) ctx->chain_enabled = 0;   // ldm_last_error() keeps the reason
+    ctx->use_chain = ctx->chain_enabled;
   }
   const char* pdl = getenv("LDM_PDL");
   ctx->use_pdl = pdl ? atoi(pdl) : 0;
@@ -279,7 +280,17 @@ extern "C" LDM_API int ldm_unet_pack(ldm_ctx* ctx, const ldm_unet_weights* w, vo
   cudaError_t e = cudaStreamSynchronize(st);
   free_pool(tmp);
   LDM_CUDA(e);
-  if (ctx->use_chain) LDM_TRY(chain_pack(ctx, st));
+  // the persistent chain kernel covers the architectures chain_pack accepts; any other ConditionalUNet shape runs the
+  // one-kernel-per-layer sequence (ldm_get_info("chain") tells which; ldm_last_error() keeps chain_pack's reason)
+  ctx->use_chain = ctx->chain_enabled;
+  if (ctx->use_chain && chain_pack(ctx, st) != 0) ctx->use_chain = 0;
+  // the activation workspace depends on the path (operand buffers of the chain): rebuild it on the next call
+  cudaDeviceSynchronize();
+  ctx->act_maps.clear();
+  free_pool(ctx->ws_allocs);
+  ctx->cap = 0;
+  ctx->batch_cls = -1;
+  ctx->has_cls = false;
   U.packed = true;
   return 0;
 }

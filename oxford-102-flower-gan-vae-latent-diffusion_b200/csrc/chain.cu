@@ -309,9 +309,9 @@ struct Unit { int tile, kp, kb0, nk; };
 __device__ __forceinline__ bool unit_of(const ChainPhase& ph, int rank, Unit& u) {
   const int un = rank - ph.first;
   if (un < 0 || un >= ph.tiles * ph.ks) return false;
-  u.tile = un / ph.ks;
-  u.kp = un - u.tile * ph.ks;
-  u.nk = ph.K / BK / ph.ks;
+  u.tile = un >> (ph.ks - 1);          // ks is 1 or 2
+  u.kp = un & (ph.ks - 1);
+  u.nk = (ph.K / BK) >> (ph.ks - 1);
   u.kb0 = u.kp * u.nk;
   return true;
 }
@@ -457,7 +457,9 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
     int tr_n = 0;
     bool tr_on = false;
     auto stamp = [&]() {
+#ifdef LDM_CHAIN_TRACE
       if (tr_on && tr_n < 64) P.trace[(rank * 2 + (et == 0 ? 0 : 1)) * 64 + tr_n++] = clock64();
+#endif
     };
     auto epi_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(G::kEpiThreads) : "memory"); };
     auto group_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory"); };   // the 4 warps of row group g
@@ -910,7 +912,7 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
   for (void* p : C.allocs) cudaFree(p);
   C = ChainModel();
   const int nst = U.nst, L = U.latent;
-  LDM_CHECK(nst + 2 <= LDM_CHAIN_MAX_PHASES, "chain: too many stages");
+  LDM_CHECK(nst + 2 <= LDM_CHAIN_MAX_PHASES && kAccCols + (nst + 2) * 64 <= kTmemCols, "chain: too many stages (%d) for the TMEM-resident per-sample terms", nst);
   LDM_CHECK(L % 128 == 0 && L / 128 <= kSlots, "chain: latent_dim %d unsupported", L);
   for (int i = 0; i < nst; ++i)
     LDM_CHECK(U.hid[i] % 64 == 0 && U.hid[i] / 64 <= CS && U.hid[i] / 64 <= kSlots, "chain: hidden dim %d unsupported", U.hid[i]);

@@ -250,7 +250,8 @@ struct ldm_ctx {
   unsigned long long launches = 0;
   bool capturing = false;
   // persistent chain kernel (bf16 path)
-  int use_chain = 0;              // 1: chain.cu runs the denoiser; 0: one kernel per layer (gemm_tc.cu + rowwise.cu)
+  int chain_enabled = 0;          // LDM_CHAIN (default 1) and the device can co-schedule the clusters
+  int use_chain = 0;              // 1: chain.cu runs the packed denoiser; 0: one kernel per layer (gemm_tc.cu + rowwise.cu)
   int chain_max_clusters = 0;     // co-resident clusters the device offers
   bf16* opbuf[LDM_MAX_STAGES] = {nullptr};   // (cap, 2 hid[j]): [h2 | n] operand written by stage phase j
   float4* coef_dev = nullptr;     // [n_steps] (c2, sqrt_alpha, sigma, 0)

@@ -266,3 +266,33 @@ print("per-layer path ok")
     env = dict(os.environ, LDM_CHAIN="0", PYTHONPATH=root)
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "per-layer path ok" in r.stdout, r.stdout + r.stderr
+
+
+# ----------------------------------------------------------------------------- other ConditionalUNet shapes
+@pytest.mark.parametrize("hidden", [[128, 384, 128], [256, 256, 512, 256, 256, 256, 256]])
+def test_non_default_architectures(hidden, precision):
+    """ConditionalUNet(latent_dim, hidden_dims, num_classes) with other sizes (v2:502-503): 2 stages (runs on the chain
+    kernel in bf16) and 6 stages (more phases than the chain kernel keeps in TMEM: the per-layer path takes over)."""
+    import ldm_b200
+    latent, ncls, nst = hidden[0], 7, len(hidden) - 1
+    sd = weights.make_state(weights.unet_spec(latent, hidden, 256, ncls), 11, "perturbed")
+    m = ldm_b200.ConditionalUNet(latent_dim=latent, hidden_dims=hidden, num_classes=ncls, precision=precision)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()
+    B = 21
+    x = torch.from_numpy(philox.normal_rows(5, 0, B, 1, latent))
+    c = torch.arange(B) % ncls
+    for t in (0, 417, 999):
+        want = R.unet_forward(sd, x, torch.tensor([t]), c, n_stages=nst)
+        got = m(x.to(DEV), torch.tensor([t], device=DEV), c.to(DEV)).cpu()
+        assert R.max_rel(got, want) < EPS_TOL[precision], (t, R.max_rel(got, want))
+    d = _diffusion(m)
+    noise = chain_noise(9, 0, B, 24, dim=latent)
+    want, _ = R.sample(sd, R.schedule(1000), x, c, noise_fn=lambda t: torch.from_numpy(noise[24 - t]), t_start=24)
+    eng = m.engine(DEV, 1000)
+    eng.set_schedule(*d._host_schedule)
+    xs = x.to(DEV).clone()
+    eng.sample(xs, 24, 0, c.to(DEV), noise=torch.from_numpy(noise).to(DEV))
+    assert R.rel_l2(xs.cpu(), want) < LATENT_TOL[precision]
+    if precision == "bf16":
+        assert int(m.engine(DEV, 1000).info("chain")) == (1 if nst == 2 else 0)
