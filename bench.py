@@ -264,7 +264,7 @@ def run_ours(args, rank, world, local_rank):
                                        "1000-step launch at B=256; weights and operands stay in L2, hit rate 96.7 %)",
                      "peak_source": pk["src"], "ms_per_launch": loop_s * 1000.0,
                      "algorithmic_flop_per_launch": loop_flops,
-                     "note": "the loop is a chain of 6 dependent contractions per step x 1000 steps on 96 of 148 SMs: it is bound by "
+                     "note": "the loop is a chain of 5 dependent contractions per step x 1000 steps on 96 of 148 SMs: it is bound by "
                              "L2->SM operand latency and cluster hand-overs, not by the tensor pipe (DESIGN.md section 5); the decoder "
                              "convolutions are the tensor-bound kernels (62 % tensor-pipe active in ncu, profiles/r01_f_conv_full_summary.txt)"},
         "decode": {"ms": dec_s * 1000.0, "tflops": FLOP_DECODE_PER_SAMPLE * B / dec_s / 1e12 if dec_s > 0 else None},

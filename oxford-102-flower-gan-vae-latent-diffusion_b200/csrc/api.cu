@@ -102,6 +102,8 @@ extern "C" LDM_API int ldm_ctx_create(ldm_ctx** out, int device, int precision) 
   if (r == 0 && precision == LDM_PRECISION_BF16) r = tc_init(ctx);
   if (r == 0) r = ldm_alloc_t(ctx, ctx->allocs, &ctx->chain_err, 2);
   if (r == 0) r = (int)cudaMemset(ctx->chain_err, 0, 2 * sizeof(int));
+  if (r == 0) r = ldm_alloc_t(ctx, ctx->allocs, &ctx->coef_one, 1);
+  if (r == 0) { const float4 one = make_float4(1.f, 1.f, 0.f, 0.f); r = (int)cudaMemcpy(ctx->coef_one, &one, sizeof(one), cudaMemcpyHostToDevice); }
   if (r == 0 && precision == LDM_PRECISION_BF16) {
     // the persistent cluster kernel is the bf16 denoiser; LDM_CHAIN=0 selects the one-kernel-per-layer sequence
     const char* ch = getenv("LDM_CHAIN");
@@ -321,7 +323,13 @@ static int ensure_workspace(ldm_ctx* ctx, int B) {
   LDM_TRY(ldm_alloc(ctx, P, &ctx->af_op[0], naf * op));
   LDM_TRY(ldm_alloc(ctx, P, &ctx->af_op[1], naf * op));
   if (ctx->use_chain)
+  {
     for (int j = 0; j < U.nst; ++j) LDM_TRY(ldm_alloc_t(ctx, P, &ctx->opbuf[j], (size_t)cap * 2 * U.hid[j]));
+    for (int k = 0; k < 2; ++k) {
+      LDM_TRY(ldm_alloc_t(ctx, P, &ctx->caf[k], (size_t)cap * 3 * U.latent));
+      LDM_CUDA(cudaMemset(ctx->caf[k], 0, (size_t)cap * 3 * U.latent * sizeof(bf16)));
+    }
+  }
   LDM_TRY(ldm_alloc_t(ctx, P, &ctx->x_state, (size_t)cap * U.latent));
   LDM_TRY(ldm_alloc_t(ctx, P, &ctx->cls, (size_t)cap));
   // zero everything once: rows beyond the batch are read by full 128-row TMA boxes
@@ -465,7 +473,7 @@ extern "C" LDM_API int ldm_unet_forward(ldm_ctx* ctx, const float* x_dev, const 
   StepMode md; md.t_idx = t_dev; md.t_len = t_len; md.eps_out = eps_out_dev;
   if (ctx->precision == LDM_PRECISION_BF16) {
     LDM_TRY(stage_x<bf16>(ctx, x_dev, batch, 0, st));
-    if (ctx->use_chain) return launch_chain(ctx, batch, 1, 0, 0, t_dev, t_len, nullptr, eps_out_dev, nullptr, st);
+    if (ctx->use_chain) return launch_chain(ctx, batch, 1, 0, 0, t_dev, t_len, const_cast<float*>(x_dev), eps_out_dev, nullptr, st);
     return denoise<bf16>(ctx, batch, 0, md, st);
   }
   LDM_TRY(stage_x<float>(ctx, x_dev, batch, 0, st));

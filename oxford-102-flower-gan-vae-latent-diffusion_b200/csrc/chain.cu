@@ -74,6 +74,9 @@ struct ChainPhase {
   int xmap_alt;        // 1: the operand alternates between xmap and xmap + 1 with the step parity ([LN_f(h) | x])
   int xcol;            // first column of the operand inside that buffer
   int cadd_col;        // TMEM column of this phase's per-sample additive term (-1: none)
+  int nst_tiles;       // MERGED: tiles [0, nst_tiles) are stage tiles, the rest finish eps
+  int eps_kb0;         // MERGED: first k-block the eps tiles read (they skip the x~ block)
+  const float* g0b;    // MERGED: G_0 . b_fin (tile order)
   const float* bias;   // [rows]       tile order
   const float* tab_t;  // [n_t, rows]  tile order (null: none)
   const float* tab_c;  // [ncls, rows] tile order (null: none)
@@ -102,7 +105,8 @@ struct ChainParams {
   const float* noise;         // explicit draws (n_iter, B, latent) or null -> Philox
   const unsigned long long* rng;   // {seed, sample_offset}
   const float4* coef;         // [n_steps]: (c2, sqrt_alpha, sigma, 0)
-  bf16* af[2];                // (B, ld_af): [LN_f(h) | x] operand of the last phase, double-buffered over steps
+  const float4* coef_or_one;  // sample: coef; forward(): one entry (1, 1, 0, 0)
+  bf16* af[2];                // (B, ld_af): [x~ | -c_b LN_f(h) | -c_b x] operand of the merged phase, double-buffered over steps
   int ld_af;
   int writer_fence;           // 1: every writer thread issues fence.proxy.async before the hand-over; 0: the operand producer does
   int z_col;                  // TMEM column where the eps owners park the step's noise
@@ -304,15 +308,23 @@ __device__ __forceinline__ float2 warp_row_stats16(const float (&v)[16], int lan
 __device__ __forceinline__ float swish_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 __device__ __forceinline__ int clamp_t(long long t, int n_t) { return (int)(t < 0 ? 0 : (t >= n_t ? n_t - 1 : t)); }
 
-// work unit of cluster rank `rank` in a phase: tile, k-part and k-block range; false: no unit
-struct Unit { int tile, kp, kb0, nk; };
-__device__ __forceinline__ bool unit_of(const ChainPhase& ph, int rank, Unit& u) {
+// work unit of cluster rank `rank` in a phase: tile, k-part and k-block range; false: no unit.
+// `tail`: the extra merged phase after the last step, in which only the eps tiles work.
+struct Unit { int tile, kp, kb0, nk; bool is_eps; };
+__device__ __forceinline__ bool unit_of(const ChainPhase& ph, int rank, bool tail, Unit& u) {
   const int un = rank - ph.first;
   if (un < 0 || un >= ph.tiles * ph.ks) return false;
   u.tile = un >> (ph.ks - 1);          // ks is 1 or 2
   u.kp = un & (ph.ks - 1);
-  u.nk = (ph.K / BK) >> (ph.ks - 1);
-  u.kb0 = u.kp * u.nk;
+  int lo = 0;
+  u.is_eps = false;
+  if (ph.type == LDM_PH_MERGED) {
+    u.is_eps = u.tile >= ph.nst_tiles;
+    if (u.is_eps) lo = ph.eps_kb0;
+    else if (tail) return false;
+  }
+  u.nk = (ph.K / BK - lo) >> (ph.ks - 1);
+  u.kb0 = lo + u.kp * u.nk;
   return true;
 }
 
@@ -336,6 +348,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
   __shared__ __align__(8) uint64_t pbar;      // split-K: the partner's partial accumulator has landed in pbuf
   __shared__ uint32_t tmem_slot;
   __shared__ int abort_flag;
+  __shared__ ChainPhase sphase[LDM_CHAIN_MAX_PHASES];   // shared-memory copy: indexed constant-bank reads are slow
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = blockIdx.x;                 // gridDim.x == CS: rank in cluster
@@ -360,6 +373,12 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
     for (int p = 0; p < kMaxXMaps; ++p) tc::prefetch_tmap(&P.xmaps[p]);
   }
   if (warp == 2) tc::tmem_alloc<kTmemCols>(&tmem_slot);
+  if (warp == 3) {
+    const int nw = (int)(sizeof(ChainPhase) / 4) * P.n_phases;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&P.ph[0]);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sphase[0]);
+    for (int i = lane; i < nw; i += 32) dst[i] = src[i];
+  }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -371,10 +390,11 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
     if (lane == 0) {
       uint32_t n = 0;
       bool ok = true;
-      for (int it = 0; it < P.n_iter && ok; ++it) {
-        for (int p = 0; p < NP && ok; ++p) {
+      for (int it = 0; it <= P.n_iter && ok; ++it) {
+        const bool tail = it == P.n_iter;
+        for (int p = 0; p < (tail ? 1 : NP) && ok; ++p) {
           Unit un;
-          if (!unit_of(P.ph[p], rank, un)) continue;
+          if (!unit_of(sphase[p], rank, tail, un)) continue;
           for (int kb = un.kb0; kb < un.kb0 + un.nk; ++kb, ++n) {
             const uint32_t s = n % S, par = (n / S) & 1u;
             if (!W.wait(&empty_bar[s], par ^ 1u, 1)) { ok = false; break; }
@@ -391,17 +411,18 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
       bool ok = true;
       tc::mbar_arrive(&obar[0]);   // this thread's share of hand-overs 0 and 1
       tc::mbar_arrive(&obar[1]);
-      for (int it = 0; it < P.n_iter && ok; ++it) {
-        for (int p = 0; p < NP && ok; ++p, ++gp) {
+      for (int it = 0; it <= P.n_iter && ok; ++it) {
+        const bool tail = it == P.n_iter;
+        for (int p = 0; p < (tail ? 1 : NP) && ok; ++p, ++gp) {
           if (gp > 0) {
             const uint32_t f = gp - 1;   // hand-over that publishes this phase's operand
             if (!W.wait_cluster(&obar[f & 1u], (f >> 1) & 1u, 2)) { ok = false; break; }
             tc::mbar_arrive(&obar[f & 1u]);   // share of hand-over f + 2 (same barrier, next phase)
             if (!P.writer_fence) fence_proxy_async_global();   // peers' generic-proxy global writes (released above) -> async-proxy reads below
           }
-          const ChainPhase& ph = P.ph[p];
+          const ChainPhase& ph = sphase[p];
           Unit un;
-          if (!unit_of(ph, rank, un)) continue;
+          if (!unit_of(ph, rank, tail, un)) continue;
           const CUtensorMap* xm = &P.xmaps[ph.xmap + (ph.xmap_alt ? (it & 1) : 0)];
           for (int kb = un.kb0; kb < un.kb0 + un.nk; ++kb, ++n) {
             const uint32_t s = n % S, par = (n / S) & 1u;
@@ -418,10 +439,11 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
       constexpr uint32_t idesc = tc::make_idesc_bf16(128, NB);
       uint32_t n = 0;
       bool ok = true;
-      for (int it = 0; it < P.n_iter && ok; ++it) {
-        for (int p = 0; p < NP && ok; ++p) {
+      for (int it = 0; it <= P.n_iter && ok; ++it) {
+        const bool tail = it == P.n_iter;
+        for (int p = 0; p < (tail ? 1 : NP) && ok; ++p) {
           Unit un;
-          if (!unit_of(P.ph[p], rank, un)) continue;
+          if (!unit_of(sphase[p], rank, tail, un)) continue;
           for (int kb = 0; kb < un.nk; ++kb, ++n) {
             const uint32_t s = n % S, par = (n / S) & 1u;
             if (!W.wait(&full_bar[s], par, 4)) { ok = false; break; }
@@ -520,9 +542,9 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
     {
       const bool per_row_t = !P.sample && P.t_len != 1;
       for (int p = 0; p < NP; ++p) {
-        const ChainPhase& ph = P.ph[p];
+        const ChainPhase& ph = sphase[p];
         Unit un;
-        if (!unit_of(ph, rank, un) || un.kp != 0 || ph.cadd_col < 0) continue;
+        if (!unit_of(ph, rank, false, un) || un.kp != 0 || un.is_eps || ph.cadd_col < 0) continue;
         const int grow = un.tile * 128 + lrow;
         float c[16];
 #pragma unroll
@@ -540,63 +562,37 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
       tc::fence_before_sync();
     }
 
-    // ---- the chain state of the rows / features this thread finishes in the eps phase stays in registers
+    // ---- the chain state of the rows / features this thread finishes in the eps tiles stays in registers
     float xr[16];
-    const ChainPhase& phe = P.ph[NP - 1];
+    const ChainPhase& ph0 = sphase[0];
     Unit eun;
-    const bool eps_owner = unit_of(phe, rank, eun) && eun.kp == 0;
-    const int etile = eps_owner ? eun.tile : 0;
-    const int ef = etile * 128 + lrow;
+    const bool eps_owner = unit_of(ph0, rank, true, eun);
+    const int ef = eps_owner ? (eun.tile - ph0.nst_tiles) * 128 + lrow : 0;   // latent feature of this thread
+    const float bfin = eps_owner ? __ldg(ph0.bias + eun.tile * 128 + lrow) : 0.f;   // (1 + s) b_f (v2:560-561)
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int r = row0 + s0 + j;
-      xr[j] = (eps_owner && P.sample && r < P.row_end) ? P.x[(size_t)r * P.latent + ef] : 0.f;
+      xr[j] = (eps_owner && r < P.row_end) ? P.x[(size_t)r * P.latent + ef] : 0.f;
     }
 
-    for (int it = 0; it < P.n_iter; ++it) {
+    for (int it = 0; it <= P.n_iter; ++it) {
+      const bool tail = it == P.n_iter;
       const int par = it & 1;
       tr_on = P.trace != nullptr && blockIdx.y == 0 && it == P.trace_step && (et == 0 || et == 64);
       stamp();
+      // timestep of this iteration's forward (t_uni) and posterior coefficients of this and the previous iteration
       const int t_uni = P.sample ? P.t_start - it : (P.t_len == 1 ? clamp_t(P.t_idx[0], P.n_t) : -1);
-      if (eps_owner && P.sample) {
-        // noise of this step (v2:589): independent of eps, generated while this CTA has no tile to finish and parked
-        // in spare TMEM columns until the eps phase
-        const int t = P.t_start - it;
-        const float sigma = P.coef[t].z;
-        float z[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) z[j] = 0.f;
-        if (sigma > 0.0f) {
-          if (P.noise) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int r = row0 + s0 + j;
-              if (r < P.row_end) z[j] = P.noise[((size_t)it * P.B + r) * P.latent + ef];
-            }
-          } else {
-            // the 4 lanes that share a Philox quad split the rows between them, then trade components
-            const unsigned long long seed = P.rng[0], off = P.rng[1] + (unsigned long long)(row0 + s0);
-            const int sub = lane & 3, base = lane & ~3;
-#pragma unroll
-            for (int gq = 0; gq < 4; ++gq) {
-              const float4 z4 = philox_normal4(seed, off + (unsigned long long)(4 * gq + sub), (uint32_t)t, (uint32_t)(ef >> 2));
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float gx = __shfl_sync(0xffffffffu, z4.x, base + i), gy = __shfl_sync(0xffffffffu, z4.y, base + i);
-                const float gz = __shfl_sync(0xffffffffu, z4.z, base + i), gw = __shfl_sync(0xffffffffu, z4.w, base + i);
-                z[4 * gq + i] = sub == 0 ? gx : (sub == 1 ? gy : (sub == 2 ? gz : gw));
-              }
-            }
-          }
-        }
-        tmem_st16(lane_taddr + (uint32_t)(P.z_col + s0), z);
-      }
-      for (int p = 0; p < NP; ++p) {
-        const ChainPhase& ph = P.ph[p];
+      // unconditional loads (clamped index), patched AFTER the first wait of the iteration: no stall on their L2 latency here
+      const int tp = P.sample ? P.t_start - it + (it > 0 ? 1 : 0) : 0, tc_ = P.sample ? P.t_start - it + (tail ? 1 : 0) : 0;
+      float4 cf_prev = P.coef_or_one[P.sample ? tp : 0], cf_cur = P.coef_or_one[P.sample ? tc_ : 0];   // (c2, sqrt_alpha, sigma)
+      // (the coefficients are only CONSUMED after the first accumulator wait of the iteration: their L2 latency is hidden)
+      for (int p = 0; p < (tail ? 1 : NP); ++p) {
+        const ChainPhase& ph = sphase[p];
         Unit un;
-        const bool has_unit = unit_of(ph, rank, un);
+        const bool has_unit = unit_of(ph, rank, tail, un);
         const bool active = has_unit && un.kp == 0;       // owns the tile: finishes it
         const bool partner = has_unit && un.kp != 0;      // split-K helper: ships its partial accumulator to the owner
+        const bool eps_tile = active && un.is_eps;
         const int tile = has_unit ? un.tile : 0;
         const int grow = tile * 128 + lrow;
         if (partner) {
@@ -613,25 +609,27 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
           for (int c = 0; c < 4; ++c)
             st_async_f4(dst + (uint32_t)(c * 128 * sizeof(float4)), pv[4 * c], pv[4 * c + 1], pv[4 * c + 2], pv[4 * c + 3], dbar);
         }
-        float v[16], zz[16];
+        float v[16];
         if (active) {
           // everything that does not depend on the accumulator is fetched before the waits
-          float tt = ph.bias ? __ldg(ph.bias + grow) : 0.f;
-          if (ph.tab_t && t_uni >= 0) tt += __ldg(ph.tab_t + (size_t)t_uni * ph.rows + grow);
+          float t_b = 0.f, t_t = 0.f, t_g = 0.f;   // loaded now, summed after the wait (no dependent use before it)
+          if (!eps_tile) {
+            if (ph.bias) t_b = __ldg(ph.bias + grow);
+            if (ph.tab_t && t_uni >= 0) t_t = __ldg(ph.tab_t + (size_t)t_uni * ph.rows + grow);
+            if (ph.type == LDM_PH_MERGED) t_g = __ldg(ph.g0b + grow);
+          }
           stamp();
           W.wait(&tmem_full_bar, tpar, 5);
           tpar ^= 1u;
           stamp();
           tc::fence_after_sync();
-          if (ph.cadd_col >= 0) {
+          const float cb_prev = it > 0 ? cf_prev.x / cf_prev.y : 0.f;   // c2 / sqrt(alpha) of the previous step (forward(): 1)
+          const float tt = t_b + t_t - cb_prev * t_g;                   // t_g: the eps bias of the previous step, seen through G_0
+          if (ph.cadd_col >= 0 && !eps_tile) {
             float c[16];
             tmem_ld16x2(lane_taddr + (uint32_t)s0, lane_taddr + (uint32_t)(ph.cadd_col + s0), v, c);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] += c[j] + tt;
-          } else if (ph.type == LDM_PH_EPS && P.sample) {
-            tmem_ld16x2(lane_taddr + (uint32_t)s0, lane_taddr + (uint32_t)(P.z_col + s0), v, zz);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += tt;
           } else {
             tc::tmem_ld16(lane_taddr + (uint32_t)s0, v);
 #pragma unroll
@@ -651,16 +649,17 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
           }
         }
 
-        if (ph.type == LDM_PH_STAGE) {
+        if (ph.type == LDM_PH_STAGE || ph.type == LDM_PH_MERGED) {
           // Tile rows: quadrant q holds 16 h features in lanes 0..15 and u = Linear_b(h) of the SAME 16 features in lanes
           // 16..31.  The two halves trade 8 rows, after which every lane owns feature f for 8 rows, h AND u: the whole
           // LayerNorm / Swish / residual chain of v2:546-553 runs in registers on all 32 lanes.
           const int f = tile * 64 + q * 16 + (lane & 15);
           const int hr = (lane >> 4) * 8;             // first of this lane's 8 rows inside the row group
-          const int nparts = ph.tiles;
+          const int ntile = ph.type == LDM_PH_MERGED ? ph.nst_tiles : ph.tiles;
+          const int nparts = ntile;
           const uint32_t b0 = sidx & 1u, b1 = b0 ^ 1u;
           sidx += 2;
-          if (active) {
+          if (active && !eps_tile) {
             const float ga = __ldg(ph.ga + f), ba = __ldg(ph.ba + f), gb = __ldg(ph.gb + f), bb = __ldg(ph.bb + f);
             float h[8], u[8];
             {
@@ -672,7 +671,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
                 u[i] = lo ? recv : v[8 + i];
               }
             }
-            publish(b0, tile, half_row_stats8(u, lane), 16.0f, ph.first, ph.tiles, ph.ks);
+            publish(b0, tile, half_row_stats8(u, lane), 16.0f, ph.first, ntile, ph.ks);
             stamp();
             exchange_wait(b0, nparts, 6);
             stamp();
@@ -682,7 +681,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
               const float2 mr = rs[hr + i];
               h[i] += swish_fast((u[i] - mr.x) * mr.y * ga + ba);
             }
-            publish(b1, tile, half_row_stats8(h, lane), 16.0f, ph.first, ph.tiles, ph.ks);
+            publish(b1, tile, half_row_stats8(h, lane), 16.0f, ph.first, ntile, ph.ks);
             // the h2 half of the next operand does not depend on the statistics: store it while they travel
             bf16* o = ph.out + (size_t)(row0 + s0 + hr) * ph.ld_out + f;
 #pragma unroll
@@ -699,47 +698,23 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
               if (row0 + s0 + hr + i < P.row_end) o[(size_t)i * ph.ld_out] = __float2bfloat16_rn((h[i] - mr.x) * mr.y * gb + bb);
             }
           }
-        } else if (ph.type == LDM_PH_FINAL_LN) {
+        } else {   // LDM_PH_FINAL_LN
           const int f = grow;
           const int nparts = ph.tiles;
           const uint32_t b0 = sidx & 1u;
           sidx += 1;
-          if (active) {   // LN_f(h + T_f[t] + C_f[c])                                     (v2:554-559)
+          if (active) {   // -c_b LN_f(h + T_f[t] + C_f[c]): block 1 of the next merged operand     (v2:554-559)
             const float ga = __ldg(ph.ga + f), be = __ldg(ph.ba + f);
             publish(b0, tile, warp_row_stats16(v, lane), 32.0f, ph.first, ph.tiles, ph.ks);
             exchange_wait(b0, nparts, 8);
             stamp();
             combine(b0, nparts, 128.0f);
-            bf16* o = P.af[par] + (size_t)(row0 + s0) * P.ld_af + f;
+            const float cb_cur = cf_cur.x / cf_cur.y;
+            bf16* o = P.af[par ^ 1] + (size_t)(row0 + s0) * P.ld_af + P.latent + f;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float2 mr = rs[j];
-              if (row0 + s0 + j < P.row_end) o[(size_t)j * P.ld_af] = __float2bfloat16_rn((v[j] - mr.x) * mr.y * ga + be);
-            }
-          }
-        } else {   // LDM_PH_EPS: v is eps_theta                                           (v2:560-561)
-          if (active) {
-            const int f = grow;
-            if (!P.sample) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int row = row0 + s0 + j;
-                if (row < P.row_end) P.eps_out[(size_t)row * P.latent + f] = v[j];
-              }
-            } else {
-              const float4 cf = P.coef[P.t_start - it];
-              bf16* o = P.af[par ^ 1] + P.latent + f;   // x operand of the NEXT step
-              const bool last = it + 1 == P.n_iter;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int row = row0 + s0 + j;
-                const float xn = ddpm_update_one(xr[j], v[j], cf.x, cf.y, cf.z, zz[j]);
-                xr[j] = xn;
-                if (row < P.row_end) {
-                  o[(size_t)row * P.ld_af] = __float2bfloat16_rn(xn);
-                  if (last) P.x[(size_t)row * P.latent + f] = xn;
-                }
-              }
+              if (row0 + s0 + j < P.row_end) o[(size_t)j * P.ld_af] = __float2bfloat16_rn(-cb_cur * ((v[j] - mr.x) * mr.y * ga + be));
             }
           }
         }
@@ -748,16 +723,84 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
         //      for all of them (the operand producer waits on the same barrier and starts the next phase's loads)
         stamp();
         if (P.writer_fence) fence_proxy_async_all();
-        stamp();
         epi_bar();
+        const uint32_t ob = oidx & 1u, opar = (oidx >> 1) & 1u;
+        if (et < CS) remote_arrive(mapa_u32(obar_local[ob], (uint32_t)et));
         stamp();
-        {
-          const uint32_t ob = oidx & 1u, opar = (oidx >> 1) & 1u;
-          if (et < CS) remote_arrive(mapa_u32(obar_local[ob], (uint32_t)et));
-          stamp();
-          W.wait(&obar[ob], opar, 9);
-          oidx++;
+
+        if (eps_tile) {
+          // ---- posterior update (v2:584-592), OFF the critical path: nothing in the cluster needs x_{t-1} itself before
+          //      the merged phase of the next step; its pieces reach global memory long before that hand-over.
+          //      v = W_f' . (-c_b [LN_f(h) | x]) = -c_b (eps - b_fin) of the previous iteration's forward.
+          const float cb_prev = it > 0 ? cf_prev.x / cf_prev.y : 0.f;
+          const float cb_cur = cf_cur.x / cf_cur.y;
+          if (it > 0) {
+            if (!P.sample) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int row = row0 + s0 + j;
+                if (row < P.row_end) P.eps_out[(size_t)row * P.latent + ef] = bfin - v[j];
+              }
+            } else {
+              float zz[16];
+              tc::tmem_ld16(lane_taddr + (uint32_t)(P.z_col + s0), zz);
+              const float inv_cb = 1.0f / cb_prev;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                xr[j] = ddpm_update_one(xr[j], bfin - v[j] * inv_cb, cf_prev.x, cf_prev.y, cf_prev.z, zz[j]);
+              if (tail) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int row = row0 + s0 + j;
+                  if (row < P.row_end) P.x[(size_t)row * P.latent + ef] = xr[j];
+                }
+              }
+            }
+          }
+          if (!tail) {
+            // pieces of the next merged operand: x~ = x / sqrt(alpha_t) + sigma_t z_t (block 0) and -c_b x (block 2)
+            float z[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) z[j] = 0.f;
+            if (P.sample && cf_cur.z > 0.0f) {
+              const int t = P.t_start - it;
+              if (P.noise) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int r = row0 + s0 + j;
+                  if (r < P.row_end) z[j] = P.noise[((size_t)it * P.B + r) * P.latent + ef];
+                }
+              } else {
+                // the 4 lanes that share a Philox quad split the rows between them, then trade components
+                const unsigned long long seed = P.rng[0], off = P.rng[1] + (unsigned long long)(row0 + s0);
+                const int sub = lane & 3, base = lane & ~3;
+#pragma unroll
+                for (int gq = 0; gq < 4; ++gq) {
+                  const float4 z4 = philox_normal4(seed, off + (unsigned long long)(4 * gq + sub), (uint32_t)t, (uint32_t)(ef >> 2));
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float gx = __shfl_sync(0xffffffffu, z4.x, base + i), gy = __shfl_sync(0xffffffffu, z4.y, base + i);
+                    const float gz = __shfl_sync(0xffffffffu, z4.z, base + i), gw = __shfl_sync(0xffffffffu, z4.w, base + i);
+                    z[4 * gq + i] = sub == 0 ? gx : (sub == 1 ? gy : (sub == 2 ? gz : gw));
+                  }
+                }
+              }
+            }
+            if (P.sample) tmem_st16(lane_taddr + (uint32_t)(P.z_col + s0), z);   // kept for the update one iteration later
+            bf16* o = P.af[par ^ 1] + (size_t)(row0 + s0) * P.ld_af + ef;
+            const float inv_sa = 1.0f / cf_cur.y;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (row0 + s0 + j < P.row_end) {
+                o[(size_t)j * P.ld_af] = __float2bfloat16_rn(xr[j] * inv_sa + cf_cur.z * z[j]);
+                o[(size_t)j * P.ld_af + 2 * P.latent] = __float2bfloat16_rn(-cb_cur * xr[j]);
+              }
+            }
+          }
         }
+
+        W.wait(&obar[ob], opar, 9);
+        oidx++;
         stamp();
       }
     }
@@ -797,23 +840,23 @@ __global__ void pack_copy2d_kernel(const float* __restrict__ src, int lds, float
   dst[(size_t)r * ldd + c] = src[(size_t)r * lds + c];
 }
 // natural row order [h_0..h_{d-1} | u_0..u_{d-1}] -> tile order (tile s, quadrant q: h[64s+16q ..+15] | u[64s+16q ..+15]); stage = 0: identity
-__device__ __forceinline__ int tile_src_row(int rt, int d, int stage) {
-  if (!stage) return rt;
+__device__ __forceinline__ int tile_src_row(int rt, int d, int stage, int nsr) {
+  if (!stage || rt >= nsr) return rt;   // rows [nsr, rows): the eps rows of the merged phase, natural order
   const int s = rt >> 7, l = rt & 127, q = l >> 5, w = l & 31;   // quadrant q: 16 h rows, then the 16 u rows of the same features
   return w < 16 ? s * 64 + q * 16 + w : d + s * 64 + q * 16 + (w - 16);
 }
-__global__ void pack_rows_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int rows, int K, int d, int stage) {
+__global__ void pack_rows_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int rows, int K, int d, int stage, int nsr) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)rows * K) return;
   const int rt = (int)(i / K), k = (int)(i % K);
-  dst[i] = __float2bfloat16_rn(src[(size_t)tile_src_row(rt, d, stage) * K + k]);
+  dst[i] = __float2bfloat16_rn(src[(size_t)tile_src_row(rt, d, stage, nsr) * K + k]);
 }
 // tables: dst[t][rt] = src[t][src_row(rt)]
-__global__ void pack_cols_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int rows, int d, int stage) {
+__global__ void pack_cols_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int rows, int d, int stage, int nsr) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)n * rows) return;
   const int t = (int)(i / rows), rt = (int)(i % rows);
-  dst[i] = src[(size_t)t * rows + tile_src_row(rt, d, stage)];
+  dst[i] = src[(size_t)t * rows + tile_src_row(rt, d, stage, nsr)];
 }
 
 #define LDM_LAUNCHED(ctx)             \
@@ -912,7 +955,7 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
   for (void* p : C.allocs) cudaFree(p);
   C = ChainModel();
   const int nst = U.nst, L = U.latent;
-  LDM_CHECK(nst + 2 <= LDM_CHAIN_MAX_PHASES && kAccCols + (nst + 2) * 64 <= kTmemCols, "chain: too many stages (%d) for the TMEM-resident per-sample terms", nst);
+  LDM_CHECK(nst + 1 <= LDM_CHAIN_MAX_PHASES && kAccCols + (nst + 2) * 64 <= kTmemCols, "chain: too many stages (%d) for the TMEM-resident per-sample terms", nst);
   LDM_CHECK(L % 128 == 0 && L / 128 <= kSlots, "chain: latent_dim %d unsupported", L);
   for (int i = 0; i < nst; ++i)
     LDM_CHECK(U.hid[i] % 64 == 0 && U.hid[i] / 64 <= CS && U.hid[i] / 64 <= kSlots, "chain: hidden dim %d unsupported", U.hid[i]);
@@ -921,33 +964,50 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
   auto free_tmp = [&]() { for (void* p : tmp) cudaFree(p); tmp.clear(); };
   int rc = 0;
   auto body = [&]() -> int {
-    C.n_phases = nst + 2;
+    C.n_phases = nst + 1;
     // ---- natural-order folded matrices, biases and tables, then the tile-order / bf16 copies
-    for (int j = 0; j <= nst + 1; ++j) {
+    for (int j = 0; j <= nst; ++j) {
       ChainPhaseHost& H = C.ph[j];
-      int rows, K, d, stage;
-      float *Gn = nullptr, *bn = nullptr, *Tn = nullptr, *Cn = nullptr;   // natural order (temporaries)
+      int rows, K, d, stage, nsr;
+      float *Gn = nullptr, *bn = nullptr, *Tn = nullptr, *Cn = nullptr, *g0n = nullptr;   // natural order (temporaries)
       if (j == 0) {
-        // [h_0 | u_0] = [W_lp ; W_b0 W_lp] x + [b_lp ; W_b0 b_lp + b_b0] + [T_0 ; W_b0 T_0][t] + [C_0 ; W_b0 C_0][c]
-        d = U.hid[0]; rows = 2 * d; K = L; stage = 1;
+        // MERGED phase.  With x_{t-1} = x~ - c_b eps, x~ = x_t / sqrt(alpha_t) + sigma_t z_t, c_b = c2 / sqrt(alpha_t)
+        // and eps = W_f' [LN_f(h) ; x_t] + b_fin (v2:560-561, 584-592), the first stage of the NEXT forward,
+        //   [h_0 | u_0] = G_0 x_{t-1} + ...,   G_0 = [W_lp ; W_b0 W_lp]                         (v2:539, 546)
+        // is linear in the operand [x~ | -c_b LN_f(h) | -c_b x_t]:
+        //   stage rows : [G_0 | G_0 W_f']        (+ tables, - c_b G_0 b_fin added by the epilogue)
+        //   eps rows   : [ 0  |   W_f'  ]        -> -c_b (eps - b_fin): finishes the PREVIOUS forward, off the critical path
+        d = U.hid[0]; nsr = 2 * d; rows = nsr + L; K = 3 * L; stage = 1;
+        LDM_CHECK(U.fin.N == L && U.fin.K == 2 * L, "chain: final layer shape");
         LDM_TRY(ldm_alloc_t(ctx, tmp, &Gn, (size_t)rows * K));
         LDM_TRY(ldm_alloc_t(ctx, tmp, &bn, (size_t)rows));
         LDM_TRY(ldm_alloc_t(ctx, tmp, &Tn, (size_t)U.n_t * rows));
         LDM_TRY(ldm_alloc_t(ctx, tmp, &Cn, (size_t)U.ncls * rows));
-        LDM_TRY(copy2d(ctx, U.latent_proj.w32, K, Gn, K, d, K, st));
-        LDM_TRY(mm(ctx, U.block[0].w32, d, U.latent_proj.w32, K, 0, Gn + (size_t)d * K, K, d, K, d, st));
+        LDM_TRY(ldm_alloc_t(ctx, tmp, &g0n, (size_t)rows));
+        LDM_CUDA(cudaMemsetAsync(Gn, 0, sizeof(float) * (size_t)rows * K, st));
+        LDM_CUDA(cudaMemsetAsync(Tn, 0, sizeof(float) * (size_t)U.n_t * rows, st));
+        LDM_CUDA(cudaMemsetAsync(Cn, 0, sizeof(float) * (size_t)U.ncls * rows, st));
+        LDM_CUDA(cudaMemsetAsync(g0n, 0, sizeof(float) * (size_t)rows, st));
+        LDM_TRY(copy2d(ctx, U.latent_proj.w32, L, Gn, K, d, L, st));                                           // W_lp
+        LDM_TRY(mm(ctx, U.block[0].w32, d, U.latent_proj.w32, L, 0, Gn + (size_t)d * K, K, d, L, d, st));     // W_b0 W_lp
+        LDM_TRY(mm(ctx, Gn, K, U.fin.w32, 2 * L, 0, Gn + L, K, nsr, 2 * L, L, st));                           // G_0 W_f'
+        LDM_TRY(copy2d(ctx, U.fin.w32, 2 * L, Gn + (size_t)nsr * K + L, K, L, 2 * L, st));                    // eps rows
         LDM_TRY(copy2d(ctx, U.latent_proj.b, 1, bn, 1, d, 1, st));
         LDM_TRY(mv(ctx, U.block[0].w32, d, U.latent_proj.b, U.block[0].b, bn + d, d, d, st));
+        LDM_TRY(copy2d(ctx, U.fin.b, 1, bn + nsr, 1, L, 1, st));                                               // b_fin on the eps rows
+        LDM_TRY(mv(ctx, Gn, K, U.fin.b, nullptr, g0n, nsr, L, st));                                            // G_0 b_fin
         LDM_TRY(copy2d(ctx, U.tab_t[0], d, Tn, rows, U.n_t, d, st));
         LDM_TRY(mm(ctx, U.tab_t[0], d, U.block[0].w32, d, 1, Tn + d, rows, U.n_t, d, d, st));
         LDM_TRY(copy2d(ctx, U.tab_c[0], d, Cn, rows, U.ncls, d, st));
         LDM_TRY(mm(ctx, U.tab_c[0], d, U.block[0].w32, d, 1, Cn + d, rows, U.ncls, d, d, st));
-        H.type = LDM_PH_STAGE;
-      } else if (j <= nst) {
+        H.type = LDM_PH_MERGED;
+        H.nst_tiles = nsr / 128;
+        H.eps_kb0 = L / BK;
+      } else {
         // D = [W_d | W_d A] (dn x 2dp), db = W_d a + b_d with A, a the folded L = 1 attention of stage j-1
         const int i = j - 1, dp = U.hid[i], dn = U.hid[i + 1];
         const bool last = j == nst;
-        d = dn; K = 2 * dp; rows = last ? dn : 2 * dn; stage = last ? 0 : 1;
+        d = dn; K = 2 * dp; rows = last ? dn : 2 * dn; stage = last ? 0 : 1; nsr = rows;
         LDM_TRY(ldm_alloc_t(ctx, tmp, &Gn, (size_t)rows * K));
         LDM_TRY(ldm_alloc_t(ctx, tmp, &bn, (size_t)rows));
         LDM_TRY(ldm_alloc_t(ctx, tmp, &Tn, (size_t)U.n_t * rows));
@@ -965,11 +1025,6 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
           LDM_TRY(mm(ctx, U.tab_c[j], dn, Wb, dn, 1, Cn + dn, rows, U.ncls, dn, dn, st));
         }
         H.type = last ? LDM_PH_FINAL_LN : LDM_PH_STAGE;
-      } else {
-        // eps = [W_f | s W_f] [LN_f(h) ; x] + (1 + s) b_f : already folded by api.cu (U.fin)
-        d = L; rows = U.fin.N; K = U.fin.K; stage = 0;
-        Gn = U.fin.w32; bn = U.fin.b;
-        H.type = LDM_PH_EPS;
       }
       LDM_CHECK(rows % 128 == 0 && K % BK == 0 && rows / 128 <= CS, "chain: phase %d shape (%d x %d) unsupported", j, rows, K);
       H.K = K; H.rows = rows; H.tiles = rows / 128; H.d = d;
@@ -978,19 +1033,24 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
       LDM_TRY(ldm_alloc_t(ctx, PA, &H.bias, (size_t)rows));
       {
         const size_t n = (size_t)rows * K;
-        pack_rows_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Gn, H.w, rows, K, d, stage);
+        pack_rows_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Gn, H.w, rows, K, d, stage, nsr);
         LDM_LAUNCHED(ctx);
-        pack_cols_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(bn, H.bias, 1, rows, d, stage);
+        pack_cols_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(bn, H.bias, 1, rows, d, stage, nsr);
+        LDM_LAUNCHED(ctx);
+        if (g0n) {
+          LDM_TRY(ldm_alloc_t(ctx, PA, &H.g0b, (size_t)rows));
+          pack_cols_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(g0n, H.g0b, 1, rows, d, stage, nsr);
+        }
         LDM_LAUNCHED(ctx);
       }
       if (Tn) {
         LDM_TRY(ldm_alloc_t(ctx, PA, &H.tab_t, (size_t)U.n_t * rows));
         LDM_TRY(ldm_alloc_t(ctx, PA, &H.tab_c, (size_t)U.ncls * rows));
         size_t n = (size_t)U.n_t * rows;
-        pack_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Tn, H.tab_t, U.n_t, rows, d, stage);
+        pack_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Tn, H.tab_t, U.n_t, rows, d, stage, nsr);
         LDM_LAUNCHED(ctx);
         n = (size_t)U.ncls * rows;
-        pack_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Cn, H.tab_c, U.ncls, rows, d, stage);
+        pack_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Cn, H.tab_c, U.ncls, rows, d, stage, nsr);
         LDM_LAUNCHED(ctx);
       }
       LDM_TRY(tc_make_weight_map(ctx, H.w, rows, K, 128, &H.map));   // box = 128 rows x 64 k
@@ -1017,10 +1077,8 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
       int best = 0;
       double best_peak = 1e300, best_sum = 1e300;
       const int nu = H.tiles * H.ks;
-      // the CTAs that finish the eps phase also generate the step's noise at the top of the step, while phase 0 runs:
-      // keep them off the CTAs that own a phase-0 tile (phase 0 is placed before the eps phase: it is heavier)
-      const bool avoid0 = order[a] == C.n_phases - 1;
-      const int p0a = C.ph[0].first, p0b = C.ph[0].first + C.ph[0].tiles * C.ph[0].ks;
+      const bool avoid0 = false;
+      const int p0a = 0, p0b = 0;
       for (int pass = 0; pass < 2 && best_peak > 1e299; ++pass)
       for (int f = 0; f + nu <= CS; ++f) {
         if (pass == 0 && avoid0 && f < p0b && f + nu > p0a) continue;
@@ -1055,7 +1113,7 @@ static int chain_pick_nw(int B) {
 }
 
 // Run `n_iter` reverse steps (sample = 1) or one forward evaluation (sample = 0) for `B` rows.
-// The bf16 operand copy of x must already sit in ctx->af_op[0] (columns [latent, 2 latent)).
+// `x`: (B, latent) fp32 input; in sample mode it is also the state that receives x_{t_end - 1}.
 int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const int64_t* t_idx, int t_len, float* x,
                  float* eps_out, const float* noise, cudaStream_t st) {
   UnetModel& U = ctx->unet;
@@ -1070,9 +1128,12 @@ int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const
   const int nst = U.nst, L = U.latent;
   LDM_CHECK(kAccCols + (C.n_phases + 1) * NB <= kTmemCols + NB, "chain: %d phases x %d rows exceed the TMEM columns", C.n_phases, NB);
   LDM_CHECK(nst + 2 <= kMaxXMaps, "chain: too many stages");
+  // stage the first merged operand: [x | 0 | 0] (the stage tiles see G_0 x; the eps tiles have nothing to finish yet)
+  LDM_TRY(launch_load_x<bf16>(ctx, x, ctx->caf[0], 3 * L, B, L, st));
+  LDM_CUDA(cudaMemset2DAsync(ctx->caf[0] + L, (size_t)3 * L * sizeof(bf16), 0, (size_t)2 * L * sizeof(bf16), (size_t)B, st));
   // operand descriptors: rows beyond the batch are zero-filled by the TMA unit
-  LDM_TRY(tc_make_act_map(ctx->af_op[0], B, 2 * L, 2 * L, NB, &P.xmaps[0]));
-  LDM_TRY(tc_make_act_map(ctx->af_op[1], B, 2 * L, 2 * L, NB, &P.xmaps[1]));
+  LDM_TRY(tc_make_act_map(ctx->caf[0], B, 3 * L, 3 * L, NB, &P.xmaps[0]));
+  LDM_TRY(tc_make_act_map(ctx->caf[1], B, 3 * L, 3 * L, NB, &P.xmaps[1]));
   for (int j = 0; j < nst; ++j) LDM_TRY(tc_make_act_map(ctx->opbuf[j], B, 2 * U.hid[j], 2 * U.hid[j], NB, &P.xmaps[2 + j]));
   for (int j = nst; j < kMaxXMaps - 2; ++j) P.xmaps[2 + j] = P.xmaps[0];
   int cadd = kAccCols;
@@ -1081,14 +1142,14 @@ int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const
     ChainPhase& D = P.ph[j];
     P.wmap[j] = H.map;
     D.type = H.type; D.K = H.K; D.tiles = H.tiles; D.first = H.first; D.ks = H.ks; D.d = H.d; D.rows = H.rows;
+    D.nst_tiles = H.nst_tiles; D.eps_kb0 = H.eps_kb0; D.g0b = H.g0b;
     D.bias = H.bias; D.tab_t = H.tab_t; D.tab_c = ctx->has_cls ? H.tab_c : nullptr;
     D.cadd_col = -1;
     if (H.tab_t) { D.cadd_col = cadd; cadd += NB; }
     if (j < nst) { D.ga = U.ln_a_w[j]; D.ba = U.ln_a_b[j]; D.gb = U.ln_b_w[j]; D.bb = U.ln_b_b[j]; }
-    else if (j == nst) { D.ga = U.ln_f_w; D.ba = U.ln_f_b; }
-    if (j == 0) { D.xmap = 0; D.xmap_alt = 1; D.xcol = L; }
-    else if (j <= nst) { D.xmap = 2 + (j - 1); D.xmap_alt = 0; D.xcol = 0; }
-    else { D.xmap = 0; D.xmap_alt = 1; D.xcol = 0; }
+    else { D.ga = U.ln_f_w; D.ba = U.ln_f_b; }
+    if (j == 0) { D.xmap = 0; D.xmap_alt = 1; D.xcol = 0; }
+    else { D.xmap = 2 + (j - 1); D.xmap_alt = 0; D.xcol = 0; }
     if (j < nst) { D.out = ctx->opbuf[j]; D.ld_out = 2 * U.hid[j]; }
   }
   for (int j = C.n_phases; j < LDM_CHAIN_MAX_PHASES; ++j) P.wmap[j] = C.ph[0].map;
@@ -1102,7 +1163,8 @@ int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const
   P.cls = ctx->has_cls ? ctx->cls : nullptr;
   P.x = x; P.eps_out = eps_out; P.noise = noise; P.rng = ctx->rng_dev;
   P.coef = ctx->coef_dev;
-  P.af[0] = (bf16*)ctx->af_op[0]; P.af[1] = (bf16*)ctx->af_op[1]; P.ld_af = 2 * L;
+  P.coef_or_one = sample ? ctx->coef_dev : ctx->coef_one;
+  P.af[0] = ctx->caf[0]; P.af[1] = ctx->caf[1]; P.ld_af = 3 * L;
   P.err = ctx->chain_err;
   P.trace = ctx->chain_trace;
   P.trace_step = ctx->chain_trace_step;
