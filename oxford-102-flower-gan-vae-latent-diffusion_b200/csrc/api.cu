@@ -324,7 +324,7 @@ static int ensure_workspace(ldm_ctx* ctx, int B) {
   LDM_TRY(ldm_alloc(ctx, P, &ctx->af_op[1], naf * op));
   if (ctx->use_chain)
   {
-    for (int j = 0; j < U.nst; ++j) LDM_TRY(ldm_alloc_t(ctx, P, &ctx->opbuf[j], (size_t)cap * 2 * U.hid[j]));
+    for (int j = 0; j < U.nst; ++j) LDM_TRY(ldm_alloc_t(ctx, P, &ctx->opbuf[j], (size_t)cap * U.hid[j]));
     for (int k = 0; k < 2; ++k) {
       LDM_TRY(ldm_alloc_t(ctx, P, &ctx->caf[k], (size_t)cap * 3 * U.latent));
       LDM_CUDA(cudaMemset(ctx->caf[k], 0, (size_t)cap * 3 * U.latent * sizeof(bf16)));

@@ -41,7 +41,8 @@ constexpr int kCtlThreads = 128;        // warp 0: weight TMA, warp 1: operand T
 constexpr uint32_t kWBytes = 128 * BK * 2;               // one weight k-block: 16 KiB
 constexpr int kSlots = CS;                               // partial-statistics slots per buffer: one per tile of a phase
 constexpr int kMaxStagesRing = 10;
-constexpr int kAccCols = 64;                             // TMEM columns reserved for the accumulator
+constexpr int kChains = 4;                               // independent accumulation chains (TMEM column blocks of NB): a dependent
+                                                         // tcgen05.mma chain is latency bound (~140 cycles per MMA at N = 48), 4 chains interleave
 constexpr int kTmemCols = 512;
 constexpr int kMaxXMaps = LDM_MAX_STAGES + 2;
 
@@ -67,7 +68,12 @@ struct ChainPhase {
   int K;               // reduction length, multiple of 64
   int tiles;           // 128-row weight tiles
   int first;           // cluster rank of the CTA that owns unit 0; unit = tile * ks + k-part -> rank first + unit
-  int ks;              // split of the reduction: 1, or 2 (the odd unit sends its partial accumulator to the even one)
+  int ks;              // 1, or 2 units per tile (the odd unit sends its accumulator to the even one): a K split (plain
+                       // phases) or one unit per accumulator (dual phases)
+  int dual;            // 1: operand = raw h2 of the previous stage, LayerNorm applied AFTER the contraction: two weight
+                       //    blocks [W1 | W2] (columns [0,K) and [K,2K)) and two accumulators, out = acc1 + r (acc2 - mu q)
+  const float* q;      // dual: q = W2 . 1 (tile order)
+  int prev_tiles;      // dual: stage tiles of the phase that produced the operand (partials of its row statistics)
   int d;               // LayerNorm width (stage: d_j; final-LN / eps: latent)
   int rows;            // tiles * 128: leading dimension of the tables
   int xmap;            // index of the operand's tensor map (+ 1 on odd steps when xmap_alt)
@@ -181,6 +187,22 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float (&a)
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(s[i]); }
+}
+
+// out = sum of `n` accumulation chains (16 columns each, `stride` columns apart)
+__device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr, uint32_t stride, int n, float (&out)[16]) {
+  float b[16];
+  if (n == 4) {
+    float c[16], d[16];
+    tmem_ld16x2(taddr, taddr + stride, out, b);
+    tmem_ld16x2(taddr + 2 * stride, taddr + 3 * stride, c, d);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) out[i] = (out[i] + b[i]) + (c[i] + d[i]);
+  } else {
+    tmem_ld16x2(taddr, taddr + stride, out, b);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) out[i] += b[i];
+  }
 }
 
 // Every wait in this kernel is bounded and abortable: the first timeout raises the abort flag of all CTAs of the
@@ -308,24 +330,42 @@ __device__ __forceinline__ float2 warp_row_stats16(const float (&v)[16], int lan
 __device__ __forceinline__ float swish_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 __device__ __forceinline__ int clamp_t(long long t, int n_t) { return (int)(t < 0 ? 0 : (t >= n_t ? n_t - 1 : t)); }
 
-// work unit of cluster rank `rank` in a phase: tile, k-part and k-block range; false: no unit.
+// work unit of cluster rank `rank` in a phase: tile, unit-in-tile and the list of ring jobs; false: no unit.
 // `tail`: the extra merged phase after the last step, in which only the eps tiles work.
-struct Unit { int tile, kp, kb0, nk; bool is_eps; };
+// A job moves one 128 x 64 weight tile (and, unless it shares the previous job's, one operand k-block) into a ring slot:
+//   plain phase          : job i = k-block kb0 + i of [W | X]
+//   dual phase, one unit : job 2m = (W1 k-block m, X k-block m) -> accumulator 0; job 2m+1 = (W2 k-block m, same X) -> accumulator 1
+//   dual phase, two units: unit kp streams W_{kp+1} and the whole operand into its own accumulator 0
+struct Unit { int tile, kp, kb0, njobs, mode; bool is_eps; };
 __device__ __forceinline__ bool unit_of(const ChainPhase& ph, int rank, bool tail, Unit& u) {
   const int un = rank - ph.first;
   if (un < 0 || un >= ph.tiles * ph.ks) return false;
   u.tile = un >> (ph.ks - 1);          // ks is 1 or 2
   u.kp = un & (ph.ks - 1);
-  int lo = 0;
   u.is_eps = false;
+  const int nkb = ph.K / BK;
+  if (ph.dual) {
+    u.mode = ph.ks == 1 ? 1 : 2;
+    u.kb0 = 0;
+    u.njobs = ph.ks == 1 ? 2 * nkb : nkb;
+    return true;
+  }
+  u.mode = 0;
+  int lo = 0;
   if (ph.type == LDM_PH_MERGED) {
     u.is_eps = u.tile >= ph.nst_tiles;
     if (u.is_eps) lo = ph.eps_kb0;
     else if (tail) return false;
   }
-  u.nk = (ph.K / BK - lo) >> (ph.ks - 1);
-  u.kb0 = lo + u.kp * u.nk;
+  u.njobs = (nkb - lo) >> (ph.ks - 1);
+  u.kb0 = lo + u.kp * u.njobs;
   return true;
+}
+// column of job i's weight tile in the phase's weight matrix, and of its operand k-block (-1: shares the previous job's)
+__device__ __forceinline__ void job_cols(const ChainPhase& ph, const Unit& u, int i, int& wcol, int& xcol) {
+  if (u.mode == 0) { wcol = (u.kb0 + i) * BK; xcol = ph.xcol + (u.kb0 + i) * BK; }
+  else if (u.mode == 1) { wcol = (i & 1) * ph.K + (i >> 1) * BK; xcol = (i & 1) ? -1 : (i >> 1) * BK; }
+  else { wcol = u.kp * ph.K + i * BK; xcol = i * BK; }
 }
 
 template <int NW>
@@ -387,7 +427,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
 
   if (warp == 0) {
     // ------------------------------------------------------------------ weight-tile producer (runs ahead of the phases)
-    if (lane == 0) {
+    if (tc::elect_one()) {
       uint32_t n = 0;
       bool ok = true;
       for (int it = 0; it <= P.n_iter && ok; ++it) {
@@ -395,18 +435,20 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
         for (int p = 0; p < (tail ? 1 : NP) && ok; ++p) {
           Unit un;
           if (!unit_of(sphase[p], rank, tail, un)) continue;
-          for (int kb = un.kb0; kb < un.kb0 + un.nk; ++kb, ++n) {
+          for (int i = 0; i < un.njobs; ++i, ++n) {
             const uint32_t s = n % S, par = (n / S) & 1u;
             if (!W.wait(&empty_bar[s], par ^ 1u, 1)) { ok = false; break; }
+            int wcol, xcol;
+            job_cols(sphase[p], un, i, wcol, xcol);
             tc::mbar_arrive_expect_tx(&full_bar[s], kWBytes);
-            tc::tma_load_2d(ring + (size_t)s * G::kStageBytes, &P.wmap[p], &full_bar[s], kb * BK, un.tile * 128);
+            tc::tma_load_2d(ring + (size_t)s * G::kStageBytes, &P.wmap[p], &full_bar[s], wcol, un.tile * 128);
           }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ operand producer: waits for the phase hand-over
-    if (lane == 0) {
+    if (tc::elect_one()) {
       uint32_t n = 0, gp = 0;
       bool ok = true;
       tc::mbar_arrive(&obar[0]);   // this thread's share of hand-overs 0 and 1
@@ -424,18 +466,21 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
           Unit un;
           if (!unit_of(ph, rank, tail, un)) continue;
           const CUtensorMap* xm = &P.xmaps[ph.xmap + (ph.xmap_alt ? (it & 1) : 0)];
-          for (int kb = un.kb0; kb < un.kb0 + un.nk; ++kb, ++n) {
+          for (int i = 0; i < un.njobs; ++i, ++n) {
             const uint32_t s = n % S, par = (n / S) & 1u;
             if (!W.wait(&empty_bar[s], par ^ 1u, 3)) { ok = false; break; }
+            int wcol, xcol;
+            job_cols(ph, un, i, wcol, xcol);
+            if (xcol < 0) { tc::mbar_arrive(&full_bar[s]); continue; }   // this job multiplies the previous job's operand block
             tc::mbar_arrive_expect_tx(&full_bar[s], G::kXBytes);
-            tc::tma_load_2d(ring + (size_t)s * G::kStageBytes + kWBytes, xm, &full_bar[s], ph.xcol + kb * BK, row0);
+            tc::tma_load_2d(ring + (size_t)s * G::kStageBytes + kWBytes, xm, &full_bar[s], xcol, row0);
           }
         }
       }
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (tc::elect_one()) {
       constexpr uint32_t idesc = tc::make_idesc_bf16(128, NB);
       uint32_t n = 0;
       bool ok = true;
@@ -444,17 +489,38 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
         for (int p = 0; p < (tail ? 1 : NP) && ok; ++p) {
           Unit un;
           if (!unit_of(sphase[p], rank, tail, un)) continue;
-          for (int kb = 0; kb < un.nk; ++kb, ++n) {
-            const uint32_t s = n % S, par = (n / S) & 1u;
-            if (!W.wait(&full_bar[s], par, 4)) { ok = false; break; }
-            tc::fence_after_sync();
-            const uint32_t base = tc::smem_u32(ring + (size_t)s * G::kStageBytes);
-            const uint64_t dw = tc::make_desc_sw128(base);
-            const uint64_t dx = tc::make_desc_sw128(base + kWBytes);
+          if (un.mode == 1) {
+            // dual k-block: both weight tiles against the same operand block.  Chains 0,1: accumulator 1 (even / odd k-steps),
+            // chains 2,3: accumulator 2; consecutive MMAs never depend on each other
+            for (int i = 0; i < un.njobs; i += 2, n += 2) {
+              const uint32_t sa = n % S, pa = (n / S) & 1u, sb = (n + 1) % S, pb = ((n + 1) / S) & 1u;
+              if (!W.wait(&full_bar[sa], pa, 4) || !W.wait(&full_bar[sb], pb, 4)) { ok = false; break; }
+              tc::fence_after_sync();
+              const uint32_t ba = tc::smem_u32(ring + (size_t)sa * G::kStageBytes), bb = tc::smem_u32(ring + (size_t)sb * G::kStageBytes);
+              const uint64_t dwa = tc::make_desc_sw128(ba), dwb = tc::make_desc_sw128(bb), dx = tc::make_desc_sw128(ba + kWBytes);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              tc::umma_bf16(tmem_base, dw + (uint64_t)(2 * k), dx + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
-            tc::umma_commit(&empty_bar[s]);
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint32_t ch = (uint32_t)(k & 1), acc = (uint32_t)(i != 0 || k >= 2);
+                tc::umma_bf16(tmem_base + ch * NB, dwa + (uint64_t)(2 * k), dx + (uint64_t)(2 * k), idesc, acc);
+                tc::umma_bf16(tmem_base + (2u + ch) * NB, dwb + (uint64_t)(2 * k), dx + (uint64_t)(2 * k), idesc, acc);
+              }
+              tc::umma_commit(&empty_bar[sa]);
+              tc::umma_commit(&empty_bar[sb]);
+            }
+          } else {
+            // one accumulator: k-step k of every k-block goes to chain k
+            for (int i = 0; i < un.njobs; ++i, ++n) {
+              const uint32_t s = n % S, par = (n / S) & 1u;
+              if (!W.wait(&full_bar[s], par, 4)) { ok = false; break; }
+              tc::fence_after_sync();
+              const uint32_t base = tc::smem_u32(ring + (size_t)s * G::kStageBytes);
+              const uint64_t dw = tc::make_desc_sw128(base);
+              const uint64_t dx = tc::make_desc_sw128(base + kWBytes);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                tc::umma_bf16(tmem_base + (uint32_t)(k * NB), dw + (uint64_t)(2 * k), dx + (uint64_t)(2 * k), idesc, (uint32_t)(i != 0));
+              tc::umma_commit(&empty_bar[s]);
+            }
           }
           if (ok) tc::umma_commit(&tmem_full_bar);
         }
@@ -600,7 +666,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
           tpar ^= 1u;
           tc::fence_after_sync();
           float pv[16];
-          tc::tmem_ld16(lane_taddr + (uint32_t)s0, pv);
+          tmem_ld16_sum(lane_taddr + (uint32_t)s0, (uint32_t)NB, kChains, pv);
           tc::fence_before_sync();
           const uint32_t owner = (uint32_t)(ph.first + tile * ph.ks);
           const uint32_t dst = mapa_u32(tc::smem_u32(pbuf + (size_t)(g * 4) * 128 + lrow), owner);
@@ -610,13 +676,17 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
             st_async_f4(dst + (uint32_t)(c * 128 * sizeof(float4)), pv[4 * c], pv[4 * c + 1], pv[4 * c + 2], pv[4 * c + 3], dbar);
         }
         float v[16];
+        float h2k[8];                 // h2 of this lane's feature x 8 rows: its statistics are published AFTER the hand-over
+        bool pub_b = false;
+        const uint32_t sidx0 = sidx;  // exchange index before this phase: sidx0 - 1 is the previous phase's background exchange
         if (active) {
           // everything that does not depend on the accumulator is fetched before the waits
-          float t_b = 0.f, t_t = 0.f, t_g = 0.f;   // loaded now, summed after the wait (no dependent use before it)
+          float t_b = 0.f, t_t = 0.f, t_g = 0.f, t_q = 0.f;   // loaded now, summed after the wait (no dependent use before it)
           if (!eps_tile) {
             if (ph.bias) t_b = __ldg(ph.bias + grow);
             if (ph.tab_t && t_uni >= 0) t_t = __ldg(ph.tab_t + (size_t)t_uni * ph.rows + grow);
             if (ph.type == LDM_PH_MERGED) t_g = __ldg(ph.g0b + grow);
+            if (ph.dual) t_q = __ldg(ph.q + grow);
           }
           stamp();
           W.wait(&tmem_full_bar, tpar, 5);
@@ -624,19 +694,24 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
           stamp();
           tc::fence_after_sync();
           const float cb_prev = it > 0 ? cf_prev.x / cf_prev.y : 0.f;   // c2 / sqrt(alpha) of the previous step (forward(): 1)
-          const float tt = t_b + t_t - cb_prev * t_g;                   // t_g: the eps bias of the previous step, seen through G_0
+          const float t_e = cb_prev * t_g;                              // the eps bias of the previous step, seen through G_0
+          float a2[16];
+          const int nch = (ph.dual && ph.ks == 1) ? 2 : kChains;   // chains of the (first) accumulator
+          tmem_ld16_sum(lane_taddr + (uint32_t)s0, (uint32_t)NB, nch, v);
           if (ph.cadd_col >= 0 && !eps_tile) {
+            // one association for every mode (uniform t: t_t = T[t], c = C[c_r]; per-row t: t_t = 0, c = C[c_r] + T[t_r]), so
+            // that a row's result does not depend on how its timestep was passed: acc + (b + (T + C)) - e
             float c[16];
-            tmem_ld16x2(lane_taddr + (uint32_t)s0, lane_taddr + (uint32_t)(ph.cadd_col + s0), v, c);
+            tc::tmem_ld16(lane_taddr + (uint32_t)(ph.cadd_col + s0), c);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += c[j] + tt;
+            for (int j = 0; j < 16; ++j) v[j] = (v[j] + (t_b + (t_t + c[j]))) - t_e;
           } else {
-            tc::tmem_ld16(lane_taddr + (uint32_t)s0, v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += tt;
+            for (int j = 0; j < 16; ++j) v[j] = (v[j] + (t_b + t_t)) - t_e;
           }
+          if (ph.dual && ph.ks == 1) tmem_ld16_sum(lane_taddr + (uint32_t)(2 * NB + s0), (uint32_t)NB, 2, a2);
           tc::fence_before_sync();            // ordered before the next phase's MMAs through the hand-over
-          if (ph.ks > 1) {   // add the partner's half of the reduction
+          if (ph.ks > 1) {   // the partner unit's accumulator: acc2 of a dual phase (or the other K half of a plain one)
             if (et == 0) tc::mbar_arrive_expect_tx(&pbar, G::kPbufBytes);
             W.wait(&pbar, ppar, 10);
             ppar ^= 1u;
@@ -644,59 +719,60 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               const float4 a = pp[c * 128];
-              v[4 * c] += a.x; v[4 * c + 1] += a.y; v[4 * c + 2] += a.z; v[4 * c + 3] += a.w;
+              if (ph.dual) { a2[4 * c] = a.x; a2[4 * c + 1] = a.y; a2[4 * c + 2] = a.z; a2[4 * c + 3] = a.w; }
+              else { v[4 * c] += a.x; v[4 * c + 1] += a.y; v[4 * c + 2] += a.z; v[4 * c + 3] += a.w; }
             }
+          }
+          if (ph.dual) {
+            // LayerNorm of the operand rows applied after the contraction: W2 . LN_b(h2) = r (W2' h2 - mu q) + const
+            // (gamma, beta folded into W2' / the bias at pack time).  (mu, r) of the 16 rows: the previous phase's
+            // background statistics exchange, long complete by now.
+            const uint32_t bb = (sidx0 - 1u) & 1u;
+            exchange_wait(bb, ph.prev_tiles, 11);
+            combine(bb, ph.prev_tiles, 64.0f);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 mr = rs[j];
+              v[j] += mr.y * (a2[j] - mr.x * t_q);
+            }
+            __syncwarp();
           }
         }
 
         if (ph.type == LDM_PH_STAGE || ph.type == LDM_PH_MERGED) {
           // Tile rows: quadrant q holds 16 h features in lanes 0..15 and u = Linear_b(h) of the SAME 16 features in lanes
-          // 16..31.  The two halves trade 8 rows, after which every lane owns feature f for 8 rows, h AND u: the whole
-          // LayerNorm / Swish / residual chain of v2:546-553 runs in registers on all 32 lanes.
+          // 16..31.  The two halves trade 8 rows, after which every lane owns feature f for 8 rows, h AND u: the
+          // LayerNorm / Swish / residual chain of v2:546-548 runs in registers on all 32 lanes.
           const int f = tile * 64 + q * 16 + (lane & 15);
           const int hr = (lane >> 4) * 8;             // first of this lane's 8 rows inside the row group
           const int ntile = ph.type == LDM_PH_MERGED ? ph.nst_tiles : ph.tiles;
-          const int nparts = ntile;
-          const uint32_t b0 = sidx & 1u, b1 = b0 ^ 1u;
-          sidx += 2;
+          const uint32_t b0 = sidx & 1u;
+          sidx += 2;                                  // [A: statistics of u, waited here] [B: statistics of h2, background]
           if (active && !eps_tile) {
-            const float ga = __ldg(ph.ga + f), ba = __ldg(ph.ba + f), gb = __ldg(ph.gb + f), bb = __ldg(ph.bb + f);
-            float h[8], u[8];
+            const float ga = __ldg(ph.ga + f), ba = __ldg(ph.ba + f);
+            float u[8];
             {
               const bool lo = lane < 16;
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const float recv = __shfl_xor_sync(0xffffffffu, lo ? v[8 + i] : v[i], 16);
-                h[i] = lo ? v[i] : recv;
+                h2k[i] = lo ? v[i] : recv;
                 u[i] = lo ? recv : v[8 + i];
               }
             }
             publish(b0, tile, half_row_stats8(u, lane), 16.0f, ph.first, ntile, ph.ks);
             stamp();
-            exchange_wait(b0, nparts, 6);
+            exchange_wait(b0, ntile, 6);
             stamp();
-            combine(b0, nparts, 64.0f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {   // h2 = swish(LN_a(u)) + h                       (v2:520-522, 547)
-              const float2 mr = rs[hr + i];
-              h[i] += swish_fast((u[i] - mr.x) * mr.y * ga + ba);
-            }
-            publish(b1, tile, half_row_stats8(h, lane), 16.0f, ph.first, ntile, ph.ks);
-            // the h2 half of the next operand does not depend on the statistics: store it while they travel
+            combine(b0, ntile, 64.0f);
             bf16* o = ph.out + (size_t)(row0 + s0 + hr) * ph.ld_out + f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (row0 + s0 + hr + i < P.row_end) o[(size_t)i * ph.ld_out] = __float2bfloat16_rn(h[i]);
-            stamp();
-            exchange_wait(b1, nparts, 7);
-            stamp();
-            combine(b1, nparts, 64.0f);
-            o += ph.d;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {   // n = LN_b(h2); operand of the next phase is [h2 | n]   (v2:548-553)
+            for (int i = 0; i < 8; ++i) {   // h2 = swish(LN_a(u)) + h: the next phase's operand (its LayerNorm is applied there)
               const float2 mr = rs[hr + i];
-              if (row0 + s0 + hr + i < P.row_end) o[(size_t)i * ph.ld_out] = __float2bfloat16_rn((h[i] - mr.x) * mr.y * gb + bb);
+              h2k[i] += swish_fast((u[i] - mr.x) * mr.y * ga + ba);
+              if (row0 + s0 + hr + i < P.row_end) o[(size_t)i * ph.ld_out] = __float2bfloat16_rn(h2k[i]);
             }
+            pub_b = true;
           }
         } else {   // LDM_PH_FINAL_LN
           const int f = grow;
@@ -802,6 +878,13 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
         W.wait(&obar[ob], opar, 9);
         oidx++;
         stamp();
+        if (pub_b) {
+          // ---- background exchange, issued once the hand-over is through (the operand producer's proxy fence must not
+          //      queue behind these stores): (mean, M2) of h2 over this warp's 16 features -> the tile owners of the NEXT
+          //      phase, who apply LayerNorm_b (v2:549) after their contraction
+          const ChainPhase& nx = sphase[p + 1];
+          publish((sidx0 + 1u) & 1u, tile, half_row_stats8(h2k, lane), 16.0f, nx.first, nx.tiles, nx.ks);
+        }
       }
     }
   }
@@ -857,6 +940,18 @@ __global__ void pack_cols_kernel(const float* __restrict__ src, float* __restric
   if (i >= (size_t)n * rows) return;
   const int t = (int)(i / rows), rt = (int)(i % rows);
   dst[i] = src[(size_t)t * rows + tile_src_row(rt, d, stage, nsr)];
+}
+
+// M[r][c] *= g[c] on a (rows x cols) block with pitch ld
+__global__ void pack_scale_cols_kernel(float* __restrict__ M, int ld, const float* __restrict__ g, int rows, int cols) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * cols) return;
+  const int r = (int)(i / cols), c = (int)(i % cols);
+  M[(size_t)r * ld + c] *= g[c];
+}
+__global__ void pack_fill_kernel(float* __restrict__ p, float v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
 }
 
 #define LDM_LAUNCHED(ctx)             \
@@ -955,7 +1050,7 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
   for (void* p : C.allocs) cudaFree(p);
   C = ChainModel();
   const int nst = U.nst, L = U.latent;
-  LDM_CHECK(nst + 1 <= LDM_CHAIN_MAX_PHASES && kAccCols + (nst + 2) * 64 <= kTmemCols, "chain: too many stages (%d) for the TMEM-resident per-sample terms", nst);
+  LDM_CHECK(nst + 1 <= LDM_CHAIN_MAX_PHASES && kChains * 48 + (nst + 2) * 48 <= kTmemCols, "chain: too many stages (%d) for the TMEM-resident per-sample terms", nst);
   LDM_CHECK(L % 128 == 0 && L / 128 <= kSlots, "chain: latent_dim %d unsupported", L);
   for (int i = 0; i < nst; ++i)
     LDM_CHECK(U.hid[i] % 64 == 0 && U.hid[i] / 64 <= CS && U.hid[i] / 64 <= kSlots, "chain: hidden dim %d unsupported", U.hid[i]);
@@ -969,7 +1064,7 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
     for (int j = 0; j <= nst; ++j) {
       ChainPhaseHost& H = C.ph[j];
       int rows, K, d, stage, nsr;
-      float *Gn = nullptr, *bn = nullptr, *Tn = nullptr, *Cn = nullptr, *g0n = nullptr;   // natural order (temporaries)
+      float *Gn = nullptr, *bn = nullptr, *Tn = nullptr, *Cn = nullptr, *g0n = nullptr, *qn = nullptr;   // natural order (temporaries)
       if (j == 0) {
         // MERGED phase.  With x_{t-1} = x~ - c_b eps, x~ = x_t / sqrt(alpha_t) + sigma_t z_t, c_b = c2 / sqrt(alpha_t)
         // and eps = W_f' [LN_f(h) ; x_t] + b_fin (v2:560-561, 584-592), the first stage of the NEXT forward,
@@ -1004,17 +1099,33 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
         H.nst_tiles = nsr / 128;
         H.eps_kb0 = L / BK;
       } else {
-        // D = [W_d | W_d A] (dn x 2dp), db = W_d a + b_d with A, a the folded L = 1 attention of stage j-1
+        // Operand: raw h2 of stage i = j-1 (dp wide).  With n = LN_b(h2) = r Gamma (h2 - mu) + beta (v2:549) and the folded
+        // L = 1 attention A n + a (v2:550-552), h_{j} = D (h2 + A n + a) + b_d (v2:553) becomes
+        //   h_j = W1 h2 + r (W2 h2 - mu q) + const,  W1 = D, W2 = D A Gamma, q = W2 1, const = D (A beta + a) + b_d
+        // so LayerNorm_b is applied AFTER the contraction from the per-row (mu, r) that the previous phase exchanges in the
+        // background.  Weights: [W1 | W2] (rows x 2dp), two accumulators.
         const int i = j - 1, dp = U.hid[i], dn = U.hid[i + 1];
         const bool last = j == nst;
         d = dn; K = 2 * dp; rows = last ? dn : 2 * dn; stage = last ? 0 : 1; nsr = rows;
+        float *wv = nullptr, *ones = nullptr;
         LDM_TRY(ldm_alloc_t(ctx, tmp, &Gn, (size_t)rows * K));
         LDM_TRY(ldm_alloc_t(ctx, tmp, &bn, (size_t)rows));
         LDM_TRY(ldm_alloc_t(ctx, tmp, &Tn, (size_t)U.n_t * rows));
         LDM_TRY(ldm_alloc_t(ctx, tmp, &Cn, (size_t)U.ncls * rows));
-        LDM_TRY(copy2d(ctx, U.down[i].w32, dp, Gn, K, dn, dp, st));
-        LDM_TRY(mm(ctx, U.down[i].w32, dp, U.ov[i].w32, dp, 0, Gn + dp, K, dn, dp, dp, st));
-        LDM_TRY(mv(ctx, U.down[i].w32, dp, U.ov[i].b, U.down[i].b, bn, dn, dp, st));
+        LDM_TRY(ldm_alloc_t(ctx, tmp, &qn, (size_t)rows));
+        LDM_TRY(ldm_alloc_t(ctx, tmp, &wv, (size_t)dp));
+        LDM_TRY(ldm_alloc_t(ctx, tmp, &ones, (size_t)dp));
+        LDM_TRY(copy2d(ctx, U.down[i].w32, dp, Gn, K, dn, dp, st));                                   // W1 = D
+        LDM_TRY(mm(ctx, U.down[i].w32, dp, U.ov[i].w32, dp, 0, Gn + dp, K, dn, dp, dp, st));          // D A
+        {
+          const size_t n = (size_t)dn * dp;
+          pack_scale_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Gn + dp, K, U.ln_b_w[i], dn, dp);   // W2 = D A Gamma
+          LDM_LAUNCHED(ctx);
+          pack_fill_kernel<<<ceil_div(dp, 256), 256, 0, st>>>(ones, 1.0f, dp);
+          LDM_LAUNCHED(ctx);
+        }
+        LDM_TRY(mv(ctx, U.ov[i].w32, dp, U.ln_b_b[i], U.ov[i].b, wv, dp, dp, st));                    // A beta + a
+        LDM_TRY(mv(ctx, U.down[i].w32, dp, wv, U.down[i].b, bn, dn, dp, st));                         // D (A beta + a) + b_d
         LDM_TRY(copy2d(ctx, U.tab_t[j], dn, Tn, rows, U.n_t, dn, st));
         LDM_TRY(copy2d(ctx, U.tab_c[j], dn, Cn, rows, U.ncls, dn, st));
         if (!last) {   // u_j rows: W_b,j applied to everything above
@@ -1024,10 +1135,13 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
           LDM_TRY(mm(ctx, U.tab_t[j], dn, Wb, dn, 1, Tn + dn, rows, U.n_t, dn, dn, st));
           LDM_TRY(mm(ctx, U.tab_c[j], dn, Wb, dn, 1, Cn + dn, rows, U.ncls, dn, dn, st));
         }
+        LDM_TRY(mv(ctx, Gn + dp, K, ones, nullptr, qn, rows, dp, st));                                 // q = W2 1 (all rows)
+        H.dual = 1;
         H.type = last ? LDM_PH_FINAL_LN : LDM_PH_STAGE;
       }
       LDM_CHECK(rows % 128 == 0 && K % BK == 0 && rows / 128 <= CS, "chain: phase %d shape (%d x %d) unsupported", j, rows, K);
-      H.K = K; H.rows = rows; H.tiles = rows / 128; H.d = d;
+      H.K = H.dual ? K / 2 : K; H.rows = rows; H.tiles = rows / 128; H.d = d;
+      // two units per tile when few tiles carry a long reduction: one per accumulator (dual) / one per K half (plain)
       H.ks = (K >= 1024 && H.tiles * 2 <= CS && (K / BK) % 2 == 0 && !getenv("LDM_CHAIN_NO_SPLITK")) ? 2 : 1;
       LDM_TRY(ldm_alloc_t(ctx, PA, &H.w, (size_t)rows * K));
       LDM_TRY(ldm_alloc_t(ctx, PA, &H.bias, (size_t)rows));
@@ -1040,6 +1154,11 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
         if (g0n) {
           LDM_TRY(ldm_alloc_t(ctx, PA, &H.g0b, (size_t)rows));
           pack_cols_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(g0n, H.g0b, 1, rows, d, stage, nsr);
+          LDM_LAUNCHED(ctx);
+        }
+        if (qn) {
+          LDM_TRY(ldm_alloc_t(ctx, PA, &H.q, (size_t)rows));
+          pack_cols_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(qn, H.q, 1, rows, d, stage, nsr);
         }
         LDM_LAUNCHED(ctx);
       }
@@ -1067,7 +1186,11 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
     double load[CS] = {0};
     int order[LDM_CHAIN_MAX_PHASES];
     for (int j = 0; j < C.n_phases; ++j) order[j] = j;
-    auto bytes = [&](int j) { return ((double)C.ph[j].K * 256.0 + (double)C.ph[j].K * 48 * 2.0) / C.ph[j].ks; };   // weight tile + operand of one unit
+    auto bytes = [&](int j) {   // weight tile(s) + operand of one unit
+      const ChainPhaseHost& H = C.ph[j];
+      if (H.dual) return H.ks == 1 ? (double)H.K * (512.0 + 96.0) : (double)H.K * (256.0 + 96.0);
+      return ((double)H.K * 256.0 + (double)H.K * 96.0) / H.ks;
+    };
     auto units = [&](int j) { return C.ph[j].tiles * C.ph[j].ks; };
     for (int a = 0; a < C.n_phases; ++a)
       for (int b = a + 1; b < C.n_phases; ++b)
@@ -1104,7 +1227,7 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
 // fewest rows per cluster (shortest epilogue).
 static int chain_pick_nw(int B) {
   int best = 0, best_waves = 1 << 30;
-  for (int nw = 2; nw <= 4; ++nw) {
+  for (int nw = 2; nw <= 3; ++nw) {   // NW = 4 (64 rows) does not fit 4 accumulation chains + the per-sample terms in 512 TMEM columns
     if (g_chain_clusters[nw] < 1) continue;
     const int waves = ceil_div(ceil_div(B, 16 * nw), g_chain_clusters[nw]);
     if (waves < best_waves) { best_waves = waves; best = nw; }
@@ -1126,7 +1249,7 @@ int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const
   ChainParams P;
   memset(&P, 0, sizeof(P));
   const int nst = U.nst, L = U.latent;
-  LDM_CHECK(kAccCols + (C.n_phases + 1) * NB <= kTmemCols + NB, "chain: %d phases x %d rows exceed the TMEM columns", C.n_phases, NB);
+  LDM_CHECK(kChains * NB + (C.n_phases + 1) * NB <= kTmemCols, "chain: %d phases x %d rows exceed the TMEM columns", C.n_phases, NB);
   LDM_CHECK(nst + 2 <= kMaxXMaps, "chain: too many stages");
   // stage the first merged operand: [x | 0 | 0] (the stage tiles see G_0 x; the eps tiles have nothing to finish yet)
   LDM_TRY(launch_load_x<bf16>(ctx, x, ctx->caf[0], 3 * L, B, L, st));
@@ -1134,15 +1257,17 @@ int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const
   // operand descriptors: rows beyond the batch are zero-filled by the TMA unit
   LDM_TRY(tc_make_act_map(ctx->caf[0], B, 3 * L, 3 * L, NB, &P.xmaps[0]));
   LDM_TRY(tc_make_act_map(ctx->caf[1], B, 3 * L, 3 * L, NB, &P.xmaps[1]));
-  for (int j = 0; j < nst; ++j) LDM_TRY(tc_make_act_map(ctx->opbuf[j], B, 2 * U.hid[j], 2 * U.hid[j], NB, &P.xmaps[2 + j]));
+  for (int j = 0; j < nst; ++j) LDM_TRY(tc_make_act_map(ctx->opbuf[j], B, U.hid[j], U.hid[j], NB, &P.xmaps[2 + j]));
   for (int j = nst; j < kMaxXMaps - 2; ++j) P.xmaps[2 + j] = P.xmaps[0];
-  int cadd = kAccCols;
+  int cadd = kChains * NB;
   for (int j = 0; j < C.n_phases; ++j) {
     const ChainPhaseHost& H = C.ph[j];
     ChainPhase& D = P.ph[j];
     P.wmap[j] = H.map;
     D.type = H.type; D.K = H.K; D.tiles = H.tiles; D.first = H.first; D.ks = H.ks; D.d = H.d; D.rows = H.rows;
     D.nst_tiles = H.nst_tiles; D.eps_kb0 = H.eps_kb0; D.g0b = H.g0b;
+    D.dual = H.dual; D.q = H.q;
+    D.prev_tiles = j == 0 ? 0 : (j == 1 ? C.ph[0].nst_tiles : C.ph[j - 1].tiles);
     D.bias = H.bias; D.tab_t = H.tab_t; D.tab_c = ctx->has_cls ? H.tab_c : nullptr;
     D.cadd_col = -1;
     if (H.tab_t) { D.cadd_col = cadd; cadd += NB; }
@@ -1150,7 +1275,7 @@ int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const
     else { D.ga = U.ln_f_w; D.ba = U.ln_f_b; }
     if (j == 0) { D.xmap = 0; D.xmap_alt = 1; D.xcol = 0; }
     else { D.xmap = 2 + (j - 1); D.xmap_alt = 0; D.xcol = 0; }
-    if (j < nst) { D.out = ctx->opbuf[j]; D.ld_out = 2 * U.hid[j]; }
+    if (j < nst) { D.out = ctx->opbuf[j]; D.ld_out = U.hid[j]; }
   }
   for (int j = C.n_phases; j < LDM_CHAIN_MAX_PHASES; ++j) P.wmap[j] = C.ph[0].map;
   P.z_col = cadd;

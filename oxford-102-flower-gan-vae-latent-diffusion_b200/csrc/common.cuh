@@ -146,6 +146,8 @@ enum { LDM_PH_STAGE = 0, LDM_PH_FINAL_LN = 1, LDM_PH_MERGED = 3 };   // MERGED: 
 struct ChainPhaseHost {
   int type = 0, K = 0, tiles = 0, first = 0, ks = 1, d = 0, rows = 0;
   int nst_tiles = 0, eps_kb0 = 0;   // MERGED: leading stage tiles; first k-block the eps tiles read
+  int dual = 0;                     // operand = raw h2 of the previous stage; weights [W1 | W2], K = width of ONE block
+  float* q = nullptr;               // dual: W2 . 1 in tile order
   float* g0b = nullptr;             // MERGED: G_0 . b_fin in tile order (the eps bias seen through the next latent_proj / block Linear)
   bf16* w = nullptr;              // (rows, K) bf16, 128-row tiles
   float *bias = nullptr, *tab_t = nullptr, *tab_c = nullptr;
@@ -255,7 +257,7 @@ struct ldm_ctx {
   int chain_enabled = 0;          // LDM_CHAIN (default 1) and the device can co-schedule the clusters
   int use_chain = 0;              // 1: chain.cu runs the packed denoiser; 0: one kernel per layer (gemm_tc.cu + rowwise.cu)
   int chain_max_clusters = 0;     // co-resident clusters the device offers
-  bf16* opbuf[LDM_MAX_STAGES] = {nullptr};   // (cap, 2 hid[j]): [h2 | n] operand written by stage phase j
+  bf16* opbuf[LDM_MAX_STAGES] = {nullptr};   // (cap, hid[j]): h2 of stage j, operand of the next phase (chain kernel)
   bf16* caf[2] = {nullptr, nullptr};         // (cap, 3 latent): [x~ | -c_b LN_f(h) | -c_b x] operand of the merged phase, double-buffered over steps
   float4* coef_dev = nullptr;     // [n_steps] (c2, sqrt_alpha, sigma, 0)
   float4* coef_one = nullptr;     // one entry (1, 1, 0, 0): the 'coefficients' of a plain forward() in the chain kernel

@@ -54,7 +54,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % S;
         const uint32_t ph = (uint32_t)(kb / S) & 1u;
@@ -66,7 +66,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       constexpr uint32_t idesc = tc::make_idesc_bf16(BM, BN);
       bool ok = true;
       for (int kb = 0; kb < nkb && ok; ++kb) {
