@@ -41,7 +41,15 @@ constexpr int kCtlThreads = 128;        // warp 0: weight TMA, warp 1: operand T
 constexpr uint32_t kWBytes = 128 * BK * 2;               // one weight k-block: 16 KiB
 constexpr int kSlots = CS;                               // partial-statistics slots per buffer: one per tile of a phase
 constexpr int kMaxStagesRing = 10;
-constexpr int kChains = 4;                               // independent accumulation chains (TMEM column blocks of NB): a dependent
+// (measured: with clean UTCHMMA issue a single accumulation chain is fastest; more chains only add TMEM loads)
+#ifndef LDM_CH1
+#define LDM_CH1 1
+#endif
+#ifndef LDM_CH2
+#define LDM_CH2 1
+#endif
+constexpr int kCh1 = LDM_CH1, kCh2 = LDM_CH2;   // chains per accumulator: single-accumulator units / dual units
+constexpr int kChains = kCh1 > 2 * kCh2 ? kCh1 : 2 * kCh2;                               // independent accumulation chains (TMEM column blocks of NB): a dependent
                                                          // tcgen05.mma chain is latency bound (~140 cycles per MMA at N = 48), 4 chains interleave
 constexpr int kTmemCols = 512;
 constexpr int kMaxXMaps = LDM_MAX_STAGES + 2;
@@ -192,7 +200,9 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float (&a)
 // out = sum of `n` accumulation chains (16 columns each, `stride` columns apart)
 __device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr, uint32_t stride, int n, float (&out)[16]) {
   float b[16];
-  if (n == 4) {
+  if (n == 1) {
+    tc::tmem_ld16(taddr, out);
+  } else if (n == 4) {
     float c[16], d[16];
     tmem_ld16x2(taddr, taddr + stride, out, b);
     tmem_ld16x2(taddr + 2 * stride, taddr + 3 * stride, c, d);
@@ -500,9 +510,9 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
               const uint64_t dwa = tc::make_desc_sw128(ba), dwb = tc::make_desc_sw128(bb), dx = tc::make_desc_sw128(ba + kWBytes);
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
-                const uint32_t ch = (uint32_t)(k & 1), acc = (uint32_t)(i != 0 || k >= 2);
+                const uint32_t ch = (uint32_t)(k % kCh2), acc = (uint32_t)(i != 0 || k >= kCh2);
                 tc::umma_bf16(tmem_base + ch * NB, dwa + (uint64_t)(2 * k), dx + (uint64_t)(2 * k), idesc, acc);
-                tc::umma_bf16(tmem_base + (2u + ch) * NB, dwb + (uint64_t)(2 * k), dx + (uint64_t)(2 * k), idesc, acc);
+                tc::umma_bf16(tmem_base + ((uint32_t)kCh2 + ch) * NB, dwb + (uint64_t)(2 * k), dx + (uint64_t)(2 * k), idesc, acc);
               }
               tc::umma_commit(&empty_bar[sa]);
               tc::umma_commit(&empty_bar[sb]);
@@ -518,7 +528,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
               const uint64_t dx = tc::make_desc_sw128(base + kWBytes);
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k)
-                tc::umma_bf16(tmem_base + (uint32_t)(k * NB), dw + (uint64_t)(2 * k), dx + (uint64_t)(2 * k), idesc, (uint32_t)(i != 0));
+                tc::umma_bf16(tmem_base + (uint32_t)((k % kCh1) * NB), dw + (uint64_t)(2 * k), dx + (uint64_t)(2 * k), idesc, (uint32_t)(i != 0 || k >= kCh1));
               tc::umma_commit(&empty_bar[s]);
             }
           }
@@ -666,7 +676,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
           tpar ^= 1u;
           tc::fence_after_sync();
           float pv[16];
-          tmem_ld16_sum(lane_taddr + (uint32_t)s0, (uint32_t)NB, kChains, pv);
+          tmem_ld16_sum(lane_taddr + (uint32_t)s0, (uint32_t)NB, kCh1, pv);
           tc::fence_before_sync();
           const uint32_t owner = (uint32_t)(ph.first + tile * ph.ks);
           const uint32_t dst = mapa_u32(tc::smem_u32(pbuf + (size_t)(g * 4) * 128 + lrow), owner);
@@ -696,7 +706,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
           const float cb_prev = it > 0 ? cf_prev.x / cf_prev.y : 0.f;   // c2 / sqrt(alpha) of the previous step (forward(): 1)
           const float t_e = cb_prev * t_g;                              // the eps bias of the previous step, seen through G_0
           float a2[16];
-          const int nch = (ph.dual && ph.ks == 1) ? 2 : kChains;   // chains of the (first) accumulator
+          const int nch = (ph.dual && ph.ks == 1) ? kCh2 : kCh1;   // chains of the (first) accumulator
           tmem_ld16_sum(lane_taddr + (uint32_t)s0, (uint32_t)NB, nch, v);
           if (ph.cadd_col >= 0 && !eps_tile) {
             // one association for every mode (uniform t: t_t = T[t], c = C[c_r]; per-row t: t_t = 0, c = C[c_r] + T[t_r]), so
@@ -709,7 +719,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = (v[j] + (t_b + t_t)) - t_e;
           }
-          if (ph.dual && ph.ks == 1) tmem_ld16_sum(lane_taddr + (uint32_t)(2 * NB + s0), (uint32_t)NB, 2, a2);
+          if (ph.dual && ph.ks == 1) tmem_ld16_sum(lane_taddr + (uint32_t)(kCh2 * NB + s0), (uint32_t)NB, kCh2, a2);
           tc::fence_before_sync();            // ordered before the next phase's MMAs through the hand-over
           if (ph.ks > 1) {   // the partner unit's accumulator: acc2 of a dual phase (or the other K half of a plain one)
             if (et == 0) tc::mbar_arrive_expect_tx(&pbar, G::kPbufBytes);
@@ -1225,9 +1235,10 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
 
 // Batch rows per cluster for a batch of B rows: the variant with the fewest waves of co-resident clusters, then the
 // fewest rows per cluster (shortest epilogue).
-static int chain_pick_nw(int B) {
+static int chain_pick_nw(int B, int n_phases) {
   int best = 0, best_waves = 1 << 30;
-  for (int nw = 2; nw <= 3; ++nw) {   // NW = 4 (64 rows) does not fit 4 accumulation chains + the per-sample terms in 512 TMEM columns
+  for (int nw = 2; nw <= 4; ++nw) {
+    if ((kChains + n_phases + 1) * 16 * nw > kTmemCols) continue;   // accumulators + per-sample terms + parked noise must fit the TMEM columns
     if (g_chain_clusters[nw] < 1) continue;
     const int waves = ceil_div(ceil_div(B, 16 * nw), g_chain_clusters[nw]);
     if (waves < best_waves) { best_waves = waves; best = nw; }
@@ -1243,7 +1254,7 @@ int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const
   ChainModel& C = ctx->chain;
   LDM_CHECK(C.ready, "chain: weights not packed");
   LDM_CHECK(!sample || ctx->coef_dev != nullptr, "chain: schedule not set");
-  const int nw = chain_pick_nw(B);
+  const int nw = chain_pick_nw(B, C.n_phases);
   LDM_CHECK(nw >= 2, "chain: no cluster variant fits this device");
   const int NB = 16 * nw;
   ChainParams P;
