@@ -124,6 +124,7 @@ struct ChainParams {
   int ld_af;
   int writer_fence;           // 1: every writer thread issues fence.proxy.async before the hand-over; 0: the operand producer does
   int z_col;                  // TMEM column where the eps owners park the step's noise
+  int x_col;                  // TMEM column of the fp32 chain state of the eps owners
   int* err;                   // [2]: first failure code, detail
   long long* trace;           // profiling aid: [CS][2][64] clock64 stamps of cluster 0 in step trace_step (null: off); [0]: an h-warp thread, [1]: a u-warp thread
   int trace_step;
@@ -639,16 +640,20 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
     }
 
     // ---- the chain state of the rows / features this thread finishes in the eps tiles stays in registers
-    float xr[16];
+    // (kept in spare TMEM columns between the eps tiles' visits, so that it costs no registers in the other phases)
     const ChainPhase& ph0 = sphase[0];
     Unit eun;
     const bool eps_owner = unit_of(ph0, rank, true, eun);
     const int ef = eps_owner ? (eun.tile - ph0.nst_tiles) * 128 + lrow : 0;   // latent feature of this thread
     const float bfin = eps_owner ? __ldg(ph0.bias + eun.tile * 128 + lrow) : 0.f;   // (1 + s) b_f (v2:560-561)
+    if (eps_owner) {
+      float x0[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int r = row0 + s0 + j;
-      xr[j] = (eps_owner && r < P.row_end) ? P.x[(size_t)r * P.latent + ef] : 0.f;
+      for (int j = 0; j < 16; ++j) {
+        const int r = row0 + s0 + j;
+        x0[j] = r < P.row_end ? P.x[(size_t)r * P.latent + ef] : 0.f;
+      }
+      tmem_st16(lane_taddr + (uint32_t)(P.x_col + s0), x0);
     }
 
     for (int it = 0; it <= P.n_iter; ++it) {
@@ -698,6 +703,13 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
             if (ph.type == LDM_PH_MERGED) t_g = __ldg(ph.g0b + grow);
             if (ph.dual) t_q = __ldg(ph.q + grow);
           }
+          if (ph.dual) {
+            // (mu, r) of the operand rows: the previous phase's background statistics exchange lands while the tensor core
+            // is still busy with this phase; merged here, used after the accumulator wait
+            const uint32_t bb = (sidx0 - 1u) & 1u;
+            exchange_wait(bb, ph.prev_tiles, 11);
+            combine(bb, ph.prev_tiles, 64.0f);
+          }
           stamp();
           W.wait(&tmem_full_bar, tpar, 5);
           tpar ^= 1u;
@@ -733,13 +745,10 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
               else { v[4 * c] += a.x; v[4 * c + 1] += a.y; v[4 * c + 2] += a.z; v[4 * c + 3] += a.w; }
             }
           }
+          stamp();
           if (ph.dual) {
             // LayerNorm of the operand rows applied after the contraction: W2 . LN_b(h2) = r (W2' h2 - mu q) + const
-            // (gamma, beta folded into W2' / the bias at pack time).  (mu, r) of the 16 rows: the previous phase's
-            // background statistics exchange, long complete by now.
-            const uint32_t bb = (sidx0 - 1u) & 1u;
-            exchange_wait(bb, ph.prev_tiles, 11);
-            combine(bb, ph.prev_tiles, 64.0f);
+            // (gamma, beta folded into W2' / the bias at pack time); (mu, r) of the 16 rows were merged before the wait
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float2 mr = rs[j];
@@ -747,6 +756,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
             }
             __syncwarp();
           }
+          stamp();
         }
 
         if (ph.type == LDM_PH_STAGE || ph.type == LDM_PH_MERGED) {
@@ -820,6 +830,8 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
           //      v = W_f' . (-c_b [LN_f(h) | x]) = -c_b (eps - b_fin) of the previous iteration's forward.
           const float cb_prev = it > 0 ? cf_prev.x / cf_prev.y : 0.f;
           const float cb_cur = cf_cur.x / cf_cur.y;
+          float xr[16];
+          tc::tmem_ld16(lane_taddr + (uint32_t)(P.x_col + s0), xr);
           if (it > 0) {
             if (!P.sample) {
 #pragma unroll
@@ -840,6 +852,8 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
                   const int row = row0 + s0 + j;
                   if (row < P.row_end) P.x[(size_t)row * P.latent + ef] = xr[j];
                 }
+              } else {
+                tmem_st16(lane_taddr + (uint32_t)(P.x_col + s0), xr);
               }
             }
           }
@@ -1060,7 +1074,7 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
   for (void* p : C.allocs) cudaFree(p);
   C = ChainModel();
   const int nst = U.nst, L = U.latent;
-  LDM_CHECK(nst + 1 <= LDM_CHAIN_MAX_PHASES && kChains * 48 + (nst + 2) * 48 <= kTmemCols, "chain: too many stages (%d) for the TMEM-resident per-sample terms", nst);
+  LDM_CHECK(nst + 1 <= LDM_CHAIN_MAX_PHASES && kChains * 48 + (nst + 3) * 48 <= kTmemCols, "chain: too many stages (%d) for the TMEM-resident per-sample terms", nst);
   LDM_CHECK(L % 128 == 0 && L / 128 <= kSlots, "chain: latent_dim %d unsupported", L);
   for (int i = 0; i < nst; ++i)
     LDM_CHECK(U.hid[i] % 64 == 0 && U.hid[i] / 64 <= CS && U.hid[i] / 64 <= kSlots, "chain: hidden dim %d unsupported", U.hid[i]);
@@ -1238,7 +1252,7 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
 static int chain_pick_nw(int B, int n_phases) {
   int best = 0, best_waves = 1 << 30;
   for (int nw = 2; nw <= 4; ++nw) {
-    if ((kChains + n_phases + 1) * 16 * nw > kTmemCols) continue;   // accumulators + per-sample terms + parked noise must fit the TMEM columns
+    if ((kChains + n_phases + 2) * 16 * nw > kTmemCols) continue;   // accumulators + per-sample terms + parked noise + state must fit the TMEM columns
     if (g_chain_clusters[nw] < 1) continue;
     const int waves = ceil_div(ceil_div(B, 16 * nw), g_chain_clusters[nw]);
     if (waves < best_waves) { best_waves = waves; best = nw; }
@@ -1260,7 +1274,7 @@ int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const
   ChainParams P;
   memset(&P, 0, sizeof(P));
   const int nst = U.nst, L = U.latent;
-  LDM_CHECK(kChains * NB + (C.n_phases + 1) * NB <= kTmemCols, "chain: %d phases x %d rows exceed the TMEM columns", C.n_phases, NB);
+  LDM_CHECK(kChains * NB + (C.n_phases + 2) * NB <= kTmemCols, "chain: %d phases x %d rows exceed the TMEM columns", C.n_phases, NB);
   LDM_CHECK(nst + 2 <= kMaxXMaps, "chain: too many stages");
   // stage the first merged operand: [x | 0 | 0] (the stage tiles see G_0 x; the eps tiles have nothing to finish yet)
   LDM_TRY(launch_load_x<bf16>(ctx, x, ctx->caf[0], 3 * L, B, L, st));
@@ -1290,8 +1304,9 @@ int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const
   }
   for (int j = C.n_phases; j < LDM_CHAIN_MAX_PHASES; ++j) P.wmap[j] = C.ph[0].map;
   P.z_col = cadd;
+  P.x_col = cadd + NB;
   { const char* wf = getenv("LDM_CHAIN_WRITER_FENCE"); P.writer_fence = wf ? atoi(wf) : 0; }
-  LDM_CHECK(cadd + NB <= kTmemCols, "chain: TMEM columns exhausted (%d phases x %d rows)", C.n_phases, NB);
+  LDM_CHECK(cadd + 2 * NB <= kTmemCols, "chain: TMEM columns exhausted (%d phases x %d rows)", C.n_phases, NB);
   P.n_phases = C.n_phases;
   P.B = B; P.row_begin = 0; P.row_end = B;
   P.n_iter = n_iter; P.t_start = t_start; P.sample = sample; P.latent = L; P.n_t = U.n_t;
