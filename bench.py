@@ -30,7 +30,7 @@ FLOP_DECODE_PER_SAMPLE = 2_809_570_560
 N_STEPS = 1000
 LATENT = 256
 IMG_BYTES = 3 * 64 * 64 * 4
-CHAIN_DRAM_BYTES_PER_LAUNCH = 33_072_128 + 83_712   # ncu capture r01_f (see roofline.traffic_source)
+CHAIN_DRAM_BYTES_PER_LAUNCH = 33_692_160 + 111_360   # ncu capture r01_g (see roofline.traffic_source)
 
 
 def peaks():
@@ -43,8 +43,10 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons.  The sampler is started early (nvidia-smi takes a second to come up) and
+    every line carries a timestamp; stop(t0, t1) keeps the samples that fall inside the wall-clock window of the timed
+    region."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
@@ -55,11 +57,12 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                                          "-lms", "25"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -68,19 +71,27 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, every = [], [], set(), []
         for line in open(self.path):
-            f = [s.strip() for s in line.split(",")]
-            if len(f) < 9:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                v, m = float(f[2]), float(f[3])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
+            every.append((v, m))
+            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.05):
+                continue
+            sm.append(v); mx.append(m)
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[6:10]):
+                if val.lower().startswith("active"):
                     reasons.add(name)
         os.unlink(self.path)
+        if not sm and every:          # window shorter than the sampling period: fall back to the samples under load
+            hi = max(v for v, _ in every)
+            sm = [v for v, _ in every if v >= 0.5 * hi]; mx = [m for _, m in every]
         if sm:
             out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
         return out
@@ -146,7 +157,7 @@ def run_reference_arm(args, rank):
 # ------------------------------------------------------------------------------------------------------
 def loop_kernel_name(eng):
     if int(eng.info("chain")):
-        return "chain_kernel: the whole 1000-step loop is ONE persistent launch (16-CTA clusters x 48 samples, tcgen05 + TMA + DSMEM)"
+        return "chain_kernel: the whole 1000-step loop is ONE persistent launch (16-CTA clusters x 48 samples, 5 dependent tcgen05 contractions per step, TMA operands, DSMEM statistics)"
     return "sampling loop (one CUDA-graph launch = 1000 steps x %d kernels)" % int(eng.info("launches_per_step"))
 
 
@@ -159,6 +170,8 @@ def run_ours(args, rank, world, local_rank):
     torch.set_grad_enabled(False)
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     B, K, W = args.batch, args.steps, args.warmup
     prec = args.precision
 
@@ -201,10 +214,9 @@ def run_ours(args, rank, world, local_rank):
     # ---- device-timed region: K steps, L2 flushed between iterations (flush outside the event pairs)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(K)]
-    sampler = ClockSampler(local_rank)
     launches0 = eng.launches()
     barrier()
-    sampler.start()
+    t_win0 = time.time()
     for i in range(K):
         flush.zero_()
         s, m, e = ev[i]
@@ -216,7 +228,7 @@ def run_ours(args, rank, world, local_rank):
             dist.all_gather_into_tensor(gathered, img)
         e.record()
     barrier()
-    clocks = sampler.stop()
+    t_win1 = time.time()
     launches = eng.launches() - launches0
     t_loop_ms = sum(s.elapsed_time(m) for s, m, e in ev)
     t_total_ms = sum(s.elapsed_time(e) for s, m, e in ev)
@@ -232,6 +244,7 @@ def run_ours(args, rank, world, local_rank):
         eng.generate_host(c_host, img_host, None, seed=500 + i, sample_offset=lo)   # synchronous: returns with the images on the host
     barrier()
     t_e2e = time.perf_counter() - t0
+    clocks = sampler.stop(t_win0, time.time())   # clocks during the device-timed and the end-to-end regions
 
     if world > 1:
         t = torch.tensor([t_total_ms, t_loop_ms, t_e2e * 1000.0], device=dev, dtype=torch.float64)
@@ -260,13 +273,13 @@ def run_ours(args, rank, world, local_rank):
         "roofline": {"bound": "tensor", "kernel": loop_kernel_name(eng),
                      "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
                      "traffic": CHAIN_DRAM_BYTES_PER_LAUNCH if (prec == "bf16" and B == 256 and int(eng.info("chain"))) else None,
-                     "traffic_source": "ncu --set full, profiles/r01_f_chain_full_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum of one "
+                     "traffic_source": "ncu --set full, profiles/r01_g_chain_full_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum of one "
                                        "1000-step launch at B=256; weights and operands stay in L2, hit rate 96.7 %)",
                      "peak_source": pk["src"], "ms_per_launch": loop_s * 1000.0,
                      "algorithmic_flop_per_launch": loop_flops,
                      "note": "the loop is a chain of 5 dependent contractions per step x 1000 steps on 96 of 148 SMs: it is bound by "
                              "L2->SM operand latency and cluster hand-overs, not by the tensor pipe (DESIGN.md section 5); the decoder "
-                             "convolutions are the tensor-bound kernels (62 % tensor-pipe active in ncu, profiles/r01_f_conv_full_summary.txt)"},
+                             "convolutions are the tensor-bound kernels (62 % tensor-pipe active in ncu, profiles/r01_g_conv_full_summary.txt)"},
         "decode": {"ms": dec_s * 1000.0, "tflops": FLOP_DECODE_PER_SAMPLE * B / dec_s / 1e12 if dec_s > 0 else None},
     }
     if world == 1 and not args.no_cpu:

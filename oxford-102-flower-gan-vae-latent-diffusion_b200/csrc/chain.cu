@@ -1251,6 +1251,7 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
 // fewest rows per cluster (shortest epilogue).
 static int chain_pick_nw(int B, int n_phases) {
   int best = 0, best_waves = 1 << 30;
+  if (const char* f = getenv("LDM_CHAIN_NW")) { const int nw = atoi(f); if (nw >= 2 && nw <= 4 && g_chain_clusters[nw] >= 1) return nw; }
   for (int nw = 2; nw <= 4; ++nw) {
     if ((kChains + n_phases + 2) * 16 * nw > kTmemCols) continue;   // accumulators + per-sample terms + parked noise + state must fit the TMEM columns
     if (g_chain_clusters[nw] < 1) continue;

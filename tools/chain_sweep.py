@@ -47,7 +47,7 @@ import ctypes
 import numpy as np
 from ldm_b200 import _lib
 L = _lib.lib()
-B = 48
+B = int(os.environ.get("TRACE_B", "48"))
 c = (torch.arange(B) % 102).to(dev)
 x = eng.randn(B, 256, 1, 0, 1000)
 _lib.check(L.ldm_debug_chain_trace(eng.ctx, 20, None, 0))
