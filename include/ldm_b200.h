@@ -104,6 +104,39 @@ typedef struct ldm_decoder_weights {
   const float *fin3_w, *fin3_b;                       /* Conv2d(32,3,3) */
 } ldm_decoder_weights;
 
+/* v3 ConditionalUNet parameters (v3/model_train_test.py:769-803): flower + colour condition through
+ * MultiConditionEmbedding (v3:739-749) and per-stage cond_projections; nn.MultiheadAttention is used in full (its
+ * input (B,1,d) makes the B samples of a call attend to each other, v3:832-835); no final residual (v3:853). */
+typedef struct ldm_unet3_weights {
+  int32_t latent_dim, time_dim, num_classes, num_colors, n_stages;
+  int32_t hidden[LDM_MAX_STAGES + 1];
+  int32_t n_t;
+  const float* sinusoid;                         /* (n_t, time_dim), as in ldm_unet_weights */
+  const float *time_lin1_w, *time_lin1_b, *time_lin2_w, *time_lin2_b;
+  const float *flower_emb, *color_emb;           /* (num_classes, time_dim), (num_colors, time_dim) */
+  const float *cond_fc_w, *cond_fc_b;            /* Linear(2 time_dim, time_dim) */
+  const float *latent_proj_w, *latent_proj_b;
+  const float* time_proj_w[LDM_MAX_STAGES];
+  const float* time_proj_b[LDM_MAX_STAGES];
+  const float* cond_proj_w[LDM_MAX_STAGES];      /* cond_projections[i] v3:781 */
+  const float* cond_proj_b[LDM_MAX_STAGES];
+  const float* attn_in_proj_w[LDM_MAX_STAGES];   /* (3d, d): Q, K, V all used */
+  const float* attn_in_proj_b[LDM_MAX_STAGES];
+  const float* attn_out_w[LDM_MAX_STAGES];
+  const float* attn_out_b[LDM_MAX_STAGES];
+  const float* block_lin_w[LDM_MAX_STAGES];
+  const float* block_lin_b[LDM_MAX_STAGES];
+  const float* block_ln_w[LDM_MAX_STAGES];
+  const float* block_ln_b[LDM_MAX_STAGES];
+  const float* stage_ln_w[LDM_MAX_STAGES];
+  const float* stage_ln_b[LDM_MAX_STAGES];
+  const float* down_w[LDM_MAX_STAGES];
+  const float* down_b[LDM_MAX_STAGES];
+  const float *final_time_w, *final_time_b, *final_class_w, *final_class_b; /* v3:798-799 */
+  const float *final_norm_w, *final_norm_b;
+  const float *final_w, *final_b;
+} ldm_unet3_weights;
+
 LDM_API int ldm_version(void);
 LDM_API const char* ldm_last_error(void);
 
@@ -126,6 +159,13 @@ LDM_API int ldm_unet_pack(ldm_ctx* ctx, const ldm_unet_weights* w, void* stream)
  * c=None branch (v2:538,543,556).  Labels are range-checked on the device; an out-of-range
  * label makes the next synchronising call fail. */
 LDM_API int ldm_unet_set_classes(ldm_ctx* ctx, const int64_t* c_dev, int batch, void* stream);
+
+/* v3: pack the multi-conditional denoiser (v3:769-803) instead of the v2 one; ldm_unet_forward / ldm_sample /
+ * ldm_ddpm_step then run v3's forward(x, t, flower, color) / p_sample / sample (v3:804-893) on the conditions set
+ * with ldm_unet3_set_conditions.  Attention couples the rows of a call: a batch is one reference call. */
+LDM_API int ldm_unet3_pack(ldm_ctx* ctx, const ldm_unet3_weights* w, void* stream);
+LDM_API int ldm_unet3_set_conditions(ldm_ctx* ctx, const int64_t* flower_dev, const int64_t* color_dev, int batch,
+                             void* stream);
 
 /* ConditionalUNet.forward(x, t, c) (v2:535-561), eval mode. t_len is 1 or batch. */
 LDM_API int ldm_unet_forward(ldm_ctx* ctx, const float* x_dev, const int64_t* t_dev, int t_len,

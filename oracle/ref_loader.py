@@ -36,6 +36,13 @@ def load(version="v2"):
                 sys.modules[name] = types.ModuleType(name)
     if not hasattr(sys.modules["matplotlib"], "pyplot"):
         sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    if version == "v3":   # v3:25-26 mounts a Colab drive at import time
+        for name in ("google", "google.colab", "google.colab.drive"):
+            if name not in sys.modules:
+                sys.modules[name] = types.ModuleType(name)
+        sys.modules["google"].colab = sys.modules["google.colab"]
+        sys.modules["google.colab"].drive = sys.modules["google.colab.drive"]
+        sys.modules["google.colab.drive"].mount = lambda *a, **k: None
     spec = importlib.util.spec_from_file_location("_ldm_reference_" + version, path)
     mod = importlib.util.module_from_spec(spec)
     rng_state = torch.get_rng_state()

@@ -117,6 +117,60 @@ def unet_forward(sd, x, t, c=None, n_stages=None, v1=False, literal_attention=Fa
 
 
 # --------------------------------------------------------------------------
+# v3 multi-conditional denoiser: flower + colour condition, attention ACROSS the batch
+# --------------------------------------------------------------------------
+def multi_cond_embedding(sd, flower, color):
+    """MultiConditionEmbedding.forward v3:745-749."""
+    e = torch.cat((sd["multi_cond_emb.flower_emb.weight"][flower], sd["multi_cond_emb.color_emb.weight"][color]), dim=-1)
+    return F.linear(e, sd["multi_cond_emb.fc.weight"], sd["multi_cond_emb.fc.bias"])
+
+
+def batch_attention(n, w_in, b_in, w_out, b_out, heads=8):
+    """nn.MultiheadAttention on h_norm.unsqueeze(1) (v3:832-835): with batch_first=False that is (L=B, N=1, E), so the
+    B samples of a call attend to EACH OTHER.  Eval mode: no dropout."""
+    B, d = n.shape
+    hd = d // heads
+    qkv = F.linear(n, w_in, b_in)
+    q, k, v = (t.reshape(B, heads, hd).transpose(0, 1) for t in qkv.split(d, dim=1))     # (heads, B, hd)
+    p = torch.softmax((q * (hd ** -0.5)) @ k.transpose(1, 2), dim=-1)                      # (heads, B, B)
+    o = (p @ v).transpose(0, 1).reshape(B, d)
+    return F.linear(o, w_out, b_out)
+
+
+def unet3_forward(sd, x, t, flower, color, n_stages=None):
+    """v3 ConditionalUNet.forward v3:804-853 (eval mode): separate cond_projections (no double bias), real
+    cross-batch attention, and NO final residual (`return out`, v3:853; residual_weight is unused)."""
+    if n_stages is None:
+        n_stages = sum(1 for k in sd if k.startswith("layers.") and k.endswith(".2.weight"))
+    te = time_embedding(sd, t)                                   # v3:809
+    ce = multi_cond_embedding(sd, flower, color)                 # v3:810
+    h = F.linear(x, sd["latent_proj.weight"], sd["latent_proj.bias"])
+    for i in range(n_stages):
+        h = h + F.linear(te, sd[f"time_projections.{i}.weight"], sd[f"time_projections.{i}.bias"]) \
+              + F.linear(ce, sd[f"cond_projections.{i}.weight"], sd[f"cond_projections.{i}.bias"])   # v3:818-822
+        u = F.linear(h, sd[f"layers.{i}.0.0.weight"], sd[f"layers.{i}.0.0.bias"])
+        h = swish(_ln(u, sd, f"layers.{i}.0.1")) + h             # v3:825-827
+        n = _ln(h, sd, f"layers.{i}.1")                          # v3:830
+        h = h + batch_attention(n, sd[f"attention_layers.{i}.in_proj_weight"], sd[f"attention_layers.{i}.in_proj_bias"],
+                                sd[f"attention_layers.{i}.out_proj.weight"], sd[f"attention_layers.{i}.out_proj.bias"])
+        h = F.linear(h, sd[f"layers.{i}.2.weight"], sd[f"layers.{i}.2.bias"])   # v3:841
+    h = h + F.linear(te, sd["final_time_proj.weight"], sd["final_time_proj.bias"]) \
+          + F.linear(ce, sd["final_class_proj.weight"], sd["final_class_proj.bias"])   # v3:844-846
+    return F.linear(_ln(h, sd, "final_norm"), sd["final.weight"], sd["final.bias"])   # v3:849-853
+
+
+def sample3(sd, sched, x_T, flower, color, noise_fn=None, t_start=None, t_end=0):
+    """v3 ConditionalDenoiseDiffusion.sample / p_sample (v3:876-893) from a given x_T with supplied noise."""
+    n_steps = sched[0].shape[0]
+    x = x_T
+    t_start = n_steps - 1 if t_start is None else t_start
+    for t in range(t_start, t_end - 1, -1):
+        eps = unet3_forward(sd, x, torch.tensor([t]), flower, color)
+        x = ddpm_update(sched, x, eps, t, noise_fn(t) if (noise_fn is not None and t > 0) else None)
+    return x
+
+
+# --------------------------------------------------------------------------
 # DDPM reverse process (a2, a3)
 # --------------------------------------------------------------------------
 def p_sample(sd, sched, xt, t, c=None, noise=None, literal_attention=False):

@@ -49,6 +49,34 @@ def unet_spec(latent_dim=256, hidden=HIDDEN, temb=256, num_classes=102):
     return s
 
 
+def unet3_spec(latent_dim=256, hidden=HIDDEN, temb=256, num_classes=102, num_colors=10):
+    """v3 ConditionalUNet (v3:769-803), state_dict order: 91 tensors."""
+    s = [("residual_weight", (), "rw")]
+    def lin(name, o, i):
+        s.append((name + ".weight", (o, i), "w")); s.append((name + ".bias", (o,), "b"))
+    def ln(name, d):
+        s.append((name + ".weight", (d,), "g")); s.append((name + ".bias", (d,), "b"))
+    lin("time_emb.lin1", 2 * temb, temb); lin("time_emb.lin2", temb, 2 * temb)
+    s.append(("multi_cond_emb.flower_emb.weight", (num_classes, temb), "emb"))
+    s.append(("multi_cond_emb.color_emb.weight", (num_colors, temb), "emb"))
+    lin("multi_cond_emb.fc", temb, 2 * temb)
+    lin("latent_proj", hidden[0], latent_dim)
+    for i, d in enumerate(hidden):
+        lin(f"time_projections.{i}", d, temb)
+    for i, d in enumerate(hidden):
+        lin(f"cond_projections.{i}", d, temb)
+    for i, d in enumerate(hidden):
+        s.append((f"attention_layers.{i}.in_proj_weight", (3 * d, d), "xavier"))
+        s.append((f"attention_layers.{i}.in_proj_bias", (3 * d,), "b"))
+        lin(f"attention_layers.{i}.out_proj", d, d)
+    for i in range(len(hidden) - 1):
+        lin(f"layers.{i}.0.0", hidden[i], hidden[i]); ln(f"layers.{i}.0.1", hidden[i])
+        ln(f"layers.{i}.1", hidden[i]); lin(f"layers.{i}.2", hidden[i + 1], hidden[i])
+    lin("final_time_proj", hidden[-1], temb); lin("final_class_proj", hidden[-1], temb)
+    ln("final_norm", hidden[-1]); lin("final", latent_dim, hidden[-1])
+    return s
+
+
 def _resblock(s, name, c):
     for j in (1, 2):
         s.append((f"{name}.conv{j}.weight", (c, c, 3, 3), "w")); s.append((f"{name}.conv{j}.bias", (c,), "b"))
@@ -147,6 +175,10 @@ def make_state(spec, seed=42, style="init"):
 
 def make_unet_state(seed=42, style="init"):
     return make_state(unet_spec(), seed, style)
+
+
+def make_unet3_state(seed=44, style="init"):
+    return make_state(unet3_spec(), seed, style)
 
 
 def make_decoder_state(seed=43, style="init"):

@@ -31,6 +31,24 @@ class UnetWeights(ctypes.Structure):
     )
 
 
+class Unet3Weights(ctypes.Structure):
+    """ldm_unet3_weights (v3 multi-conditional denoiser)."""
+    _fields_ = (
+        [("latent_dim", ctypes.c_int32), ("time_dim", ctypes.c_int32), ("num_classes", ctypes.c_int32),
+         ("num_colors", ctypes.c_int32), ("n_stages", ctypes.c_int32), ("hidden", ctypes.c_int32 * (MAX_STAGES + 1)),
+         ("n_t", ctypes.c_int32), ("sinusoid", _vp),
+         ("time_lin1_w", _vp), ("time_lin1_b", _vp), ("time_lin2_w", _vp), ("time_lin2_b", _vp),
+         ("flower_emb", _vp), ("color_emb", _vp), ("cond_fc_w", _vp), ("cond_fc_b", _vp),
+         ("latent_proj_w", _vp), ("latent_proj_b", _vp)]
+        + [(n, _vp * MAX_STAGES) for n in (
+            "time_proj_w", "time_proj_b", "cond_proj_w", "cond_proj_b", "attn_in_proj_w", "attn_in_proj_b", "attn_out_w",
+            "attn_out_b", "block_lin_w", "block_lin_b", "block_ln_w", "block_ln_b", "stage_ln_w", "stage_ln_b", "down_w",
+            "down_b")]
+        + [(n, _vp) for n in ("final_time_w", "final_time_b", "final_class_w", "final_class_b",
+                              "final_norm_w", "final_norm_b", "final_w", "final_b")]
+    )
+
+
 class ResBlockWeights(ctypes.Structure):
     _fields_ = [(n, _vp) for n in ("conv1_w", "conv1_b", "ln1_w", "ln1_b", "conv2_w", "conv2_b", "ln2_w", "ln2_b",
                                    "ca_w0", "ca_w2", "sa_w")]
@@ -55,6 +73,8 @@ PROTOTYPES = {
     "ldm_set_schedule": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int]),
     "ldm_unet_pack": (ctypes.c_int, [_vp, ctypes.POINTER(UnetWeights), _vp]),
     "ldm_unet_set_classes": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),
+    "ldm_unet3_pack": (ctypes.c_int, [_vp, ctypes.POINTER(Unet3Weights), _vp]),
+    "ldm_unet3_set_conditions": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, _vp]),
     "ldm_unet_forward": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int, _vp]),
     "ldm_ddpm_step": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, _vp]),
     "ldm_randn": (ctypes.c_int, [_vp, _vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),

@@ -330,6 +330,11 @@ static int ensure_workspace(ldm_ctx* ctx, int B) {
       LDM_CUDA(cudaMemset(ctx->caf[k], 0, (size_t)cap * 3 * U.latent * sizeof(bf16)));
     }
   }
+  if (U.variant == 3) {
+    LDM_TRY(ldm_alloc_t(ctx, P, &ctx->qkv, (size_t)cap * 3 * U.dmax));
+    LDM_TRY(ldm_alloc(ctx, P, &ctx->a_op, nd * op));
+    LDM_CUDA(cudaMemset(ctx->a_op, 0, nd * op));
+  }
   LDM_TRY(ldm_alloc_t(ctx, P, &ctx->x_state, (size_t)cap * U.latent));
   LDM_TRY(ldm_alloc_t(ctx, P, &ctx->cls, (size_t)cap));
   // zero everything once: rows beyond the batch are read by full 128-row TMA boxes
@@ -344,8 +349,133 @@ static int ensure_workspace(ldm_ctx* ctx, int B) {
   return 0;
 }
 
+static int ensure_workspace(ldm_ctx* ctx, int B);
+
+// -------------------------------------------------------------------------------------------------
+// v3 multi-conditional denoiser (v3/model_train_test.py:739-853)
+// -------------------------------------------------------------------------------------------------
+extern "C" LDM_API int ldm_unet3_pack(ldm_ctx* ctx, const ldm_unet3_weights* w, void* stream) {
+  LDM_CHECK(ctx && w, "ldm_unet3_pack: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  LDM_CUDA(cudaSetDevice(ctx->device));
+  UnetModel& U = ctx->unet;
+  const int nst = w->n_stages;
+  LDM_CHECK(nst >= 1 && nst <= LDM_MAX_STAGES, "ldm_unet3_pack: n_stages %d out of range", nst);
+  LDM_CHECK(w->latent_dim % 64 == 0 && w->time_dim % 64 == 0 && w->latent_dim > 0 && w->time_dim > 0,
+            "ldm_unet3_pack: latent_dim and time_emb_dim must be multiples of 64");
+  for (int i = 0; i <= nst; ++i)
+    LDM_CHECK(w->hidden[i] % 128 == 0 && w->hidden[i] >= 128 && w->hidden[i] <= 1024,
+              "ldm_unet3_pack: hidden_dims[%d] = %d must be a multiple of 128 in [128, 1024]", i, w->hidden[i]);
+  LDM_CHECK(w->n_t >= 1 && w->num_classes >= 1 && w->num_colors >= 1 && w->sinusoid, "ldm_unet3_pack: sinusoid table missing");
+  LDM_CHECK(w->time_lin1_w && w->time_lin1_b && w->time_lin2_w && w->time_lin2_b && w->flower_emb && w->color_emb && w->cond_fc_w &&
+            w->cond_fc_b && w->latent_proj_w && w->latent_proj_b && w->final_time_w && w->final_time_b && w->final_class_w &&
+            w->final_class_b && w->final_norm_w && w->final_norm_b && w->final_w && w->final_b, "ldm_unet3_pack: weights missing");
+  cudaDeviceSynchronize();
+  drop_graphs(ctx);
+  free_pool(U.allocs);
+  U = UnetModel();
+  U.variant = 3;
+  U.latent = w->latent_dim; U.tdim = w->time_dim; U.ncolors = w->num_colors; U.ncls = w->num_classes * w->num_colors;
+  U.nst = nst; U.n_t = w->n_t;
+  for (int i = 0; i <= nst; ++i) { U.hid[i] = w->hidden[i]; U.dmax = U.hid[i] > U.dmax ? U.hid[i] : U.dmax; }
+  auto& P = U.allocs;
+  const int td = U.tdim, M_hint = 256;
+  // --- embeddings hoisted out of the loop: TE = time_emb(t) for every t, CE = multi_cond_emb(f, k) for every pair
+  float *sinus, *te1, *te, *pairs, *ce;
+  std::vector<void*> tmp;
+  LDM_TRY(own_copy(ctx, tmp, w->sinusoid, (size_t)U.n_t * td, &sinus, st));
+  LDM_TRY(ldm_alloc_t(ctx, tmp, &te1, (size_t)U.n_t * 2 * td));
+  LDM_TRY(ldm_alloc_t(ctx, tmp, &te, (size_t)U.n_t * td));
+  LDM_TRY(ldm_alloc_t(ctx, tmp, &pairs, (size_t)U.ncls * 2 * td));
+  LDM_TRY(ldm_alloc_t(ctx, tmp, &ce, (size_t)U.ncls * td));
+  {
+    Epilogue e; e.bias = w->time_lin1_b; e.act = LDM_ACT_SWISH; e.out_f32 = te1; e.ld_of = 2 * td;
+    LDM_TRY(launch_gemm_f32(ctx, sinus, td, w->time_lin1_w, U.n_t, 2 * td, td, e, st));
+    Epilogue e2; e2.bias = w->time_lin2_b; e2.out_f32 = te; e2.ld_of = td;
+    LDM_TRY(launch_gemm_f32(ctx, te1, 2 * td, w->time_lin2_w, U.n_t, td, 2 * td, e2, st));
+    LDM_TRY(launch_cond_pairs(ctx, w->flower_emb, w->color_emb, pairs, w->num_classes, w->num_colors, td, st));   // v3:746-748
+    Epilogue e3; e3.bias = w->cond_fc_b; e3.out_f32 = ce; e3.ld_of = td;
+    LDM_TRY(launch_gemm_f32(ctx, pairs, 2 * td, w->cond_fc_w, U.ncls, td, 2 * td, e3, st));                      // v3:749
+  }
+  for (int i = 0; i <= nst; ++i) {   // T_i[t] = time_projections[i](TE[t]); C_i[p] = cond_projections[i](CE[p])   (v3:818-822, 844-846)
+    const int d = U.hid[i];
+    const float* tw = i < nst ? w->time_proj_w[i] : w->final_time_w;
+    const float* tb = i < nst ? w->time_proj_b[i] : w->final_time_b;
+    const float* cw = i < nst ? w->cond_proj_w[i] : w->final_class_w;
+    const float* cb = i < nst ? w->cond_proj_b[i] : w->final_class_b;
+    LDM_CHECK(tw && tb && cw && cb, "ldm_unet3_pack: projection weights of stage %d missing", i);
+    LDM_TRY(ldm_alloc_t(ctx, P, &U.tab_t[i], (size_t)U.n_t * d));
+    LDM_TRY(ldm_alloc_t(ctx, P, &U.tab_c[i], (size_t)U.ncls * d));
+    Epilogue e; e.bias = tb; e.out_f32 = U.tab_t[i]; e.ld_of = d;
+    LDM_TRY(launch_gemm_f32(ctx, te, td, tw, U.n_t, d, td, e, st));
+    Epilogue e2; e2.bias = cb; e2.out_f32 = U.tab_c[i]; e2.ld_of = d;
+    LDM_TRY(launch_gemm_f32(ctx, ce, td, cw, U.ncls, d, td, e2, st));
+  }
+  LDM_TRY(dense_from(ctx, P, U.latent_proj, w->latent_proj_w, w->latent_proj_b, U.hid[0], U.latent, st));
+  LDM_TRY(finish_dense(ctx, P, U.latent_proj, M_hint, st));
+  for (int i = 0; i < nst; ++i) {
+    const int d = U.hid[i], dn = U.hid[i + 1];
+    LDM_CHECK(w->block_lin_w[i] && w->attn_in_proj_w[i] && w->attn_in_proj_b[i] && w->attn_out_w[i] && w->attn_out_b[i] &&
+              w->down_w[i] && w->block_ln_w[i] && w->stage_ln_w[i], "ldm_unet3_pack: weights of stage %d missing", i);
+    LDM_CHECK(d % 8 == 0 && d / 8 <= 128, "ldm_unet3_pack: head_dim %d unsupported", d / 8);
+    LDM_TRY(dense_from(ctx, P, U.block[i], w->block_lin_w[i], w->block_lin_b[i], d, d, st));
+    LDM_TRY(finish_dense(ctx, P, U.block[i], M_hint, st));
+    LDM_TRY(dense_from(ctx, P, U.qkv[i], w->attn_in_proj_w[i], w->attn_in_proj_b[i], 3 * d, d, st));
+    LDM_TRY(finish_dense(ctx, P, U.qkv[i], M_hint, st));
+    LDM_TRY(dense_from(ctx, P, U.attn_o[i], w->attn_out_w[i], w->attn_out_b[i], d, d, st));
+    LDM_TRY(finish_dense(ctx, P, U.attn_o[i], M_hint, st));
+    LDM_TRY(dense_from(ctx, P, U.down[i], w->down_w[i], w->down_b[i], dn, d, st));
+    LDM_TRY(finish_dense(ctx, P, U.down[i], M_hint, st));
+    LDM_TRY(own_copy(ctx, P, w->block_ln_w[i], d, &U.ln_a_w[i], st));
+    LDM_TRY(own_copy(ctx, P, w->block_ln_b[i], d, &U.ln_a_b[i], st));
+    LDM_TRY(own_copy(ctx, P, w->stage_ln_w[i], d, &U.ln_b_w[i], st));
+    LDM_TRY(own_copy(ctx, P, w->stage_ln_b[i], d, &U.ln_b_b[i], st));
+  }
+  LDM_TRY(own_copy(ctx, P, w->final_norm_w, U.hid[nst], &U.ln_f_w, st));
+  LDM_TRY(own_copy(ctx, P, w->final_norm_b, U.hid[nst], &U.ln_f_b, st));
+  {  // final(h) alone (`return out`, v3:853): the [W_f | s W_f] layout of the v2 path with s = sigmoid(-1e30) = 0
+    const int N = U.latent, K = U.hid[nst];
+    U.fin.N = N; U.fin.K = 2 * K;
+    float *s_dev, *rw_dev;
+    LDM_TRY(ldm_alloc_t(ctx, P, &U.fin.w32, (size_t)N * 2 * K));
+    LDM_TRY(ldm_alloc_t(ctx, P, &U.fin.b, (size_t)N));
+    LDM_TRY(ldm_alloc_t(ctx, tmp, &s_dev, 1));
+    LDM_TRY(ldm_alloc_t(ctx, tmp, &rw_dev, 1));
+    const float minus_big = -1e30f;
+    LDM_CUDA(cudaMemcpyAsync(rw_dev, &minus_big, sizeof(float), cudaMemcpyHostToDevice, st));
+    LDM_TRY(launch_pack_final(ctx, w->final_w, w->final_b, rw_dev, U.fin.w32, U.fin.b, s_dev, N, K, st));
+    LDM_TRY(finish_dense(ctx, P, U.fin, M_hint, st));
+    U.s_res = 0.f;
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  free_pool(tmp);
+  LDM_CUDA(e);
+  ctx->use_chain = 0;   // attention couples the rows of a call: the per-layer sequence runs v3
+  cudaDeviceSynchronize();
+  ctx->act_maps.clear();
+  free_pool(ctx->ws_allocs);
+  ctx->cap = 0;
+  ctx->batch_cls = -1;
+  ctx->has_cls = false;
+  U.packed = true;
+  return 0;
+}
+
+extern "C" LDM_API int ldm_unet3_set_conditions(ldm_ctx* ctx, const int64_t* flower_dev, const int64_t* color_dev, int batch,
+                                        void* stream) {
+  LDM_CHECK(ctx && flower_dev && color_dev && batch > 0, "ldm_unet3_set_conditions: bad arguments");
+  LDM_CHECK(ctx->unet.packed && ctx->unet.variant == 3, "ldm_unet3_set_conditions: pack a v3 denoiser first (ldm_unet3_pack)");
+  LDM_CUDA(cudaSetDevice(ctx->device));
+  LDM_TRY(ensure_workspace(ctx, batch));
+  ctx->batch_cls = batch;
+  ctx->has_cls = true;
+  const int nk = ctx->unet.ncolors;
+  return launch_set_conditions(ctx, flower_dev, color_dev, ctx->cls, batch, ctx->unet.ncls / nk, nk, ctx->dev_flags, (cudaStream_t)stream);
+}
+
 extern "C" LDM_API int ldm_unet_set_classes(ldm_ctx* ctx, const int64_t* c_dev, int batch, void* stream) {
   LDM_CHECK(ctx && batch > 0, "ldm_unet_set_classes: bad arguments");
+  LDM_CHECK(ctx->unet.variant != 3, "ldm_unet_set_classes: a v3 denoiser takes (flower, color): use ldm_unet3_set_conditions");
   LDM_CUDA(cudaSetDevice(ctx->device));
   LDM_TRY(ensure_workspace(ctx, batch));
   ctx->batch_cls = batch;
@@ -416,7 +546,15 @@ static int denoise(ldm_ctx* ctx, int B, int parity, const StepMode& md, cudaStre
     }
     // h2 = swish(LN_a(u)) + h ; n = LN_b(h2)                                  (v2:520-522,547-549)
     LDM_TRY(launch_stage_mid<TOP>(ctx, ctx->u, ctx->h, U.ln_a_w[i], U.ln_a_b[i], U.ln_b_w[i], U.ln_b_b[i], ctx->h2, n_op, d, B, d, st));
-    {  // h3 = h2 + out_proj(V(n))                                             (v2:550-552)
+    if (U.variant == 3) {  // h3 = h2 + out_proj(softmax(Q K^T / sqrt(hd)) V) over the rows of the call   (v3:832-838)
+      Epilogue eq; eq.bias = U.qkv[i].b; eq.out_f32 = ctx->qkv; eq.ld_of = 3 * d;
+      LDM_TRY(gemm<TOP>(ctx, n_op, d, B, U.qkv[i], eq, st));
+      LDM_TRY(launch_batch_attention<TOP>(ctx, ctx->qkv, (TOP*)ctx->a_op, B, d, 8, st));
+      Epilogue e; e.bias = U.attn_o[i].b; e.resid = ctx->h2; e.ld_r = d;
+      if constexpr (std::is_same<TOP, float>::value) { e.out_f32 = (float*)h3_op; e.ld_of = d; }
+      else { e.out_bf16 = h3_op; e.ld_ob = d; }
+      LDM_TRY(gemm<TOP>(ctx, (TOP*)ctx->a_op, d, B, U.attn_o[i], e, st));
+    } else {  // h3 = h2 + out_proj(V(n))                                      (v2:550-552)
       Epilogue e; e.bias = U.ov[i].b; e.resid = ctx->h2; e.ld_r = d;
       if constexpr (std::is_same<TOP, float>::value) { e.out_f32 = (float*)h3_op; e.ld_of = d; }
       else { e.out_bf16 = h3_op; e.ld_ob = d; }
@@ -665,7 +803,7 @@ extern "C" LDM_API int ldm_get_info(ldm_ctx* ctx, const char* key, double* out) 
   if (!strcmp(key, "chain_peak_bytes_per_step")) { *out = ctx->chain.peak_bytes_per_step; return 0; }
   if (!strcmp(key, "launches_per_step")) {
     if (ctx->use_chain) { *out = 0.0; return 0; }                // the loop is one launch
-    *out = ctx->unet.packed ? 3.0 + 4.0 * ctx->unet.nst : 0.0;   // G0, (G1, R1, G2, G3) x stages, R_f, G_f
+    *out = ctx->unet.packed ? 3.0 + (ctx->unet.variant == 3 ? 6.0 : 4.0) * ctx->unet.nst : 0.0;   // G0, (G1, R1, G2[, A, G2b], G3) x stages, R_f, G_f
     return 0;
   }
   if (!strcmp(key, "device_flags")) {   // bit 0: class label out of range, bit 1: timestep out of range (clears the flags)

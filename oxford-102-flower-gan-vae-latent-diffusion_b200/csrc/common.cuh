@@ -126,6 +126,9 @@ struct UnetModel {
   DenseLayer latent_proj;
   DenseLayer block[LDM_MAX_STAGES], ov[LDM_MAX_STAGES], down[LDM_MAX_STAGES];
   DenseLayer fin;                               // K = hid[nst] + latent : [W_f | s W_f], bias (1+s) b_f
+  int variant = 2;                              // 2: v2 (L = 1 attention folded into ov); 3: v3 (attention across the batch)
+  int ncolors = 1;                              // v3: ncls = num_classes * num_colors condition pairs
+  DenseLayer qkv[LDM_MAX_STAGES], attn_o[LDM_MAX_STAGES];   // v3: in_proj (3d x d) and out_proj
   float *ln_a_w[LDM_MAX_STAGES], *ln_a_b[LDM_MAX_STAGES];  // layers[i][0][1]
   float *ln_b_w[LDM_MAX_STAGES], *ln_b_b[LDM_MAX_STAGES];  // layers[i][1]
   float *ln_f_w = nullptr, *ln_f_b = nullptr;
@@ -229,6 +232,8 @@ struct ldm_ctx {
   float *h = nullptr, *u = nullptr, *h2 = nullptr;   // (cap, dmax) fp32
   void *h_op = nullptr, *n_op = nullptr, *h3_op = nullptr;  // operand-typed (fp32 or bf16)
   void* af_op[2] = {nullptr, nullptr};  // [LN_f(h) | x] operand of the final GEMM, double-buffered across steps
+  float* qkv = nullptr;                 // v3: (cap, 3 dmax) fp32 projections
+  void* a_op = nullptr;                 // v3: attention output, operand of out_proj
   float* x_state = nullptr;       // (cap, latent) fp32 chain state the captured graph works on
   unsigned long long* rng_dev = nullptr;  // {seed, sample_offset}
   cudaStream_t cap_stream = nullptr;      // capture-only stream (the caller may be on the legacy stream)
@@ -307,6 +312,11 @@ template <typename TOP>
 int launch_load_x(ldm_ctx* ctx, const float* x, TOP* dst, int ld_dst, int M, int d, cudaStream_t st);
 int launch_set_classes(ldm_ctx* ctx, const int64_t* c, int32_t* out, int M, int ncls, int* flags,
                        cudaStream_t st);
+int launch_set_conditions(ldm_ctx* ctx, const int64_t* f, const int64_t* k, int32_t* out, int M, int nf, int nk, int* flags,
+                          cudaStream_t st);
+int launch_cond_pairs(ldm_ctx* ctx, const float* fe, const float* ke, float* out, int nf, int nk, int td, cudaStream_t st);
+template <typename TOP>
+int launch_batch_attention(ldm_ctx* ctx, const float* qkv, TOP* out, int B, int d, int heads, cudaStream_t st);
 int launch_check_t(ldm_ctx* ctx, const int64_t* t, int n, int n_t, int* flags, cudaStream_t st);
 int launch_ddpm_update(ldm_ctx* ctx, float* x, const float* eps, float c2, float sqrt_alpha, float sigma,
                        const float* noise, unsigned long long seed, unsigned long long sample_offset,

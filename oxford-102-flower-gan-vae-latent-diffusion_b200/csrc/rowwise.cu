@@ -163,6 +163,81 @@ __global__ void set_classes_kernel(const int64_t* __restrict__ c, int32_t* __res
   out[i] = (int32_t)v;
 }
 
+// v3: condition pair index f * nk + k of every row (range-checked like nn.Embedding would)
+__global__ void set_conditions_kernel(const int64_t* __restrict__ f, const int64_t* __restrict__ k, int32_t* __restrict__ out,
+                                      int M, int nf, int nk, int* __restrict__ flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  long long a = f[i], b = k[i];
+  if (a < 0 || a >= nf) { atomicOr(flags, 1); a = a < 0 ? 0 : nf - 1; }
+  if (b < 0 || b >= nk) { atomicOr(flags, 1); b = b < 0 ? 0 : nk - 1; }
+  out[i] = (int32_t)(a * nk + b);
+}
+// v3: out[(f * nk + k)] = [flower_emb[f] | color_emb[k]]   (torch.cat of v3:748)
+__global__ void cond_pairs_kernel(const float* __restrict__ fe, const float* __restrict__ ke, float* __restrict__ out, int nf,
+                                  int nk, int td) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)nf * nk * 2 * td) return;
+  const int e = (int)(i % (2 * td));
+  const int p = (int)(i / (2 * td)), a = p / nk, b = p - a * nk;
+  out[i] = e < td ? fe[(size_t)a * td + e] : ke[(size_t)b * td + (e - td)];
+}
+
+// v3 attention ACROSS the batch (v3:832-835, nn.MultiheadAttention on (L = B, N = 1, E = d), eval mode):
+//   out[i, h*hd:(h+1)*hd] = sum_j softmax_j(q_i . k_j / sqrt(hd)) v_j     per head h.
+// qkv: (B, 3d) fp32 = [Q | K | V].  One warp per (query row, head); 32 keys per tile, lane j scores key j, online
+// softmax in fp32, lanes own output dims e = lane, lane + 32, ...
+template <typename TOP>
+__global__ void __launch_bounds__(128)
+batch_attention_kernel(const float* __restrict__ qkv, TOP* __restrict__ out, int B, int d, int hd) {
+  extern __shared__ float sm[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y, row = blockIdx.x * 4 + w;
+  float* ks = sm;                          // [32][hd + 1]
+  float* vs = ks + 32 * (hd + 1);          // [32][hd + 1]
+  float* qs = vs + 32 * (hd + 1) + w * hd; // this warp's query row
+  const float scale = rsqrtf((float)hd);
+  const bool valid = row < B;
+  if (valid)
+    for (int e = lane; e < hd; e += 32) qs[e] = qkv[(size_t)row * 3 * d + head * hd + e] * scale;   // q * hd^-0.5 as torch does
+  float m = -INFINITY, l = 0.f;
+  float o[4] = {0.f, 0.f, 0.f, 0.f};       // hd <= 128: 4 dims per lane
+  for (int j0 = 0; j0 < B; j0 += 32) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 32 * hd; idx += 128) {
+      const int j = idx / hd, e = idx - j * hd;
+      const bool in = j0 + j < B;
+      ks[j * (hd + 1) + e] = in ? qkv[(size_t)(j0 + j) * 3 * d + d + head * hd + e] : 0.f;
+      vs[j * (hd + 1) + e] = in ? qkv[(size_t)(j0 + j) * 3 * d + 2 * d + head * hd + e] : 0.f;
+    }
+    __syncthreads();
+    if (!valid) continue;
+    float s = 0.f;
+    for (int e = 0; e < hd; ++e) s += qs[e] * ks[lane * (hd + 1) + e];
+    if (j0 + lane >= B) s = -INFINITY;
+    const float mt = warp_max(s);
+    const float mn = fmaxf(m, mt);
+    const float p = __expf(s - mn);
+    const float corr = __expf(m - mn);
+    l = l * corr + warp_sum(p);
+    m = mn;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o[c] *= corr;
+    for (int j = 0; j < 32; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, p, j);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c * 32 + lane < hd) o[c] += pj * vs[j * (hd + 1) + c * 32 + lane];
+    }
+  }
+  if (valid) {
+    const float inv = 1.0f / l;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c * 32 + lane < hd) out[(size_t)row * d + head * hd + c * 32 + lane] = from_f32<TOP>(o[c] * inv);
+  }
+}
+
 __global__ void check_t_kernel(const int64_t* __restrict__ t, int n, int n_t, int* __restrict__ flags) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -282,6 +357,30 @@ int launch_set_classes(ldm_ctx* ctx, const int64_t* c, int32_t* out, int M, int 
   LDM_LAUNCHED(ctx);
   return 0;
 }
+
+int launch_set_conditions(ldm_ctx* ctx, const int64_t* f, const int64_t* k, int32_t* out, int M, int nf, int nk, int* flags,
+                          cudaStream_t st) {
+  set_conditions_kernel<<<ceil_div(M, 256), 256, 0, st>>>(f, k, out, M, nf, nk, flags);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+int launch_cond_pairs(ldm_ctx* ctx, const float* fe, const float* ke, float* out, int nf, int nk, int td, cudaStream_t st) {
+  const size_t n = (size_t)nf * nk * 2 * td;
+  cond_pairs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(fe, ke, out, nf, nk, td);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+template <typename TOP>
+int launch_batch_attention(ldm_ctx* ctx, const float* qkv, TOP* out, int B, int d, int heads, cudaStream_t st) {
+  const int hd = d / heads;
+  LDM_CHECK(d % heads == 0 && hd <= 128, "batch_attention: head_dim %d unsupported (d=%d)", hd, d);
+  const size_t smem = ((size_t)64 * (hd + 1) + 4 * hd) * sizeof(float);
+  batch_attention_kernel<TOP><<<dim3(ceil_div(B, 4), heads), 128, smem, st>>>(qkv, out, B, d, hd);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+template int launch_batch_attention<float>(ldm_ctx*, const float*, float*, int, int, int, cudaStream_t);
+template int launch_batch_attention<bf16>(ldm_ctx*, const float*, bf16*, int, int, int, cudaStream_t);
 
 int launch_check_t(ldm_ctx* ctx, const int64_t* t, int n, int n_t, int* flags, cudaStream_t st) {
   check_t_kernel<<<ceil_div(n, 256), 256, 0, st>>>(t, n, n_t, flags);

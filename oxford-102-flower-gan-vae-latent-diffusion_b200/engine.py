@@ -159,6 +159,81 @@ class Engine:
         self._unet_key = key
         self._cls_key = None
 
+    def pack_unet3(self, m, n_t):
+        """v3 multi-conditional denoiser (ldm_unet3_pack)."""
+        key = _state_key(m, (n_t, "v3"))
+        if key == self._unet_key:
+            return
+        dev, keep = self.device, []
+        def P(t):
+            v = _f32(t, dev); keep.append(v); return v.data_ptr()
+        w = _lib.Unet3Weights()
+        hidden = list(m.hidden_dims)
+        nst = len(hidden) - 1
+        if nst > _lib.MAX_STAGES:
+            raise ValueError("at most %d stages are supported" % _lib.MAX_STAGES)
+        w.latent_dim, w.time_dim, w.num_classes, w.num_colors = m.latent_dim, m.time_emb_dim, m.num_classes, m.num_colors
+        w.n_stages, w.n_t = nst, n_t
+        for i, d in enumerate(hidden):
+            w.hidden[i] = d
+        w.sinusoid = P(m.time_emb.sinusoid_table(n_t))
+        w.time_lin1_w, w.time_lin1_b = P(m.time_emb.lin1.weight), P(m.time_emb.lin1.bias)
+        w.time_lin2_w, w.time_lin2_b = P(m.time_emb.lin2.weight), P(m.time_emb.lin2.bias)
+        w.flower_emb, w.color_emb = P(m.multi_cond_emb.flower_emb.weight), P(m.multi_cond_emb.color_emb.weight)
+        w.cond_fc_w, w.cond_fc_b = P(m.multi_cond_emb.fc.weight), P(m.multi_cond_emb.fc.bias)
+        w.latent_proj_w, w.latent_proj_b = P(m.latent_proj.weight), P(m.latent_proj.bias)
+        for i in range(nst):
+            w.time_proj_w[i], w.time_proj_b[i] = P(m.time_projections[i].weight), P(m.time_projections[i].bias)
+            w.cond_proj_w[i], w.cond_proj_b[i] = P(m.cond_projections[i].weight), P(m.cond_projections[i].bias)
+            att = m.attention_layers[i]
+            w.attn_in_proj_w[i], w.attn_in_proj_b[i] = P(att.in_proj_weight), P(att.in_proj_bias)
+            w.attn_out_w[i], w.attn_out_b[i] = P(att.out_proj.weight), P(att.out_proj.bias)
+            block, ln, down = m.layers[i]
+            w.block_lin_w[i], w.block_lin_b[i] = P(block[0].weight), P(block[0].bias)
+            w.block_ln_w[i], w.block_ln_b[i] = P(block[1].weight), P(block[1].bias)
+            w.stage_ln_w[i], w.stage_ln_b[i] = P(ln.weight), P(ln.bias)
+            w.down_w[i], w.down_b[i] = P(down.weight), P(down.bias)
+        w.final_time_w, w.final_time_b = P(m.final_time_proj.weight), P(m.final_time_proj.bias)
+        w.final_class_w, w.final_class_b = P(m.final_class_proj.weight), P(m.final_class_proj.bias)
+        w.final_norm_w, w.final_norm_b = P(m.final_norm.weight), P(m.final_norm.bias)
+        w.final_w, w.final_b = P(m.final.weight), P(m.final.bias)
+        check(lib().ldm_unet3_pack(self.ctx, ctypes.byref(w), self.stream()), "ldm_unet3_pack")
+        self._unet_key = key
+        self._cls_key = None
+
+    def set_conditions(self, flower, color, batch):
+        f = flower.detach().to(device=self.device, dtype=torch.int64).contiguous()
+        k = color.detach().to(device=self.device, dtype=torch.int64).contiguous()
+        if f.dim() != 1 or f.numel() != batch or k.shape != f.shape:
+            raise ValueError("flower / color labels must both have shape (%d,)" % batch)
+        check(lib().ldm_unet3_set_conditions(self.ctx, _ptr(f), _ptr(k), batch, self.stream()), "ldm_unet3_set_conditions")
+        return f, k
+
+    def unet3_forward(self, x, t, flower, color):
+        x = x.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        B = x.shape[0]
+        t = t.detach().to(device=self.device, dtype=torch.int64).contiguous().reshape(-1)
+        if t.numel() not in (1, B):
+            raise ValueError("t must have 1 or %d entries, got %d" % (B, t.numel()))
+        keep = self.set_conditions(flower, color, B)
+        out = torch.empty_like(x)
+        check(lib().ldm_unet_forward(self.ctx, _ptr(x), _ptr(t), t.numel(), _ptr(out), B, self.stream()), "ldm_unet_forward")
+        del keep
+        return out
+
+    def sample3(self, x, t_start, t_end, flower, color, noise=None, seed=0, sample_offset=0, use_graph=True):
+        """In-place v3 chain on x (B, latent) for t = t_start .. t_end."""
+        B = x.shape[0]
+        keep = self.set_conditions(flower, color, B)
+        if noise is not None:
+            noise = noise.detach().to(device=self.device, dtype=torch.float32).contiguous()
+            if noise.shape != (t_start - t_end + 1, B, x.shape[1]):
+                raise ValueError("noise must have shape (%d, %d, %d)" % (t_start - t_end + 1, B, x.shape[1]))
+        check(lib().ldm_sample(self.ctx, _ptr(x), int(t_start), int(t_end), _ptr(noise) if noise is not None else None,
+                               seed, sample_offset, B, 1 if use_graph else 0, self.stream()), "ldm_sample")
+        del keep
+        return x
+
     def set_classes(self, c, batch):
         if c is None:
             check(lib().ldm_unet_set_classes(self.ctx, None, batch, self.stream()), "ldm_unet_set_classes")
