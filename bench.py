@@ -176,13 +176,18 @@ def run_ours(args, rank, world, local_rank):
     prec = args.precision
 
     # random-init weights of the named architecture (ConditionalUNet + init_weights, SimpleAutoencoder())
-    unet = ldm_b200.ConditionalUNet(precision=prec)
-    unet.load_state_dict(weights.make_unet_state(42, "init"), strict=True)
+    v3 = args.workload == "v3"
+    if v3:
+        unet = ldm_b200.v3.ConditionalUNet(precision=prec)
+        unet.load_state_dict(weights.make_unet3_state(44, "init"), strict=True)
+    else:
+        unet = ldm_b200.ConditionalUNet(precision=prec)
+        unet.load_state_dict(weights.make_unet_state(42, "init"), strict=True)
     unet = unet.to(dev).eval()
     ae = ldm_b200.SimpleAutoencoder(precision=prec)
     ae.load_state_dict(weights.make_autoencoder_state(43, "init"), strict=True)
     ae = ae.to(dev).eval()
-    diffusion = ldm_b200.ConditionalDenoiseDiffusion(unet, N_STEPS, dev)
+    diffusion = (ldm_b200.v3 if v3 else ldm_b200).ConditionalDenoiseDiffusion(unet, N_STEPS, dev)
     eng = unet.engine(dev, N_STEPS)
     eng.set_schedule(*diffusion._host_schedule)
     eng.pack_decoder(ae.decoder)
@@ -194,8 +199,15 @@ def run_ours(args, rank, world, local_rank):
     gathered = torch.empty(total, 3, 64, 64, device=dev) if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
+    k_dev = ((torch.arange(total) * 7) % 10)[lo:lo + B].to(dev)     # v3: colour labels
+
+    def draw(seed):
+        if v3:
+            return diffusion.sample((B, LATENT), dev, c_dev, k_dev, seed=seed, sample_offset=lo)
+        return diffusion.sample((B, LATENT), dev, c_dev, seed=seed, sample_offset=lo)
+
     def step(i):
-        x0 = diffusion.sample((B, LATENT), dev, c_dev, seed=1234 + i, sample_offset=lo)
+        x0 = draw(1234 + i)
         img = ae.decode(x0)
         if world > 1:
             dist.all_gather_into_tensor(gathered, img)
@@ -221,7 +233,7 @@ def run_ours(args, rank, world, local_rank):
         flush.zero_()
         s, m, e = ev[i]
         s.record()
-        x0 = diffusion.sample((B, LATENT), dev, c_dev, seed=99 + i, sample_offset=lo)
+        x0 = draw(99 + i)
         m.record()
         img = ae.decode(x0)
         if world > 1:
@@ -237,11 +249,22 @@ def run_ours(args, rank, world, local_rank):
     # ---- end to end through the host-buffer entry point: pinned labels in, pinned images out, every step
     c_host = classes[lo:lo + B].clone().pin_memory()
     img_host = torch.empty(B, 3, 64, 64).pin_memory()
-    eng.generate_host(c_host, img_host, None, seed=5, sample_offset=lo)
+    if v3:
+        k_host = k_dev.cpu().pin_memory()
+
+        def host_call(seed):   # v3 has no single C entry point with host buffers yet: pinned labels in, pinned images out
+            f_d, k_d = c_host.to(dev, non_blocking=True), k_host.to(dev, non_blocking=True)
+            z = diffusion.sample((B, LATENT), dev, f_d, k_d, seed=seed, sample_offset=lo)
+            img_host.copy_(ae.decode(z), non_blocking=True)
+            torch.cuda.synchronize()
+    else:
+        def host_call(seed):
+            eng.generate_host(c_host, img_host, None, seed=seed, sample_offset=lo)   # synchronous: returns with the images on the host
+    host_call(5)
     barrier()
     t0 = time.perf_counter()
     for i in range(K):
-        eng.generate_host(c_host, img_host, None, seed=500 + i, sample_offset=lo)   # synchronous: returns with the images on the host
+        host_call(500 + i)
     barrier()
     t_e2e = time.perf_counter() - t0
     clocks = sampler.stop(t_win0, time.time())   # clocks during the device-timed and the end-to-end regions
@@ -255,7 +278,8 @@ def run_ours(args, rank, world, local_rank):
         return
     pk = peaks()
     value = total * K / (t_total_ms / 1000.0)
-    loop_flops = FLOP_DENOISER_PER_SAMPLE_STEP * B * N_STEPS                      # per graph launch, per GPU
+    flop_step = FLOP_DENOISER_PER_SAMPLE_STEP if not v3 else 2 * (9_633_792 + 2 * B * 2304)   # v3: + Q, K projections and B x B attention
+    loop_flops = flop_step * B * N_STEPS                                          # per graph launch, per GPU
     loop_s = t_loop_ms / 1000.0 / K
     achieved = loop_flops / loop_s / 1e12
     dec_s = (t_total_ms - t_loop_ms) / 1000.0 / K
@@ -263,16 +287,17 @@ def run_ours(args, rank, world, local_rank):
         "metric": "samples/s (1000-step DDPM + VAE decode)", "value": value, "unit": "samples/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_total_ms / K, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if prec == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": "v2 latent U-Net 1000-step sampling + VAE decode, batch %d per GPU%s" %
+        "config": {"workload": ("v3 multi-conditional (class + color) latent U-Net" if v3 else "v2 latent U-Net") +
+                               " 1000-step sampling + VAE decode, batch %d per GPU%s" %
                                (B, "" if world == 1 else ", %d total, final NCCL all-gather of images" % total),
                    "batch_per_gpu": B, "global_batch": total, "n_steps": N_STEPS, "precision": prec,
                    "l2": "flushed (256 MiB write) between timed iterations", "weights": "random-init (seeded), eval mode"},
-        "e2e": {"value": total * K / t_e2e, "unit": "samples/s", "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": B * IMG_BYTES},
+        "e2e": {"value": total * K / t_e2e, "unit": "samples/s", "h2d_bytes_per_step": B * (16 if v3 else 8), "d2h_bytes_per_step": B * IMG_BYTES},
         "gpu_launches": int(launches),
         "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
         "roofline": {"bound": "tensor", "kernel": loop_kernel_name(eng),
                      "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
-                     "traffic": CHAIN_DRAM_BYTES_PER_LAUNCH if (prec == "bf16" and B == 256 and int(eng.info("chain"))) else None,
+                     "traffic": CHAIN_DRAM_BYTES_PER_LAUNCH if (prec == "bf16" and B == 256 and not v3 and int(eng.info("chain"))) else None,
                      "traffic_source": "ncu --set full, profiles/r01_g_chain_full_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum of one "
                                        "1000-step launch at B=256; weights and operands stay in L2, hit rate 96.7 %)",
                      "peak_source": pk["src"], "ms_per_launch": loop_s * 1000.0,
@@ -298,11 +323,20 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="samples per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="v2", choices=["v2", "v3"],
+                    help="v2: BASELINE configs[1]/[2] (default). v3: configs[3], multi-conditional denoiser, --batch rows per GPU (default 128), each GPU one reference call")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
+    if args.workload == "v3":
+        if "--batch" not in " ".join(sys.argv):
+            args.batch = 128
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the v3 workload is a secondary line; the reference arm covers the v2 headline"}))
+            return
+    elif args.impl == "reference":
         run_reference_arm(args, rank)
         return
     if world > 1:

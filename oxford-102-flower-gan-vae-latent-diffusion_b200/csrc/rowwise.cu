@@ -187,54 +187,79 @@ __global__ void cond_pairs_kernel(const float* __restrict__ fe, const float* __r
 //   out[i, h*hd:(h+1)*hd] = sum_j softmax_j(q_i . k_j / sqrt(hd)) v_j     per head h.
 // qkv: (B, 3d) fp32 = [Q | K | V].  One warp per (query row, head); 32 keys per tile, lane j scores key j, online
 // softmax in fp32, lanes own output dims e = lane, lane + 32, ...
-template <typename TOP>
-__global__ void __launch_bounds__(128)
-batch_attention_kernel(const float* __restrict__ qkv, TOP* __restrict__ out, int B, int d, int hd) {
-  extern __shared__ float sm[];
+template <typename TOP, int HD>
+__global__ void __launch_bounds__(256)
+batch_attention_kernel(const float* __restrict__ qkv, TOP* __restrict__ out, int B, int d) {
+  // 8 warps x 2 query rows per block; K / V tiles of 32 keys staged in shared memory (row pitch HD + 1: lane j reads
+  // key j without bank conflicts); compile-time head_dim so that the dot products unroll
+  constexpr int R = 2, NC = (HD + 31) / 32;
+  __shared__ float ks[32][HD + 1];
+  __shared__ float vs[32][HD + 1];
+  __shared__ float qs[8 * R][HD];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.y, row = blockIdx.x * 4 + w;
-  float* ks = sm;                          // [32][hd + 1]
-  float* vs = ks + 32 * (hd + 1);          // [32][hd + 1]
-  float* qs = vs + 32 * (hd + 1) + w * hd; // this warp's query row
-  const float scale = rsqrtf((float)hd);
-  const bool valid = row < B;
-  if (valid)
-    for (int e = lane; e < hd; e += 32) qs[e] = qkv[(size_t)row * 3 * d + head * hd + e] * scale;   // q * hd^-0.5 as torch does
-  float m = -INFINITY, l = 0.f;
-  float o[4] = {0.f, 0.f, 0.f, 0.f};       // hd <= 128: 4 dims per lane
+  const int head = blockIdx.y, row0 = blockIdx.x * (8 * R) + w * R;
+  const float scale = rsqrtf((float)HD);
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    for (int e = lane; e < HD; e += 32)
+      qs[w * R + r][e] = row0 + r < B ? qkv[(size_t)(row0 + r) * 3 * d + head * HD + e] * scale : 0.f;   // q * hd^-0.5 as torch does
+  float m[R], l[R], o[R][NC];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    m[r] = -INFINITY; l[r] = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) o[r][c] = 0.f;
+  }
   for (int j0 = 0; j0 < B; j0 += 32) {
     __syncthreads();
-    for (int idx = threadIdx.x; idx < 32 * hd; idx += 128) {
-      const int j = idx / hd, e = idx - j * hd;
+    for (int idx = threadIdx.x; idx < 32 * HD; idx += 256) {
+      const int j = idx / HD, e = idx - j * HD;
       const bool in = j0 + j < B;
-      ks[j * (hd + 1) + e] = in ? qkv[(size_t)(j0 + j) * 3 * d + d + head * hd + e] : 0.f;
-      vs[j * (hd + 1) + e] = in ? qkv[(size_t)(j0 + j) * 3 * d + 2 * d + head * hd + e] : 0.f;
+      ks[j][e] = in ? qkv[(size_t)(j0 + j) * 3 * d + d + head * HD + e] : 0.f;
+      vs[j][e] = in ? qkv[(size_t)(j0 + j) * 3 * d + 2 * d + head * HD + e] : 0.f;
     }
     __syncthreads();
-    if (!valid) continue;
-    float s = 0.f;
-    for (int e = 0; e < hd; ++e) s += qs[e] * ks[lane * (hd + 1) + e];
-    if (j0 + lane >= B) s = -INFINITY;
-    const float mt = warp_max(s);
-    const float mn = fmaxf(m, mt);
-    const float p = __expf(s - mn);
-    const float corr = __expf(m - mn);
-    l = l * corr + warp_sum(p);
-    m = mn;
+    float s[R];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) o[c] *= corr;
+    for (int r = 0; r < R; ++r) s[r] = 0.f;
+#pragma unroll 8
+    for (int e = 0; e < HD; ++e) {
+      const float kv = ks[lane][e];
+#pragma unroll
+      for (int r = 0; r < R; ++r) s[r] += qs[w * R + r][e] * kv;
+    }
+    float p[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (j0 + lane >= B) s[r] = -INFINITY;
+      const float mn = fmaxf(m[r], warp_max(s[r]));
+      p[r] = __expf(s[r] - mn);
+      const float corr = __expf(m[r] - mn);
+      l[r] = l[r] * corr + warp_sum(p[r]);
+      m[r] = mn;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) o[r][c] *= corr;
+    }
+#pragma unroll 4
     for (int j = 0; j < 32; ++j) {
-      const float pj = __shfl_sync(0xffffffffu, p, j);
+      float pj[R];
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c * 32 + lane < hd) o[c] += pj * vs[j * (hd + 1) + c * 32 + lane];
+      for (int r = 0; r < R; ++r) pj[r] = __shfl_sync(0xffffffffu, p[r], j);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const float vv = (c * 32 + lane < HD) ? vs[j][c * 32 + lane] : 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) o[r][c] += pj[r] * vv;
+      }
     }
   }
-  if (valid) {
-    const float inv = 1.0f / l;
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-      if (c * 32 + lane < hd) out[(size_t)row * d + head * hd + c * 32 + lane] = from_f32<TOP>(o[c] * inv);
+  for (int r = 0; r < R; ++r) {
+    if (row0 + r >= B) continue;
+    const float inv = 1.0f / l[r];
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      if (c * 32 + lane < HD) out[(size_t)(row0 + r) * d + head * HD + c * 32 + lane] = from_f32<TOP>(o[r][c] * inv);
   }
 }
 
@@ -373,9 +398,17 @@ int launch_cond_pairs(ldm_ctx* ctx, const float* fe, const float* ke, float* out
 template <typename TOP>
 int launch_batch_attention(ldm_ctx* ctx, const float* qkv, TOP* out, int B, int d, int heads, cudaStream_t st) {
   const int hd = d / heads;
-  LDM_CHECK(d % heads == 0 && hd <= 128, "batch_attention: head_dim %d unsupported (d=%d)", hd, d);
-  const size_t smem = ((size_t)64 * (hd + 1) + 4 * hd) * sizeof(float);
-  batch_attention_kernel<TOP><<<dim3(ceil_div(B, 4), heads), 128, smem, st>>>(qkv, out, B, d, hd);
+  LDM_CHECK(d % heads == 0 && (hd == 16 || hd == 32 || hd == 48 || hd == 64 || hd == 96 || hd == 128),
+            "batch_attention: head_dim %d unsupported (d=%d)", hd, d);
+  const dim3 grid(ceil_div(B, 16), heads);
+  switch (hd) {
+    case 16: batch_attention_kernel<TOP, 16><<<grid, 256, 0, st>>>(qkv, out, B, d); break;
+    case 32: batch_attention_kernel<TOP, 32><<<grid, 256, 0, st>>>(qkv, out, B, d); break;
+    case 48: batch_attention_kernel<TOP, 48><<<grid, 256, 0, st>>>(qkv, out, B, d); break;
+    case 64: batch_attention_kernel<TOP, 64><<<grid, 256, 0, st>>>(qkv, out, B, d); break;
+    case 96: batch_attention_kernel<TOP, 96><<<grid, 256, 0, st>>>(qkv, out, B, d); break;
+    default: batch_attention_kernel<TOP, 128><<<grid, 256, 0, st>>>(qkv, out, B, d); break;
+  }
   LDM_LAUNCHED(ctx);
   return 0;
 }
