@@ -137,6 +137,22 @@ typedef struct ldm_unet3_weights {
   const float *final_w, *final_b;
 } ldm_unet3_weights;
 
+/* v4 / v5 pixel-space SimpleUNet (v4:37-97), raw fp32 device pointers in the reference's state_dict layout
+ * (Conv2d weight (Cout, Cin, k, k); ConvTranspose2d weight (Cin, Cout, 4, 4)).  res_ratio: the scalar parameter of v5
+ * (v5:54, out + res_ratio * x_input, v5:144) or NULL for v4. */
+typedef struct ldm_pix_conv { const float *w, *b; } ldm_pix_conv;
+typedef struct ldm_pix_weights {
+  int32_t in_channels;      /* 3 */
+  int32_t base_channels;    /* 64 (a multiple of 64) */
+  int32_t time_emb_dim;     /* 128 */
+  int32_t n_t;              /* rows of the per-timestep table built at pack time (= n_steps of the sampler) */
+  const float* res_ratio;
+  const float *time_embed0_w, *time_embed0_b;   /* Linear(1, temb)     v4:42 */
+  const float *time_embed2_w, *time_embed2_b;   /* Linear(temb, temb)  v4:44 */
+  const float *time_fc_w[3], *time_fc_b[3];     /* time_fc1..3         v4:47-49 */
+  ldm_pix_conv conv1[2], down1, conv2[2], down2, conv3[2], bottleneck[2], up1, conv4[2], up2, conv5[2], out_conv;
+} ldm_pix_weights;
+
 LDM_API int ldm_version(void);
 LDM_API const char* ldm_last_error(void);
 
@@ -203,6 +219,24 @@ LDM_API int ldm_decode(ldm_ctx* ctx, const float* z_dev, float* img_out_dev, int
 LDM_API int ldm_generate_host(ldm_ctx* ctx, const int64_t* c_host, int batch, uint64_t seed,
                       uint64_t sample_offset, float* img_out_host, float* latents_out_host,
                       void* stream);
+
+/* ---- v4 / v5 pixel-space diffusion (bf16 contexts only) ----------------------------------------------
+ * ldm_pix_pack: repack SimpleUNet (v4:37-97) for the implicit-GEMM kernels and tabulate the per-stage time terms
+ * time_fc_i(time_embed(t)) for t = 0..n_t-1 (v4:103-110 hoisted out of the loop).  Synchronises the stream. */
+LDM_API int ldm_pix_pack(ldm_ctx* ctx, const ldm_pix_weights* w, void* stream);
+
+/* SimpleUNet.forward(x, t) (v4:99-135 / v5:101-146): x (batch, 3, H, W) fp32 NCHW, t (batch,) fp32 (the reference
+ * feeds `t.view(B, 1).float()` to a Linear, v4:104) -> eps (batch, 3, H, W) fp32 NCHW.  H, W: multiples of 4 whose
+ * three resolution levels tile into 128-pixel boxes (64 x 64 and 32 x 32 do). */
+LDM_API int ldm_pix_forward(ldm_ctx* ctx, const float* x_dev, const float* t_dev, float* eps_out_dev, int batch, int H, int W,
+                    void* stream);
+
+/* DiffusionModel.p_sample repeated for t = t_start .. t_end (v4:155-175) on x (batch, 3, H, W) in place; schedule from
+ * ldm_set_schedule.  noise_dev: NULL (in-kernel Philox: counter quad = element / 4 of the flattened (3, H, W) sample,
+ * global sample index sample_offset + n, step t) or (t_start - t_end + 1, batch, 3, H, W) explicit draws.  use_graph
+ * != 0 replays the loop as one CUDA graph. */
+LDM_API int ldm_pix_sample(ldm_ctx* ctx, float* x_inout_dev, int t_start, int t_end, const float* noise_dev, uint64_t seed,
+                   uint64_t sample_offset, int batch, int H, int W, int use_graph, void* stream);
 
 /* Introspection for tests and the benchmark. */
 LDM_API int ldm_kernel_launch_count(ldm_ctx* ctx, uint64_t* out); /* kernels launched (graph nodes count per replay) */

@@ -46,7 +46,30 @@ def load(version="v2"):
     spec = importlib.util.spec_from_file_location("_ldm_reference_" + version, path)
     mod = importlib.util.module_from_spec(spec)
     rng_state = torch.get_rng_state()
-    spec.loader.exec_module(mod)          # runs torch.manual_seed(42) (v2:17)
+    real_flowers = None
+    if version in ("v4", "v5"):   # v4:27-32 downloads Flowers102 at import time: an empty stand-in dataset, restored below
+        import torch.utils.data
+        import torchvision.datasets
+
+        class _NoFlowers(torch.utils.data.Dataset):
+            classes = []
+
+            def __init__(self, *a, **k):
+                pass
+
+            def __len__(self):
+                return 1
+
+            def __getitem__(self, i):
+                raise IndexError(i)
+
+        real_flowers = torchvision.datasets.Flowers102
+        torchvision.datasets.Flowers102 = _NoFlowers
+    try:
+        spec.loader.exec_module(mod)          # runs torch.manual_seed(42) (v2:17)
+    finally:
+        if real_flowers is not None:
+            torchvision.datasets.Flowers102 = real_flowers
     torch.set_rng_state(rng_state)
     mod.tqdm = lambda it, **kw: it        # v2:596 wraps the sampling loop in tqdm
     _cache[version] = mod

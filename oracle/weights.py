@@ -140,6 +140,33 @@ def autoencoder_spec():
             + encoder_spec() + decoder_spec() + classifier_spec())
 
 
+def pix_unet_spec(in_channels=3, base=64, temb=128, v5=False):
+    """v4 SimpleUNet (v4:37-97), state_dict order: 44 tensors; v5 adds the scalar `res_ratio` first (v5:54).
+    The reference never re-initialises this model, so "init" is torch's default: U(+-1/sqrt(fan_in)) for weights
+    AND biases (kinds "u:<fan_in>")."""
+    s = [("res_ratio", (), "rw")] if v5 else []
+    def lin(name, o, i):
+        s.append((name + ".weight", (o, i), "u:%d" % i)); s.append((name + ".bias", (o,), "u:%d" % i))
+    def conv(name, o, i, k):
+        s.append((name + ".weight", (o, i, k, k), "u:%d" % (i * k * k))); s.append((name + ".bias", (o,), "u:%d" % (i * k * k)))
+    def convT(name, i, o, k):   # weight (Cin, Cout, k, k); torch's fan_in of it is Cout * k * k
+        s.append((name + ".weight", (i, o, k, k), "u:%d" % (o * k * k))); s.append((name + ".bias", (o,), "u:%d" % (o * k * k)))
+    lin("time_embed.0", temb, 1); lin("time_embed.2", temb, temb)
+    lin("time_fc1", base, temb); lin("time_fc2", 2 * base, temb); lin("time_fc3", 4 * base, temb)
+    conv("conv1.0", base, in_channels, 3); conv("conv1.2", base, base, 3)
+    conv("down1", 2 * base, base, 4)
+    conv("conv2.0", 2 * base, 2 * base, 3); conv("conv2.2", 2 * base, 2 * base, 3)
+    conv("down2", 4 * base, 2 * base, 4)
+    conv("conv3.0", 4 * base, 4 * base, 3); conv("conv3.2", 4 * base, 4 * base, 3)
+    conv("bottleneck.0", 8 * base, 4 * base, 3); conv("bottleneck.2", 4 * base, 8 * base, 3)
+    convT("up1", 4 * base, 2 * base, 4)
+    conv("conv4.0", 2 * base, 4 * base, 3); conv("conv4.2", 2 * base, 2 * base, 3)
+    convT("up2", 2 * base, base, 4)
+    conv("conv5.0", base, 2 * base, 3); conv("conv5.2", base, base, 3)
+    conv("out_conv", in_channels, base, 3)
+    return s
+
+
 def _draw(key, shape, kind, seed, style):
     g = torch.Generator().manual_seed((int(seed) * 1000003 + zlib.crc32(key.encode())) & 0x7FFFFFFFFFFFFFFF)
     n = lambda: torch.randn(shape, generator=g, dtype=torch.float32)
@@ -151,6 +178,9 @@ def _draw(key, shape, kind, seed, style):
             fan_in = shape[1]
         gain = math.sqrt(2.0 / (1 + 0.2 ** 2))
         t = n() * (gain / math.sqrt(fan_in))
+    elif kind.startswith("u:"):
+        bound = 1.0 / math.sqrt(int(kind[2:]))
+        t = (torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1) * bound
     elif kind == "xavier":
         bound = math.sqrt(6.0 / (shape[0] + shape[1]))
         t = (torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1) * bound
@@ -162,7 +192,9 @@ def _draw(key, shape, kind, seed, style):
         t = torch.tensor(0.1)
     else:  # "b", "buf"
         t = torch.zeros(shape)
-    if style == "perturbed":
+    if style == "perturbed" and kind.startswith("u:"):
+        t = t + 0.5 / math.sqrt(int(kind[2:])) * n()     # relative to the init scale, so that 17 stacked convolutions keep a finite gain
+    elif style == "perturbed":
         t = t + 0.05 * n()
     elif style != "init":
         raise ValueError(style)
@@ -179,6 +211,11 @@ def make_unet_state(seed=42, style="init"):
 
 def make_unet3_state(seed=44, style="init"):
     return make_state(unet3_spec(), seed, style)
+
+
+def make_pix_state(seed=45, style="init", v5=False):
+    """"perturbed" adds 0.5 / sqrt(fan_in) * randn to every tensor (half the init bound), res_ratio 0.1 + 0.05 randn."""
+    return make_state(pix_unet_spec(v5=v5), seed, style)
 
 
 def make_decoder_state(seed=43, style="init"):

@@ -10,6 +10,7 @@ from .modules import (CALayer, ClassEmbedding, ConditionalDenoiseDiffusion, Cond
                       euclidean_distance_loss, generate_class_samples, init_weights, load_autoencoder_checkpoint)
 from .sharding import generate_sharded, shard_bounds                       # noqa: F401
 from . import v3                                                            # noqa: F401  (v3 multi-conditional denoiser)
+from . import v4                                                            # noqa: F401  (v4 / v5 pixel-space diffusion)
 from ._lib import LIB_PATH, LdmError                                        # noqa: F401
 
 __all__ = ["ConditionalUNet", "ConditionalDenoiseDiffusion", "SimpleAutoencoder", "Decoder", "Encoder",

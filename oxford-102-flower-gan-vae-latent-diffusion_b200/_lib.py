@@ -64,6 +64,23 @@ class DecoderWeights(ctypes.Structure):
     )
 
 
+class PixConv(ctypes.Structure):
+    _fields_ = [("w", _vp), ("b", _vp)]
+
+
+class PixWeights(ctypes.Structure):
+    """ldm_pix_weights (v4 / v5 pixel-space SimpleUNet)."""
+    _fields_ = (
+        [("in_channels", ctypes.c_int32), ("base_channels", ctypes.c_int32), ("time_emb_dim", ctypes.c_int32),
+         ("n_t", ctypes.c_int32), ("res_ratio", _vp),
+         ("time_embed0_w", _vp), ("time_embed0_b", _vp), ("time_embed2_w", _vp), ("time_embed2_b", _vp),
+         ("time_fc_w", _vp * 3), ("time_fc_b", _vp * 3),
+         ("conv1", PixConv * 2), ("down1", PixConv), ("conv2", PixConv * 2), ("down2", PixConv), ("conv3", PixConv * 2),
+         ("bottleneck", PixConv * 2), ("up1", PixConv), ("conv4", PixConv * 2), ("up2", PixConv), ("conv5", PixConv * 2),
+         ("out_conv", PixConv)]
+    )
+
+
 # name -> (restype, argtypes); exactly the prototypes of include/ldm_b200.h
 PROTOTYPES = {
     "ldm_version": (ctypes.c_int, []),
@@ -83,6 +100,10 @@ PROTOTYPES = {
     "ldm_decoder_pack": (ctypes.c_int, [_vp, ctypes.POINTER(DecoderWeights), _vp]),
     "ldm_decode": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, _vp]),
     "ldm_generate_host": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, _vp, _vp, _vp]),
+    "ldm_pix_pack": (ctypes.c_int, [_vp, ctypes.POINTER(PixWeights), _vp]),
+    "ldm_pix_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
+    "ldm_pix_sample": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_uint64, ctypes.c_uint64,
+                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
     "ldm_kernel_launch_count": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64)]),
     "ldm_get_info": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]),
     "ldm_debug_chain_trace": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int]),

@@ -44,7 +44,11 @@ static void free_pool(std::vector<void*>& pool) {
   pool.clear();
 }
 
+void pix_drop_graphs(ldm_ctx* ctx);
+void pix_free(ldm_ctx* ctx);
+
 static void drop_graphs(ldm_ctx* ctx) {
+  pix_drop_graphs(ctx);
   for (auto& kv : ctx->graphs) {
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
@@ -134,6 +138,7 @@ extern "C" LDM_API int ldm_ctx_destroy(ldm_ctx* ctx) {
   free_pool(ctx->dec.allocs);
   free_pool(ctx->stage_allocs);
   free_pool(ctx->chain.allocs);
+  pix_free(ctx);
   if (ctx->coef_dev) cudaFree(ctx->coef_dev);
   if (ctx->chain_trace) cudaFree(ctx->chain_trace);
   if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);

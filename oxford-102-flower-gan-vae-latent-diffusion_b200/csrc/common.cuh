@@ -171,6 +171,7 @@ struct ConvLayer {       // implicit GEMM: out[pix, co] = sum_{tap, ci} in[pix +
   bf16* w16 = nullptr;
   float* b = nullptr;
   CUtensorMap map_w;
+  int bn = 0;            // output-channel tile of conv_tc_kernel (0: conv_tc_pick_bn(Cout))
 };
 
 struct ResBlockModel {
@@ -210,6 +211,27 @@ struct GraphEntry {
   bool has_cls = false;           // captured with / without class tables
 };
 
+// v4 / v5 pixel-space SimpleUNet (pixel.cu)
+struct PixModel {
+  bool packed = false;
+  std::vector<void*> allocs;
+  int base = 0, temb = 0, n_t = 0;
+  float *te0_w, *te0_b, *te2_w, *te2_b;     // time_embed
+  float* tfc_w[3]; float* tfc_b[3];         // time_fc1..3
+  float* tab = nullptr;                     // (n_t, 7 base): [time_fc1 | time_fc2 | time_fc3](time_embed(t)), t = 0..n_t-1
+  float *in_w = nullptr, *in_b = nullptr;   // conv1.0 as (base, 27) tap-major (ky, kx, ci)
+  float *out_w = nullptr, *out_b = nullptr; // out_conv as (3, 9 base)
+  float* res_ratio = nullptr;               // device scalar (v5) or null (v4)
+  ConvLayer c1b, down1, c2a, c2b, down2, c3a, c3b, b0, b2, up1, c4a, c4b, up2, c5a, c5b;   // up1 / up2: 4 stacked sub-pixel kernels
+  // activation workspace (NHWC bf16) for `cap` samples of cap_h x cap_w
+  int cap = 0, cap_h = 0, cap_w = 0;
+  std::vector<void*> ws;
+  bf16 *a1, *cat5, *d1, *a2, *cat4, *d2, *a3, *x3, *bt, *x4, *a4, *x5, *a5, *x6;
+  float* tsample = nullptr;                 // (cap, 7 base) per-sample time terms of forward(x, t)
+  float* x_state = nullptr;                 // (cap, 3, H, W) fp32 chain state the captured graph works on
+  std::map<std::tuple<int, int, int, int, int, int>, GraphEntry> graphs;   // (batch, H, W, t_start, t_end, noise mode)
+};
+
 struct ldm_ctx {
   int device = 0;
   int precision = LDM_PRECISION_FP32;
@@ -222,6 +244,7 @@ struct ldm_ctx {
   UnetModel unet;
   ChainModel chain;
   DecoderModel dec;
+  PixModel pix;
   // per-batch state
   int cap = 0;                    // rows the activation workspace holds
   int batch_cls = -1;             // batch of the last set_classes (-1: none)

@@ -28,12 +28,17 @@ constexpr int kMaxStages = 8;
 struct ConvTcArgs {
   int H, W;         // input spatial size
   int Cin, Cout;    // Cout: output channels of one parity
-  int taps;         // 9 (3x3) or 4 (sub-pixel of the transposed conv)
-  int up;           // 1 or 2
-  int total_pix;    // B * H * W input-resolution pixels
+  int taps;         // 9 (3x3), 4 (sub-pixel of the transposed conv) or 16 (4x4 stride-2 conv)
+  int up;           // 1: 3x3; 2: sub-pixel of ConvTranspose2d(4,2,1); 0: Conv2d(4, stride 2, pad 1) - H, W are then the OUTPUT size
+  int total_pix;    // B * H * W pixels of the grid the CTAs tile
   int stages;
+  int in_pitch;     // channel pitch of the input buffer (>= Cin: the input may be a channel slice of a concat buffer)
+  int out_pitch;    // channel pitch of the output buffer
+  int relu;         // ReLU after the bias
+  const float* post;   // optional per-channel term added AFTER the activation (v4:114: x1 = conv1(x) + t_emb1), row n * post_stride
+  int post_stride;     // 0: one row for the whole batch
   const float* bias;
-  bf16* out;        // (B, up*H, up*W, Cout)
+  bf16* out;        // (B, up*H, up*W, out_pitch), already offset to the first output channel
 };
 
 template <int BN>
@@ -84,7 +89,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (!tc::mbar_wait(&empty_bar[s], ph ^ 1u, 1)) break;
         const int tap = kb / cblocks, cb = kb - tap * cblocks;
         int dy, dx;
-        if (a.up == 1) {
+        if (a.up == 0) {
+          // Conv2d(4, stride 2, pad 1): input row 2Y + ky - 1 = 2 (Y + dy) + p with ky -> (dy, p) = (-1,1), (0,0), (0,1), (1,0);
+          // the 5-D map splits rows and columns into (index / 2, parity), so a tap is again ONE box of 128 output pixels
+          const int ky = tap >> 2, kx = tap & 3;
+          dy = ky == 0 ? -1 : (ky == 3 ? 1 : 0);
+          dx = kx == 0 ? -1 : (kx == 3 ? 1 : 0);
+          const int py = (ky == 0 || ky == 2) ? 1 : 0, px = (kx == 0 || kx == 2) ? 1 : 0;
+          uint8_t* sa = smem + (size_t)s * kStageBytes;
+          tc::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+          tc::tma_load_5d(sa, &map_a, &full_bar[s], px * a.in_pitch + cb * BK, dx, py, y0 + dy, n0);
+          tc::tma_load_2d(sa + kABytes, &map_w, &full_bar[s], tap * a.Cin + cb * BK, nc0);
+          continue;
+        } else if (a.up == 1) {
           dy = tap / 3 - 1;
           dx = tap - (tap / 3) * 3 - 1;
         } else {   // sub-pixel (pa, pb) of ConvTranspose2d(4, 2, 1): tap 0 reads offset 0, tap 1 reads -1 (parity 0) or +1
@@ -124,7 +141,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int n = p / HW, rem = p - n * HW, y = rem / a.W, x = rem - y * a.W;
       op = ((size_t)n * (2 * a.H) + (size_t)(2 * y + pa)) * (size_t)(2 * a.W) + (size_t)(2 * x + pb);
     }
-    bf16* dst = a.out + op * (size_t)a.Cout + nc0;
+    bf16* dst = a.out + op * (size_t)a.out_pitch + nc0;
+    const float* prow = a.post ? a.post + (size_t)(valid ? p / HW : 0) * a.post_stride + nc0 : nullptr;
     tc::mbar_wait(&tmem_full_bar, 0, 3);
     tc::fence_after_sync();
 #pragma unroll 1
@@ -134,8 +152,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (valid) {
         uint32_t pk[8];
 #pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          v[j] += bias_s[c0 + j];
+          if (a.relu) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (prow) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(prow + c0) + j);
+            v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
+          }
+        }
+#pragma unroll
         for (int j = 0; j < 8; ++j) {
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j] + bias_s[c0 + 2 * j], v[2 * j + 1] + bias_s[c0 + 2 * j + 1]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
           pk[j] = *reinterpret_cast<uint32_t*>(&h2);
         }
         uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
@@ -212,14 +242,16 @@ int conv_init(ldm_ctx* ctx) {
   return 0;
 }
 
-// NHWC bf16 activation (B, H, W, C) as a 4-D tensor (C, W, H, B); box = 64 channels x 128 pixels
-int make_act_map(const bf16* base, int B, int H, int W, int C, CUtensorMap* out) {
+// NHWC bf16 activation (B, H, W, C of pitch P) as a 4-D tensor (C, W, H, B); box = 64 channels x 128 pixels
+int make_act_map(const bf16* base, int B, int H, int W, int C, int P, CUtensorMap* out) {
+  LDM_CHECK(W > 0 && H > 0 && W <= 128 && 128 % W == 0, "conv_tc: spatial size %dx%d does not tile into 128-pixel boxes", H, W);
   int bw = W, bh = 128 / W, bn = 1;
   if (bh > H) { bh = H; bn = 128 / (H * W); }
-  LDM_CHECK(bw * bh * bn == 128 && W <= 128, "conv_tc: spatial size %dx%d does not tile into 128-pixel boxes", H, W);
-  LDM_CHECK(((uintptr_t)base & 15) == 0 && C % 64 == 0, "conv_tc: activation must be 16-byte aligned with C %% 64 == 0 (C=%d)", C);
+  LDM_CHECK(bw * bh * bn == 128 && H % bh == 0, "conv_tc: spatial size %dx%d does not tile into 128-pixel boxes", H, W);
+  LDM_CHECK(((uintptr_t)base & 15) == 0 && C % 64 == 0 && P % 8 == 0 && P >= C,
+            "conv_tc: activation must be 16-byte aligned with C %% 64 == 0 (C=%d, pitch %d)", C, P);
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)P * 2, (cuuint64_t)W * P * 2, (cuuint64_t)H * W * P * 2};
   cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = g_encode4(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims, strides, box, estr,
@@ -227,6 +259,31 @@ int make_act_map(const bf16* base, int B, int H, int W, int C, CUtensorMap* out)
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     ldm_set_error("cuTensorMapEncodeTiled (4-D activation) failed: CUresult %d (B=%d H=%d W=%d C=%d)", (int)r, B, H, W, C);
+    return (int)r;
+  }
+  return 0;
+}
+
+// Input of Conv2d(4, stride 2, pad 1): NHWC bf16 (B, H, W, C of pitch P) as the 5-D tensor
+// (px * P + c, W/2, py, H/2, B) - rows and columns split into (index / 2, parity); box = 64 channels x 128 OUTPUT pixels
+int make_act_map_down(const bf16* base, int B, int H, int W, int C, int P, CUtensorMap* out) {
+  LDM_CHECK(H % 2 == 0 && W % 2 == 0, "conv_tc: stride-2 convolution needs even H, W (%dx%d)", H, W);
+  const int Ho = H / 2, Wo = W / 2;
+  LDM_CHECK(Wo > 0 && Wo <= 128 && 128 % Wo == 0, "conv_tc: output size %dx%d does not tile into 128-pixel boxes", Ho, Wo);
+  int bw = Wo, bh = 128 / Wo, bn = 1;
+  if (bh > Ho) { bh = Ho; bn = 128 / (Ho * Wo); }
+  LDM_CHECK(bw * bh * bn == 128 && Ho % bh == 0, "conv_tc: output size %dx%d does not tile into 128-pixel boxes", Ho, Wo);
+  LDM_CHECK(((uintptr_t)base & 15) == 0 && C % 64 == 0 && P % 8 == 0 && P >= C,
+            "conv_tc: activation must be 16-byte aligned with C %% 64 == 0 (C=%d, pitch %d)", C, P);
+  cuuint64_t dims[5] = {(cuuint64_t)(P + C), (cuuint64_t)Wo, 2, (cuuint64_t)Ho, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)2 * P * 2, (cuuint64_t)W * P * 2, (cuuint64_t)2 * W * P * 2, (cuuint64_t)H * W * P * 2};
+  cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)bw, 1, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode4(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ldm_set_error("cuTensorMapEncodeTiled (5-D stride-2 activation) failed: CUresult %d (B=%d H=%d W=%d C=%d P=%d)", (int)r, B, H, W, C, P);
     return (int)r;
   }
   return 0;
@@ -252,20 +309,29 @@ int launch_bn(ldm_ctx* ctx, const CUtensorMap& ma, const ConvLayer& L, const Con
 
 int conv_tc_pick_bn(int Cout) { return Cout >= 256 ? 256 : Cout; }
 
-// in: (B, H, W, Cin) bf16; out: (B, up*H, up*W, Cout) bf16.  L.w16 / L.map_w: (nz * Cout, taps * Cin), box (64, bn).
-int launch_conv_tc(ldm_ctx* ctx, const bf16* in, const ConvLayer& L, const float* bias, bf16* out, int B, int H, int W,
-                   int up, cudaStream_t st) {
+// in: (B, H, W, Cin of pitch in_pitch) bf16; out: (B, up*H, up*W, Cout of pitch out_pitch) bf16 (mode 0: (B, H/2, W/2, .)).
+// L.w16 / L.map_w: (nz * Cout, taps * Cin), box (64, bn).  mode = ConvTcArgs::up.
+int launch_conv_tc_ex(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer& L, const float* bias, bf16* out, int out_pitch,
+                      int B, int H, int W, int mode, int relu, const float* post, int post_stride, cudaStream_t st) {
   LDM_TRY(conv_init(ctx));
   LDM_CHECK(L.w16 != nullptr, "conv_tc: layer not packed for the tensor-core path");
   LDM_CHECK(L.Cin % BK == 0, "conv_tc: Cin %% 64 == 0 required (Cin=%d)", L.Cin);
-  LDM_CHECK((up == 1 && L.taps == 9) || (up == 2 && L.taps == 4), "conv_tc: unsupported taps/up combination");
+  LDM_CHECK((mode == 1 && L.taps == 9) || (mode == 2 && L.taps == 4) || (mode == 0 && L.taps == 16), "conv_tc: unsupported taps/mode combination");
+  LDM_CHECK(out_pitch % 8 == 0 && ((uintptr_t)out & 15) == 0, "conv_tc: output must be 16-byte aligned (pitch %d)", out_pitch);
   CUtensorMap ma;
-  LDM_TRY(make_act_map(in, B, H, W, L.Cin, &ma));
   ConvTcArgs a;
-  a.H = H; a.W = W; a.Cin = L.Cin; a.Cout = L.Cout; a.taps = L.taps; a.up = up; a.total_pix = B * H * W; a.stages = 0;
+  if (mode == 0) {
+    LDM_TRY(make_act_map_down(in, B, H, W, L.Cin, in_pitch, &ma));
+    a.H = H / 2; a.W = W / 2;
+  } else {
+    LDM_TRY(make_act_map(in, B, H, W, L.Cin, in_pitch, &ma));
+    a.H = H; a.W = W;
+  }
+  a.Cin = L.Cin; a.Cout = L.Cout; a.taps = L.taps; a.up = mode; a.total_pix = B * a.H * a.W; a.stages = 0;
+  a.in_pitch = in_pitch; a.out_pitch = out_pitch; a.relu = relu; a.post = post; a.post_stride = post_stride;
   a.bias = bias; a.out = out;
-  const int nz = up == 2 ? 4 : 1;
-  switch (conv_tc_pick_bn(L.Cout)) {
+  const int nz = mode == 2 ? 4 : 1;
+  switch (L.bn ? L.bn : conv_tc_pick_bn(L.Cout)) {
     case 32: return launch_bn<32>(ctx, ma, L, a, nz, st);
     case 64: return launch_bn<64>(ctx, ma, L, a, nz, st);
     case 128: return launch_bn<128>(ctx, ma, L, a, nz, st);
@@ -273,6 +339,11 @@ int launch_conv_tc(ldm_ctx* ctx, const bf16* in, const ConvLayer& L, const float
   }
   ldm_set_error("conv_tc: unsupported Cout %d", L.Cout);
   return -1;
+}
+
+int launch_conv_tc(ldm_ctx* ctx, const bf16* in, const ConvLayer& L, const float* bias, bf16* out, int B, int H, int W,
+                   int up, cudaStream_t st) {
+  return launch_conv_tc_ex(ctx, in, L.Cin, L, bias, out, L.Cout, B, H, W, up, 0, nullptr, 0, st);
 }
 
 int launch_conv_out3(ldm_ctx* ctx, const bf16* in, const float* w, const float* bias, float* out, int B, int H, int W,

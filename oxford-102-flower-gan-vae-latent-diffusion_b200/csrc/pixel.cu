@@ -1,0 +1,469 @@
+// v4 / v5 pixel-space diffusion: SimpleUNet.forward (v4:99-135, v5:101-146) and DiffusionModel.p_sample /
+// sample (v4:155-175) over NHWC bf16 activations.
+//
+//   x (fp32 NCHW state) --pix_conv_in--> conv1.0+ReLU --conv_tc--> ... 15 implicit-GEMM layers ... --pix_conv_out--> eps
+//
+// * every Conv2d(3x3), the two Conv2d(4, stride 2) and the two ConvTranspose2d(4, 2, 1) with 64..512 channels run on the
+//   tensor cores (conv_tc.cu: TMA boxes as the im2col, tcgen05 / TMEM); bias, ReLU and the per-stage time term
+//   (x_i = conv_i(x) + t_emb_i, added AFTER the ReLU, v4:114,118,122) are its epilogue;
+// * torch.cat([x5, x2]) / torch.cat([x6, x1]) (v4:127,131) cost nothing: the producers write channel slices of one
+//   concat buffer (output pitch) and the stride-2 convolutions read their slice back through a pitched TMA map;
+// * the time path (Linear(1,128) on the RAW timestep -> ReLU -> Linear -> time_fc1..3, v4:103-110) does not depend on x:
+//   it is a (n_t, 7 base) table built at pack time for the sampler, one tiny kernel for forward(x, t) with per-sample t;
+// * conv1.0 (3 input channels, K = 27) and out_conv (3 output channels) are no tensor-core shapes: CUDA cores, fused with
+//   the NCHW fp32 <-> NHWC bf16 layout change and, in the sampler, with the posterior update and its Philox noise, so
+//   eps never goes to memory.
+#include "common.cuh"
+#include "philox.cuh"
+
+int launch_conv_tc_ex(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer& L, const float* bias, bf16* out, int out_pitch,
+                      int B, int H, int W, int mode, int relu, const float* post, int post_stride, cudaStream_t st);
+int tc_make_weight_map(ldm_ctx* ctx, const bf16* w, int N, int K, int bn, CUtensorMap* out);
+int tc_init(ldm_ctx* ctx);
+
+namespace {
+
+#define LDM_LAUNCHED(ctx)         \
+  do {                            \
+    (ctx)->launches++;            \
+    LDM_CUDA(cudaGetLastError()); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------------------------
+// time terms: out[row] = [time_fc1 | time_fc2 | time_fc3](Linear2(relu(Linear1(t))))     (v4:103-110)
+// t == nullptr: t = row index (the sampler's table).  One block per row.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+pix_time_terms_kernel(const float* __restrict__ t, const float* __restrict__ w0, const float* __restrict__ b0,
+                      const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ wf1,
+                      const float* __restrict__ bf1, const float* __restrict__ wf2, const float* __restrict__ bf2,
+                      const float* __restrict__ wf3, const float* __restrict__ bf3, float* __restrict__ out, int temb, int base) {
+  extern __shared__ float sm[];
+  float* h = sm;            // [temb]
+  float* te = sm + temb;    // [temb]
+  const int row = blockIdx.x;
+  const float tv = t ? t[row] : (float)row;
+  for (int i = threadIdx.x; i < temb; i += blockDim.x) h[i] = fmaxf(w0[i] * tv + b0[i], 0.f);
+  __syncthreads();
+  for (int i = threadIdx.x; i < temb; i += blockDim.x) {
+    float acc = 0.f;
+    const float* wr = w2 + (size_t)i * temb;
+    for (int j = 0; j < temb; ++j) acc += wr[j] * h[j];
+    te[i] = acc + b2[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 7 * base; c += blockDim.x) {
+    const float* wr;
+    float bias;
+    if (c < base) { wr = wf1 + (size_t)c * temb; bias = bf1[c]; }
+    else if (c < 3 * base) { wr = wf2 + (size_t)(c - base) * temb; bias = bf2[c - base]; }
+    else { wr = wf3 + (size_t)(c - 3 * base) * temb; bias = bf3[c - 3 * base]; }
+    float acc = 0.f;
+    for (int j = 0; j < temb; ++j) acc += wr[j] * te[j];
+    out[(size_t)row * 7 * base + c] = acc + bias;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// conv1.0 + ReLU (v4:55-56): x (B, 3, H, W) fp32 NCHW -> (B, H, W, C) bf16 NHWC.  One thread per pixel; weights
+// (C, 27) k = (ky*3 + kx)*3 + ci in shared memory (every lane reads the same address: broadcast).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+pix_conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ out,
+                   int H, int W, int C, int total_pix) {
+  extern __shared__ float sm[];
+  float* ws = sm;             // [C * 27]
+  float* bs = sm + C * 27;    // [C]
+  for (int i = threadIdx.x; i < C * 27; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) bs[i] = b[i];
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total_pix) return;
+  const int HW = H * W, n = p / HW, rem = p - n * HW, y = rem / W, xx = rem - y * W;
+  float in[27];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = y + tap / 3 - 1, xc = xx + tap % 3 - 1;
+    const bool ok = yy >= 0 && yy < H && xc >= 0 && xc < W;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) in[tap * 3 + ci] = ok ? __ldg(x + ((size_t)n * 3 + ci) * HW + (size_t)yy * W + xc) : 0.f;
+  }
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)p * C);
+  for (int c8 = 0; c8 < C / 8; ++c8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float* wr = ws + (c8 * 8 + j) * 27;
+      float acc = bs[c8 * 8 + j];
+#pragma unroll
+      for (int k = 0; k < 27; ++k) acc += in[k] * wr[k];
+      v[j] = fmaxf(acc, 0.f);
+    }
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+    dst[c8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// out_conv (v4:96,134) [+ res_ratio * x_input, v5:144], one thread per pixel over NHWC bf16, three fp32 outputs.
+// DDPM == 0: eps (B, 3, H, W) fp32 NCHW is stored.   DDPM == 1: the posterior update of p_sample (v4:159-168) is applied
+// to the state x in place with explicit or in-kernel Philox noise; eps is never stored.
+// ------------------------------------------------------------------------------------------------------------------
+struct PixOutArgs {
+  const bf16* in;           // (B, H, W, C)
+  const float* w;           // (3, 9 C), k = tap * C + ci
+  const float* bias;        // (3)
+  const float* res_ratio;   // device scalar or null
+  const float* x_in;        // (B, 3, H, W): input of the forward (residual term of v5); the state when DDPM
+  float* out;               // DDPM == 0: eps;  DDPM == 1: the state (== x_in)
+  const float* noise;       // DDPM: explicit (B, 3, H, W) draws or null
+  const unsigned long long* rng;   // DDPM: {seed, sample_offset}
+  float c2, sqrt_alpha, sigma;
+  int step, H, W, C, total_pix;
+};
+
+template <int DDPM>
+__global__ void __launch_bounds__(128)
+pix_conv_out_kernel(const PixOutArgs a) {
+  extern __shared__ float ws[];   // [3 * 9 * C]
+  const int C = a.C, K = 9 * C;
+  for (int i = threadIdx.x; i < 3 * K; i += blockDim.x) ws[i] = a.w[i];
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.total_pix) return;
+  const int H = a.H, W = a.W, HW = H * W, n = p / HW, rem = p - n * HW, y = rem / W, x = rem - y * W;
+  float acc0 = a.bias[0], acc1 = a.bias[1], acc2 = a.bias[2];
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+    const uint4* src = reinterpret_cast<const uint4*>(a.in + ((size_t)n * HW + (size_t)yy * W + xx) * C);
+    const float* w0 = ws + tap * C;
+    for (int j = 0; j < C / 8; ++j) {
+      const uint4 u = __ldg(src + j);
+      const uint32_t wd[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&wd[e]);
+        const float f0 = __low2float(h2), f1 = __high2float(h2);
+        const int k = j * 8 + e * 2;
+        acc0 += f0 * w0[k] + f1 * w0[k + 1];
+        acc1 += f0 * w0[K + k] + f1 * w0[K + k + 1];
+        acc2 += f0 * w0[2 * K + k] + f1 * w0[2 * K + k + 1];
+      }
+    }
+  }
+  float eps[3] = {acc0, acc1, acc2};
+  const size_t i0 = (size_t)n * 3 * HW + rem;
+  if (a.res_ratio) {
+    const float rr = __ldg(a.res_ratio);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) eps[c] = __fadd_rn(eps[c], __fmul_rn(rr, a.x_in[i0 + (size_t)c * HW]));
+  }
+  if (DDPM == 0) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) a.out[i0 + (size_t)c * HW] = eps[c];
+  } else {
+    unsigned long long seed = 0, sample = 0;
+    if (!a.noise && a.sigma > 0.f) { seed = a.rng[0]; sample = a.rng[1] + (unsigned long long)n; }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float z = 0.f;
+      if (a.sigma > 0.f) {
+        if (a.noise) z = a.noise[i0 + (size_t)c * HW];
+        else {
+          const uint32_t e = (uint32_t)(c * HW + rem);
+          const float4 z4 = philox_normal4(seed, sample, (uint32_t)a.step, e >> 2);
+          const int j = e & 3;
+          z = j == 0 ? z4.x : (j == 1 ? z4.y : (j == 2 ? z4.z : z4.w));
+        }
+      }
+      a.out[i0 + (size_t)c * HW] = ddpm_update_one(a.x_in[i0 + (size_t)c * HW], eps[c], a.c2, a.sqrt_alpha, a.sigma, z);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// packing
+// ------------------------------------------------------------------------------------------------------------------
+int own(ldm_ctx* ctx, std::vector<void*>& pool, const float* src, size_t n, float** out, cudaStream_t st) {
+  LDM_CHECK(src != nullptr, "ldm_pix_pack: null weight pointer");
+  LDM_TRY(ldm_alloc_t(ctx, pool, out, n));
+  LDM_CUDA(cudaMemcpyAsync(*out, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int pick_bn(int Cout) { return Cout >= 256 ? 256 : Cout; }
+
+// Conv2d (Cout, Cin, k, k) -> (Cout, k*k*Cin) tap-major bf16 + TMA map
+int pack_conv(ldm_ctx* ctx, std::vector<void*>& P, ConvLayer& L, const ldm_pix_conv& c, int Cout, int Cin, int k, cudaStream_t st) {
+  LDM_CHECK(c.w && c.b, "ldm_pix_pack: convolution weights missing");
+  LDM_CHECK(Cin % 64 == 0 && Cout % 64 == 0, "ldm_pix_pack: channel counts must be multiples of 64 (Cin=%d, Cout=%d)", Cin, Cout);
+  L.Cin = Cin; L.Cout = Cout; L.taps = k * k; L.bn = pick_bn(Cout);
+  const size_t n = (size_t)Cout * k * k * Cin;
+  LDM_TRY(ldm_alloc_t(ctx, P, &L.w32, n));
+  LDM_TRY(launch_pack_conv(ctx, c.w, L.w32, Cout, Cin, k, k, st));
+  LDM_TRY(own(ctx, P, c.b, Cout, &L.b, st));
+  LDM_TRY(ldm_alloc_t(ctx, P, &L.w16, n));
+  LDM_TRY(launch_to_bf16(ctx, L.w32, L.w16, n, st));
+  return tc_make_weight_map(ctx, L.w16, Cout, L.taps * Cin, L.bn, &L.map_w);
+}
+
+// ConvTranspose2d (Cin, Cout, 4, 4) -> four sub-pixel 2x2-tap kernels stacked along the output-channel axis
+int pack_convT(ldm_ctx* ctx, std::vector<void*>& P, ConvLayer& L, const ldm_pix_conv& c, int Cin, int Cout, cudaStream_t st) {
+  LDM_CHECK(c.w && c.b, "ldm_pix_pack: transposed-convolution weights missing");
+  LDM_CHECK(Cin % 64 == 0 && Cout % 64 == 0, "ldm_pix_pack: channel counts must be multiples of 64 (Cin=%d, Cout=%d)", Cin, Cout);
+  L.Cin = Cin; L.Cout = Cout; L.taps = 4; L.bn = pick_bn(Cout);
+  const size_t per = (size_t)Cout * 4 * Cin;
+  LDM_TRY(ldm_alloc_t(ctx, P, &L.w32, 4 * per));
+  for (int z = 0; z < 4; ++z) LDM_TRY(launch_pack_convT(ctx, c.w, L.w32 + (size_t)z * per, Cin, Cout, z >> 1, z & 1, st));
+  LDM_TRY(own(ctx, P, c.b, Cout, &L.b, st));
+  LDM_TRY(ldm_alloc_t(ctx, P, &L.w16, 4 * per));
+  LDM_TRY(launch_to_bf16(ctx, L.w32, L.w16, 4 * per, st));
+  return tc_make_weight_map(ctx, L.w16, 4 * Cout, 4 * Cin, L.bn, &L.map_w);
+}
+
+int launch_time_terms(ldm_ctx* ctx, const float* t, float* out, int rows, cudaStream_t st) {
+  PixModel& M = ctx->pix;
+  pix_time_terms_kernel<<<rows, 128, 2 * M.temb * sizeof(float), st>>>(t, M.te0_w, M.te0_b, M.te2_w, M.te2_b, M.tfc_w[0], M.tfc_b[0],
+                                                                         M.tfc_w[1], M.tfc_b[1], M.tfc_w[2], M.tfc_b[2], out, M.temb, M.base);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+
+int ensure_pix_workspace(ldm_ctx* ctx, int B, int H, int W) {
+  PixModel& M = ctx->pix;
+  if (B <= M.cap && H == M.cap_h && W == M.cap_w) return 0;
+  LDM_CUDA(cudaDeviceSynchronize());
+  for (auto& kv : M.graphs) {
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
+  }
+  M.graphs.clear();
+  for (void* p : M.ws) cudaFree(p);
+  M.ws.clear();
+  M.cap = 0;
+  const size_t c = M.base, p1 = (size_t)B * H * W, p2 = p1 / 4, p3 = p1 / 16;
+  LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.a1, p1 * c));
+  LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.cat5, p1 * 2 * c));
+  LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.d1, p2 * 2 * c));
+  LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.a2, p2 * 2 * c));
+  LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.cat4, p2 * 4 * c));
+  LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.d2, p3 * 4 * c));
+  LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.a3, p3 * 4 * c));
+  LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.x3, p3 * 4 * c));
+  LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.bt, p3 * 8 * c));
+  LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.x4, p3 * 4 * c));
+  LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.a4, p2 * 2 * c));
+  LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.x5, p2 * 2 * c));
+  LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.a5, p1 * c));
+  LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.x6, p1 * c));
+  LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.tsample, (size_t)B * 7 * c));
+  LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.x_state, p1 * 3));
+  M.cap = B; M.cap_h = H; M.cap_w = W;
+  return 0;
+}
+
+// One forward over the workspace.  terms: (rows, 7 base) time terms, row stride tstride (0: one row for the batch).
+// fin: what out_conv does with eps.
+int run_forward(ldm_ctx* ctx, const float* x, const float* terms, int tstride, int B, int H, int W, PixOutArgs fin, int ddpm,
+                cudaStream_t st) {
+  PixModel& M = ctx->pix;
+  const int c = M.base, H2 = H / 2, H4 = H / 4, W2 = W / 2, W4 = W / 4;
+  const int P1 = B * H * W;
+  pix_conv_in_kernel<<<ceil_div(P1, 128), 128, (size_t)c * 28 * sizeof(float), st>>>(x, M.in_w, M.in_b, M.a1, H, W, c, P1);
+  LDM_LAUNCHED(ctx);
+  const float *t1 = terms, *t2 = terms + c, *t3 = terms + 3 * c;
+  // encoder (v4:113-122); x1 -> cat5[:, c:2c], x2 -> cat4[:, 2c:4c]
+  LDM_TRY(launch_conv_tc_ex(ctx, M.a1, c, M.c1b, M.c1b.b, M.cat5 + c, 2 * c, B, H, W, 1, 1, t1, tstride, st));
+  LDM_TRY(launch_conv_tc_ex(ctx, M.cat5 + c, 2 * c, M.down1, M.down1.b, M.d1, 2 * c, B, H, W, 0, 0, nullptr, 0, st));
+  LDM_TRY(launch_conv_tc_ex(ctx, M.d1, 2 * c, M.c2a, M.c2a.b, M.a2, 2 * c, B, H2, W2, 1, 1, nullptr, 0, st));
+  LDM_TRY(launch_conv_tc_ex(ctx, M.a2, 2 * c, M.c2b, M.c2b.b, M.cat4 + 2 * c, 4 * c, B, H2, W2, 1, 1, t2, tstride, st));
+  LDM_TRY(launch_conv_tc_ex(ctx, M.cat4 + 2 * c, 4 * c, M.down2, M.down2.b, M.d2, 4 * c, B, H2, W2, 0, 0, nullptr, 0, st));
+  LDM_TRY(launch_conv_tc_ex(ctx, M.d2, 4 * c, M.c3a, M.c3a.b, M.a3, 4 * c, B, H4, W4, 1, 1, nullptr, 0, st));
+  LDM_TRY(launch_conv_tc_ex(ctx, M.a3, 4 * c, M.c3b, M.c3b.b, M.x3, 4 * c, B, H4, W4, 1, 1, t3, tstride, st));
+  // bottleneck (v4:124)
+  LDM_TRY(launch_conv_tc_ex(ctx, M.x3, 4 * c, M.b0, M.b0.b, M.bt, 8 * c, B, H4, W4, 1, 1, nullptr, 0, st));
+  LDM_TRY(launch_conv_tc_ex(ctx, M.bt, 8 * c, M.b2, M.b2.b, M.x4, 4 * c, B, H4, W4, 1, 1, nullptr, 0, st));
+  // decoder (v4:126-133)
+  LDM_TRY(launch_conv_tc_ex(ctx, M.x4, 4 * c, M.up1, M.up1.b, M.cat4, 4 * c, B, H4, W4, 2, 0, nullptr, 0, st));
+  LDM_TRY(launch_conv_tc_ex(ctx, M.cat4, 4 * c, M.c4a, M.c4a.b, M.a4, 2 * c, B, H2, W2, 1, 1, nullptr, 0, st));
+  LDM_TRY(launch_conv_tc_ex(ctx, M.a4, 2 * c, M.c4b, M.c4b.b, M.x5, 2 * c, B, H2, W2, 1, 1, nullptr, 0, st));
+  LDM_TRY(launch_conv_tc_ex(ctx, M.x5, 2 * c, M.up2, M.up2.b, M.cat5, 2 * c, B, H2, W2, 2, 0, nullptr, 0, st));
+  LDM_TRY(launch_conv_tc_ex(ctx, M.cat5, 2 * c, M.c5a, M.c5a.b, M.a5, c, B, H, W, 1, 1, nullptr, 0, st));
+  LDM_TRY(launch_conv_tc_ex(ctx, M.a5, c, M.c5b, M.c5b.b, M.x6, c, B, H, W, 1, 1, nullptr, 0, st));
+  fin.in = M.x6; fin.w = M.out_w; fin.bias = M.out_b; fin.res_ratio = M.res_ratio; fin.x_in = x;
+  fin.H = H; fin.W = W; fin.C = c; fin.total_pix = P1;
+  const size_t smem = (size_t)27 * c * sizeof(float);
+  if (ddpm) pix_conv_out_kernel<1><<<ceil_div(P1, 128), 128, smem, st>>>(fin);
+  else pix_conv_out_kernel<0><<<ceil_div(P1, 128), 128, smem, st>>>(fin);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+
+int check_shape(int B, int H, int W) {
+  LDM_CHECK(B > 0 && H >= 8 && W >= 8 && H % 4 == 0 && W % 4 == 0, "pixel path: need batch > 0 and H, W multiples of 4 (got %d x %d x %d)", B, H, W);
+  LDM_CHECK((long long)B * H * W * 8 < (1ll << 31), "pixel path: batch %d at %dx%d exceeds the 32-bit pixel index range", B, H, W);
+  return 0;
+}
+
+int run_loop(ldm_ctx* ctx, int B, int H, int W, int t_start, int t_end, const float* noise, cudaStream_t st) {
+  PixModel& M = ctx->pix;
+  const size_t slab = (size_t)B * 3 * H * W;
+  for (int t = t_start, j = 0; t >= t_end; --t, ++j) {
+    PixOutArgs f = {};
+    f.out = M.x_state;
+    f.noise = noise ? noise + (size_t)j * slab : nullptr;
+    f.rng = ctx->rng_dev;
+    f.c2 = ctx->c2[t]; f.sqrt_alpha = ctx->sqrt_alpha[t]; f.sigma = ctx->sigma[t]; f.step = t;
+    LDM_TRY(run_forward(ctx, M.x_state, M.tab + (size_t)t * 7 * M.base, 0, B, H, W, f, 1, st));
+  }
+  return 0;
+}
+
+}  // namespace
+
+void pix_drop_graphs(ldm_ctx* ctx) {
+  for (auto& kv : ctx->pix.graphs) {
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
+  }
+  ctx->pix.graphs.clear();
+}
+
+void pix_free(ldm_ctx* ctx) {
+  pix_drop_graphs(ctx);
+  for (void* p : ctx->pix.ws) cudaFree(p);
+  for (void* p : ctx->pix.allocs) cudaFree(p);
+  ctx->pix.ws.clear();
+  ctx->pix.allocs.clear();
+}
+
+extern "C" LDM_API int ldm_pix_pack(ldm_ctx* ctx, const ldm_pix_weights* w, void* stream) {
+  LDM_CHECK(ctx && w, "ldm_pix_pack: null argument");
+  LDM_CHECK(ctx->precision == LDM_PRECISION_BF16, "ldm_pix_pack: the pixel-space path runs on the bf16 tensor-core kernels only (context precision %d)",
+            ctx->precision);
+  LDM_CHECK(w->in_channels == 3, "ldm_pix_pack: in_channels must be 3 (got %d)", w->in_channels);
+  LDM_CHECK(w->base_channels >= 64 && w->base_channels % 64 == 0 && w->base_channels <= 256,
+            "ldm_pix_pack: base_channels must be 64, 128, 192 or 256 (got %d)", w->base_channels);
+  LDM_CHECK(w->time_emb_dim > 0 && w->time_emb_dim <= 4096 && w->n_t > 0, "ldm_pix_pack: bad time_emb_dim / n_t");
+  cudaStream_t st = (cudaStream_t)stream;
+  LDM_CUDA(cudaSetDevice(ctx->device));
+  LDM_TRY(tc_init(ctx));
+  LDM_CUDA(cudaDeviceSynchronize());
+  pix_free(ctx);
+  ctx->pix = PixModel();
+  PixModel& M = ctx->pix;
+  auto& P = M.allocs;
+  const int c = w->base_channels, te = w->time_emb_dim;
+  M.base = c; M.temb = te; M.n_t = w->n_t;
+  LDM_TRY(own(ctx, P, w->time_embed0_w, te, &M.te0_w, st));
+  LDM_TRY(own(ctx, P, w->time_embed0_b, te, &M.te0_b, st));
+  LDM_TRY(own(ctx, P, w->time_embed2_w, (size_t)te * te, &M.te2_w, st));
+  LDM_TRY(own(ctx, P, w->time_embed2_b, te, &M.te2_b, st));
+  const int tc[3] = {c, 2 * c, 4 * c};
+  for (int i = 0; i < 3; ++i) {
+    LDM_TRY(own(ctx, P, w->time_fc_w[i], (size_t)tc[i] * te, &M.tfc_w[i], st));
+    LDM_TRY(own(ctx, P, w->time_fc_b[i], tc[i], &M.tfc_b[i], st));
+  }
+  if (w->res_ratio) LDM_TRY(own(ctx, P, w->res_ratio, 1, &M.res_ratio, st));
+  // conv1.0 and out_conv: tap-major fp32 for the CUDA-core kernels
+  LDM_CHECK(w->conv1[0].w && w->conv1[0].b && w->out_conv.w && w->out_conv.b, "ldm_pix_pack: conv1.0 / out_conv weights missing");
+  LDM_TRY(ldm_alloc_t(ctx, P, &M.in_w, (size_t)c * 27));
+  LDM_TRY(launch_pack_conv(ctx, w->conv1[0].w, M.in_w, c, 3, 3, 3, st));
+  LDM_TRY(own(ctx, P, w->conv1[0].b, c, &M.in_b, st));
+  LDM_TRY(ldm_alloc_t(ctx, P, &M.out_w, (size_t)3 * 9 * c));
+  LDM_TRY(launch_pack_conv(ctx, w->out_conv.w, M.out_w, 3, c, 3, 3, st));
+  LDM_TRY(own(ctx, P, w->out_conv.b, 3, &M.out_b, st));
+  LDM_TRY(pack_conv(ctx, P, M.c1b, w->conv1[1], c, c, 3, st));
+  LDM_TRY(pack_conv(ctx, P, M.down1, w->down1, 2 * c, c, 4, st));
+  LDM_TRY(pack_conv(ctx, P, M.c2a, w->conv2[0], 2 * c, 2 * c, 3, st));
+  LDM_TRY(pack_conv(ctx, P, M.c2b, w->conv2[1], 2 * c, 2 * c, 3, st));
+  LDM_TRY(pack_conv(ctx, P, M.down2, w->down2, 4 * c, 2 * c, 4, st));
+  LDM_TRY(pack_conv(ctx, P, M.c3a, w->conv3[0], 4 * c, 4 * c, 3, st));
+  LDM_TRY(pack_conv(ctx, P, M.c3b, w->conv3[1], 4 * c, 4 * c, 3, st));
+  LDM_TRY(pack_conv(ctx, P, M.b0, w->bottleneck[0], 8 * c, 4 * c, 3, st));
+  LDM_TRY(pack_conv(ctx, P, M.b2, w->bottleneck[1], 4 * c, 8 * c, 3, st));
+  LDM_TRY(pack_convT(ctx, P, M.up1, w->up1, 4 * c, 2 * c, st));
+  LDM_TRY(pack_conv(ctx, P, M.c4a, w->conv4[0], 2 * c, 4 * c, 3, st));
+  LDM_TRY(pack_conv(ctx, P, M.c4b, w->conv4[1], 2 * c, 2 * c, 3, st));
+  LDM_TRY(pack_convT(ctx, P, M.up2, w->up2, 2 * c, c, st));
+  LDM_TRY(pack_conv(ctx, P, M.c5a, w->conv5[0], c, 2 * c, 3, st));
+  LDM_TRY(pack_conv(ctx, P, M.c5b, w->conv5[1], c, c, 3, st));
+  // the sampler's time terms for t = 0 .. n_t-1
+  LDM_TRY(ldm_alloc_t(ctx, P, &M.tab, (size_t)M.n_t * 7 * c));
+  LDM_TRY(launch_time_terms(ctx, nullptr, M.tab, M.n_t, st));
+  LDM_CUDA(cudaStreamSynchronize(st));
+  M.packed = true;
+  return 0;
+}
+
+extern "C" LDM_API int ldm_pix_forward(ldm_ctx* ctx, const float* x_dev, const float* t_dev, float* eps_out_dev, int batch, int H, int W,
+                                       void* stream) {
+  LDM_CHECK(ctx && x_dev && t_dev && eps_out_dev, "ldm_pix_forward: null argument");
+  LDM_CHECK(ctx->pix.packed, "ldm_pix_forward: model not packed (ldm_pix_pack)");
+  LDM_TRY(check_shape(batch, H, W));
+  cudaStream_t st = (cudaStream_t)stream;
+  LDM_CUDA(cudaSetDevice(ctx->device));
+  LDM_TRY(ensure_pix_workspace(ctx, batch, H, W));
+  PixModel& M = ctx->pix;
+  LDM_TRY(launch_time_terms(ctx, t_dev, M.tsample, batch, st));
+  PixOutArgs f = {};
+  f.out = eps_out_dev;
+  return run_forward(ctx, x_dev, M.tsample, 7 * M.base, batch, H, W, f, 0, st);
+}
+
+extern "C" LDM_API int ldm_pix_sample(ldm_ctx* ctx, float* x_inout, int t_start, int t_end, const float* noise, uint64_t seed,
+                                      uint64_t sample_offset, int batch, int H, int W, int use_graph, void* stream) {
+  LDM_CHECK(ctx && x_inout, "ldm_pix_sample: null argument");
+  LDM_CHECK(ctx->pix.packed, "ldm_pix_sample: model not packed (ldm_pix_pack)");
+  LDM_CHECK(ctx->n_steps > 0, "ldm_pix_sample: schedule not set (ldm_set_schedule)");
+  LDM_CHECK(t_end >= 0 && t_start >= t_end && t_start < ctx->n_steps, "ldm_pix_sample: need 0 <= t_end <= t_start < n_steps (%d), got %d..%d",
+            ctx->n_steps, t_start, t_end);
+  LDM_CHECK(ctx->n_steps <= ctx->pix.n_t, "ldm_pix_sample: time table has %d rows but the schedule has %d steps", ctx->pix.n_t, ctx->n_steps);
+  LDM_TRY(check_shape(batch, H, W));
+  cudaStream_t st = (cudaStream_t)stream;
+  LDM_CUDA(cudaSetDevice(ctx->device));
+  LDM_TRY(ensure_pix_workspace(ctx, batch, H, W));
+  PixModel& M = ctx->pix;
+  const size_t xbytes = (size_t)batch * 3 * H * W * sizeof(float);
+  LDM_CUDA(cudaMemcpyAsync(M.x_state, x_inout, xbytes, cudaMemcpyDeviceToDevice, st));
+  LDM_TRY(launch_set_rng(ctx, ctx->rng_dev, seed, sample_offset, st));
+  if (!use_graph) {
+    LDM_TRY(run_loop(ctx, batch, H, W, t_start, t_end, noise, st));
+  } else {
+    const auto key = std::make_tuple(batch, H, W, t_start, t_end, noise ? 1 : 0);
+    auto it = M.graphs.find(key);
+    if (it != M.graphs.end() && it->second.noise != noise) {
+      cudaGraphExecDestroy(it->second.exec);
+      cudaGraphDestroy(it->second.graph);
+      M.graphs.erase(it);
+      it = M.graphs.end();
+    }
+    if (it == M.graphs.end()) {
+      GraphEntry ge;
+      const unsigned long long before = ctx->launches;
+      LDM_CUDA(cudaStreamBeginCapture(ctx->cap_stream, cudaStreamCaptureModeThreadLocal));
+      ctx->capturing = true;
+      int r = run_loop(ctx, batch, H, W, t_start, t_end, noise, ctx->cap_stream);
+      ctx->capturing = false;
+      cudaError_t ce = cudaStreamEndCapture(ctx->cap_stream, &ge.graph);
+      if (r != 0) { if (ge.graph) cudaGraphDestroy(ge.graph); return r; }
+      LDM_CUDA(ce);
+      ge.n_nodes = (size_t)(ctx->launches - before);
+      ctx->launches = before;
+      LDM_CUDA(cudaGraphInstantiate(&ge.exec, ge.graph, 0));
+      ge.noise = noise;
+      it = M.graphs.emplace(key, ge).first;
+    }
+    LDM_CUDA(cudaGraphLaunch(it->second.exec, st));
+    ctx->launches += it->second.n_nodes;
+  }
+  LDM_CUDA(cudaMemcpyAsync(x_inout, M.x_state, xbytes, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}

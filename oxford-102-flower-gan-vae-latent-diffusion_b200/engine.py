@@ -75,6 +75,7 @@ class Engine:
         self._dec_key = None
         self._sched_key = None
         self._cls_key = None
+        self._pix_key = None
 
     def __del__(self):
         try:
@@ -277,6 +278,53 @@ class Engine:
         check(lib().ldm_sample(self.ctx, _ptr(x), int(t_start), int(t_end), _ptr(noise) if noise is not None else None,
                                seed, sample_offset, B, 1 if use_graph else 0, self.stream()), "ldm_sample")
         del keep
+        return x
+
+    # ------------------------------------------------------------------ v4 / v5 pixel-space denoiser
+    def pack_pix(self, m, n_t):
+        key = _state_key(m, (n_t,))
+        if key == self._pix_key:
+            return
+        dev, keep = self.device, []
+        def P(t):
+            v = _f32(t, dev); keep.append(v); return v.data_ptr()
+        def C(dst, conv):
+            dst.w, dst.b = P(conv.weight), P(conv.bias)
+        w = _lib.PixWeights()
+        w.in_channels, w.base_channels, w.time_emb_dim, w.n_t = m.in_channels, m.base_channels, m.time_emb_dim, int(n_t)
+        rr = getattr(m, "res_ratio", None)
+        w.res_ratio = P(rr.reshape(1)) if rr is not None else None
+        w.time_embed0_w, w.time_embed0_b = P(m.time_embed[0].weight), P(m.time_embed[0].bias)
+        w.time_embed2_w, w.time_embed2_b = P(m.time_embed[2].weight), P(m.time_embed[2].bias)
+        for i, fc in enumerate((m.time_fc1, m.time_fc2, m.time_fc3)):
+            w.time_fc_w[i], w.time_fc_b[i] = P(fc.weight), P(fc.bias)
+        for name in ("conv1", "conv2", "conv3", "bottleneck", "conv4", "conv5"):
+            seq = getattr(m, name)
+            C(getattr(w, name)[0], seq[0]); C(getattr(w, name)[1], seq[2])
+        for name in ("down1", "down2", "up1", "up2", "out_conv"):
+            C(getattr(w, name), getattr(m, name))
+        check(lib().ldm_pix_pack(self.ctx, ctypes.byref(w), self.stream()), "ldm_pix_pack")
+        self._pix_key = key
+
+    def pix_forward(self, x, t):
+        x = x.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        B, C, H, W = x.shape
+        t = t.detach().to(device=self.device).reshape(-1).float().contiguous()      # v4:104: t.view(B, 1).float()
+        if t.numel() != B:
+            raise RuntimeError("shape '[%d, 1]' is invalid for input of size %d" % (B, t.numel()))   # what .view(B, 1) raises
+        out = torch.empty_like(x)
+        check(lib().ldm_pix_forward(self.ctx, _ptr(x), _ptr(t), _ptr(out), B, H, W, self.stream()), "ldm_pix_forward")
+        return out
+
+    def pix_sample(self, x, t_start, t_end, noise=None, seed=0, sample_offset=0, use_graph=True):
+        """In-place chain on x (B, 3, H, W) for t = t_start .. t_end."""
+        B, C, H, W = x.shape
+        if noise is not None:
+            noise = noise.detach().to(device=self.device, dtype=torch.float32).contiguous()
+            if tuple(noise.shape) != (t_start - t_end + 1, B, C, H, W):
+                raise ValueError("noise must have shape %s" % ((t_start - t_end + 1, B, C, H, W),))
+        check(lib().ldm_pix_sample(self.ctx, _ptr(x), int(t_start), int(t_end), _ptr(noise) if noise is not None else None,
+                                   seed, sample_offset, B, H, W, 1 if use_graph else 0, self.stream()), "ldm_pix_sample")
         return x
 
     # ------------------------------------------------------------------ decoder
