@@ -130,9 +130,9 @@ def test_pix_chain_against_reference_goldens(ver, style):
     sd = weights.make_pix_state(SEED, style, v5=(ver == "v5"))
     sched = R.schedule(1000)
     one = d.p_sample(x, 700, noise=noise[0])
-    assert R.rel_l2(one.cpu(), P.p_sample(sd, sched, T(g["x"]), 700, noise[0].cpu())) < 1e-3
+    assert R.rel_l2(one.cpu(), P.p_sample(sd, sched, T(g["x"]), 700, noise[0].cpu())) < 5e-3     # bf16 eps error x c2(t)
     zero = d.p_sample(x, 0, noise=noise[0])
-    assert R.rel_l2(zero.cpu(), P.p_sample(sd, sched, T(g["x"]), 0)) < 1e-3
+    assert R.rel_l2(zero.cpu(), P.p_sample(sd, sched, T(g["x"]), 0)) < 5e-3
 
 
 @pytest.mark.gpu
