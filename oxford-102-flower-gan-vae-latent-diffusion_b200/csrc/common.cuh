@@ -172,6 +172,8 @@ struct ConvLayer {       // implicit GEMM: out[pix, co] = sum_{tap, ci} in[pix +
   float* b = nullptr;
   CUtensorMap map_w;
   int bn = 0;            // output-channel tile of conv_tc_kernel (0: conv_tc_pick_bn(Cout))
+  CUtensorMap map_w_alt; // same weights with a bn_alt-row box: used when the bn grid would not fill the SMs twice
+  int bn_alt = 0;
 };
 
 struct ResBlockModel {
@@ -222,6 +224,7 @@ struct PixModel {
   float *in_w = nullptr, *in_b = nullptr;   // conv1.0 as (base, 27) tap-major (ky, kx, ci)
   float *out_w = nullptr, *out_b = nullptr; // out_conv as (3, 9 base)
   float* res_ratio = nullptr;               // device scalar (v5) or null (v4)
+  ConvLayer out16;                          // out_conv padded to 16 output rows, bf16 (tensor-core halo kernel; base == 64)
   ConvLayer c1b, down1, c2a, c2b, down2, c3a, c3b, b0, b2, up1, c4a, c4b, up2, c5a, c5b;   // up1 / up2: 4 stacked sub-pixel kernels
   // activation workspace (NHWC bf16) for `cap` samples of cap_h x cap_w
   int cap = 0, cap_h = 0, cap_w = 0;
@@ -229,6 +232,7 @@ struct PixModel {
   bf16 *a1, *cat5, *d1, *a2, *cat4, *d2, *a3, *x3, *bt, *x4, *a4, *x5, *a5, *x6;
   float* tsample = nullptr;                 // (cap, 7 base) per-sample time terms of forward(x, t)
   float* x_state = nullptr;                 // (cap, 3, H, W) fp32 chain state the captured graph works on
+  float* eps = nullptr;                     // (cap, 3, H, W) fp32 eps of the current step (sampler)
   std::map<std::tuple<int, int, int, int, int, int>, GraphEntry> graphs;   // (batch, H, W, t_start, t_end, noise mode)
 };
 

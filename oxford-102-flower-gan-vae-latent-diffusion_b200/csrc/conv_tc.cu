@@ -16,6 +16,9 @@
 //   warps 2-5 : epilogue (tcgen05.ld, + bias, bf16 pack, 16-byte stores; sub-pixel scatter for the transposed conv)
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include "pix_out.cuh"
+
+#include <cstdlib>
 
 int tc_init(ldm_ctx* ctx);
 
@@ -179,6 +182,219 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 1) tc::tmem_dealloc<kTmemCols>(tmem_base);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// conv_halo_kernel: 3x3 convolution with Cin = 64 for LARGE images (64 x 64 and up), where conv_tc_kernel is bound by
+// L2 -> shared-memory traffic (every tap reloads the 16 KB pixel tile and every CTA reloads the weights: 216 KB per
+// 128 pixels against 1152 tensor-pipe cycles).  Here a persistent CTA keeps all nine weight tiles resident and loads
+// each pixel tile ONCE, with its halo, as one TMA box (64 ch, W + 2, rows, 1) at (0, -1, r - 1, n): the out-of-bounds
+// columns / rows are zero-filled, so the box lands as rows of W + 2 "padded slots".  In that padded row-major order a
+// tap (dy, dx) is a pure shift by dy (W + 2) + dx slots, i.e. the SAME shared-memory tile read through a UMMA descriptor
+// whose start address is moved by whole 128-byte rows (the descriptor's base-offset field carries the swizzle phase
+// of a start that is not 1024-byte aligned).  A work unit is 128 consecutive padded slots of one image (W = 64: 33
+// units per image, 2 of 66 slots per row are border slots whose results are dropped): 42 KB of loads instead of 216.
+//   warp 0: TMA producer (2-stage ring of halo tiles)   warp 1: MMA issuer (9 taps x 4 UMMA 128 x BN x 16 per unit,
+//   two TMEM accumulators)                               warps 2-5: epilogue of unit j under the MMAs of unit j + 1
+// MODE 0: bias / ReLU / time term, bf16 NHWC store.  MODE 1 / 2 (BN = 16, three real output channels): out_conv of the
+// pixel path, eps store / posterior update (pix_out.cuh).
+// ------------------------------------------------------------------------------------------------------------------
+struct HaloArgs {
+  int H, W, Wp;            // Wp = W + 2
+  int nrows;               // rows of the halo box
+  int units_per_img;       // ceil(H * Wp / 128)
+  int total_units;         // B * units_per_img
+  int a_bytes, a_stride;   // bytes of one halo tile; stage pitch (1024-aligned, plus one guard row in front)
+  int out_pitch, relu, post_stride;
+  const float* post;
+  const float* bias;
+  bf16* out;
+  int base_off_mode;       // 1: descriptor base offset = (address >> 7) & 7;  0: none
+  int debug;               // timing experiments (LDM_HALO_DEBUG): 1 = load only the first two tiles, 2 = unshifted descriptors, 4 = no stores
+  PixOutArgs fin;          // MODE 1 / 2
+};
+
+__device__ __forceinline__ uint64_t make_desc_sw128_row(uint32_t smem_addr, int base_off_mode) {
+  uint64_t d = tc::make_desc_sw128(smem_addr);
+  if (base_off_mode) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
+  return d;
+}
+
+constexpr int kHaloStages = 3;       // halo tiles in flight (one 42 KB TMA box has ~2 us of latency from a cold L2)
+constexpr int kHaloTmemStages = 4;
+
+template <int BN, int MODE, int NCH>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const HaloArgs a) {
+  constexpr uint32_t kWTap = BN * BK * 2, kWBytes = 9 * kWTap, kWRegion = (kWBytes + 1023) & ~1023u;
+  // Consecutive tcgen05.mma into ONE accumulator are issued ~100 cycles apart whatever N is (measured: 36 dependent
+  // MMAs per unit took 3.2 k cycles at N = 16 and 3.7 k at N = 64), so the nine taps are dealt round-robin to NCH
+  // independent accumulators that the epilogue adds up.
+  constexpr int kAcc1 = BN < 32 ? 32 : BN;     // TMEM columns of one accumulator
+  constexpr int kAcc = NCH * kAcc1;            // TMEM columns of one unit (stage)
+  constexpr int kTS = kHaloTmemStages;         // accumulator stages: the epilogue of unit j runs under the MMAs of j+1 .. j+3
+  constexpr int kCols = kTS * kAcc <= 64 ? 64 : (kTS * kAcc <= 128 ? 128 : (kTS * kAcc <= 256 ? 256 : 512));
+  static_assert(kTS * kAcc <= 512, "TMEM budget");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w_s = smem;
+  uint8_t* a_s = smem + kWRegion + 1024;        // one guard KB: tap (-1, -1) of slot 0 reads 128 bytes in front of the tile
+  __shared__ __align__(8) uint64_t full_bar[kHaloStages], empty_bar[kHaloStages], tfull_bar[kTS], tempty_bar[kTS], w_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float bias_s[BN], post_s[BN];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool spin = (a.debug & 32) != 0;
+#define HWAIT(bar, par, code) (spin ? tc::mbar_wait_spin(bar, par, code) : tc::mbar_wait(bar, par, code))
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&map_a);
+    tc::prefetch_tmap(&map_w);
+    for (int s = 0; s < kHaloStages; ++s) {
+      tc::mbar_init(&full_bar[s], 1);
+      tc::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < kTS; ++s) {
+      tc::mbar_init(&tfull_bar[s], 1);
+      tc::mbar_init(&tempty_bar[s], 4);
+    }
+    tc::mbar_init(&w_bar, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc<kCols>(&tmem_slot);
+  if (warp >= 2)
+    for (int i = threadIdx.x - 64; i < BN; i += 128) {
+      bias_s[i] = a.bias ? a.bias[i] : 0.f;
+      post_s[i] = (a.post && a.post_stride == 0) ? a.post[i] : 0.f;      // one time term for the whole batch (the sampler)
+    }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  const int rowslots = a.Wp;
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      tc::mbar_arrive_expect_tx(&w_bar, kWBytes);
+      for (int tap = 0; tap < 9; ++tap) tc::tma_load_2d(w_s + tap * kWTap, &map_w, &w_bar, tap * BK, 0);
+      int it = 0;
+      for (int u = blockIdx.x; u < a.total_units; u += gridDim.x, ++it) {
+        const int s = it % kHaloStages;
+        if (!HWAIT(&empty_bar[s], (uint32_t)((it / kHaloStages) & 1) ^ 1u, 11)) break;
+        const int n = u / a.units_per_img, s0 = (u - n * a.units_per_img) * BM, r = s0 / rowslots;
+        if ((a.debug & 1) && it >= 2) { tc::mbar_arrive(&full_bar[s]); continue; }
+        tc::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)a.a_bytes);
+        tc::tma_load_4d(a_s + (size_t)s * a.a_stride, &map_a, &full_bar[s], 0, -1, r - 1, n);
+      }
+    }
+  } else if (warp == 1) {
+    if (tc::elect_one()) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16(BM, BN);
+      bool ok = HWAIT(&w_bar, 0, 12);
+      const uint32_t w_addr = tc::smem_u32(w_s);
+      int it = 0;
+      for (int u = blockIdx.x; u < a.total_units && ok; u += gridDim.x, ++it) {
+        const int s = it % kHaloStages, ts = it % kTS;
+        const uint32_t ph = (uint32_t)((it / kHaloStages) & 1), tph = (uint32_t)((it / kTS) & 1);
+        const int s0 = (u % a.units_per_img) * BM;
+        const int first = s0 % rowslots + rowslots;      // tile slot of output slot 0 (the tile starts one row above)
+        ok = HWAIT(&tempty_bar[ts], tph ^ 1u, 13) && HWAIT(&full_bar[s], ph, 14);
+        tc::fence_after_sync();
+        const uint32_t a_addr = tc::smem_u32(a_s + (size_t)s * a.a_stride);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ts * kAcc);
+#pragma unroll 1
+        for (int tap = 0; tap < ((a.debug & 8) ? NCH : 9); ++tap) {
+          const int shift = (a.debug & 2) ? 0 : first + (tap / 3 - 1) * rowslots + (tap % 3 - 1);
+          const uint64_t da = make_desc_sw128_row(a_addr + (uint32_t)shift * 128u, a.base_off_mode);
+          const uint64_t dw = tc::make_desc_sw128(w_addr + tap * kWTap);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            tc::umma_bf16(d_tmem + (uint32_t)((tap % NCH) * kAcc1), da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc,
+                          (uint32_t)((tap >= NCH) || k != 0));
+        }
+        tc::umma_commit(&empty_bar[s]);
+        tc::umma_commit(&tfull_bar[ts]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int HW = a.H * a.W;
+    int it = 0;
+    for (int u = blockIdx.x; u < a.total_units; u += gridDim.x, ++it) {
+      const int s = it % kTS;
+      const uint32_t ph = (uint32_t)((it / kTS) & 1);
+      const int n = u / a.units_per_img, slot = (u - n * a.units_per_img) * BM + q * 32 + lane;
+      const int y = slot / rowslots, cx = slot - y * rowslots;
+      const bool valid = y < a.H && cx >= 1 && cx <= a.W && !(a.debug & 4);
+      const int rem = y * a.W + cx - 1;
+      if (!HWAIT(&tfull_bar[s], ph, 15)) break;
+      tc::fence_after_sync();
+      const uint32_t t_addr = tmem_base + (uint32_t)(s * kAcc) + ((uint32_t)(q * 32) << 16);
+      if (a.debug & 16) {
+      } else if (MODE == 0) {
+        bf16* dst = a.out + ((size_t)n * HW + (valid ? rem : 0)) * (size_t)a.out_pitch;
+        const float* prow = (a.post && a.post_stride) ? a.post + (size_t)n * a.post_stride : nullptr;   // per-sample time terms
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          float v[16];
+          tc::tmem_ld16(t_addr + (uint32_t)c0, v);
+#pragma unroll
+          for (int ch = 1; ch < NCH; ++ch) {
+            float v2[16];
+            tc::tmem_ld16(t_addr + (uint32_t)(ch * kAcc1 + c0), v2);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += v2[j];
+          }
+          if (valid) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              v[j] += bias_s[c0 + j];
+              if (a.relu) v[j] = fmaxf(v[j], 0.f);
+              v[j] += post_s[c0 + j];
+            }
+            if (prow) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(prow + c0) + j);
+                v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+              pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+            d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+      } else {
+        float v[16];
+        tc::tmem_ld16(t_addr, v);
+#pragma unroll
+        for (int ch = 1; ch < NCH; ++ch) {
+          float v2[16];
+          tc::tmem_ld16(t_addr + (uint32_t)(ch * kAcc1), v2);
+          v[0] += v2[0]; v[1] += v2[1]; v[2] += v2[2];
+        }
+        if (valid) {
+          float eps[3] = {v[0] + bias_s[0], v[1] + bias_s[1], v[2] + bias_s[2]};
+          float z[3] = {0.f, 0.f, 0.f};
+          if (MODE == 2) pix_noise(a.fin, n, rem, HW, z);
+          pix_finish<MODE == 2 ? 1 : 0>(a.fin, eps, n, rem, HW, z);
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty_bar[s]);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<kCols>(tmem_base);
+#undef HWAIT
+}
+
 // final_conv[3] + Sigmoid (v2:277-278): Conv2d(32, 3, 3, padding 1) over NHWC bf16 -> NCHW fp32.  N = 3 output
 // channels is no tensor-core shape: one thread per pixel on the CUDA cores, weights in shared memory.
 __global__ void __launch_bounds__(256)
@@ -290,7 +506,7 @@ int make_act_map_down(const bf16* base, int B, int H, int W, int C, int P, CUten
 }
 
 template <int BN>
-int launch_bn(ldm_ctx* ctx, const CUtensorMap& ma, const ConvLayer& L, const ConvTcArgs& a0, int nz, cudaStream_t st) {
+int launch_bn(ldm_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, const ConvTcArgs& a0, int nz, cudaStream_t st) {
   ConvTcArgs a = a0;
   const int nkb = a.taps * (a.Cin / BK);
   const size_t stage_bytes = (size_t)BM * BK * 2 + (size_t)BN * BK * 2;
@@ -299,7 +515,7 @@ int launch_bn(ldm_ctx* ctx, const CUtensorMap& ma, const ConvLayer& L, const Con
   a.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024;
   dim3 grid(ceil_div(a.total_pix, BM), a.Cout / BN, nz);
-  conv_tc_kernel<BN><<<grid, kThreads, smem, st>>>(ma, L.map_w, a);
+  conv_tc_kernel<BN><<<grid, kThreads, smem, st>>>(ma, mw, a);
   ctx->launches++;
   LDM_CUDA(cudaGetLastError());
   return 0;
@@ -331,11 +547,17 @@ int launch_conv_tc_ex(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLaye
   a.in_pitch = in_pitch; a.out_pitch = out_pitch; a.relu = relu; a.post = post; a.post_stride = post_stride;
   a.bias = bias; a.out = out;
   const int nz = mode == 2 ? 4 : 1;
-  switch (L.bn ? L.bn : conv_tc_pick_bn(L.Cout)) {
-    case 32: return launch_bn<32>(ctx, ma, L, a, nz, st);
-    case 64: return launch_bn<64>(ctx, ma, L, a, nz, st);
-    case 128: return launch_bn<128>(ctx, ma, L, a, nz, st);
-    case 256: return launch_bn<256>(ctx, ma, L, a, nz, st);
+  int bn = L.bn ? L.bn : conv_tc_pick_bn(L.Cout);
+  const CUtensorMap* mw = &L.map_w;
+  if (L.bn_alt && L.bn_alt < bn && ceil_div(a.total_pix, BM) * (L.Cout / bn) * nz < ctx->sm_count) {
+    bn = L.bn_alt;      // fewer tiles than SMs: halve the tile (measured: 128 tiles of 256 channels 33 us -> 256 tiles of 128 channels 24 us)
+    mw = &L.map_w_alt;
+  }
+  switch (bn) {
+    case 32: return launch_bn<32>(ctx, ma, *mw, a, nz, st);
+    case 64: return launch_bn<64>(ctx, ma, *mw, a, nz, st);
+    case 128: return launch_bn<128>(ctx, ma, *mw, a, nz, st);
+    case 256: return launch_bn<256>(ctx, ma, *mw, a, nz, st);
   }
   ldm_set_error("conv_tc: unsupported Cout %d", L.Cout);
   return -1;
@@ -344,6 +566,75 @@ int launch_conv_tc_ex(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLaye
 int launch_conv_tc(ldm_ctx* ctx, const bf16* in, const ConvLayer& L, const float* bias, bf16* out, int B, int H, int W,
                    int up, cudaStream_t st) {
   return launch_conv_tc_ex(ctx, in, L.Cin, L, bias, out, L.Cout, B, H, W, up, 0, nullptr, 0, st);
+}
+
+
+// 3x3 convolution, Cin = 64, through conv_halo_kernel.  L.map_w: (Cout rows, 9 * 64), box (64, Cout); Cout = 64 (bf16
+// NHWC output) or 16 (out_conv of the pixel path: fin != nullptr, rows 3..15 of the packed weight are zero).
+int conv_halo_supported(int H, int W, int Cin, int Cout) {
+  if (Cin != 64 || (Cout != 64 && Cout != 16) || W < 30 || W + 2 > 256) return 0;
+  const int Wp = W + 2, nrows = (Wp - 1 + 128 + Wp - 1) / Wp + 2;
+  const size_t a_stride = (((size_t)nrows * Wp * 128 + 1023) & ~(size_t)1023) + 1024;
+  const size_t smem = (((size_t)9 * Cout * 128 + 1023) & ~(size_t)1023) + 1024 + kHaloStages * a_stride + 1024;
+  return nrows <= 256 && smem <= 220 * 1024;
+}
+
+int launch_conv_halo(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer& L, const float* bias, bf16* out, int out_pitch,
+                     int B, int H, int W, int relu, const float* post, int post_stride, const PixOutArgs* fin, int ddpm,
+                     cudaStream_t st) {
+  LDM_TRY(conv_init(ctx));
+  LDM_CHECK(conv_halo_supported(H, W, L.Cin, L.Cout), "conv_halo: unsupported shape (H=%d W=%d Cin=%d Cout=%d)", H, W, L.Cin, L.Cout);
+  LDM_CHECK(((uintptr_t)in & 15) == 0 && in_pitch % 8 == 0, "conv_halo: input must be 16-byte aligned");
+  static bool attr_set = false;
+  if (!attr_set) {
+    LDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<64, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
+    LDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<16, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
+    LDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<16, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
+    attr_set = true;
+  }
+  HaloArgs a = {};
+  a.H = H; a.W = W; a.Wp = W + 2;
+  a.nrows = (a.Wp - 1 + 128 + a.Wp - 1) / a.Wp + 2;      // rows a 128-slot run can touch, plus one above and one below
+  a.units_per_img = ceil_div(H * a.Wp, BM);
+  a.total_units = B * a.units_per_img;
+  a.a_bytes = a.nrows * a.Wp * 128;
+  a.a_stride = ((a.a_bytes + 1023) & ~1023) + 1024;
+  a.out_pitch = out_pitch; a.relu = relu; a.post = post; a.post_stride = post_stride; a.bias = bias; a.out = out;
+  static int base_off_mode = -1;
+  if (base_off_mode < 0) {
+    const char* e = getenv("LDM_HALO_BASE_OFFSET");
+    base_off_mode = e ? atoi(e) : 0;   // measured on B200: the swizzle is a function of the absolute shared-memory address, no base offset
+  }
+  a.base_off_mode = base_off_mode;
+  static int debug = -1;
+  if (debug < 0) {
+    const char* e = getenv("LDM_HALO_DEBUG");
+    debug = e ? atoi(e) : 0;
+  }
+  a.debug = debug;
+  if (fin) a.fin = *fin;
+  CUtensorMap ma;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)in_pitch * 2, (cuuint64_t)W * in_pitch * 2, (cuuint64_t)H * W * in_pitch * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)a.Wp, (cuuint32_t)a.nrows, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode4(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(in), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      ldm_set_error("cuTensorMapEncodeTiled (halo box %d x %d) failed: CUresult %d", a.Wp, a.nrows, (int)r);
+      return (int)r;
+    }
+  }
+  const size_t smem = (((size_t)9 * L.Cout * 128 + 1023) & ~(size_t)1023) + 1024 + kHaloStages * (size_t)a.a_stride + 1024;
+  const int grid = a.total_units < ctx->sm_count ? a.total_units : ctx->sm_count;
+  if (!fin) conv_halo_kernel<64, 0, 1><<<grid, kThreads, smem, st>>>(ma, L.map_w, a);
+  else if (ddpm) conv_halo_kernel<16, 2, 2><<<grid, kThreads, smem, st>>>(ma, L.map_w, a);
+  else conv_halo_kernel<16, 1, 2><<<grid, kThreads, smem, st>>>(ma, L.map_w, a);
+  ctx->launches++;
+  LDM_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int launch_conv_out3(ldm_ctx* ctx, const bf16* in, const float* w, const float* bias, float* out, int B, int H, int W,

@@ -15,14 +15,22 @@
 //   eps never goes to memory.
 #include "common.cuh"
 #include "philox.cuh"
+#include "pix_out.cuh"
+
+#include <cstdlib>
 
 int launch_conv_tc_ex(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer& L, const float* bias, bf16* out, int out_pitch,
                       int B, int H, int W, int mode, int relu, const float* post, int post_stride, cudaStream_t st);
 int tc_make_weight_map(ldm_ctx* ctx, const bf16* w, int N, int K, int bn, CUtensorMap* out);
 int tc_init(ldm_ctx* ctx);
+int conv_halo_supported(int H, int W, int Cin, int Cout);
+int launch_conv_halo(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer& L, const float* bias, bf16* out, int out_pitch,
+                     int B, int H, int W, int relu, const float* post, int post_stride, const PixOutArgs* fin, int ddpm,
+                     cudaStream_t st);
 
 namespace {
 
+#define HW_MULT4(H, W) ((((H) * (W)) & 3) == 0)
 #define LDM_LAUNCHED(ctx)         \
   do {                            \
     (ctx)->launches++;            \
@@ -65,48 +73,102 @@ pix_time_terms_kernel(const float* __restrict__ t, const float* __restrict__ w0,
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// conv1.0 + ReLU (v4:55-56): x (B, 3, H, W) fp32 NCHW -> (B, H, W, C) bf16 NHWC.  One thread per pixel; weights
-// (C, 27) k = (ky*3 + kx)*3 + ci in shared memory (every lane reads the same address: broadcast).
+// conv1.0 + ReLU (v4:55-56): x (B, 3, H, W) fp32 NCHW -> (B, H, W, C) bf16 NHWC.  One thread per (4 pixels of a row, 8
+// output channels): the 3 x 6 x 3 input window sits in registers and every weight fetched from shared memory feeds four
+// pixels (the kernel is bound by shared-memory wavefronts otherwise).  Weights are k-major in shared memory, and the 8
+// channels of group g are stored as two 4-float runs at g * 4 and C / 2 + g * 4 so that the 8 lanes of a quarter warp
+// read one contiguous 128-byte line per 16-byte load (no bank conflicts).  W % 4 == 0.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-pix_conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ out,
-                   int H, int W, int C, int total_pix) {
-  extern __shared__ float sm[];
-  float* ws = sm;             // [C * 27]
+__global__ void __launch_bounds__(256)
+pix_conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w /* (C, 27) */, const float* __restrict__ b,
+                   bf16* __restrict__ out, int H, int W, int C, int total_quads) {
+  extern __shared__ __align__(16) float sm[];
+  float* ws = sm;             // [27][C] permuted
   float* bs = sm + C * 27;    // [C]
-  for (int i = threadIdx.x; i < C * 27; i += blockDim.x) ws[i] = w[i];
+  const int half = C >> 1;
+  for (int i = threadIdx.x; i < C * 27; i += blockDim.x) {
+    const int k = i / C, pos = i - k * C;
+    const int hi = pos >= half, r = pos - hi * half, g = r >> 2, j = (r & 3) + 4 * hi;     // channel g * 8 + j
+    ws[i] = __ldg(w + (g * 8 + j) * 27 + k);
+  }
   for (int i = threadIdx.x; i < C; i += blockDim.x) bs[i] = b[i];
   __syncthreads();
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= total_pix) return;
-  const int HW = H * W, n = p / HW, rem = p - n * HW, y = rem / W, xx = rem - y * W;
-  float in[27];
+  const int groups = C >> 3;
+  const long long total = (long long)total_quads * groups;
+#pragma unroll 1
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long long)gridDim.x * blockDim.x) {
+  const int quad = (int)(gid / groups), g = (int)(gid - (long long)quad * groups);
+  const int qpr = W >> 2, HW = H * W;
+  const int row = quad / qpr, x0 = (quad - row * qpr) << 2;
+  const int n = row / H, y = row - n * H;
+  float in[3][6][3];
 #pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
-    const int yy = y + tap / 3 - 1, xc = xx + tap % 3 - 1;
-    const bool ok = yy >= 0 && yy < H && xc >= 0 && xc < W;
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = y + ky - 1;
 #pragma unroll
-    for (int ci = 0; ci < 3; ++ci) in[tap * 3 + ci] = ok ? __ldg(x + ((size_t)n * 3 + ci) * HW + (size_t)yy * W + xc) : 0.f;
-  }
-  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)p * C);
-  for (int c8 = 0; c8 < C / 8; ++c8) {
-    float v[8];
+    for (int cx = 0; cx < 6; ++cx) {
+      const int xx = x0 + cx - 1;
+      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float* wr = ws + (c8 * 8 + j) * 27;
-      float acc = bs[c8 * 8 + j];
-#pragma unroll
-      for (int k = 0; k < 27; ++k) acc += in[k] * wr[k];
-      v[j] = fmaxf(acc, 0.f);
+      for (int ci = 0; ci < 3; ++ci) in[ky][cx][ci] = ok ? __ldg(x + ((size_t)n * 3 + ci) * HW + (size_t)yy * W + xx) : 0.f;
     }
+  }
+  float acc[4][8];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[p][j] = bs[g * 8 + j];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float* wr = ws + ((ky * 3 + kx) * 3 + ci) * C;
+        const float4 w0 = *reinterpret_cast<const float4*>(wr + g * 4);
+        const float4 w1 = *reinterpret_cast<const float4*>(wr + half + g * 4);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float v = in[ky][p + kx][ci];
+          acc[p][0] += v * w0.x; acc[p][1] += v * w0.y; acc[p][2] += v * w0.z; acc[p][3] += v * w0.w;
+          acc[p][4] += v * w1.x; acc[p][5] += v * w1.y; acc[p][6] += v * w1.z; acc[p][7] += v * w1.w;
+        }
+      }
+  const size_t p0 = (size_t)n * HW + (size_t)y * W + x0;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
     uint32_t pk[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(acc[p][2 * j], 0.f), fmaxf(acc[p][2 * j + 1], 0.f));
       pk[j] = *reinterpret_cast<uint32_t*>(&h2);
     }
-    dst[c8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    reinterpret_cast<uint4*>(out + (p0 + p) * C)[g] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
+  }
+}
+
+// The posterior update of p_sample alone (v4:159-168) on the flattened (B, 3 H W) state: four consecutive elements are
+// one Philox counter (oracle/philox.py); seed / first sample index are read from device memory so that a captured
+// graph replays with new seeds.
+__global__ void __launch_bounds__(256)
+pix_ddpm_kernel(float* __restrict__ x, const float* __restrict__ eps, float c2, float sqrt_alpha, float sigma,
+                const float* __restrict__ noise, const unsigned long long* __restrict__ rng, int step, int total4, int d4) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int row = i / d4, q = i - row * d4;
+  float4 xv = reinterpret_cast<float4*>(x)[i];
+  const float4 e = reinterpret_cast<const float4*>(eps)[i];
+  float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (sigma > 0.0f) {
+    if (noise) z = reinterpret_cast<const float4*>(noise)[i];
+    else z = philox_normal4(rng[0], rng[1] + (unsigned long long)row, (uint32_t)step, (uint32_t)q);
+  }
+  xv.x = ddpm_update_one(xv.x, e.x, c2, sqrt_alpha, sigma, z.x);
+  xv.y = ddpm_update_one(xv.y, e.y, c2, sqrt_alpha, sigma, z.y);
+  xv.z = ddpm_update_one(xv.z, e.z, c2, sqrt_alpha, sigma, z.z);
+  xv.w = ddpm_update_one(xv.w, e.w, c2, sqrt_alpha, sigma, z.w);
+  reinterpret_cast<float4*>(x)[i] = xv;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -114,19 +176,96 @@ pix_conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, con
 // DDPM == 0: eps (B, 3, H, W) fp32 NCHW is stored.   DDPM == 1: the posterior update of p_sample (v4:159-168) is applied
 // to the state x in place with explicit or in-kernel Philox noise; eps is never stored.
 // ------------------------------------------------------------------------------------------------------------------
-struct PixOutArgs {
-  const bf16* in;           // (B, H, W, C)
-  const float* w;           // (3, 9 C), k = tap * C + ci
-  const float* bias;        // (3)
-  const float* res_ratio;   // device scalar or null
-  const float* x_in;        // (B, 3, H, W): input of the forward (residual term of v5); the state when DDPM
-  float* out;               // DDPM == 0: eps;  DDPM == 1: the state (== x_in)
-  const float* noise;       // DDPM: explicit (B, 3, H, W) draws or null
-  const unsigned long long* rng;   // DDPM: {seed, sample_offset}
-  float c2, sqrt_alpha, sigma;
-  int step, H, W, C, total_pix;
-};
+// C == 64, W % 32 == 0: one warp per 32-pixel row segment, lane = channel pair (2 lane, 2 lane + 1).  The lane's 54
+// weights stay in registers for the whole kernel, a pixel is ONE coalesced 128-byte load per tap row (three loads per
+// column, each column feeds its three neighbouring outputs), and the 32 x 3 per-lane partial sums are reduced across the
+// warp with a transposing shuffle tree (31 shuffles per 32 values), leaving pixel x0 + lane on lane `lane`.
+template <int DDPM>
+__global__ void __launch_bounds__(128)
+pix_conv_out64_kernel(const PixOutArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int seg = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (seg >= (a.total_pix >> 5)) return;
+  const int H = a.H, W = a.W, HW = H * W, spr = W >> 5;
+  const int row = seg / spr, x0 = (seg - row * spr) << 5;
+  const int n = row / H, y = row - n * H;
+  float w[3][9][2];
+#pragma unroll
+  for (int o = 0; o < 3; ++o)
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const float2 t = __ldg(reinterpret_cast<const float2*>(a.w + o * 576 + tap * 64) + lane);
+      w[o][tap][0] = t.x; w[o][tap][1] = t.y;
+    }
+  float acc[3][32];
+#pragma unroll
+  for (int o = 0; o < 3; ++o)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[o][i] = 0.f;
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(a.in) + (size_t)n * HW * 32 + lane;
+#pragma unroll
+  for (int j = 0; j < 34; ++j) {          // input column x0 - 1 + j feeds outputs j - 2, j - 1, j (kx = 2, 1, 0)
+    const int xx = x0 - 1 + j;
+    float v[3][2];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      const bool ok = xx >= 0 && xx < W && yy >= 0 && yy < H;
+      const uint32_t u = ok ? __ldg(base + ((size_t)yy * W + xx) * 32) : 0u;
+      const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&u);
+      v[ky][0] = __low2float(h2); v[ky][1] = __high2float(h2);
+    }
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int p = j - kx;
+      if (p < 0 || p >= 32) continue;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int o = 0; o < 3; ++o)
+          acc[o][p] += v[ky][0] * w[o][ky * 3 + kx][0] + v[ky][1] * w[o][ky * 3 + kx][1];
+    }
+  }
+  float eps[3];
+#pragma unroll
+  for (int o = 0; o < 3; ++o) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < off; ++i) {
+        const float send = upper ? acc[o][i] : acc[o][i + off];
+        const float keep = upper ? acc[o][i + off] : acc[o][i];
+        acc[o][i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    eps[o] = acc[o][0] + __ldg(a.bias + o);
+  }
+  const int rem = y * W + x0 + lane;
+  float z[3] = {0.f, 0.f, 0.f};
+  if (DDPM && a.sigma > 0.f) {
+    if (a.noise) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) z[c] = a.noise[(size_t)n * 3 * HW + (size_t)c * HW + rem];
+    } else {
+      // the 4 lanes of a pixel quad share the Philox counter of each channel: lane (q, c) draws channel c for all four
+      const int c_own = (lane & 3) < 3 ? (lane & 3) : 0;
+      const uint32_t e = (uint32_t)(c_own * HW + (rem & ~3));
+      const float4 z4 = philox_normal4(a.rng[0], a.rng[1] + (unsigned long long)n, (uint32_t)a.step, e >> 2);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int src = (lane & ~3) + c;
+        const float t0 = __shfl_sync(0xffffffffu, z4.x, src), t1 = __shfl_sync(0xffffffffu, z4.y, src);
+        const float t2 = __shfl_sync(0xffffffffu, z4.z, src), t3 = __shfl_sync(0xffffffffu, z4.w, src);
+        const int jj = lane & 3;
+        z[c] = jj == 0 ? t0 : (jj == 1 ? t1 : (jj == 2 ? t2 : t3));
+      }
+    }
+  }
+  pix_finish<DDPM>(a, eps, n, rem, HW, z);
+}
 
+// generic shape: one thread per pixel, weights in shared memory
 template <int DDPM>
 __global__ void __launch_bounds__(128)
 pix_conv_out_kernel(const PixOutArgs a) {
@@ -159,33 +298,20 @@ pix_conv_out_kernel(const PixOutArgs a) {
     }
   }
   float eps[3] = {acc0, acc1, acc2};
-  const size_t i0 = (size_t)n * 3 * HW + rem;
-  if (a.res_ratio) {
-    const float rr = __ldg(a.res_ratio);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) eps[c] = __fadd_rn(eps[c], __fmul_rn(rr, a.x_in[i0 + (size_t)c * HW]));
-  }
-  if (DDPM == 0) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) a.out[i0 + (size_t)c * HW] = eps[c];
-  } else {
-    unsigned long long seed = 0, sample = 0;
-    if (!a.noise && a.sigma > 0.f) { seed = a.rng[0]; sample = a.rng[1] + (unsigned long long)n; }
+  float z[3] = {0.f, 0.f, 0.f};
+  if (DDPM && a.sigma > 0.f) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      float z = 0.f;
-      if (a.sigma > 0.f) {
-        if (a.noise) z = a.noise[i0 + (size_t)c * HW];
-        else {
-          const uint32_t e = (uint32_t)(c * HW + rem);
-          const float4 z4 = philox_normal4(seed, sample, (uint32_t)a.step, e >> 2);
-          const int j = e & 3;
-          z = j == 0 ? z4.x : (j == 1 ? z4.y : (j == 2 ? z4.z : z4.w));
-        }
+      if (a.noise) z[c] = a.noise[(size_t)n * 3 * HW + (size_t)c * HW + rem];
+      else {
+        const uint32_t e = (uint32_t)(c * HW + rem);
+        const float4 z4 = philox_normal4(a.rng[0], a.rng[1] + (unsigned long long)n, (uint32_t)a.step, e >> 2);
+        const int j = e & 3;
+        z[c] = j == 0 ? z4.x : (j == 1 ? z4.y : (j == 2 ? z4.z : z4.w));
       }
-      a.out[i0 + (size_t)c * HW] = ddpm_update_one(a.x_in[i0 + (size_t)c * HW], eps[c], a.c2, a.sqrt_alpha, a.sigma, z);
     }
   }
+  pix_finish<DDPM>(a, eps, n, rem, HW, z);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -211,6 +337,10 @@ int pack_conv(ldm_ctx* ctx, std::vector<void*>& P, ConvLayer& L, const ldm_pix_c
   LDM_TRY(own(ctx, P, c.b, Cout, &L.b, st));
   LDM_TRY(ldm_alloc_t(ctx, P, &L.w16, n));
   LDM_TRY(launch_to_bf16(ctx, L.w32, L.w16, n, st));
+  if (L.bn > 128) {
+    L.bn_alt = 128;
+    LDM_TRY(tc_make_weight_map(ctx, L.w16, Cout, L.taps * Cin, L.bn_alt, &L.map_w_alt));
+  }
   return tc_make_weight_map(ctx, L.w16, Cout, L.taps * Cin, L.bn, &L.map_w);
 }
 
@@ -265,8 +395,26 @@ int ensure_pix_workspace(ldm_ctx* ctx, int B, int H, int W) {
   LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.x6, p1 * c));
   LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.tsample, (size_t)B * 7 * c));
   LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.x_state, p1 * 3));
+  LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.eps, p1 * 3));
   M.cap = B; M.cap_h = H; M.cap_w = W;
   return 0;
+}
+
+bool use_halo() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LDM_PIX_HALO");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
+// 3x3 convolution + bias + ReLU [+ time term]: the halo kernel where it applies (Cin = 64 on a large image), else conv_tc
+int conv3(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer& L, bf16* out, int out_pitch, int B, int H, int W,
+          const float* post, int post_stride, cudaStream_t st) {
+  if (use_halo() && conv_halo_supported(H, W, L.Cin, L.Cout))
+    return launch_conv_halo(ctx, in, in_pitch, L, L.b, out, out_pitch, B, H, W, 1, post, post_stride, nullptr, 0, st);
+  return launch_conv_tc_ex(ctx, in, in_pitch, L, L.b, out, out_pitch, B, H, W, 1, 1, post, post_stride, st);
 }
 
 // One forward over the workspace.  terms: (rows, 7 base) time terms, row stride tstride (0: one row for the batch).
@@ -276,11 +424,16 @@ int run_forward(ldm_ctx* ctx, const float* x, const float* terms, int tstride, i
   PixModel& M = ctx->pix;
   const int c = M.base, H2 = H / 2, H4 = H / 4, W2 = W / 2, W4 = W / 4;
   const int P1 = B * H * W;
-  pix_conv_in_kernel<<<ceil_div(P1, 128), 128, (size_t)c * 28 * sizeof(float), st>>>(x, M.in_w, M.in_b, M.a1, H, W, c, P1);
+  {   // persistent blocks (two per SM): the weights are staged in shared memory once per block
+    const long long items = (long long)(P1 / 4) * (c / 8);
+    const long long want = (items + 255) / 256;
+    const unsigned grid = (unsigned)(want < 2ll * ctx->sm_count ? want : 2ll * ctx->sm_count);
+    pix_conv_in_kernel<<<grid, 256, (size_t)c * 28 * sizeof(float), st>>>(x, M.in_w, M.in_b, M.a1, H, W, c, P1 / 4);
+  }
   LDM_LAUNCHED(ctx);
   const float *t1 = terms, *t2 = terms + c, *t3 = terms + 3 * c;
   // encoder (v4:113-122); x1 -> cat5[:, c:2c], x2 -> cat4[:, 2c:4c]
-  LDM_TRY(launch_conv_tc_ex(ctx, M.a1, c, M.c1b, M.c1b.b, M.cat5 + c, 2 * c, B, H, W, 1, 1, t1, tstride, st));
+  LDM_TRY(conv3(ctx, M.a1, c, M.c1b, M.cat5 + c, 2 * c, B, H, W, t1, tstride, st));
   LDM_TRY(launch_conv_tc_ex(ctx, M.cat5 + c, 2 * c, M.down1, M.down1.b, M.d1, 2 * c, B, H, W, 0, 0, nullptr, 0, st));
   LDM_TRY(launch_conv_tc_ex(ctx, M.d1, 2 * c, M.c2a, M.c2a.b, M.a2, 2 * c, B, H2, W2, 1, 1, nullptr, 0, st));
   LDM_TRY(launch_conv_tc_ex(ctx, M.a2, 2 * c, M.c2b, M.c2b.b, M.cat4 + 2 * c, 4 * c, B, H2, W2, 1, 1, t2, tstride, st));
@@ -296,12 +449,33 @@ int run_forward(ldm_ctx* ctx, const float* x, const float* terms, int tstride, i
   LDM_TRY(launch_conv_tc_ex(ctx, M.a4, 2 * c, M.c4b, M.c4b.b, M.x5, 2 * c, B, H2, W2, 1, 1, nullptr, 0, st));
   LDM_TRY(launch_conv_tc_ex(ctx, M.x5, 2 * c, M.up2, M.up2.b, M.cat5, 2 * c, B, H2, W2, 2, 0, nullptr, 0, st));
   LDM_TRY(launch_conv_tc_ex(ctx, M.cat5, 2 * c, M.c5a, M.c5a.b, M.a5, c, B, H, W, 1, 1, nullptr, 0, st));
-  LDM_TRY(launch_conv_tc_ex(ctx, M.a5, c, M.c5b, M.c5b.b, M.x6, c, B, H, W, 1, 1, nullptr, 0, st));
+  LDM_TRY(conv3(ctx, M.a5, c, M.c5b, M.x6, c, B, H, W, nullptr, 0, st));
   fin.in = M.x6; fin.w = M.out_w; fin.bias = M.out_b; fin.res_ratio = M.res_ratio; fin.x_in = x;
   fin.H = H; fin.W = W; fin.C = c; fin.total_pix = P1;
-  const size_t smem = (size_t)27 * c * sizeof(float);
-  if (ddpm) pix_conv_out_kernel<1><<<ceil_div(P1, 128), 128, smem, st>>>(fin);
-  else pix_conv_out_kernel<0><<<ceil_div(P1, 128), 128, smem, st>>>(fin);
+  if (use_halo() && M.out16.w16 && conv_halo_supported(H, W, c, 16)) {
+    // out_conv on the tensor cores; in the sampler eps goes through a (B, 3, H, W) fp32 buffer to a full-occupancy
+    // update kernel (the four epilogue warps of a persistent tensor-core CTA are too few for the Philox arithmetic:
+    // fused, the kernel took 57 us per step at B = 64 against 25 us with a plain store)
+    PixOutArgs f2 = fin;
+    if (ddpm) f2.out = M.eps;
+    LDM_TRY(launch_conv_halo(ctx, M.x6, c, M.out16, M.out_b, nullptr, 0, B, H, W, 0, nullptr, 0, &f2, 0, st));
+    if (ddpm) {
+      const int total4 = P1 * 3 / 4;
+      pix_ddpm_kernel<<<ceil_div(total4, 256), 256, 0, st>>>(fin.out, M.eps, fin.c2, fin.sqrt_alpha, fin.sigma, fin.noise, fin.rng,
+                                                             fin.step, total4, 3 * H * W / 4);
+      LDM_LAUNCHED(ctx);
+    }
+    return 0;
+  }
+  if (c == 64 && W % 32 == 0 && HW_MULT4(H, W)) {
+    const int blocks = ceil_div(P1 / 32, 4);
+    if (ddpm) pix_conv_out64_kernel<1><<<blocks, 128, 0, st>>>(fin);
+    else pix_conv_out64_kernel<0><<<blocks, 128, 0, st>>>(fin);
+  } else {
+    const size_t smem = (size_t)27 * c * sizeof(float);
+    if (ddpm) pix_conv_out_kernel<1><<<ceil_div(P1, 128), 128, smem, st>>>(fin);
+    else pix_conv_out_kernel<0><<<ceil_div(P1, 128), 128, smem, st>>>(fin);
+  }
   LDM_LAUNCHED(ctx);
   return 0;
 }
@@ -380,6 +554,13 @@ extern "C" LDM_API int ldm_pix_pack(ldm_ctx* ctx, const ldm_pix_weights* w, void
   LDM_TRY(ldm_alloc_t(ctx, P, &M.out_w, (size_t)3 * 9 * c));
   LDM_TRY(launch_pack_conv(ctx, w->out_conv.w, M.out_w, 3, c, 3, 3, st));
   LDM_TRY(own(ctx, P, w->out_conv.b, 3, &M.out_b, st));
+  if (c == 64) {   // out_conv on the tensor cores: N padded 3 -> 16 with zero rows (conv_halo_kernel, BN = 16)
+    M.out16.Cin = c; M.out16.Cout = 16; M.out16.taps = 9; M.out16.bn = 16;
+    LDM_TRY(ldm_alloc_t(ctx, P, &M.out16.w16, (size_t)16 * 9 * c));
+    LDM_CUDA(cudaMemsetAsync(M.out16.w16, 0, (size_t)16 * 9 * c * sizeof(bf16), st));
+    LDM_TRY(launch_to_bf16(ctx, M.out_w, M.out16.w16, (size_t)3 * 9 * c, st));
+    LDM_TRY(tc_make_weight_map(ctx, M.out16.w16, 16, 9 * c, 16, &M.out16.map_w));
+  }
   LDM_TRY(pack_conv(ctx, P, M.c1b, w->conv1[1], c, c, 3, st));
   LDM_TRY(pack_conv(ctx, P, M.down1, w->down1, 2 * c, c, 4, st));
   LDM_TRY(pack_conv(ctx, P, M.c2a, w->conv2[0], 2 * c, 2 * c, 3, st));
