@@ -314,6 +314,143 @@ def run_ours(args, rank, world, local_rank):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------------
+# v4 pixel-space workload (BASELINE configs[4]): secondary line, `--workload v4`
+# ------------------------------------------------------------------------------------------------------
+PIX_MAC_PER_SAMPLE_STEP = (4096 * 64 * 27 + 4096 * 64 * 576 + 1024 * 128 * 1024 + 2 * 1024 * 128 * 1152 + 256 * 256 * 2048
+                           + 2 * 256 * 256 * 2304 + 256 * 512 * 2304 + 256 * 256 * 4608 + 1024 * 128 * 1024 + 1024 * 128 * 2304
+                           + 1024 * 128 * 1152 + 4096 * 64 * 512 + 4096 * 64 * 1152 + 4096 * 64 * 576 + 4096 * 3 * 576)   # v4:54-96 at 64 x 64
+
+
+def pix_cpu_rate(batch, steps, threads=None):
+    """images/s of the v4 reference path (oracle/restate_pix.py, bit-equal to the reference) on the host cores,
+    extrapolated from `steps` of the 1000 reverse steps at `batch` images."""
+    import torch
+    from oracle import philox, restate as R, restate_pix as P, weights
+    torch.set_grad_enabled(False)
+    torch.set_num_threads(threads or os.cpu_count() or 1)
+    sd = weights.make_pix_state(45, "init")
+    sched = R.schedule(N_STEPS)
+    x = torch.from_numpy(philox.normal_rows(1234, 0, batch, N_STEPS, 3 * 64 * 64)).view(batch, 3, 64, 64)
+    P.p_sample(sd, sched, x, N_STEPS - 1)
+    t0 = time.perf_counter()
+    for t in range(N_STEPS - 1, N_STEPS - 1 - steps, -1):
+        x = P.p_sample(sd, sched, x, t)
+    dt = (time.perf_counter() - t0) / steps * N_STEPS
+    return batch / dt, torch.get_num_threads()
+
+
+def run_pix(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from ldm_b200 import v4
+    from oracle import weights
+
+    torch.set_grad_enabled(False)
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    B, K, W = args.batch, args.steps, args.warmup
+    model = v4.SimpleUNet()
+    model.load_state_dict(weights.make_pix_state(45, "init"), strict=True)     # torch-default init statistics (v4 never re-initialises)
+    model = model.to(dev).eval()
+    diffusion = v4.DiffusionModel(model, N_STEPS, device=dev)
+    eng = diffusion._engine(dev)
+    total, lo = B * world, rank * B
+    gathered = torch.empty(total, 3, 64, 64, device=dev) if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(seed):
+        img = diffusion.sample((B, 3, 64, 64), seed=seed, sample_offset=lo)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, img)
+        return img
+
+    for i in range(W):
+        step(1234 + i)
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    launches0 = eng.launches()
+    barrier()
+    t_win0 = time.time()
+    for i in range(K):
+        flush.zero_()
+        ev[i][0].record()
+        img = step(99 + i)
+        ev[i][1].record()
+    barrier()
+    launches = eng.launches() - launches0
+    t_ms = sum(s.elapsed_time(e) for s, e in ev)
+    assert torch.isfinite(img).all()
+    # end to end: images land in pinned host memory every step (the only per-step input is the seed)
+    img_host = torch.empty(B, 3, 64, 64).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        img_host.copy_(diffusion.sample((B, 3, 64, 64), seed=500 + i, sample_offset=lo), non_blocking=True)
+        torch.cuda.synchronize()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    clocks = sampler.stop(t_win0, time.time())
+    if world > 1:
+        t = torch.tensor([t_ms, t_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_ms, t_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+    pk = peaks()
+    flop = 2.0 * PIX_MAC_PER_SAMPLE_STEP * B * N_STEPS
+    achieved = flop / (t_ms / 1000.0 / K) / 1e12
+    line = {
+        "metric": "samples/s (1000-step pixel-space DDPM, 64x64 images)", "value": total * K / (t_ms / 1000.0), "unit": "samples/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "v4 pixel-space diffusion U-Net 1000-step sampling at 64x64, batch %d per GPU%s" %
+                               (B, "" if world == 1 else ", %d total, final NCCL all-gather of images" % total),
+                   "batch_per_gpu": B, "global_batch": total, "n_steps": N_STEPS, "precision": "bf16",
+                   "l2": "flushed (256 MiB write) between timed iterations", "weights": "random-init (seeded, torch default statistics), eval mode"},
+        "e2e": {"value": total * K / t_e2e, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": B * IMG_BYTES},
+        "gpu_launches": int(launches),
+        "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
+        "roofline": {"bound": "tensor", "kernel": "sampling loop (one CUDA-graph launch = 1000 steps x %d kernels: 15 tcgen05 implicit-GEMM convolutions, "
+                                                  "conv1.0 / out_conv / posterior update)" % (launches // (K * N_STEPS)),
+                     "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
+                     "traffic": None, "peak_source": pk["src"], "ms_per_launch": t_ms / K,
+                     "algorithmic_flop_per_launch": flop},
+    }
+    if not args.no_cpu:
+        v, th = pix_cpu_rate(4, 3)
+        line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": th, "kind": "port",
+                                "sample": "batch 4, 3 of the 1000 reverse steps, extrapolated linearly (oracle/restate_pix.py, bit-equal to the v4 reference)"}
+    print(json.dumps(line))
+
+
+def run_pix_reference_arm(args, rank):
+    if rank != 0:
+        return
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, th = pix_cpu_rate(min(args.batch, 8), 2)
+        if i >= args.warmup:
+            vals.append(v)
+    value = sum(vals) / len(vals)
+    print(json.dumps({
+        "impl": "reference", "metric": "samples/s (1000-step pixel-space DDPM, 64x64 images)", "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * args.batch / value, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "v4 pixel-space diffusion U-Net 1000-step sampling at 64x64, batch %d per GPU" % args.batch,
+                   "where": "host CPU cores (rank 0 only), reference algorithm", "n_steps": N_STEPS},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": th, "kind": "port",
+                         "sample": "per step: batch %d, 2 of the 1000 reverse steps, extrapolated linearly" % min(args.batch, 8)},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -323,12 +460,19 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="samples per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="v2", choices=["v2", "v3"],
-                    help="v2: BASELINE configs[1]/[2] (default). v3: configs[3], multi-conditional denoiser, --batch rows per GPU (default 128), each GPU one reference call")
+    ap.add_argument("--workload", default="v2", choices=["v2", "v3", "v4"],
+                    help="v2: BASELINE configs[1]/[2] (default). v3: configs[3], multi-conditional denoiser, --batch rows per GPU (default 128), "
+                         "each GPU one reference call. v4: configs[4], pixel-space U-Net at 64x64, --batch images per GPU (default 64)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "v4":
+        if "--batch" not in " ".join(sys.argv):
+            args.batch = 64
+        if args.impl == "reference":
+            run_pix_reference_arm(args, rank)
+            return
     if args.workload == "v3":
         if "--batch" not in " ".join(sys.argv):
             args.batch = 128
@@ -346,7 +490,7 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        (run_pix if args.workload == "v4" else run_ours)(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist
