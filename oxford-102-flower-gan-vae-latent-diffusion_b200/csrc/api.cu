@@ -115,6 +115,8 @@ extern "C" LDM_API int ldm_ctx_create(ldm_ctx** out, int device, int precision) 
     if (ctx->chain_enabled && chain_init(ctx) != 0) ctx->chain_enabled = 0;   // ldm_last_error() keeps the reason
     ctx->use_chain = ctx->chain_enabled;
   }
+  const char* atc = getenv("LDM_ATTN_TC");
+  ctx->use_attn_tc = atc ? atoi(atc) : 1;
   const char* pdl = getenv("LDM_PDL");
   ctx->use_pdl = pdl ? atoi(pdl) : 0;
   if (r != 0) {
@@ -339,6 +341,12 @@ static int ensure_workspace(ldm_ctx* ctx, int B) {
     LDM_TRY(ldm_alloc_t(ctx, P, &ctx->qkv, (size_t)cap * 3 * U.dmax));
     LDM_TRY(ldm_alloc(ctx, P, &ctx->a_op, nd * op));
     LDM_CUDA(cudaMemset(ctx->a_op, 0, nd * op));
+    if (op == 2) {
+      LDM_TRY(ldm_alloc_t(ctx, P, &ctx->qk16, (size_t)cap * 2 * U.dmax));
+      LDM_TRY(ldm_alloc_t(ctx, P, &ctx->vt16, (size_t)U.dmax * cap));
+      LDM_CUDA(cudaMemset(ctx->qk16, 0, (size_t)cap * 2 * U.dmax * sizeof(bf16)));
+      LDM_CUDA(cudaMemset(ctx->vt16, 0, (size_t)U.dmax * cap * sizeof(bf16)));
+    }
   }
   LDM_TRY(ldm_alloc_t(ctx, P, &ctx->x_state, (size_t)cap * U.latent));
   LDM_TRY(ldm_alloc_t(ctx, P, &ctx->cls, (size_t)cap));
@@ -554,7 +562,14 @@ static int denoise(ldm_ctx* ctx, int B, int parity, const StepMode& md, cudaStre
     if (U.variant == 3) {  // h3 = h2 + out_proj(softmax(Q K^T / sqrt(hd)) V) over the rows of the call   (v3:832-838)
       Epilogue eq; eq.bias = U.qkv[i].b; eq.out_f32 = ctx->qkv; eq.ld_of = 3 * d;
       LDM_TRY(gemm<TOP>(ctx, n_op, d, B, U.qkv[i], eq, st));
-      LDM_TRY(launch_batch_attention<TOP>(ctx, ctx->qkv, (TOP*)ctx->a_op, B, d, 8, st));
+      bool tc_attn = false;
+      if constexpr (std::is_same<TOP, bf16>::value) tc_attn = attn_tc_supported(d / 8) && ctx->use_attn_tc;
+      if (tc_attn) {   // softmax(Q K^T) V on the tensor cores (gemm_tc.cu: attn_tc_kernel)
+        LDM_TRY(launch_attn_prep(ctx, ctx->qkv, ctx->qk16, ctx->vt16, B, d, ctx->cap, st));
+        LDM_TRY(launch_attn_tc(ctx, ctx->qk16, 2 * d, 2 * d, ctx->vt16, ctx->cap, B, 1, 8, d / 8, 0, d, ctx->a_op, 1, d, d / 8, 1, st));
+      } else {
+        LDM_TRY(launch_batch_attention<TOP>(ctx, ctx->qkv, (TOP*)ctx->a_op, B, d, 8, st));
+      }
       Epilogue e; e.bias = U.attn_o[i].b; e.resid = ctx->h2; e.ld_r = d;
       if constexpr (std::is_same<TOP, float>::value) { e.out_f32 = (float*)h3_op; e.ld_of = d; }
       else { e.out_bf16 = h3_op; e.ld_ob = d; }

@@ -261,6 +261,7 @@ struct ldm_ctx {
   void* af_op[2] = {nullptr, nullptr};  // [LN_f(h) | x] operand of the final GEMM, double-buffered across steps
   float* qkv = nullptr;                 // v3: (cap, 3 dmax) fp32 projections
   void* a_op = nullptr;                 // v3: attention output, operand of out_proj
+  bf16 *qk16 = nullptr, *vt16 = nullptr; // v3 tensor-core attention: [Q | K] bf16 (cap, 2 dmax) and V^T bf16 (dmax, cap)
   float* x_state = nullptr;       // (cap, latent) fp32 chain state the captured graph works on
   unsigned long long* rng_dev = nullptr;  // {seed, sample_offset}
   cudaStream_t cap_stream = nullptr;      // capture-only stream (the caller may be on the legacy stream)
@@ -297,6 +298,7 @@ struct ldm_ctx {
   long long* chain_trace = nullptr;   // [16][64] clock stamps (ldm_debug_chain_trace), null = off
   int chain_trace_step = 0;
   int use_pdl = 0;
+  int use_attn_tc = 1;            // v3 bf16: attention on tcgen05 (LDM_ATTN_TC=0 selects the CUDA-core kernel)
 };
 
 // memory helpers (api.cu)
@@ -400,3 +402,7 @@ int tc_init(ldm_ctx* ctx);
 int tc_make_weight_map(ldm_ctx* ctx, const bf16* w, int N, int K, int bn, CUtensorMap* out);
 int launch_gemm_tc(ldm_ctx* ctx, const bf16* A, int lda, int M, const DenseLayer& L, const Epilogue& epi,
                    cudaStream_t st);
+int attn_tc_supported(int hd);
+int launch_attn_prep(ldm_ctx* ctx, const float* qkv, bf16* qk, bf16* vt, int rows, int d, int ldv, cudaStream_t st);
+int launch_attn_tc(ldm_ctx* ctx, const bf16* qk, int ld_qk, int qk_cols, const bf16* vt, int ldv, int L, int batches, int heads, int hd,
+                   int q_col0, int k_col0, void* out, int out_bf16, int out_pitch, int out_sh, int out_se, cudaStream_t st);

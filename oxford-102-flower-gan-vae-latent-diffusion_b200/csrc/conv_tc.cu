@@ -28,6 +28,20 @@ constexpr int BM = 128, BK = 64;
 constexpr int kThreads = 192;
 constexpr int kMaxStages = 8;
 
+// Launch with programmatic dependent launch (PDL): the grid may start while its predecessor in the stream drains, runs its
+// prologue (barrier init, TMEM allocation, descriptor prefetch, resident weights) and blocks in griddepcontrol.wait until
+// the predecessor has completed and its writes are visible.
+template <typename Kern, typename... Args>
+cudaError_t launch_maybe_pdl(Kern kern, dim3 grid, int threads, size_t smem, cudaStream_t st, int pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 struct ConvTcArgs {
   int H, W;         // input spatial size
   int Cin, Cout;    // Cout: output channels of one parity
@@ -83,6 +97,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
+  tc::pdl_wait();      // everything above overlaps the previous kernel's tail (no-op without the PDL launch attribute)
 
   if (warp == 0) {
     if (tc::elect_one()) {
@@ -258,6 +273,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     tc::mbar_init(&w_bar, 1);
     tc::fence_barrier_init();
+    tc::mbar_arrive_expect_tx(&w_bar, kWBytes);      // weights do not depend on the previous kernel: fetched before the PDL wait
+    for (int tap = 0; tap < 9; ++tap) tc::tma_load_2d(w_s + tap * kWTap, &map_w, &w_bar, tap * BK, 0);
   }
   if (warp == 1) tc::tmem_alloc<kCols>(&tmem_slot);
   if (warp >= 2)
@@ -270,11 +287,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   tc::fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
   const int rowslots = a.Wp;
+  tc::pdl_wait();
 
   if (warp == 0) {
     if (tc::elect_one()) {
-      tc::mbar_arrive_expect_tx(&w_bar, kWBytes);
-      for (int tap = 0; tap < 9; ++tap) tc::tma_load_2d(w_s + tap * kWTap, &map_w, &w_bar, tap * BK, 0);
       int it = 0;
       for (int u = blockIdx.x; u < a.total_units; u += gridDim.x, ++it) {
         const int s = it % kHaloStages;
@@ -515,7 +531,7 @@ int launch_bn(ldm_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, const 
   a.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024;
   dim3 grid(ceil_div(a.total_pix, BM), a.Cout / BN, nz);
-  conv_tc_kernel<BN><<<grid, kThreads, smem, st>>>(ma, mw, a);
+  LDM_CUDA(launch_maybe_pdl(conv_tc_kernel<BN>, grid, kThreads, smem, st, ctx->use_pdl, ma, mw, a));
   ctx->launches++;
   LDM_CUDA(cudaGetLastError());
   return 0;
@@ -629,9 +645,9 @@ int launch_conv_halo(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer
   }
   const size_t smem = (((size_t)9 * L.Cout * 128 + 1023) & ~(size_t)1023) + 1024 + kHaloStages * (size_t)a.a_stride + 1024;
   const int grid = a.total_units < ctx->sm_count ? a.total_units : ctx->sm_count;
-  if (!fin) conv_halo_kernel<64, 0, 1><<<grid, kThreads, smem, st>>>(ma, L.map_w, a);
-  else if (ddpm) conv_halo_kernel<16, 2, 2><<<grid, kThreads, smem, st>>>(ma, L.map_w, a);
-  else conv_halo_kernel<16, 1, 2><<<grid, kThreads, smem, st>>>(ma, L.map_w, a);
+  if (!fin) LDM_CUDA(launch_maybe_pdl(conv_halo_kernel<64, 0, 1>, dim3(grid), kThreads, smem, st, ctx->use_pdl, ma, L.map_w, a));
+  else if (ddpm) LDM_CUDA(launch_maybe_pdl(conv_halo_kernel<16, 2, 2>, dim3(grid), kThreads, smem, st, ctx->use_pdl, ma, L.map_w, a));
+  else LDM_CUDA(launch_maybe_pdl(conv_halo_kernel<16, 1, 2>, dim3(grid), kThreads, smem, st, ctx->use_pdl, ma, L.map_w, a));
   ctx->launches++;
   LDM_CUDA(cudaGetLastError());
   return 0;

@@ -107,6 +107,203 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 1) tc::tmem_dealloc<kTmemCols>(tmem_base);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// attn_tc_kernel<HD>: softmax(Q K^T / sqrt(HD)) V on the tensor cores, one CTA per (128 queries, head, batch element).
+// v3's nn.MultiheadAttention over the rows of a call (v3:832-838: L = batch, 8 heads) and the spatial self-attention of
+// UNetAttentionBlock (v2:434-459: L = H W tokens, 4 heads) are both this.
+//   S = Q K^T : UMMA 128 x 128 x 16, HD / 16 steps, Q and K tiles (tokens x 64-column atoms, K-major) by TMA -> TMEM cols 0..127
+//   softmax   : warps 2-5, thread = query row: two passes over the S row in TMEM (max, then exp / sum), P written as bf16
+//               into shared memory in the 128-byte-swizzled K-major operand layout, online rescale across key tiles
+//   O_j = P V : UMMA 128 x HD x 16, 8 steps; B operand = V^T tile (HD rows x keys), from the transposed copy the prep
+//               kernel writes -> TMEM cols 128..128+HD; the row threads fold O_j into their fp32 accumulator registers
+// Keys beyond L are masked by index; queries beyond L are not stored.
+// ------------------------------------------------------------------------------------------------------------------
+struct AttnArgs {
+  int L, heads;
+  int q_col0, k_col0;        // first column of Q / K of head 0 in the QK matrix (head h adds h * HD)
+  float scale;
+  void* out;                 // (batches * L, out_pitch): column of (head h, dim e) = h * out_sh + e * out_se
+  int out_bf16, out_pitch, out_sh, out_se;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_constant__ CUtensorMap map_vt, const AttnArgs a) {
+  constexpr int NA = (HD + 63) / 64;                 // 64-column atoms of a Q / K tile
+  constexpr uint32_t kAtom = 128 * 128;              // 128 rows x 128 bytes
+  constexpr uint32_t kQ = NA * kAtom, kVAtom = HD * 128, kV = 2 * kVAtom, kP = 2 * kAtom;
+  constexpr uint32_t kVRegion = (kV + 1023) & ~1023u;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_s = smem;
+  uint8_t* k_s = q_s + kQ;
+  uint8_t* v_s = k_s + kQ;
+  uint8_t* p_s = v_s + kVRegion;
+  __shared__ __align__(8) uint64_t bar_q, bar_kv, bar_s, bar_p, bar_o;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, z = blockIdx.z;
+  const int L = a.L, ntiles = (L + 127) / 128;
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&map_qk);
+    tc::prefetch_tmap(&map_vt);
+    tc::mbar_init(&bar_q, 1);
+    tc::mbar_init(&bar_kv, 1);
+    tc::mbar_init(&bar_s, 1);
+    tc::mbar_init(&bar_p, 128);
+    tc::mbar_init(&bar_o, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc<256>(&tmem_slot);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  tc::pdl_wait();
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      tc::mbar_arrive_expect_tx(&bar_q, kQ);
+      for (int at = 0; at < NA; ++at) tc::tma_load_2d(q_s + at * kAtom, &map_qk, &bar_q, a.q_col0 + h * HD + at * 64, z * L + q0);
+      for (int j = 0; j < ntiles; ++j) {
+        if (j > 0 && !tc::mbar_wait(&bar_o, (uint32_t)((j - 1) & 1), 21)) break;     // K / V^T / P of the previous tile consumed
+        tc::mbar_arrive_expect_tx(&bar_kv, kQ + kV);
+        for (int at = 0; at < NA; ++at) tc::tma_load_2d(k_s + at * kAtom, &map_qk, &bar_kv, a.k_col0 + h * HD + at * 64, z * L + j * 128);
+        for (int at = 0; at < 2; ++at) tc::tma_load_2d(v_s + at * kVAtom, &map_vt, &bar_kv, j * 128 + at * 64, (z * a.heads + h) * HD);
+      }
+    }
+  } else if (warp == 1) {
+    if (tc::elect_one()) {
+      constexpr uint32_t idesc_s = tc::make_idesc_bf16(128, 128), idesc_o = tc::make_idesc_bf16(128, HD);
+      bool ok = tc::mbar_wait(&bar_q, 0, 22);
+      const uint32_t qa = tc::smem_u32(q_s), ka = tc::smem_u32(k_s), va = tc::smem_u32(v_s), pa = tc::smem_u32(p_s);
+      for (int j = 0; j < ntiles && ok; ++j) {
+        const uint32_t ph = (uint32_t)(j & 1);
+        ok = tc::mbar_wait(&bar_kv, ph, 23);
+        tc::fence_after_sync();
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks) {
+          const uint32_t off = (uint32_t)(ks / 4) * kAtom + (uint32_t)(ks % 4) * 32u;
+          tc::umma_bf16(tmem_base, tc::make_desc_sw128(qa + off), tc::make_desc_sw128(ka + off), idesc_s, (uint32_t)(ks != 0));
+        }
+        tc::umma_commit(&bar_s);
+        ok = ok && tc::mbar_wait(&bar_p, ph, 24);
+        tc::fence_after_sync();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t kk = (uint32_t)(ks % 4) * 32u;
+          tc::umma_bf16(tmem_base + 128u, tc::make_desc_sw128(pa + (uint32_t)(ks / 4) * kAtom + kk),
+                        tc::make_desc_sw128(va + (uint32_t)(ks / 4) * kVAtom + kk), idesc_o, (uint32_t)(ks != 0));
+        }
+        tc::umma_commit(&bar_o);
+      }
+    }
+  } else {
+    const int q = warp & 3, r = q * 32 + lane;
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    float m = -INFINITY, l = 0.f;
+    float o[HD];
+#pragma unroll
+    for (int e = 0; e < HD; ++e) o[e] = 0.f;
+    uint8_t* p_row = p_s + r * 128;
+    bool ok = true;
+    for (int j = 0; j < ntiles && ok; ++j) {
+      const uint32_t ph = (uint32_t)(j & 1);
+      const int nvalid = L - j * 128;            // keys of this tile that exist
+      ok = tc::mbar_wait(&bar_s, ph, 25);
+      tc::fence_after_sync();
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(t_row + (uint32_t)c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c0 + i < nvalid) mx = fmaxf(mx, v[i] * a.scale);
+      }
+      const float m_new = fmaxf(m, mx);
+      const float corr = __expf(m - m_new);
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(t_row + (uint32_t)c0, v);
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float p0 = (c0 + 2 * i < nvalid) ? __expf(v[2 * i] * a.scale - m_new) : 0.f;
+          const float p1 = (c0 + 2 * i + 1 < nvalid) ? __expf(v[2 * i + 1] * a.scale - m_new) : 0.f;
+          sum += p0 + p1;
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+          pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        // keys c0 .. c0 + 15 = 16-byte chunks (c0 % 64) / 8 and the next one of atom c0 / 64, XOR-swizzled with the row
+        uint8_t* base = p_row + (c0 / 64) * kAtom;
+        const int ch = (c0 % 64) / 8;
+        *reinterpret_cast<uint4*>(base + (((ch) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(base + (((ch + 1) ^ (r & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      l = l * corr + sum;
+      m = m_new;
+      tc::fence_proxy_async();       // the generic-proxy writes of P must be visible to the tensor core's async proxy
+      tc::fence_before_sync();
+      tc::mbar_arrive(&bar_p);
+      ok = ok && tc::mbar_wait(&bar_o, ph, 26);
+      tc::fence_after_sync();
+#pragma unroll
+      for (int c0 = 0; c0 < HD; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(t_row + 128u + (uint32_t)c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[c0 + i] = o[c0 + i] * corr + v[i];
+      }
+      tc::fence_before_sync();
+    }
+    if (ok && q0 + r < L) {
+      const float inv = 1.0f / l;
+      const size_t row = (size_t)z * L + q0 + r;
+      if (a.out_bf16) {
+        bf16* dst = reinterpret_cast<bf16*>(a.out) + row * a.out_pitch + (size_t)h * a.out_sh;
+        if (a.out_se == 1) {
+#pragma unroll
+          for (int e = 0; e < HD; e += 8) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(o[e + 2 * i] * inv, o[e + 2 * i + 1] * inv);
+              pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            *reinterpret_cast<uint4*>(dst + e) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < HD; ++e) dst[(size_t)e * a.out_se] = __float2bfloat16_rn(o[e] * inv);
+        }
+      } else {
+        float* dst = reinterpret_cast<float*>(a.out) + row * a.out_pitch + (size_t)h * a.out_sh;
+#pragma unroll
+        for (int e = 0; e < HD; ++e) dst[(size_t)e * a.out_se] = o[e] * inv;
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<256>(tmem_base);
+}
+
+// qkv fp32 (rows, 3 d) = [Q | K | V] (the in_proj output, v3:832) -> QK bf16 (rows, 2 d) and V^T bf16 (d, ldv)
+__global__ void __launch_bounds__(256)
+attn_prep_kernel(const float* __restrict__ qkv, bf16* __restrict__ qk, bf16* __restrict__ vt, int rows, int d, int ldv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 3 * d) return;
+  const int row = i / (3 * d), col = i - row * 3 * d;
+  const bf16 v = __float2bfloat16_rn(qkv[i]);
+  if (col < 2 * d) qk[(size_t)row * 2 * d + col] = v;
+  else vt[(size_t)(col - 2 * d) * ldv + row] = v;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -176,6 +373,55 @@ int tc_make_weight_map(ldm_ctx* ctx, const bf16* w, int N, int K, int bn, CUtens
   LDM_TRY(tc_init(ctx));
   LDM_CHECK(K % BK == 0 && N % bn == 0, "tensor-core GEMM needs K %% 64 == 0 and N %% %d == 0 (N=%d K=%d)", bn, N, K);
   return make_map_2d(w, N, K, K, bn, out);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// attention launchers
+// ------------------------------------------------------------------------------------------------------------------
+int attn_tc_supported(int hd) { return hd == 16 || hd == 32 || hd == 64 || hd == 128; }
+
+int launch_attn_prep(ldm_ctx* ctx, const float* qkv, bf16* qk, bf16* vt, int rows, int d, int ldv, cudaStream_t st) {
+  const int n = rows * 3 * d;
+  attn_prep_kernel<<<ceil_div(n, 256), 256, 0, st>>>(qkv, qk, vt, rows, d, ldv);
+  ctx->launches++;
+  LDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int HD>
+static int launch_attn_hd(ldm_ctx* ctx, const CUtensorMap& mqk, const CUtensorMap& mvt, const AttnArgs& a, int batches, cudaStream_t st) {
+  constexpr int NA = (HD + 63) / 64;
+  const size_t smem = (size_t)2 * NA * 16384 + (((size_t)2 * HD * 128 + 1023) & ~(size_t)1023) + 2 * 16384 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    LDM_CUDA(cudaFuncSetAttribute(attn_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  attn_tc_kernel<HD><<<dim3(ceil_div(a.L, 128), a.heads, batches), kThreads, smem, st>>>(mqk, mvt, a);
+  ctx->launches++;
+  LDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// qk: bf16 (batches * L, ld_qk) holding Q at columns q_col0 + h * hd and K at k_col0 + h * hd; vt: bf16
+// (batches * heads * hd, ldv) = V transposed (row = (batch, head, dim), column = token).
+int launch_attn_tc(ldm_ctx* ctx, const bf16* qk, int ld_qk, int qk_cols, const bf16* vt, int ldv, int L, int batches, int heads, int hd,
+                   int q_col0, int k_col0, void* out, int out_bf16, int out_pitch, int out_sh, int out_se, cudaStream_t st) {
+  LDM_TRY(tc_init(ctx));
+  LDM_CHECK(attn_tc_supported(hd), "attn_tc: head_dim %d unsupported", hd);
+  CUtensorMap mqk, mvt;
+  LDM_TRY(make_map_2d(qk, batches * L, qk_cols, ld_qk, 128, &mqk));
+  LDM_TRY(make_map_2d(vt, batches * heads * hd, L, ldv, hd, &mvt));
+  AttnArgs a;
+  a.L = L; a.heads = heads; a.q_col0 = q_col0; a.k_col0 = k_col0; a.scale = 1.0f / sqrtf((float)hd);
+  a.out = out; a.out_bf16 = out_bf16; a.out_pitch = out_pitch; a.out_sh = out_sh; a.out_se = out_se;
+  switch (hd) {
+    case 16: return launch_attn_hd<16>(ctx, mqk, mvt, a, batches, st);
+    case 32: return launch_attn_hd<32>(ctx, mqk, mvt, a, batches, st);
+    case 64: return launch_attn_hd<64>(ctx, mqk, mvt, a, batches, st);
+    default: return launch_attn_hd<128>(ctx, mqk, mvt, a, batches, st);
+  }
 }
 
 int launch_gemm_tc(ldm_ctx* ctx, const bf16* A, int lda, int M, const DenseLayer& L, const Epilogue& epi,

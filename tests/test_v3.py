@@ -109,6 +109,12 @@ def test_v3_chain_and_larger_batches(precision):
     want = R.unet3_forward(sd, xb, torch.tensor([321]), fb, kb)
     got = u(xb.cuda(), torch.tensor([321], device="cuda"), fb.cuda(), kb.cuda()).cpu()
     assert R.max_rel(got, want) < EPS_TOL[precision], R.max_rel(got, want)
+    # several query / key tiles of the tensor-core attention kernel (128 rows each): online-softmax rescale across tiles
+    B = 300
+    xb2, fb2, kb2 = torch.randn(B, 256) * 2, torch.randint(0, 102, (B,)), torch.randint(0, 10, (B,))
+    want2 = R.unet3_forward(sd, xb2, torch.tensor([77]), fb2, kb2)
+    got2 = u(xb2.cuda(), torch.tensor([77], device="cuda"), fb2.cuda(), kb2.cuda()).cpu()
+    assert R.max_rel(got2, want2) < EPS_TOL[precision], R.max_rel(got2, want2)
     # out-of-range labels raise like nn.Embedding would
     with pytest.raises(IndexError):
         u(xb.cuda(), torch.tensor([1], device="cuda"), fb.cuda(), (kb + 10).cuda())
