@@ -153,6 +153,25 @@ typedef struct ldm_pix_weights {
   ldm_pix_conv conv1[2], down1, conv2[2], down2, conv3[2], bottleneck[2], up1, conv4[2], up2, conv5[2], out_conv;
 } ldm_pix_weights;
 
+/* The conv U-Net blocks defined (and never instantiated) by the v2 script: UNetResidualBlock v2:462-486 and
+ * UNetAttentionBlock v2:434-459; raw fp32 device pointers in the modules' state_dict layout. */
+typedef struct ldm_ublock_res_weights {
+  int32_t in_channels, out_channels, d_time;     /* channels: multiples of 64 */
+  const float *norm1_w, *norm1_b;                /* LayerNorm2d(in_channels) */
+  const float *conv1_w, *conv1_b;                /* (out, in, 3, 3) */
+  const float *time_w, *time_b;                  /* Linear(d_time, out) */
+  const float *class_w, *class_b;                /* Linear(d_time, out) */
+  const float *norm2_w, *norm2_b;
+  const float *conv2_w, *conv2_b;                /* (out, out, 3, 3) */
+  const float *res_w, *res_b;                    /* (out, in, 1, 1) when in != out, else NULL (nn.Identity) */
+} ldm_ublock_res_weights;
+typedef struct ldm_ublock_attn_weights {
+  int32_t channels, num_heads;                   /* channels / num_heads in {16, 32, 64, 128} */
+  const float *norm_w, *norm_b;                  /* GroupNorm(1, channels) */
+  const float *qkv_w, *qkv_b;                    /* (3 channels, channels, 1, 1) */
+  const float *proj_w, *proj_b;                  /* (channels, channels, 1, 1) */
+} ldm_ublock_attn_weights;
+
 LDM_API int ldm_version(void);
 LDM_API const char* ldm_last_error(void);
 
@@ -237,6 +256,18 @@ LDM_API int ldm_pix_forward(ldm_ctx* ctx, const float* x_dev, const float* t_dev
  * != 0 replays the loop as one CUDA graph. */
 LDM_API int ldm_pix_sample(ldm_ctx* ctx, float* x_inout_dev, int t_start, int t_end, const float* noise_dev, uint64_t seed,
                    uint64_t sample_offset, int batch, int H, int W, int use_graph, void* stream);
+
+/* ---- conv U-Net blocks of the v2 script (bf16 contexts only; module-level operators) -------------------
+ * *_pack copies and repacks one module's weights and returns a handle that lives until ldm_ctx_destroy.
+ * ldm_ublock_res_forward  = UNetResidualBlock.forward(x, t, c) v2:475-486 (eval mode): x (B, Cin, H, W), t and c
+ *   (B, d_time) embedding vectors (c may be NULL) -> out (B, Cout, H, W), all fp32 NCHW / row-major device pointers.
+ * ldm_ublock_attn_forward = UNetAttentionBlock.forward(x) v2:444-459: x, out (B, C, H, W). H * W: a multiple of 8, >= 16. */
+LDM_API int ldm_ublock_res_pack(ldm_ctx* ctx, const ldm_ublock_res_weights* w, int* handle_out, void* stream);
+LDM_API int ldm_ublock_res_forward(ldm_ctx* ctx, int handle, const float* x_dev, const float* t_dev, const float* c_dev_or_null,
+                           float* out_dev, int batch, int H, int W, void* stream);
+LDM_API int ldm_ublock_attn_pack(ldm_ctx* ctx, const ldm_ublock_attn_weights* w, int* handle_out, void* stream);
+LDM_API int ldm_ublock_attn_forward(ldm_ctx* ctx, int handle, const float* x_dev, float* out_dev, int batch, int H, int W,
+                            void* stream);
 
 /* Introspection for tests and the benchmark. */
 LDM_API int ldm_kernel_launch_count(ldm_ctx* ctx, uint64_t* out); /* kernels launched (graph nodes count per replay) */

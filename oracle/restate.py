@@ -297,6 +297,45 @@ def decode(sd, z, p="decoder.", stages=None):
 
 
 # --------------------------------------------------------------------------
+# the conv U-Net blocks the v2 script defines but never instantiates
+# --------------------------------------------------------------------------
+def unet_residual_block(sd, p, x, t, c=None):
+    """UNetResidualBlock.forward v2:475-486, eval mode (Dropout v2:484 = identity). x (B, Cin, H, W); t, c (B, d_time)
+    embedding vectors.  `residual` is nn.Identity (no parameters) when in_channels == out_channels (v2:473)."""
+    h = swish(layernorm2d(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"]))
+    h = F.conv2d(h, sd[p + "conv1.weight"], sd[p + "conv1.bias"], padding=1)
+    t_emb = swish(F.linear(t, sd[p + "time_emb.weight"], sd[p + "time_emb.bias"]))
+    h = h + t_emb.view(-1, t_emb.shape[1], 1, 1)
+    if c is not None:
+        c_emb = swish(F.linear(c, sd[p + "class_emb.weight"], sd[p + "class_emb.bias"]))
+        h = h + c_emb.view(-1, c_emb.shape[1], 1, 1)
+    h = swish(layernorm2d(h, sd[p + "norm2.weight"], sd[p + "norm2.bias"]))
+    h = F.conv2d(h, sd[p + "conv2.weight"], sd[p + "conv2.bias"], padding=1)
+    res = F.conv2d(x, sd[p + "residual.weight"], sd[p + "residual.bias"]) if p + "residual.weight" in sd else x
+    return h + res
+
+
+def unet_attention_block(sd, p, x, num_heads=4):
+    """UNetAttentionBlock.forward v2:444-459, line by line (including the (head_dim, head) channel order that
+    out.permute(0, 3, 1, 2).reshape(b, c, h, w) produces, v2:456-457)."""
+    b, c, h, w = x.shape
+    residual = x
+    x = F.group_norm(x, 1, sd[p + "norm.weight"], sd[p + "norm.bias"], eps=1e-5)
+    qkv = F.conv2d(x, sd[p + "qkv.weight"], sd[p + "qkv.bias"]).reshape(b, 3, num_heads, c // num_heads, h * w)
+    q, k, v = qkv[:, 0], qkv[:, 1], qkv[:, 2]
+    q = q.permute(0, 1, 3, 2)
+    k = k.permute(0, 1, 2, 3)
+    v = v.permute(0, 1, 3, 2)
+    scale = (c // num_heads) ** -0.5
+    attn = torch.matmul(q, k) * scale
+    attn = F.softmax(attn, dim=-1)
+    out = torch.matmul(attn, v)
+    out = out.permute(0, 3, 1, 2)
+    out = out.reshape(b, c, h, w)
+    return F.conv2d(out, sd[p + "proj.weight"], sd[p + "proj.bias"]) + residual
+
+
+# --------------------------------------------------------------------------
 # error measures used by every parity test
 # --------------------------------------------------------------------------
 def max_rel(a, ref):

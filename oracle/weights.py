@@ -167,6 +167,26 @@ def pix_unet_spec(in_channels=3, base=64, temb=128, v5=False):
     return s
 
 
+def ublock_res_spec(cin, cout, d_time=256, prefix=""):
+    """UNetResidualBlock (v2:462-473) state_dict order; torch default init ("u:<fan_in>")."""
+    s = [(prefix + "norm1.weight", (cin,), "g"), (prefix + "norm1.bias", (cin,), "b"),
+         (prefix + "conv1.weight", (cout, cin, 3, 3), "u:%d" % (cin * 9)), (prefix + "conv1.bias", (cout,), "u:%d" % (cin * 9)),
+         (prefix + "time_emb.weight", (cout, d_time), "u:%d" % d_time), (prefix + "time_emb.bias", (cout,), "u:%d" % d_time),
+         (prefix + "class_emb.weight", (cout, d_time), "u:%d" % d_time), (prefix + "class_emb.bias", (cout,), "u:%d" % d_time),
+         (prefix + "norm2.weight", (cout,), "g"), (prefix + "norm2.bias", (cout,), "b"),
+         (prefix + "conv2.weight", (cout, cout, 3, 3), "u:%d" % (cout * 9)), (prefix + "conv2.bias", (cout,), "u:%d" % (cout * 9))]
+    if cin != cout:
+        s += [(prefix + "residual.weight", (cout, cin, 1, 1), "u:%d" % cin), (prefix + "residual.bias", (cout,), "u:%d" % cin)]
+    return s
+
+
+def ublock_attn_spec(c, prefix=""):
+    """UNetAttentionBlock (v2:435-442) state_dict order."""
+    return [(prefix + "norm.weight", (c,), "g"), (prefix + "norm.bias", (c,), "b"),
+            (prefix + "qkv.weight", (3 * c, c, 1, 1), "u:%d" % c), (prefix + "qkv.bias", (3 * c,), "u:%d" % c),
+            (prefix + "proj.weight", (c, c, 1, 1), "u:%d" % c), (prefix + "proj.bias", (c,), "u:%d" % c)]
+
+
 def _draw(key, shape, kind, seed, style):
     g = torch.Generator().manual_seed((int(seed) * 1000003 + zlib.crc32(key.encode())) & 0x7FFFFFFFFFFFFFFF)
     n = lambda: torch.randn(shape, generator=g, dtype=torch.float32)

@@ -6,7 +6,8 @@ shim at the repository root:  `import ldm_b200`.
 """
 from .engine import default_precision, get_engine, set_default_precision   # noqa: F401
 from .modules import (CALayer, ClassEmbedding, ConditionalDenoiseDiffusion, ConditionalUNet, Decoder, Encoder,  # noqa: F401
-                      LayerNorm2d, ResidualBlock, SimpleAutoencoder, SpatialAttention, Swish, TimeEmbedding,
+                      LayerNorm2d, ResidualBlock, SimpleAutoencoder, SpatialAttention, SwitchSequential, Swish, TimeEmbedding,
+                      UNetAttentionBlock, UNetResidualBlock,
                       euclidean_distance_loss, generate_class_samples, init_weights, load_autoencoder_checkpoint)
 from .sharding import generate_sharded, shard_bounds                       # noqa: F401
 from . import v3                                                            # noqa: F401  (v3 multi-conditional denoiser)
@@ -15,5 +16,5 @@ from ._lib import LIB_PATH, LdmError                                        # no
 
 __all__ = ["ConditionalUNet", "ConditionalDenoiseDiffusion", "SimpleAutoencoder", "Decoder", "Encoder",
            "TimeEmbedding", "ClassEmbedding", "ResidualBlock", "CALayer", "SpatialAttention", "LayerNorm2d", "Swish",
-           "generate_class_samples", "generate_sharded", "shard_bounds", "init_weights", "load_autoencoder_checkpoint",
+           "UNetResidualBlock", "UNetAttentionBlock", "SwitchSequential", "generate_class_samples", "generate_sharded", "shard_bounds", "init_weights", "load_autoencoder_checkpoint",
            "get_engine", "set_default_precision", "default_precision", "LdmError", "LIB_PATH"]

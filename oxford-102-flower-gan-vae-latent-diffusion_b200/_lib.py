@@ -81,6 +81,17 @@ class PixWeights(ctypes.Structure):
     )
 
 
+class UBlockResWeights(ctypes.Structure):
+    _fields_ = ([("in_channels", ctypes.c_int32), ("out_channels", ctypes.c_int32), ("d_time", ctypes.c_int32)]
+                + [(n, _vp) for n in ("norm1_w", "norm1_b", "conv1_w", "conv1_b", "time_w", "time_b", "class_w", "class_b",
+                                      "norm2_w", "norm2_b", "conv2_w", "conv2_b", "res_w", "res_b")])
+
+
+class UBlockAttnWeights(ctypes.Structure):
+    _fields_ = ([("channels", ctypes.c_int32), ("num_heads", ctypes.c_int32)]
+                + [(n, _vp) for n in ("norm_w", "norm_b", "qkv_w", "qkv_b", "proj_w", "proj_b")])
+
+
 # name -> (restype, argtypes); exactly the prototypes of include/ldm_b200.h
 PROTOTYPES = {
     "ldm_version": (ctypes.c_int, []),
@@ -104,6 +115,10 @@ PROTOTYPES = {
     "ldm_pix_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
     "ldm_pix_sample": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_uint64, ctypes.c_uint64,
                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
+    "ldm_ublock_res_pack": (ctypes.c_int, [_vp, ctypes.POINTER(UBlockResWeights), ctypes.POINTER(ctypes.c_int), _vp]),
+    "ldm_ublock_res_forward": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
+    "ldm_ublock_attn_pack": (ctypes.c_int, [_vp, ctypes.POINTER(UBlockAttnWeights), ctypes.POINTER(ctypes.c_int), _vp]),
+    "ldm_ublock_attn_forward": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
     "ldm_kernel_launch_count": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64)]),
     "ldm_get_info": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]),
     "ldm_debug_chain_trace": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int]),

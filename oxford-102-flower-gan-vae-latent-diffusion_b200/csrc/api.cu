@@ -46,6 +46,7 @@ static void free_pool(std::vector<void*>& pool) {
 
 void pix_drop_graphs(ldm_ctx* ctx);
 void pix_free(ldm_ctx* ctx);
+void ublock_free_all(ldm_ctx* ctx);
 
 static void drop_graphs(ldm_ctx* ctx) {
   pix_drop_graphs(ctx);
@@ -141,6 +142,7 @@ extern "C" LDM_API int ldm_ctx_destroy(ldm_ctx* ctx) {
   free_pool(ctx->stage_allocs);
   free_pool(ctx->chain.allocs);
   pix_free(ctx);
+  ublock_free_all(ctx);
   if (ctx->coef_dev) cudaFree(ctx->coef_dev);
   if (ctx->chain_trace) cudaFree(ctx->chain_trace);
   if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);

@@ -236,6 +236,21 @@ struct PixModel {
   std::map<std::tuple<int, int, int, int, int, int>, GraphEntry> graphs;   // (batch, H, W, t_start, t_end, noise mode)
 };
 
+// stand-alone conv U-Net blocks of the v2 script (ublock.cu): type 1 = UNetResidualBlock, 2 = UNetAttentionBlock
+struct UBlock {
+  int type = 0, cin = 0, cout = 0, dt = 0, heads = 0;
+  std::vector<void*> allocs, ws;
+  float *n1w = nullptr, *n1b = nullptr, *n2w = nullptr, *n2b = nullptr;   // norm1 / norm (attention block), norm2
+  float *tw = nullptr, *tb = nullptr, *cw = nullptr, *cb = nullptr;       // time_emb, class_emb Linears
+  ConvLayer conv1, conv2;
+  DenseLayer d1, d2;              // residual 1x1 (type 1); qkv and proj 1x1 (type 2)
+  size_t ws_elems = 0;
+  bf16* buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bf16* qkv3 = nullptr;
+  float2* coef = nullptr;
+  float* post = nullptr;
+};
+
 struct ldm_ctx {
   int device = 0;
   int precision = LDM_PRECISION_FP32;
@@ -249,6 +264,7 @@ struct ldm_ctx {
   ChainModel chain;
   DecoderModel dec;
   PixModel pix;
+  std::vector<UBlock> ublocks;
   // per-batch state
   int cap = 0;                    // rows the activation workspace holds
   int batch_cls = -1;             // batch of the last set_classes (-1: none)

@@ -76,6 +76,7 @@ class Engine:
         self._sched_key = None
         self._cls_key = None
         self._pix_key = None
+        self._ublocks = {}      # id(module) -> (state key, handle)
 
     def __del__(self):
         try:
@@ -326,6 +327,65 @@ class Engine:
         check(lib().ldm_pix_sample(self.ctx, _ptr(x), int(t_start), int(t_end), _ptr(noise) if noise is not None else None,
                                    seed, sample_offset, B, H, W, 1 if use_graph else 0, self.stream()), "ldm_pix_sample")
         return x
+
+    # ------------------------------------------------------------------ conv U-Net blocks (v2:434-486)
+    def _ublock(self, m, build):
+        key = _state_key(m)
+        hit = self._ublocks.get(id(m))
+        if hit is None or hit[0] != key:
+            hit = (key, build())
+            self._ublocks[id(m)] = hit
+        return hit[1]
+
+    def ublock_res_forward(self, m, x, t, c=None):
+        dev = self.device
+
+        def build():
+            keep = []
+            def P(v):
+                v = _f32(v, dev); keep.append(v); return v.data_ptr()
+            w = _lib.UBlockResWeights()
+            w.in_channels, w.out_channels, w.d_time = m.conv1.in_channels, m.conv1.out_channels, m.time_emb.in_features
+            w.norm1_w, w.norm1_b, w.conv1_w, w.conv1_b = P(m.norm1.weight), P(m.norm1.bias), P(m.conv1.weight), P(m.conv1.bias)
+            w.time_w, w.time_b, w.class_w, w.class_b = P(m.time_emb.weight), P(m.time_emb.bias), P(m.class_emb.weight), P(m.class_emb.bias)
+            w.norm2_w, w.norm2_b, w.conv2_w, w.conv2_b = P(m.norm2.weight), P(m.norm2.bias), P(m.conv2.weight), P(m.conv2.bias)
+            if isinstance(m.residual, torch.nn.Conv2d):
+                w.res_w, w.res_b = P(m.residual.weight), P(m.residual.bias)
+            h = ctypes.c_int()
+            check(lib().ldm_ublock_res_pack(self.ctx, ctypes.byref(w), ctypes.byref(h), self.stream()), "ldm_ublock_res_pack")
+            return h.value
+
+        handle = self._ublock(m, build)
+        x = _f32(x, dev)
+        B, _, H, W = x.shape
+        t = _f32(t, dev).reshape(B, -1)
+        cc = _f32(c, dev).reshape(B, -1) if c is not None else None
+        out = torch.empty(B, m.conv1.out_channels, H, W, device=dev, dtype=torch.float32)
+        check(lib().ldm_ublock_res_forward(self.ctx, handle, _ptr(x), _ptr(t), _ptr(cc) if cc is not None else None, _ptr(out),
+                                           B, H, W, self.stream()), "ldm_ublock_res_forward")
+        return out
+
+    def ublock_attn_forward(self, m, x):
+        dev = self.device
+
+        def build():
+            keep = []
+            def P(v):
+                v = _f32(v, dev); keep.append(v); return v.data_ptr()
+            w = _lib.UBlockAttnWeights()
+            w.channels, w.num_heads = m.channels, m.num_heads
+            w.norm_w, w.norm_b, w.qkv_w, w.qkv_b = P(m.norm.weight), P(m.norm.bias), P(m.qkv.weight), P(m.qkv.bias)
+            w.proj_w, w.proj_b = P(m.proj.weight), P(m.proj.bias)
+            h = ctypes.c_int()
+            check(lib().ldm_ublock_attn_pack(self.ctx, ctypes.byref(w), ctypes.byref(h), self.stream()), "ldm_ublock_attn_pack")
+            return h.value
+
+        handle = self._ublock(m, build)
+        x = _f32(x, dev)
+        B, _, H, W = x.shape
+        out = torch.empty_like(x)
+        check(lib().ldm_ublock_attn_forward(self.ctx, handle, _ptr(x), _ptr(out), B, H, W, self.stream()), "ldm_ublock_attn_forward")
+        return out
 
     # ------------------------------------------------------------------ decoder
     def pack_decoder(self, dec):

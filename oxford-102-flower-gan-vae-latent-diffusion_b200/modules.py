@@ -382,6 +382,60 @@ class SimpleAutoencoder(nn.Module):
         return self.decode(z), z
 
 
+class UNetAttentionBlock(nn.Module):
+    """v2:434-459 (defined by the reference, never instantiated there).  forward runs in the library: GroupNorm(1, C),
+    the 1x1 qkv / proj convolutions as tcgen05 GEMMs over pixels, the 4-head attention over the H W tokens as the
+    tcgen05 attention kernel."""
+
+    def __init__(self, channels, num_heads=4, *, precision=None):
+        super().__init__()
+        self.channels = channels
+        self.num_heads = num_heads
+        self.precision = precision
+        self.norm = nn.GroupNorm(1, channels)
+        self.qkv = nn.Conv2d(channels, channels * 3, 1)
+        self.proj = nn.Conv2d(channels, channels, 1)
+
+    def forward(self, x):
+        _require_eval(self, "UNetAttentionBlock.forward")
+        return get_engine(x.device, self.precision or "bf16").ublock_attn_forward(self, x)
+
+
+class UNetResidualBlock(nn.Module):
+    """v2:462-486 (defined by the reference, never instantiated there).  forward(x, t, c=None): t and c are the
+    (B, d_time) embedding vectors.  Runs in the library: LayerNorm2d + Swish passes, 3x3 implicit-GEMM convolutions on
+    tcgen05 with the time / class term as the epilogue's per-sample add, identity or 1x1 residual."""
+
+    def __init__(self, in_channels, out_channels, d_time=256, dropout_rate=0.2, *, precision=None):
+        super().__init__()
+        self.precision = precision
+        self.norm1 = LayerNorm2d(in_channels)
+        self.conv1 = nn.Conv2d(in_channels, out_channels, kernel_size=3, padding=1)
+        self.time_emb = nn.Linear(d_time, out_channels)
+        self.class_emb = nn.Linear(d_time, out_channels)
+        self.act = Swish()
+        self.dropout = nn.Dropout(dropout_rate)
+        self.norm2 = LayerNorm2d(out_channels)
+        self.conv2 = nn.Conv2d(out_channels, out_channels, kernel_size=3, padding=1)
+        self.residual = nn.Identity() if in_channels == out_channels else nn.Conv2d(in_channels, out_channels, 1)
+
+    def forward(self, x, t, c=None):
+        _require_eval(self, "UNetResidualBlock.forward")
+        return get_engine(x.device, self.precision or "bf16").ublock_res_forward(self, x, t, c)
+
+
+class SwitchSequential(nn.Sequential):
+    """v2:489-498."""
+
+    def forward(self, x, t=None, c=None):
+        for layer in self:
+            if isinstance(layer, UNetResidualBlock):
+                x = layer(x, t, c)
+            else:
+                x = layer(x)
+        return x
+
+
 def init_weights(m):
     """The denoiser initialisation of main() (v2:1346-1350), used for the benchmark's random-init weights."""
     if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d, nn.Linear)):

@@ -1,0 +1,108 @@
+"""The conv U-Net blocks of the v2 script: UNetResidualBlock v2:462-486, UNetAttentionBlock v2:434-459,
+SwitchSequential v2:489-498.  The reference defines them but never runs them, so parity is module-level: the oracle
+restatement is pinned to the reference classes (tests/golden/ublock.npz from the unmodified script; live reference when
+present) and the sm_100a operators are compared with it (bf16 tensor-core path, max|d|/max|ref| <= 2e-2)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_loader, restate as R, weights
+from tests._util import EPS_TOL, T
+
+torch.set_grad_enabled(False)
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ublock.npz"))
+CASES_RES = [(64, 64), (64, 128)]
+CASES_ATTN = [128, 64]
+
+
+@pytest.mark.parametrize("cin,cout", CASES_RES)
+def test_residual_block_restatement_reproduces_reference_goldens(cin, cout):
+    sd = weights.make_state(weights.ublock_res_spec(cin, cout), 46, "perturbed")
+    k = "res_%d_%d_" % (cin, cout)
+    x, t, c = T(G[k + "x"]), T(G[k + "t"]), T(G[k + "c"])
+    assert R.max_rel(R.unet_residual_block(sd, "", x, t, c), T(G[k + "y_tc"])) < 1e-5
+    assert R.max_rel(R.unet_residual_block(sd, "", x, t), T(G[k + "y_t"])) < 1e-5
+
+
+@pytest.mark.parametrize("ch", CASES_ATTN)
+def test_attention_block_restatement_reproduces_reference_goldens(ch):
+    sd = weights.make_state(weights.ublock_attn_spec(ch), 47, "perturbed")
+    assert R.max_rel(R.unet_attention_block(sd, "", T(G["attn_%d_x" % ch])), T(G["attn_%d_y" % ch])) < 1e-5
+
+
+@pytest.mark.skipif(not ref_loader.available("v2"), reason="the reference tree is only present in the build container")
+def test_block_restatements_against_the_live_reference():
+    m = ref_loader.load("v2")
+    torch.manual_seed(1)
+    sd = weights.make_state(weights.ublock_res_spec(128, 64), 46, "perturbed")
+    blk = m.UNetResidualBlock(128, 64).eval()
+    blk.load_state_dict(sd, strict=True)
+    x, t, c = torch.randn(2, 128, 8, 8), torch.randn(2, 256), torch.randn(2, 256)
+    assert torch.equal(blk(x, t, c), R.unet_residual_block(sd, "", x, t, c))
+    sd = weights.make_state(weights.ublock_attn_spec(256), 47, "perturbed")
+    att = m.UNetAttentionBlock(256).eval()
+    att.load_state_dict(sd, strict=True)
+    x = torch.randn(2, 256, 4, 4)
+    assert torch.equal(att(x), R.unet_attention_block(sd, "", x))
+
+
+def test_block_mirrors_state_dict_layout():
+    import ldm_b200
+    for cin, cout in ((64, 64), (64, 128)):
+        m = ldm_b200.UNetResidualBlock(cin, cout)
+        sd = weights.make_state(weights.ublock_res_spec(cin, cout), 46, "init")
+        assert list(m.state_dict().keys()) == list(sd.keys())
+        m.load_state_dict(sd, strict=True)
+    a = ldm_b200.UNetAttentionBlock(128)
+    sd = weights.make_state(weights.ublock_attn_spec(128), 47, "init")
+    assert list(a.state_dict().keys()) == list(sd.keys())
+    a.load_state_dict(sd, strict=True)
+    with pytest.raises(RuntimeError):          # no CPU fallback
+        a.eval()(torch.zeros(1, 128, 8, 8))
+
+
+# ----------------------------------------------------------------------------- GPU: parity through the C ABI
+@pytest.mark.gpu
+@pytest.mark.parametrize("cin,cout", CASES_RES)
+def test_residual_block_against_reference_goldens(cin, cout):
+    import ldm_b200
+    m = ldm_b200.UNetResidualBlock(cin, cout)
+    m.load_state_dict(weights.make_state(weights.ublock_res_spec(cin, cout), 46, "perturbed"), strict=True)
+    m = m.cuda().eval()
+    k = "res_%d_%d_" % (cin, cout)
+    x, t, c = T(G[k + "x"]).cuda(), T(G[k + "t"]).cuda(), T(G[k + "c"]).cuda()
+    e = R.max_rel(m(x, t, c).cpu(), T(G[k + "y_tc"]))
+    assert e < EPS_TOL["bf16"], e
+    e = R.max_rel(m(x, t).cpu(), T(G[k + "y_t"]))
+    assert e < EPS_TOL["bf16"], e
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ch", CASES_ATTN)
+def test_attention_block_against_reference_goldens(ch):
+    import ldm_b200
+    m = ldm_b200.UNetAttentionBlock(ch)
+    m.load_state_dict(weights.make_state(weights.ublock_attn_spec(ch), 47, "perturbed"), strict=True)
+    m = m.cuda().eval()
+    e = R.max_rel(m(T(G["attn_%d_x" % ch]).cuda()).cpu(), T(G["attn_%d_y" % ch]))
+    assert e < EPS_TOL["bf16"], e
+
+
+@pytest.mark.gpu
+def test_switch_sequential_and_long_sequences():
+    """SwitchSequential (v2:489-498) routes (x, t, c) to residual blocks and x alone to attention blocks; a 32 x 32 map
+    gives 1024 tokens = 8 query tiles x 8 key tiles of the attention kernel (online softmax across tiles)."""
+    import ldm_b200
+    sd_r = weights.make_state(weights.ublock_res_spec(64, 128), 46, "perturbed")
+    sd_a = weights.make_state(weights.ublock_attn_spec(128), 47, "perturbed")
+    seq = ldm_b200.SwitchSequential(ldm_b200.UNetResidualBlock(64, 128), ldm_b200.UNetAttentionBlock(128))
+    seq[0].load_state_dict(sd_r, strict=True)
+    seq[1].load_state_dict(sd_a, strict=True)
+    seq = seq.cuda().eval()
+    torch.manual_seed(7)
+    x, t, c = torch.randn(2, 64, 32, 32), torch.randn(2, 256), torch.randn(2, 256)
+    want = R.unet_attention_block(sd_a, "", R.unet_residual_block(sd_r, "", x, t, c))
+    got = seq(x.cuda(), t.cuda(), c.cuda()).cpu()
+    assert R.max_rel(got, want) < EPS_TOL["bf16"], R.max_rel(got, want)
