@@ -10,6 +10,7 @@ from .modules import (CALayer, ClassEmbedding, ConditionalDenoiseDiffusion, Cond
                       UNetAttentionBlock, UNetResidualBlock,
                       euclidean_distance_loss, generate_class_samples, init_weights, load_autoencoder_checkpoint)
 from .sharding import generate_sharded, shard_bounds                       # noqa: F401
+from .io_utils import load_unet_checkpoint, parse_epoch_from_filename, save_image_grid, to_uint8, write_png   # noqa: F401
 from . import v3                                                            # noqa: F401  (v3 multi-conditional denoiser)
 from . import v4                                                            # noqa: F401  (v4 / v5 pixel-space diffusion)
 from ._lib import LIB_PATH, LdmError                                        # noqa: F401

@@ -451,10 +451,16 @@ def load_autoencoder_checkpoint(autoencoder, obj, strict=False):
     return autoencoder.load_state_dict(sd, strict=strict)
 
 
-def generate_class_samples(autoencoder, diffusion, target_class, num_samples=5, *, seed=None, sample_offset=0):
-    """The compute section of the reference's generate_class_samples (v2:856-869): returns
-    (images (n, 3, 64, 64), latents (n, latent)) on the model's device.  `target_class` is an int
-    (the reference also accepts a name through its global class_names; pass the index here)."""
+def generate_class_samples(autoencoder, diffusion, target_class, num_samples=5, *, save_path=None, class_names=None, seed=None,
+                           sample_offset=0):
+    """The reference's generate_class_samples (v2:856-882): returns (images (n, 3, 64, 64), latents (n, latent)) on the
+    model's device and, with `save_path`, writes the row of samples as a PNG (io_utils.save_image_grid in place of the
+    matplotlib figure of v2:870-881).  `target_class` is an index, or a name looked up in `class_names` (the reference
+    reads its global list, v2:860-864)."""
+    if isinstance(target_class, str):
+        if class_names is None or target_class not in class_names:
+            raise ValueError("Invalid class name: %s. Must be one of %s" % (target_class, class_names))
+        target_class = class_names.index(target_class)
     device = next(autoencoder.parameters()).device
     autoencoder.eval()
     diffusion.eps_model.eval()
@@ -463,4 +469,7 @@ def generate_class_samples(autoencoder, diffusion, target_class, num_samples=5, 
         latents = diffusion.sample((num_samples, autoencoder.latent_dim), device, class_tensor, seed=seed,
                                    sample_offset=sample_offset)
         samples = autoencoder.decode(latents)
+    if save_path:
+        from .io_utils import save_image_grid
+        save_image_grid(samples, save_path)
     return samples, latents

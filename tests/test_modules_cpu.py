@@ -78,3 +78,37 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(root, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "oracle." not in src.replace("oracle/", ""), f
+
+
+def test_checkpoint_conventions_and_png_writer(tmp_path):
+    """epoch-in-filename resume (v2:1352-1364), both autoencoder wrappings (v2:1179-1191,1326), PNG grid."""
+    import struct
+    import zlib
+    import ldm_b200
+    from oracle import weights
+    sd = weights.make_unet_state(42, "perturbed")
+    p = tmp_path / "conditional_diffusion_epoch_340.pt"
+    torch.save(sd, p)
+    u = ldm_b200.ConditionalUNet()
+    assert ldm_b200.load_unet_checkpoint(u, str(p)) == 340
+    assert all(torch.equal(u.state_dict()[k], v) for k, v in sd.items())
+    q = tmp_path / "conditional_diffusion_final.pt"
+    torch.save(sd, q)
+    assert ldm_b200.load_unet_checkpoint(ldm_b200.ConditionalUNet(), str(q)) == 0          # no epoch in the name: start from 0
+    assert ldm_b200.load_unet_checkpoint(u, str(tmp_path / "missing_epoch_3.pt")) == 0
+    sd_a = weights.make_autoencoder_state(43, "perturbed")
+    for obj in (sd_a, {"autoencoder": sd_a, "discriminator": {}}):
+        ae = ldm_b200.SimpleAutoencoder()
+        ldm_b200.load_autoencoder_checkpoint(ae, obj)
+        assert torch.equal(ae.state_dict()["decoder.fc.0.weight"], sd_a["decoder.fc.0.weight"])
+    imgs = torch.rand(5, 3, 8, 8)
+    out = ldm_b200.save_image_grid(imgs, str(tmp_path / "row.png"))
+    raw = open(out, "rb").read()
+    assert raw[:8] == b"\x89PNG\r\n\x1a\n"
+    w, h = struct.unpack(">II", raw[16:24])
+    assert (w, h) == (5 * 8 + 6 * 2, 8 + 2 * 2)
+    idat = raw[raw.index(b"IDAT") + 4: raw.index(b"IEND") - 8]
+    rows = zlib.decompress(idat)
+    assert len(rows) == h * (1 + 3 * w)
+    px = torch.frombuffer(bytearray(rows), dtype=torch.uint8).view(h, 1 + 3 * w)[:, 1:].view(h, w, 3)
+    assert torch.equal(px[2:10, 2:10], ldm_b200.to_uint8(imgs)[0])
