@@ -411,6 +411,182 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #undef HWAIT
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// conv_halo_stream_kernel<BN>: the halo scheme for Cin = 64 * KB > 64, where the nine weight tiles of every 64-channel
+// block no longer fit next to the pixel tiles.  Pixel tiles keep the halo layout (ONE box per (unit, channel block)
+// instead of nine), the weight tiles (BN x 64, one per (channel block, tap)) stream through their own TMA ring in
+// consumption order.  Operand bytes per 128 x 128 output tile of a 128 -> 128 convolution at 32 x 32: 61 KB of pixels +
+// 288 KB of weights instead of 288 + 288 (conv_tc_kernel is at the L2 bandwidth cap on those layers).
+//   warp 0: TMA producer (pixel tile of the NEXT channel block one step ahead of the weight tiles)
+//   warp 1: MMA issuer: per unit KB x 9 taps x 4 UMMA 128 x BN x 16 into one of four TMEM accumulators
+//   warps 2-5: epilogue (bias, ReLU, time term, bf16 NHWC store) under the MMAs of the following units
+// ------------------------------------------------------------------------------------------------------------------
+struct HaloStreamArgs {
+  int H, W, Wp, nrows, units_per_img, total_units;
+  int a_bytes, a_stride;     // one pixel tile; stage pitch (1024-aligned + guard)
+  int KB;                    // 64-channel blocks of the input
+  int NA, NW;                // ring depths: pixel tiles, weight tiles
+  int Cin;
+  int out_pitch, relu, post_stride;
+  const float* post;
+  const float* bias;
+  bf16* out;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_halo_stream_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const HaloStreamArgs a) {
+  constexpr uint32_t kWTile = BN * BK * 2;
+  constexpr int kTS = 512 / BN < 4 ? 512 / BN : 4;      // TMEM accumulator stages
+  constexpr int kMaxRing = 8;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w_s = smem;                                   // NW weight tiles
+  uint8_t* a_s = smem + (size_t)a.NW * kWTile + 1024;    // NA pixel tiles, one guard KB in front
+  __shared__ __align__(8) uint64_t afull[kMaxRing], aempty[kMaxRing], wfull[kMaxRing], wempty[kMaxRing], tfull[kTS], tempty[kTS];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float bias_s[BN], post_s[BN];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NA = a.NA, NW = a.NW, KB = a.KB;
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&map_a);
+    tc::prefetch_tmap(&map_w);
+    for (int s = 0; s < kMaxRing; ++s) {
+      tc::mbar_init(&afull[s], 1); tc::mbar_init(&aempty[s], 1);
+      tc::mbar_init(&wfull[s], 1); tc::mbar_init(&wempty[s], 1);
+    }
+    for (int s = 0; s < kTS; ++s) { tc::mbar_init(&tfull[s], 1); tc::mbar_init(&tempty[s], 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc<kTS * BN>(&tmem_slot);
+  if (warp >= 2)
+    for (int i = threadIdx.x - 64; i < BN; i += 128) {
+      bias_s[i] = a.bias ? a.bias[i] : 0.f;
+      post_s[i] = (a.post && a.post_stride == 0) ? a.post[i] : 0.f;
+    }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  const int rowslots = a.Wp;
+  tc::pdl_wait();
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      int ia = 0, iw = 0;        // running indices of the pixel / weight tiles issued
+      auto load_a = [&](int u, int kb) -> bool {
+        const int s = ia % NA;
+        if (!tc::mbar_wait(&aempty[s], (uint32_t)((ia / NA) & 1) ^ 1u, 31)) return false;
+        const int n = u / a.units_per_img, s0 = (u - n * a.units_per_img) * BM, r = s0 / rowslots;
+        tc::mbar_arrive_expect_tx(&afull[s], (uint32_t)a.a_bytes);
+        tc::tma_load_4d(a_s + (size_t)s * a.a_stride, &map_a, &afull[s], kb * BK, -1, r - 1, n);
+        ++ia;
+        return true;
+      };
+      bool ok = blockIdx.x < a.total_units ? load_a(blockIdx.x, 0) : true;
+      for (int u = blockIdx.x; u < a.total_units && ok; u += gridDim.x) {
+        for (int kb = 0; kb < KB && ok; ++kb) {
+          // the pixel tile the MMA warp will need AFTER the nine weight tiles below
+          if (kb + 1 < KB) ok = load_a(u, kb + 1);
+          else if (u + (int)gridDim.x < a.total_units) ok = load_a(u + gridDim.x, 0);
+          for (int tap = 0; tap < 9 && ok; ++tap) {
+            const int s = iw % NW;
+            ok = tc::mbar_wait(&wempty[s], (uint32_t)((iw / NW) & 1) ^ 1u, 32);
+            tc::mbar_arrive_expect_tx(&wfull[s], kWTile);
+            tc::tma_load_2d(w_s + (size_t)s * kWTile, &map_w, &wfull[s], tap * a.Cin + kb * BK, 0);
+            ++iw;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (tc::elect_one()) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16(BM, BN);
+      bool ok = true;
+      int ia = 0, iw = 0, it = 0;
+      for (int u = blockIdx.x; u < a.total_units && ok; u += gridDim.x, ++it) {
+        const int ts = it % kTS;
+        const int s0 = (u % a.units_per_img) * BM;
+        const int first = s0 % rowslots + rowslots;
+        ok = tc::mbar_wait(&tempty[ts], (uint32_t)((it / kTS) & 1) ^ 1u, 33);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ts * BN);
+        for (int kb = 0; kb < KB && ok; ++kb, ++ia) {
+          const int sa = ia % NA;
+          ok = tc::mbar_wait(&afull[sa], (uint32_t)((ia / NA) & 1), 34);
+          const uint32_t a_addr = tc::smem_u32(a_s + (size_t)sa * a.a_stride);
+#pragma unroll 1
+          for (int tap = 0; tap < 9 && ok; ++tap, ++iw) {
+            const int sw = iw % NW;
+            ok = tc::mbar_wait(&wfull[sw], (uint32_t)((iw / NW) & 1), 35);
+            tc::fence_after_sync();
+            const int shift = first + (tap / 3 - 1) * rowslots + (tap % 3 - 1);
+            const uint64_t da = tc::make_desc_sw128(a_addr + (uint32_t)shift * 128u);
+            const uint64_t dw = tc::make_desc_sw128(tc::smem_u32(w_s + (size_t)sw * kWTile));
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              tc::umma_bf16(d_tmem, da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc, (uint32_t)((kb | tap | k) != 0));
+            tc::umma_commit(&wempty[sw]);
+          }
+          tc::umma_commit(&aempty[sa]);
+        }
+        tc::umma_commit(&tfull[ts]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int HW = a.H * a.W;
+    int it = 0;
+    for (int u = blockIdx.x; u < a.total_units; u += gridDim.x, ++it) {
+      const int ts = it % kTS;
+      const int n = u / a.units_per_img, slot = (u - n * a.units_per_img) * BM + q * 32 + lane;
+      const int y = slot / rowslots, cx = slot - y * rowslots;
+      const bool valid = y < a.H && cx >= 1 && cx <= a.W;
+      const int rem = y * a.W + cx - 1;
+      if (!tc::mbar_wait(&tfull[ts], (uint32_t)((it / kTS) & 1), 36)) break;
+      tc::fence_after_sync();
+      const uint32_t t_addr = tmem_base + (uint32_t)(ts * BN) + ((uint32_t)(q * 32) << 16);
+      bf16* dst = a.out + ((size_t)n * HW + (valid ? rem : 0)) * (size_t)a.out_pitch;
+      const float* prow = (a.post && a.post_stride) ? a.post + (size_t)n * a.post_stride : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(t_addr + (uint32_t)c0, v);
+        if (valid) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            v[j] += bias_s[c0 + j];
+            if (a.relu) v[j] = fmaxf(v[j], 0.f);
+            v[j] += post_s[c0 + j];
+          }
+          if (prow) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(prow + c0) + j);
+              v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+          d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty[ts]);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<kTS * BN>(tmem_base);
+}
+
 // final_conv[3] + Sigmoid (v2:277-278): Conv2d(32, 3, 3, padding 1) over NHWC bf16 -> NCHW fp32.  N = 3 output
 // channels is no tensor-core shape: one thread per pixel on the CUDA cores, weights in shared memory.
 __global__ void __launch_bounds__(256)
@@ -648,6 +824,70 @@ int launch_conv_halo(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer
   if (!fin) LDM_CUDA(launch_maybe_pdl(conv_halo_kernel<64, 0, 1>, dim3(grid), kThreads, smem, st, ctx->use_pdl, ma, L.map_w, a));
   else if (ddpm) LDM_CUDA(launch_maybe_pdl(conv_halo_kernel<16, 2, 2>, dim3(grid), kThreads, smem, st, ctx->use_pdl, ma, L.map_w, a));
   else LDM_CUDA(launch_maybe_pdl(conv_halo_kernel<16, 1, 2>, dim3(grid), kThreads, smem, st, ctx->use_pdl, ma, L.map_w, a));
+  ctx->launches++;
+  LDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// 3x3 convolution with Cin = 64 * KB (KB >= 1) and Cout = 64 or 128 through conv_halo_stream_kernel.  L.map_w must be
+// boxed (64, Cout).  Returns 0 from *_supported when the shape does not fit (the caller falls back to conv_tc_kernel).
+static void halo_stream_plan(int H, int W, int Cin, int Cout, int* nrows, int* a_stride, int* NA, int* NW, size_t* smem) {
+  const int Wp = W + 2, KB = Cin / 64;
+  *nrows = (Wp - 1 + 128 + Wp - 1) / Wp + 2;
+  *a_stride = (((*nrows) * Wp * 128 + 1023) & ~1023) + 1024;
+  const size_t budget = 218 * 1024, wtile = (size_t)Cout * 128;
+  int nw = 4, na = (int)((budget - 2048 - nw * wtile) / (size_t)(*a_stride));
+  if (na > 2 * KB) na = 2 * KB;
+  if (na > 8) na = 8;
+  while (nw < 8 && 2048 + (nw + 1) * wtile + (size_t)na * (*a_stride) <= budget) ++nw;
+  *NA = na; *NW = nw;
+  *smem = 2048 + nw * wtile + (size_t)na * (*a_stride) + 1024;
+}
+
+int conv_halo_stream_supported(int H, int W, int Cin, int Cout) {
+  if (Cin % 64 != 0 || Cin < 64 || (Cout != 64 && Cout != 128) || W < 30 || W + 2 > 256) return 0;
+  int nrows, a_stride, NA, NW;
+  size_t smem;
+  halo_stream_plan(H, W, Cin, Cout, &nrows, &a_stride, &NA, &NW, &smem);
+  return nrows <= 256 && NA >= 2 && smem <= 222 * 1024;
+}
+
+int launch_conv_halo_stream(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer& L, const CUtensorMap& map_w, const float* bias,
+                            bf16* out, int out_pitch, int B, int H, int W, int relu, const float* post, int post_stride, cudaStream_t st) {
+  LDM_TRY(conv_init(ctx));
+  LDM_CHECK(conv_halo_stream_supported(H, W, L.Cin, L.Cout), "conv_halo_stream: unsupported shape (H=%d W=%d Cin=%d Cout=%d)", H, W, L.Cin, L.Cout);
+  LDM_CHECK(((uintptr_t)in & 15) == 0 && in_pitch % 8 == 0, "conv_halo_stream: input must be 16-byte aligned");
+  static bool attr_set = false;
+  if (!attr_set) {
+    LDM_CUDA(cudaFuncSetAttribute(conv_halo_stream_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024));
+    LDM_CUDA(cudaFuncSetAttribute(conv_halo_stream_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024));
+    attr_set = true;
+  }
+  HaloStreamArgs a = {};
+  size_t smem;
+  a.H = H; a.W = W; a.Wp = W + 2; a.KB = L.Cin / 64; a.Cin = L.Cin;
+  halo_stream_plan(H, W, L.Cin, L.Cout, &a.nrows, &a.a_stride, &a.NA, &a.NW, &smem);
+  a.units_per_img = ceil_div(H * a.Wp, BM);
+  a.total_units = B * a.units_per_img;
+  a.a_bytes = a.nrows * a.Wp * 128;
+  a.out_pitch = out_pitch; a.relu = relu; a.post = post; a.post_stride = post_stride; a.bias = bias; a.out = out;
+  CUtensorMap ma;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)L.Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)in_pitch * 2, (cuuint64_t)W * in_pitch * 2, (cuuint64_t)H * W * in_pitch * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)a.Wp, (cuuint32_t)a.nrows, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode4(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(in), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      ldm_set_error("cuTensorMapEncodeTiled (halo box %d x %d) failed: CUresult %d", a.Wp, a.nrows, (int)r);
+      return (int)r;
+    }
+  }
+  const int grid = a.total_units < ctx->sm_count ? a.total_units : ctx->sm_count;
+  if (L.Cout == 64) LDM_CUDA(launch_maybe_pdl(conv_halo_stream_kernel<64>, dim3(grid), kThreads, smem, st, ctx->use_pdl, ma, map_w, a));
+  else LDM_CUDA(launch_maybe_pdl(conv_halo_stream_kernel<128>, dim3(grid), kThreads, smem, st, ctx->use_pdl, ma, map_w, a));
   ctx->launches++;
   LDM_CUDA(cudaGetLastError());
   return 0;

@@ -24,6 +24,9 @@ int launch_conv_tc_ex(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLaye
 int tc_make_weight_map(ldm_ctx* ctx, const bf16* w, int N, int K, int bn, CUtensorMap* out);
 int tc_init(ldm_ctx* ctx);
 int conv_halo_supported(int H, int W, int Cin, int Cout);
+int conv_halo_stream_supported(int H, int W, int Cin, int Cout);
+int launch_conv_halo_stream(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer& L, const CUtensorMap& map_w, const float* bias,
+                            bf16* out, int out_pitch, int B, int H, int W, int relu, const float* post, int post_stride, cudaStream_t st);
 int launch_conv_halo(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer& L, const float* bias, bf16* out, int out_pitch,
                      int B, int H, int W, int relu, const float* post, int post_stride, const PixOutArgs* fin, int ddpm,
                      cudaStream_t st);
@@ -400,13 +403,17 @@ int ensure_pix_workspace(ldm_ctx* ctx, int B, int H, int W) {
   return 0;
 }
 
-bool use_halo() {
+int use_halo() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("LDM_PIX_HALO");
+    // bit 0: resident-weight halo kernel (Cin = 64).  bit 1: streamed-weight halo kernel (Cin > 64) - parity-green but
+    // slower than conv_tc_kernel (measured at B = 64: conv2.x 36 vs 30 us, conv4.0 64 vs 47, conv5.0 112 vs 79): one
+    // persistent CTA per SM keeps only ~5 weight tiles (40-80 KB) in flight against ~1 us of L2 latency, two conv_tc
+    // CTAs per SM keep ~200 KB.  Off by default.
     v = e ? atoi(e) : 1;
   }
-  return v != 0;
+  return v;
 }
 
 // 3x3 convolution + bias + ReLU [+ time term]: the halo kernel where it applies (Cin = 64 on a large image), else conv_tc
@@ -414,6 +421,8 @@ int conv3(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer& L, bf16* 
           const float* post, int post_stride, cudaStream_t st) {
   if (use_halo() && conv_halo_supported(H, W, L.Cin, L.Cout))
     return launch_conv_halo(ctx, in, in_pitch, L, L.b, out, out_pitch, B, H, W, 1, post, post_stride, nullptr, 0, st);
+  if ((use_halo() & 2) && L.bn == L.Cout && conv_halo_stream_supported(H, W, L.Cin, L.Cout))
+    return launch_conv_halo_stream(ctx, in, in_pitch, L, L.map_w, L.b, out, out_pitch, B, H, W, 1, post, post_stride, st);
   return launch_conv_tc_ex(ctx, in, in_pitch, L, L.b, out, out_pitch, B, H, W, 1, 1, post, post_stride, st);
 }
 
@@ -435,20 +444,20 @@ int run_forward(ldm_ctx* ctx, const float* x, const float* terms, int tstride, i
   // encoder (v4:113-122); x1 -> cat5[:, c:2c], x2 -> cat4[:, 2c:4c]
   LDM_TRY(conv3(ctx, M.a1, c, M.c1b, M.cat5 + c, 2 * c, B, H, W, t1, tstride, st));
   LDM_TRY(launch_conv_tc_ex(ctx, M.cat5 + c, 2 * c, M.down1, M.down1.b, M.d1, 2 * c, B, H, W, 0, 0, nullptr, 0, st));
-  LDM_TRY(launch_conv_tc_ex(ctx, M.d1, 2 * c, M.c2a, M.c2a.b, M.a2, 2 * c, B, H2, W2, 1, 1, nullptr, 0, st));
-  LDM_TRY(launch_conv_tc_ex(ctx, M.a2, 2 * c, M.c2b, M.c2b.b, M.cat4 + 2 * c, 4 * c, B, H2, W2, 1, 1, t2, tstride, st));
+  LDM_TRY(conv3(ctx, M.d1, 2 * c, M.c2a, M.a2, 2 * c, B, H2, W2, nullptr, 0, st));
+  LDM_TRY(conv3(ctx, M.a2, 2 * c, M.c2b, M.cat4 + 2 * c, 4 * c, B, H2, W2, t2, tstride, st));
   LDM_TRY(launch_conv_tc_ex(ctx, M.cat4 + 2 * c, 4 * c, M.down2, M.down2.b, M.d2, 4 * c, B, H2, W2, 0, 0, nullptr, 0, st));
-  LDM_TRY(launch_conv_tc_ex(ctx, M.d2, 4 * c, M.c3a, M.c3a.b, M.a3, 4 * c, B, H4, W4, 1, 1, nullptr, 0, st));
-  LDM_TRY(launch_conv_tc_ex(ctx, M.a3, 4 * c, M.c3b, M.c3b.b, M.x3, 4 * c, B, H4, W4, 1, 1, t3, tstride, st));
+  LDM_TRY(conv3(ctx, M.d2, 4 * c, M.c3a, M.a3, 4 * c, B, H4, W4, nullptr, 0, st));
+  LDM_TRY(conv3(ctx, M.a3, 4 * c, M.c3b, M.x3, 4 * c, B, H4, W4, t3, tstride, st));
   // bottleneck (v4:124)
-  LDM_TRY(launch_conv_tc_ex(ctx, M.x3, 4 * c, M.b0, M.b0.b, M.bt, 8 * c, B, H4, W4, 1, 1, nullptr, 0, st));
-  LDM_TRY(launch_conv_tc_ex(ctx, M.bt, 8 * c, M.b2, M.b2.b, M.x4, 4 * c, B, H4, W4, 1, 1, nullptr, 0, st));
+  LDM_TRY(conv3(ctx, M.x3, 4 * c, M.b0, M.bt, 8 * c, B, H4, W4, nullptr, 0, st));
+  LDM_TRY(conv3(ctx, M.bt, 8 * c, M.b2, M.x4, 4 * c, B, H4, W4, nullptr, 0, st));
   // decoder (v4:126-133)
   LDM_TRY(launch_conv_tc_ex(ctx, M.x4, 4 * c, M.up1, M.up1.b, M.cat4, 4 * c, B, H4, W4, 2, 0, nullptr, 0, st));
-  LDM_TRY(launch_conv_tc_ex(ctx, M.cat4, 4 * c, M.c4a, M.c4a.b, M.a4, 2 * c, B, H2, W2, 1, 1, nullptr, 0, st));
-  LDM_TRY(launch_conv_tc_ex(ctx, M.a4, 2 * c, M.c4b, M.c4b.b, M.x5, 2 * c, B, H2, W2, 1, 1, nullptr, 0, st));
+  LDM_TRY(conv3(ctx, M.cat4, 4 * c, M.c4a, M.a4, 2 * c, B, H2, W2, nullptr, 0, st));
+  LDM_TRY(conv3(ctx, M.a4, 2 * c, M.c4b, M.x5, 2 * c, B, H2, W2, nullptr, 0, st));
   LDM_TRY(launch_conv_tc_ex(ctx, M.x5, 2 * c, M.up2, M.up2.b, M.cat5, 2 * c, B, H2, W2, 2, 0, nullptr, 0, st));
-  LDM_TRY(launch_conv_tc_ex(ctx, M.cat5, 2 * c, M.c5a, M.c5a.b, M.a5, c, B, H, W, 1, 1, nullptr, 0, st));
+  LDM_TRY(conv3(ctx, M.cat5, 2 * c, M.c5a, M.a5, c, B, H, W, nullptr, 0, st));
   LDM_TRY(conv3(ctx, M.a5, c, M.c5b, M.x6, c, B, H, W, nullptr, 0, st));
   fin.in = M.x6; fin.w = M.out_w; fin.bias = M.out_b; fin.res_ratio = M.res_ratio; fin.x_in = x;
   fin.H = H; fin.W = W; fin.C = c; fin.total_pix = P1;
