@@ -225,6 +225,7 @@ struct HaloArgs {
   bf16* out;
   int base_off_mode;       // 1: descriptor base offset = (address >> 7) & 7;  0: none
   int debug;               // timing experiments (LDM_HALO_DEBUG): 1 = load only the first two tiles, 2 = unshifted descriptors, 4 = no stores
+  int box_rows;            // image rows per TMA operation (the halo tile is nrows / box_rows boxes)
   PixOutArgs fin;          // MODE 1 / 2
 };
 
@@ -298,7 +299,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int n = u / a.units_per_img, s0 = (u - n * a.units_per_img) * BM, r = s0 / rowslots;
         if ((a.debug & 1) && it >= 2) { tc::mbar_arrive(&full_bar[s]); continue; }
         tc::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)a.a_bytes);
-        tc::tma_load_4d(a_s + (size_t)s * a.a_stride, &map_a, &full_bar[s], 0, -1, r - 1, n);
+        for (int rr = 0; rr < a.nrows; rr += a.box_rows)
+          tc::tma_load_4d(a_s + (size_t)s * a.a_stride + (size_t)rr * rowslots * 128, &map_a, &full_bar[s], 0, -1, r - 1 + rr, n);
       }
     }
   } else if (warp == 1) {
@@ -804,12 +806,18 @@ int launch_conv_halo(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer
     debug = e ? atoi(e) : 0;
   }
   a.debug = debug;
+  static int box_rows = -1;
+  if (box_rows < 0) {
+    const char* e = getenv("LDM_HALO_BOX_ROWS");
+    box_rows = e ? atoi(e) : 0;
+  }
+  a.box_rows = (box_rows > 0 && a.nrows % box_rows == 0) ? box_rows : a.nrows;
   if (fin) a.fin = *fin;
   CUtensorMap ma;
   {
     cuuint64_t dims[4] = {(cuuint64_t)64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)in_pitch * 2, (cuuint64_t)W * in_pitch * 2, (cuuint64_t)H * W * in_pitch * 2};
-    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)a.Wp, (cuuint32_t)a.nrows, 1};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)a.Wp, (cuuint32_t)a.box_rows, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = g_encode4(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(in), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
