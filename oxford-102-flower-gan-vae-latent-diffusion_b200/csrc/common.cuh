@@ -317,6 +317,23 @@ struct ldm_ctx {
   int use_attn_tc = 1;            // v3 bf16: attention on tcgen05 (LDM_ATTN_TC=0 selects the CUDA-core kernel)
 };
 
+// Launch with programmatic dependent launch (PDL): the grid may start while its predecessor in the stream drains, runs its
+// prologue (barrier init, TMEM allocation, descriptor prefetch, resident weights) and blocks in griddepcontrol.wait until
+// the predecessor has completed and its writes are visible.
+template <typename Kern, typename... Args>
+static inline cudaError_t launch_maybe_pdl(Kern kern, dim3 grid, int threads, size_t smem, cudaStream_t st, int pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+__device__ __forceinline__ void ldm_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void ldm_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // memory helpers (api.cu)
 int ldm_alloc(ldm_ctx* ctx, std::vector<void*>& pool, void** out, size_t bytes);
 template <typename T>

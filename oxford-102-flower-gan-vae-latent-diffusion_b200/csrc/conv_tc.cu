@@ -28,20 +28,6 @@ constexpr int BM = 128, BK = 64;
 constexpr int kThreads = 192;
 constexpr int kMaxStages = 8;
 
-// Launch with programmatic dependent launch (PDL): the grid may start while its predecessor in the stream drains, runs its
-// prologue (barrier init, TMEM allocation, descriptor prefetch, resident weights) and blocks in griddepcontrol.wait until
-// the predecessor has completed and its writes are visible.
-template <typename Kern, typename... Args>
-cudaError_t launch_maybe_pdl(Kern kern, dim3 grid, int threads, size_t smem, cudaStream_t st, int pdl, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, args...);
-}
-
 struct ConvTcArgs {
   int H, W;         // input spatial size
   int Cin, Cout;    // Cout: output channels of one parity

@@ -52,10 +52,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
+  // PDL (no-ops without the launch attribute): the NEXT kernel of the stream may start its prologue now, on the SMs this
+  // small grid leaves idle; this kernel fetches its first weight tiles (they do not depend on the previous kernel) and
+  // only then waits for the previous kernel's results.
+  tc::pdl_launch_dependents();
 
   if (warp == 0) {
     if (tc::elect_one()) {
-      for (int kb = 0; kb < nkb; ++kb) {
+      const int pre = nkb < S ? nkb : S;
+      for (int kb = 0; kb < pre; ++kb) {
+        uint8_t* sa = smem + (size_t)kb * kStageBytes;
+        tc::mbar_arrive_expect_tx(&full_bar[kb], kStageBytes);
+        tc::tma_load_2d(sa + kABytes, &map_w, &full_bar[kb], kb * BK, n0);
+      }
+      tc::pdl_wait();
+      for (int kb = 0; kb < pre; ++kb) tc::tma_load_2d(smem + (size_t)kb * kStageBytes, &map_a, &full_bar[kb], kb * BK, m0);
+      for (int kb = pre; kb < nkb; ++kb) {
         const int s = kb % S;
         const uint32_t ph = (uint32_t)(kb / S) & 1u;
         if (!tc::mbar_wait(&empty_bar[s], ph ^ 1u, 1)) break;
@@ -87,6 +99,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // epilogue warps 2..5 own TMEM lanes [32*(warp%4), +32)
     const int q = warp & 3;
     const int row = m0 + q * 32 + lane;
+    tc::pdl_wait();                       // the epilogue reads residuals / state written by earlier kernels
     tc::mbar_wait(&tmem_full_bar, 0, 3);
     tc::fence_after_sync();
 #pragma unroll 1
@@ -161,6 +174,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_constant
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
+  tc::pdl_launch_dependents();
   tc::pdl_wait();
 
   if (warp == 0) {
@@ -296,6 +310,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_constant
 // qkv fp32 (rows, 3 d) = [Q | K | V] (the in_proj output, v3:832) -> QK bf16 (rows, 2 d) and V^T bf16 (d, ldv)
 __global__ void __launch_bounds__(256)
 attn_prep_kernel(const float* __restrict__ qkv, bf16* __restrict__ qk, bf16* __restrict__ vt, int rows, int d, int ldv) {
+  ldm_pdl_launch_dependents();
+  ldm_pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * 3 * d) return;
   const int row = i / (3 * d), col = i - row * 3 * d;
@@ -337,7 +353,7 @@ int launch_bn(ldm_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, int M,
   const size_t smem = (size_t)stages * stage_bytes + 1024;
   TcArgs a{M, N, K, stages};
   dim3 grid(N / BN, ceil_div(M, BM));
-  gemm_tc_kernel<BN><<<grid, kThreads, smem, st>>>(ma, mw, a, epi);
+  LDM_CUDA(launch_maybe_pdl(gemm_tc_kernel<BN>, grid, kThreads, smem, st, ctx->use_pdl, ma, mw, a, epi));
   ctx->launches++;
   LDM_CUDA(cudaGetLastError());
   return 0;
@@ -383,7 +399,7 @@ int attn_tc_supported(int hd) { return hd == 16 || hd == 32 || hd == 64 || hd ==
 
 int launch_attn_prep(ldm_ctx* ctx, const float* qkv, bf16* qk, bf16* vt, int rows, int d, int ldv, cudaStream_t st) {
   const int n = rows * 3 * d;
-  attn_prep_kernel<<<ceil_div(n, 256), 256, 0, st>>>(qkv, qk, vt, rows, d, ldv);
+  LDM_CUDA(launch_maybe_pdl(attn_prep_kernel, dim3(ceil_div(n, 256)), 256, 0, st, ctx->use_pdl, qkv, qk, vt, rows, d, ldv));
   ctx->launches++;
   LDM_CUDA(cudaGetLastError());
   return 0;
@@ -398,7 +414,7 @@ static int launch_attn_hd(ldm_ctx* ctx, const CUtensorMap& mqk, const CUtensorMa
     LDM_CUDA(cudaFuncSetAttribute(attn_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  attn_tc_kernel<HD><<<dim3(ceil_div(a.L, 128), a.heads, batches), kThreads, smem, st>>>(mqk, mvt, a);
+  LDM_CUDA(launch_maybe_pdl(attn_tc_kernel<HD>, dim3(ceil_div(a.L, 128), a.heads, batches), kThreads, smem, st, ctx->use_pdl, mqk, mvt, a));
   ctx->launches++;
   LDM_CUDA(cudaGetLastError());
   return 0;

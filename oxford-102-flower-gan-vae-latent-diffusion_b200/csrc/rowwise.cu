@@ -47,6 +47,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 stage_mid_kernel(const float* __restrict__ u, const float* __restrict__ h, const float* __restrict__ ga,
                  const float* __restrict__ ba, const float* __restrict__ gb, const float* __restrict__ bb,
                  float* __restrict__ h2, TOP* __restrict__ n_op, int ld_op, int M, int d) {
+  ldm_pdl_launch_dependents();      // PDL (no-ops without the launch attribute): let the next kernel set itself up ...
+  ldm_pdl_wait();                   // ... and wait for the previous one's results
   const int row = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -84,6 +86,8 @@ template <int NV4, typename TOP>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 row_ln_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ g_, const float* __restrict__ b_,
               int act, TOP* __restrict__ out, int ld_out, int M, int d) {
+  ldm_pdl_launch_dependents();
+  ldm_pdl_wait();
   const int row = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -334,7 +338,8 @@ int launch_stage_mid(ldm_ctx* ctx, const float* u, const float* h, const float* 
   LDM_CHECK(d % 128 == 0 && d >= 128 && d <= 1024, "stage_mid: hidden dim %d must be a multiple of 128 in [128,1024]", d);
   dim3 grid(ceil_div(M, kWarpsPerCta)), block(kWarpsPerCta * 32);
   dispatch_nv4(d, [&](auto nv) {
-    stage_mid_kernel<decltype(nv)::value, TOP><<<grid, block, 0, st>>>(u, h, ga, ba, gb, bb, h2, n_op, ld_op, M, d);
+    (void)launch_maybe_pdl(stage_mid_kernel<decltype(nv)::value, TOP>, grid, kWarpsPerCta * 32, 0, st, ctx->use_pdl, u, h, ga, ba, gb, bb, h2,
+                           n_op, ld_op, M, d);      // a launch error is picked up by LDM_LAUNCHED below
     return 0;
   });
   LDM_LAUNCHED(ctx);
@@ -352,7 +357,8 @@ int launch_row_ln(ldm_ctx* ctx, const float* in, int ld_in, const float* g, cons
   if (d % 128 == 0 && d <= 1024) {
     dim3 grid(ceil_div(M, kWarpsPerCta)), block(kWarpsPerCta * 32);
     dispatch_nv4(d, [&](auto nv) {
-      row_ln_kernel<decltype(nv)::value, TOP><<<grid, block, 0, st>>>(in, ld_in, g, b, act, out, ld_out, M, d);
+      (void)launch_maybe_pdl(row_ln_kernel<decltype(nv)::value, TOP>, grid, kWarpsPerCta * 32, 0, st, ctx->use_pdl, in, ld_in, g, b, act, out,
+                             ld_out, M, d);
       return 0;
     });
   } else {
