@@ -44,11 +44,13 @@ struct ConvTcArgs {
   bf16* out;        // (B, up*H, up*W, out_pitch), already offset to the first output channel
 };
 
-template <int BN>
+// MT = pixel tiles per CTA (1 or 2): with MT = 2 a weight tile fetched from L2 feeds two 128-pixel tiles (two TMEM
+// accumulators), which cuts the operand traffic of the L2-bound 64 / 128-channel layers by a quarter.
+template <int BN, int MT>
 __global__ void __launch_bounds__(kThreads, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const ConvTcArgs a) {
-  constexpr int kTmemCols = BN < 32 ? 32 : BN;
-  constexpr uint32_t kABytes = BM * BK * 2, kWBytes = BN * BK * 2, kStageBytes = kABytes + kWBytes;
+  constexpr int kTmemCols = MT * BN < 32 ? 32 : MT * BN;
+  constexpr uint32_t kABytes = BM * BK * 2, kWBytes = BN * BK * 2, kStageBytes = MT * kABytes + kWBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -58,10 +60,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __shared__ float bias_s[BN];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, nc0 = blockIdx.y * BN, z = blockIdx.z;
+  const int m0 = blockIdx.x * (BM * MT), nc0 = blockIdx.y * BN, z = blockIdx.z;
   const int pa = z >> 1, pb = z & 1;
   const int HW = a.H * a.W;
-  const int n0 = m0 / HW, y0 = (m0 - n0 * HW) / a.W;
   const int cblocks = a.Cin / BK;
   const int nkb = a.taps * cblocks, S = a.stages;
 
@@ -87,11 +88,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (warp == 0) {
     if (tc::elect_one()) {
-      for (int kb = 0; kb < nkb; ++kb) {
+      int tn0[MT], ty0[MT];     // image and first row of each pixel tile (hoisted: the producer loop must stay short)
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const int mm = m0 + mt * BM;
+        tn0[mt] = mm / HW;
+        ty0[mt] = (mm - tn0[mt] * HW) / a.W;
+      }
+      int tap = 0, cb = 0;
+      for (int kb = 0; kb < nkb; ++kb, ++cb) {
         const int s = kb % S;
         const uint32_t ph = (uint32_t)(kb / S) & 1u;
         if (!tc::mbar_wait(&empty_bar[s], ph ^ 1u, 1)) break;
-        const int tap = kb / cblocks, cb = kb - tap * cblocks;
+        if (cb == cblocks) { cb = 0; ++tap; }
         int dy, dx;
         if (a.up == 0) {
           // Conv2d(4, stride 2, pad 1): input row 2Y + ky - 1 = 2 (Y + dy) + p with ky -> (dy, p) = (-1,1), (0,0), (0,1), (1,0);
@@ -102,8 +111,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int py = (ky == 0 || ky == 2) ? 1 : 0, px = (kx == 0 || kx == 2) ? 1 : 0;
           uint8_t* sa = smem + (size_t)s * kStageBytes;
           tc::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-          tc::tma_load_5d(sa, &map_a, &full_bar[s], px * a.in_pitch + cb * BK, dx, py, y0 + dy, n0);
-          tc::tma_load_2d(sa + kABytes, &map_w, &full_bar[s], tap * a.Cin + cb * BK, nc0);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+            tc::tma_load_5d(sa + mt * kABytes, &map_a, &full_bar[s], px * a.in_pitch + cb * BK, dx, py, ty0[mt] + dy, tn0[mt]);
+          tc::tma_load_2d(sa + MT * kABytes, &map_w, &full_bar[s], tap * a.Cin + cb * BK, nc0);
           continue;
         } else if (a.up == 1) {
           dy = tap / 3 - 1;
@@ -114,8 +125,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         uint8_t* sa = smem + (size_t)s * kStageBytes;
         tc::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-        tc::tma_load_4d(sa, &map_a, &full_bar[s], cb * BK, dx, y0 + dy, n0);
-        tc::tma_load_2d(sa + kABytes, &map_w, &full_bar[s], tap * a.Cin + cb * BK, z * a.Cout + nc0);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)      // a tile past the last pixel is out of bounds in n: zero-filled, never stored
+          tc::tma_load_4d(sa + mt * kABytes, &map_a, &full_bar[s], cb * BK, dx, ty0[mt] + dy, tn0[mt]);
+        tc::tma_load_2d(sa + MT * kABytes, &map_w, &full_bar[s], tap * a.Cin + cb * BK, z * a.Cout + nc0);
       }
     }
   } else if (warp == 1) {
@@ -128,17 +141,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         ok = tc::mbar_wait(&full_bar[s], ph, 2);
         tc::fence_after_sync();
         const uint32_t a_addr = tc::smem_u32(smem + (size_t)s * kStageBytes);
-        const uint64_t da = tc::make_desc_sw128(a_addr), dw = tc::make_desc_sw128(a_addr + kABytes);
+        const uint64_t dw = tc::make_desc_sw128(a_addr + MT * kABytes);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)
-          tc::umma_bf16(tmem_base, da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint64_t da = tc::make_desc_sw128(a_addr + mt * kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            tc::umma_bf16(tmem_base + (uint32_t)(mt * BN), da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+        }
         tc::umma_commit(&empty_bar[s]);
       }
       tc::umma_commit(&tmem_full_bar);
     }
   } else {
     const int q = warp & 3;
-    const int p = m0 + q * 32 + lane;
+    tc::mbar_wait(&tmem_full_bar, 0, 3);
+    tc::fence_after_sync();
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+    const int p = m0 + mt * BM + q * 32 + lane;
     const bool valid = p < a.total_pix;
     size_t op = (size_t)p;
     if (a.up == 2) {
@@ -147,12 +168,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     bf16* dst = a.out + op * (size_t)a.out_pitch + nc0;
     const float* prow = a.post ? a.post + (size_t)(valid ? p / HW : 0) * a.post_stride + nc0 : nullptr;
-    tc::mbar_wait(&tmem_full_bar, 0, 3);
-    tc::fence_after_sync();
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 16) {
       float v[16];
-      tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * BN + c0), v);
       if (valid) {
         uint32_t pk[8];
 #pragma unroll
@@ -176,6 +195,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       }
+    }
     }
   }
   tc::fence_before_sync();
@@ -629,10 +649,12 @@ int conv_init(ldm_ctx* ctx) {
     g_encode4 = reinterpret_cast<EncodeTiledFn>(fn);
   }
   if (!g_attr_set) {
-    LDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-    LDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-    LDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-    LDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+    LDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+    LDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+    LDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+    LDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+    LDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+    LDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
     g_attr_set = true;
   }
   return 0;
@@ -685,20 +707,40 @@ int make_act_map_down(const bf16* base, int B, int H, int W, int C, int P, CUten
   return 0;
 }
 
-template <int BN>
-int launch_bn(ldm_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, const ConvTcArgs& a0, int nz, cudaStream_t st) {
+template <int BN, int MT>
+int launch_bn_mt(ldm_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, const ConvTcArgs& a0, int nz, cudaStream_t st) {
   ConvTcArgs a = a0;
   const int nkb = a.taps * (a.Cin / BK);
-  const size_t stage_bytes = (size_t)BM * BK * 2 + (size_t)BN * BK * 2;
+  const size_t stage_bytes = (size_t)MT * BM * BK * 2 + (size_t)BN * BK * 2;
   int stages = nkb < kMaxStages ? nkb : kMaxStages;
   while (stages > 2 && (size_t)stages * stage_bytes > 100 * 1024) --stages;   // two CTAs per SM: one finishes while the other loads
   a.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024;
-  dim3 grid(ceil_div(a.total_pix, BM), a.Cout / BN, nz);
-  LDM_CUDA(launch_maybe_pdl(conv_tc_kernel<BN>, grid, kThreads, smem, st, ctx->use_pdl, ma, mw, a));
+  dim3 grid(ceil_div(a.total_pix, BM * MT), a.Cout / BN, nz);
+  LDM_CUDA(launch_maybe_pdl(conv_tc_kernel<BN, MT>, grid, kThreads, smem, st, ctx->use_pdl, ma, mw, a));
   ctx->launches++;
   LDM_CUDA(cudaGetLastError());
   return 0;
+}
+
+int conv_mt2() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LDM_CONV_MT2");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
+template <int BN>
+int launch_bn(ldm_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, const ConvTcArgs& a, int nz, cudaStream_t st) {
+  // two pixel tiles per CTA where that still leaves >= 1.5 CTAs per SM (64 / 128-channel tiles only: TMEM and
+  // shared memory of two co-resident CTAs)
+  if constexpr (BN == 64 || BN == 128) {
+    if (conv_mt2() && (long long)ceil_div(a.total_pix, 2 * BM) * (a.Cout / BN) * nz * 2 >= 3ll * ctx->sm_count)
+      return launch_bn_mt<BN, 2>(ctx, ma, mw, a, nz, st);
+  }
+  return launch_bn_mt<BN, 1>(ctx, ma, mw, a, nz, st);
 }
 
 }  // namespace

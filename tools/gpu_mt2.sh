@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_pix.py tests/test_gpu_parity.py tests/test_ublock.py -q -m gpu --timeout=600 -p no:cacheprovider 2>&1 | grep -E "passed|failed|Error|assert|rror" | head -12
+for m in 0 1; do
+  echo "== LDM_CONV_MT2=$m"
+  LDM_CONV_MT2=$m timeout 300 python tools/pix_profile.py --batch 64 --steps 50 2>&1 | tail -1
+  LDM_CONV_MT2=$m timeout 300 python tools/pix_profile.py --batch 256 --steps 20 2>&1 | tail -1
+  LDM_CONV_MT2=$m timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('v2', d['value'], d['decode'])"
+done
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_pix.csv python tools/pix_profile.py --batch 64 --steps 2 --reps 1 --no-graph > gpurun_out/ncu_pix.log 2>&1; echo "ncu rc=$?"
