@@ -232,6 +232,7 @@ struct HaloArgs {
   int base_off_mode;       // 1: descriptor base offset = (address >> 7) & 7;  0: none
   int debug;               // timing experiments (LDM_HALO_DEBUG): 1 = load only the first two tiles, 2 = unshifted descriptors, 4 = no stores
   int box_rows;            // image rows per TMA operation (the halo tile is nrows / box_rows boxes)
+  int stages;              // halo tiles in flight (<= kHaloStages)
   PixOutArgs fin;          // MODE 1 / 2
 };
 
@@ -300,8 +301,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (tc::elect_one()) {
       int it = 0;
       for (int u = blockIdx.x; u < a.total_units; u += gridDim.x, ++it) {
-        const int s = it % kHaloStages;
-        if (!HWAIT(&empty_bar[s], (uint32_t)((it / kHaloStages) & 1) ^ 1u, 11)) break;
+        const int s = it % a.stages;
+        if (!HWAIT(&empty_bar[s], (uint32_t)((it / a.stages) & 1) ^ 1u, 11)) break;
         const int n = u / a.units_per_img, s0 = (u - n * a.units_per_img) * BM, r = s0 / rowslots;
         if ((a.debug & 1) && it >= 2) { tc::mbar_arrive(&full_bar[s]); continue; }
         tc::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)a.a_bytes);
@@ -316,8 +317,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t w_addr = tc::smem_u32(w_s);
       int it = 0;
       for (int u = blockIdx.x; u < a.total_units && ok; u += gridDim.x, ++it) {
-        const int s = it % kHaloStages, ts = it % kTS;
-        const uint32_t ph = (uint32_t)((it / kHaloStages) & 1), tph = (uint32_t)((it / kTS) & 1);
+        const int s = it % a.stages, ts = it % kTS;
+        const uint32_t ph = (uint32_t)((it / a.stages) & 1), tph = (uint32_t)((it / kTS) & 1);
         const int s0 = (u % a.units_per_img) * BM;
         const int first = s0 % rowslots + rowslots;      // tile slot of output slot 0 (the tile starts one row above)
         ok = HWAIT(&tempty_bar[ts], tph ^ 1u, 13) && HWAIT(&full_bar[s], ph, 14);
@@ -855,8 +856,18 @@ int launch_conv_halo(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer
       return (int)r;
     }
   }
-  const size_t smem = (((size_t)9 * L.Cout * 128 + 1023) & ~(size_t)1023) + 1024 + kHaloStages * (size_t)a.a_stride + 1024;
-  const int grid = a.total_units < ctx->sm_count ? a.total_units : ctx->sm_count;
+  // out_conv (16 weight rows): two stages leave room for TWO CTAs per SM, which hides the exposed tile latency of the
+  // single persistent CTA (26 -> measured below); the 64-channel variant keeps its 72 KB of weights and three stages
+  static int two = -1;
+  if (two < 0) {
+    const char* e = getenv("LDM_HALO_TWO_CTAS");
+    two = e ? atoi(e) : 1;
+  }
+  const bool pair = fin && two;
+  a.stages = pair ? 2 : kHaloStages;
+  const size_t smem = (((size_t)9 * L.Cout * 128 + 1023) & ~(size_t)1023) + 1024 + a.stages * (size_t)a.a_stride + 1024;
+  const int slots = pair ? 2 * ctx->sm_count : ctx->sm_count;
+  const int grid = a.total_units < slots ? a.total_units : slots;
   if (!fin) LDM_CUDA(launch_maybe_pdl(conv_halo_kernel<64, 0, 1>, dim3(grid), kThreads, smem, st, ctx->use_pdl, ma, L.map_w, a));
   else if (ddpm) LDM_CUDA(launch_maybe_pdl(conv_halo_kernel<16, 2, 2>, dim3(grid), kThreads, smem, st, ctx->use_pdl, ma, L.map_w, a));
   else LDM_CUDA(launch_maybe_pdl(conv_halo_kernel<16, 1, 2>, dim3(grid), kThreads, smem, st, ctx->use_pdl, ma, L.map_w, a));
