@@ -562,12 +562,16 @@ static int denoise(ldm_ctx* ctx, int B, int parity, const StepMode& md, cudaStre
     // h2 = swish(LN_a(u)) + h ; n = LN_b(h2)                                  (v2:520-522,547-549)
     LDM_TRY(launch_stage_mid<TOP>(ctx, ctx->u, ctx->h, U.ln_a_w[i], U.ln_a_b[i], U.ln_b_w[i], U.ln_b_b[i], ctx->h2, n_op, d, B, d, st));
     if (U.variant == 3) {  // h3 = h2 + out_proj(softmax(Q K^T / sqrt(hd)) V) over the rows of the call   (v3:832-838)
-      Epilogue eq; eq.bias = U.qkv[i].b; eq.out_f32 = ctx->qkv; eq.ld_of = 3 * d;
-      LDM_TRY(gemm<TOP>(ctx, n_op, d, B, U.qkv[i], eq, st));
       bool tc_attn = false;
       if constexpr (std::is_same<TOP, bf16>::value) tc_attn = attn_tc_supported(d / 8) && ctx->use_attn_tc;
+      Epilogue eq; eq.bias = U.qkv[i].b;
+      if (tc_attn) {   // the in_proj epilogue writes the attention operands directly: [Q | K] bf16 row-major, V transposed
+        eq.out_bf16 = ctx->qk16; eq.ld_ob = 2 * d; eq.vt = ctx->vt16; eq.vt_col0 = 2 * d; eq.ld_vt = ctx->cap;
+      } else {
+        eq.out_f32 = ctx->qkv; eq.ld_of = 3 * d;
+      }
+      LDM_TRY(gemm<TOP>(ctx, n_op, d, B, U.qkv[i], eq, st));
       if (tc_attn) {   // softmax(Q K^T) V on the tensor cores (gemm_tc.cu: attn_tc_kernel)
-        LDM_TRY(launch_attn_prep(ctx, ctx->qkv, ctx->qk16, ctx->vt16, B, d, ctx->cap, st));
         LDM_TRY(launch_attn_tc(ctx, ctx->qk16, 2 * d, 2 * d, ctx->vt16, ctx->cap, B, 1, 8, d / 8, 0, d, ctx->a_op, 1, d, d / 8, 1, st));
       } else {
         LDM_TRY(launch_batch_attention<TOP>(ctx, ctx->qkv, (TOP*)ctx->a_op, B, d, 8, st));

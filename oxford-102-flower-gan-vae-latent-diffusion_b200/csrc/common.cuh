@@ -96,6 +96,10 @@ struct Epilogue {
   int ld_of = 0;
   bf16* out_bf16 = nullptr;
   int ld_ob = 0;
+  // attention operands straight from the in_proj GEMM (v3:832): columns < vt_col0 go to out_bf16 ([Q | K], row-major),
+  // columns >= vt_col0 are written TRANSPOSED: vt[(col - vt_col0) * ld_vt + row]  (the B operand of P . V)
+  bf16* vt = nullptr;
+  int vt_col0 = 0, ld_vt = 0;
   // fused DDPM posterior update (v2:584-592): v is eps_theta
   int ddpm = 0;
   float* x = nullptr;               // (M, N) fp32 state, updated in place
@@ -222,6 +226,8 @@ struct PixModel {
   float* tfc_w[3]; float* tfc_b[3];         // time_fc1..3
   float* tab = nullptr;                     // (n_t, 7 base): [time_fc1 | time_fc2 | time_fc3](time_embed(t)), t = 0..n_t-1
   float *in_w = nullptr, *in_b = nullptr;   // conv1.0 as (base, 27) tap-major (ky, kx, ci)
+  bf16* in_w16 = nullptr;                   // base == 64: (64, 64) bf16 [w | w | 0] for the tensor-core conv1.0 kernel
+  CUtensorMap in_map;
   float *out_w = nullptr, *out_b = nullptr; // out_conv as (3, 9 base)
   float* res_ratio = nullptr;               // device scalar (v5) or null (v4)
   ConvLayer out16;                          // out_conv padded to 16 output rows, bf16 (tensor-core halo kernel; base == 64)

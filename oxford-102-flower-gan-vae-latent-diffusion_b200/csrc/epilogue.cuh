@@ -48,6 +48,11 @@ __device__ __forceinline__ void epi_finish4(const Epilogue& e, int row, int col,
     *reinterpret_cast<float4*>(e.x + (size_t)row * N + col) = make_float4(v[0], v[1], v[2], v[3]);
   }
   if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + (size_t)row * e.ld_of + col) = make_float4(v[0], v[1], v[2], v[3]);
+  if (e.vt && col >= e.vt_col0) {      // consecutive lanes hold consecutive rows: each column is one contiguous run
+#pragma unroll
+    for (int i = 0; i < 4; ++i) e.vt[(size_t)(col - e.vt_col0 + i) * e.ld_vt + row] = __float2bfloat16_rn(v[i]);
+    return;
+  }
   if (e.out_bf16) {
     __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]);
     __nv_bfloat162 p1 = __floats2bfloat162_rn(v[2], v[3]);

@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "philox.cuh"
 #include "pix_out.cuh"
+#include "tc_ptx.cuh"
 
 #include <cstdlib>
 
@@ -149,6 +150,127 @@ pix_conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w /* (
     reinterpret_cast<uint4*>(out + (p0 + p) * C)[g] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// conv1.0 + ReLU on the tensor cores (C == 64): the im2col row of a pixel is only 27 values, so the 128 builder threads
+// write it straight into shared memory in the 128-byte-swizzled K-major operand layout - as bf16 HIGH and LOW parts
+// (x = hi + lo, |lo| <= 2^-9 |x|), K = 27 + 27 (+ 10 zero columns) = 64, against the bf16 weights repeated for both
+// parts - and ONE UMMA 128 x 64 x 64 per 128 pixels does the arithmetic the CUDA-core kernel needs 1700 FMAs per pixel
+// for.  The input therefore keeps ~17 bits of mantissa; the weights are bf16 like every other layer's.
+//   warp 0: weight TMA, TMEM, MMA issue        warps 1-4: build the A rows, then the epilogue (ReLU, bf16 NHWC store)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(160)
+pix_conv_in_tc_kernel(const __grid_constant__ CUtensorMap map_w, const float* __restrict__ x, const float* __restrict__ bias,
+                      bf16* __restrict__ out, int H, int W, int total_pix) {
+  __shared__ __align__(1024) uint8_t a_s[128 * 128];
+  __shared__ __align__(1024) uint8_t w_s[64 * 128];
+  __shared__ __align__(8) uint64_t bar_w, bar_d;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float bias_s[64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tc::prefetch_tmap(&map_w);
+    tc::mbar_init(&bar_w, 1);
+    tc::mbar_init(&bar_d, 1);
+    tc::fence_barrier_init();
+    tc::mbar_arrive_expect_tx(&bar_w, 64 * 128);
+    tc::tma_load_2d(w_s, &map_w, &bar_w, 0, 0);
+  }
+  if (warp == 0) tc::tmem_alloc<64>(&tmem_slot);
+  if (threadIdx.x >= 32 && threadIdx.x < 96) bias_s[threadIdx.x - 32] = bias[threadIdx.x - 32];
+  ldm_pdl_wait();
+  if (warp >= 1) {
+    const int q = warp & 3, r = q * 32 + lane;          // TMEM lane = tile row this thread owns
+    const int p = blockIdx.x * 128 + r;
+    const int HW = H * W;
+    uint32_t hi[14], lo[14];                           // 27 values as bf16 pairs (the 28th is zero)
+    float v[28];
+    v[27] = 0.f;
+    if (p < total_pix) {
+      const int n = p / HW, rem = p - n * HW, y = rem / W, xx = rem - y * W;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int yy = y + tap / 3 - 1, xc = xx + tap % 3 - 1;
+        const bool ok = yy >= 0 && yy < H && xc >= 0 && xc < W;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) v[tap * 3 + ci] = ok ? __ldg(x + ((size_t)n * 3 + ci) * HW + (size_t)yy * W + xc) : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 27; ++k) v[k] = 0.f;
+    }
+    // K layout: [hi_0..hi_26 | lo_0..lo_26 | 0 x 10]; element k sits at byte 2k of the 128-byte row
+    __nv_bfloat16 e[64];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+      e[k] = __float2bfloat16_rn(v[k]);
+      e[27 + k] = __float2bfloat16_rn(v[k] - __bfloat162float(e[k]));
+    }
+#pragma unroll
+    for (int k = 54; k < 64; ++k) e[k] = __float2bfloat16_rn(0.f);
+    (void)hi; (void)lo;
+    uint8_t* row = a_s + r * 128;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 h2 = __halves2bfloat162(e[c * 8 + 2 * j], e[c * 8 + 2 * j + 1]);
+        pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+      }
+      *reinterpret_cast<uint4*>(row + ((c ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    tc::fence_proxy_async();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16(128, 64);
+      if (tc::mbar_wait(&bar_w, 0, 41)) {
+        tc::fence_after_sync();
+        const uint64_t da = tc::make_desc_sw128(tc::smem_u32(a_s)), dw = tc::make_desc_sw128(tc::smem_u32(w_s));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc::umma_bf16(tmem_base, da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc, (uint32_t)(k != 0));
+      }
+      tc::umma_commit(&bar_d);
+    }
+  } else {
+    const int q = warp & 3, r = q * 32 + lane;
+    const int p = blockIdx.x * 128 + r;
+    tc::mbar_wait(&bar_d, 0, 42);
+    tc::fence_after_sync();
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)p * 64);
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      float acc[16];
+      tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+      if (p < total_pix) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(acc[2 * j] + bias_s[c0 + 2 * j], 0.f), fmaxf(acc[2 * j + 1] + bias_s[c0 + 2 * j + 1], 0.f));
+          pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        dst[c0 / 8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        dst[c0 / 8 + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<64>(tmem_base);
+}
+
+// (C, 27) fp32 -> (64, 64) bf16: [w | w | 0] for the [hi | lo | 0] K layout of pix_conv_in_tc_kernel
+__global__ void pix_pack_in_tc_kernel(const float* __restrict__ w, bf16* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 64) return;
+  const int co = i >> 6, k = i & 63;
+  out[i] = __float2bfloat16_rn(k < 27 ? w[co * 27 + k] : (k < 54 ? w[co * 27 + k - 27] : 0.f));
 }
 
 // The posterior update of p_sample alone (v4:159-168) on the flattened (B, 3 H W) state: four consecutive elements are
@@ -433,6 +555,14 @@ int run_forward(ldm_ctx* ctx, const float* x, const float* terms, int tstride, i
   PixModel& M = ctx->pix;
   const int c = M.base, H2 = H / 2, H4 = H / 4, W2 = W / 2, W4 = W / 4;
   const int P1 = B * H * W;
+  static int in_tc = -1;
+  if (in_tc < 0) {
+    const char* e = getenv("LDM_PIX_IN_TC");
+    in_tc = e ? atoi(e) : 1;
+  }
+  if (in_tc && c == 64 && M.in_w16) {
+    pix_conv_in_tc_kernel<<<ceil_div(P1, 128), 160, 0, st>>>(M.in_map, x, M.in_b, M.a1, H, W, P1);
+  } else
   {   // persistent blocks (two per SM): the weights are staged in shared memory once per block
     const long long items = (long long)(P1 / 4) * (c / 8);
     const long long want = (items + 255) / 256;
@@ -560,6 +690,12 @@ extern "C" LDM_API int ldm_pix_pack(ldm_ctx* ctx, const ldm_pix_weights* w, void
   LDM_TRY(ldm_alloc_t(ctx, P, &M.in_w, (size_t)c * 27));
   LDM_TRY(launch_pack_conv(ctx, w->conv1[0].w, M.in_w, c, 3, 3, 3, st));
   LDM_TRY(own(ctx, P, w->conv1[0].b, c, &M.in_b, st));
+  if (c == 64) {
+    LDM_TRY(ldm_alloc_t(ctx, P, &M.in_w16, (size_t)64 * 64));
+    pix_pack_in_tc_kernel<<<16, 256, 0, st>>>(M.in_w, M.in_w16);
+    LDM_LAUNCHED(ctx);
+    LDM_TRY(tc_make_weight_map(ctx, M.in_w16, 64, 64, 64, &M.in_map));
+  }
   LDM_TRY(ldm_alloc_t(ctx, P, &M.out_w, (size_t)3 * 9 * c));
   LDM_TRY(launch_pack_conv(ctx, w->out_conv.w, M.out_w, 3, c, 3, 3, st));
   LDM_TRY(own(ctx, P, w->out_conv.b, 3, &M.out_b, st));

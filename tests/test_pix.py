@@ -167,3 +167,26 @@ def test_pix_full_size_batch_properties():
     assert torch.isfinite(big).all()
     small = m(x[40:44], t[40:44])
     assert torch.equal(big[40:44], small)
+
+
+@pytest.mark.gpu
+def test_pix_boundary_errors():
+    """The pixel path fails loudly instead of degrading: fp32 contexts, channel counts off the 64 grid, training mode."""
+    import ldm_b200
+    from ldm_b200 import v4
+    m = v4.SimpleUNet(precision="fp32")
+    m.load_state_dict(weights.make_pix_state(SEED, "init"), strict=True)
+    m = m.cuda().eval()
+    with pytest.raises(ldm_b200.LdmError):
+        m(torch.zeros(1, 3, 64, 64, device="cuda"), torch.zeros(1, device="cuda"))
+    small = v4.SimpleUNet(base_channels=32).cuda().eval()
+    with pytest.raises(ldm_b200.LdmError):
+        small(torch.zeros(1, 3, 64, 64, device="cuda"), torch.zeros(1, device="cuda"))
+    ok = _model("v4", "init")
+    with pytest.raises(RuntimeError):
+        ok.train()(torch.zeros(1, 3, 64, 64, device="cuda"), torch.zeros(1, device="cuda"))
+    with pytest.raises(RuntimeError):        # t must have one entry per sample, as the reference's view(B, 1) demands
+        ok.eval()(torch.zeros(2, 3, 64, 64, device="cuda"), torch.zeros(3, device="cuda"))
+    d = v4.DiffusionModel(ok, 1000, device="cuda")
+    with pytest.raises(IndexError):
+        d.p_sample(torch.zeros(1, 3, 64, 64, device="cuda"), 1000)
