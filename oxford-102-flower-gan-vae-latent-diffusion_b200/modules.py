@@ -110,6 +110,8 @@ class ConditionalUNet(nn.Module):
     def forward(self, x, t, c=None):
         """eps_theta(x_t, t, c) (v2:535-561). x (B, latent) fp32; t int64 (1,) or (B,); c int64 (B,) or None."""
         _require_eval(self, "ConditionalUNet.forward")
+        if x.shape[0] == 0:                       # empty batch: nothing to launch (torch's own modules return empty tensors too)
+            return x.new_empty((0, self.latent_dim), dtype=torch.float32)
         eng = self.engine(x.device)
         out = eng.unet_forward(x, t, c)
         eng.check_device_flags(self.num_classes)      # IndexError on a bad label / timestep, like the reference
@@ -180,6 +182,8 @@ class ConditionalDenoiseDiffusion:
         B, D = int(shape[0]), int(shape[1])
         if D != self.eps_model.latent_dim:
             raise ValueError("shape[1] must be latent_dim=%d" % self.eps_model.latent_dim)
+        if B == 0:
+            return torch.empty((0, D), device=device, dtype=torch.float32)
         eng = self._engine(device)
         seed = _fresh_seed() if seed is None else int(seed)
         if c is not None and c.numel() and (int(c.min()) < 0 or int(c.max()) >= self.eps_model.num_classes):
@@ -321,6 +325,8 @@ class Decoder(nn.Module):
     def forward(self, z, encoder_features=None):
         """v2:280-290; `encoder_features` is accepted and ignored, as in the reference."""
         _require_eval(self, "Decoder.forward")
+        if z.numel() == 0:
+            return z.new_empty((0, 3, 64, 64), dtype=torch.float32)
         eng = get_engine(z.device, self.precision)
         eng.pack_decoder(self)
         out = eng.decode(z.reshape(-1, self.latent_dim))

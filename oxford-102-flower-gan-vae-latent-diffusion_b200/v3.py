@@ -66,6 +66,8 @@ class ConditionalUNet(nn.Module):
     def forward(self, x, t, flower_label, color_label):
         """eps_theta(x_t, t, flower, color) (v3:804-853). x (B, latent); t int64 (1,) or (B,); labels int64 (B,)."""
         _require_eval(self, "v3.ConditionalUNet.forward")
+        if x.shape[0] == 0:
+            return x.new_empty((0, self.latent_dim), dtype=torch.float32)
         eng = self.engine(x.device)
         out = eng.unet3_forward(x, t, flower_label, color_label)
         eng.check_device_flags(self.num_classes)

@@ -64,6 +64,8 @@ class SimpleUNet(nn.Module):
     def forward(self, x, t):
         """eps(x, t) (v4:99-135). x (B, 3, H, W); t (B,) or (B, 1), any numeric dtype (the reference casts to float)."""
         _require_eval(self, "v4.SimpleUNet.forward")
+        if x.shape[0] == 0:
+            return x.new_empty(tuple(x.shape), dtype=torch.float32)
         return self.engine(x.device).pix_forward(x, t)
 
 
@@ -109,8 +111,10 @@ class DiffusionModel:
     def sample(self, shape, *, seed=None, sample_offset=0, x_T=None, noise=None, use_graph=True):
         """v4:170-175: x_T ~ N(0, I) on self.device, then n_steps reverse steps as one CUDA-graph launch."""
         _require_eval(self.model, "v4.DiffusionModel.sample")
-        eng = self._engine(self.device)
         B, C, H, W = (int(s) for s in shape)
+        if B == 0:
+            return torch.empty((0, C, H, W), device=self.device, dtype=torch.float32)
+        eng = self._engine(self.device)
         seed = _fresh_seed() if seed is None else int(seed)
         if x_T is None:
             x = eng.randn(B, C * H * W, seed, int(sample_offset), self.n_steps).view(B, C, H, W)

@@ -112,3 +112,21 @@ def test_checkpoint_conventions_and_png_writer(tmp_path):
     assert len(rows) == h * (1 + 3 * w)
     px = torch.frombuffer(bytearray(rows), dtype=torch.uint8).view(h, 1 + 3 * w)[:, 1:].view(h, w, 3)
     assert torch.equal(px[2:10, 2:10], ldm_b200.to_uint8(imgs)[0])
+
+
+def test_empty_batches_return_empty_tensors():
+    """Edge case: a batch of zero samples launches nothing and returns an empty tensor of the right shape."""
+    import ldm_b200
+    from ldm_b200 import v3, v4
+    u = ldm_b200.ConditionalUNet().eval()
+    assert tuple(u(torch.zeros(0, 256), torch.tensor([3]), torch.zeros(0, dtype=torch.long)).shape) == (0, 256)
+    d = ldm_b200.ConditionalDenoiseDiffusion(u, 1000, torch.device("cpu"))
+    assert tuple(d.sample((0, 256), torch.device("cpu"), torch.zeros(0, dtype=torch.long)).shape) == (0, 256)
+    ae = ldm_b200.SimpleAutoencoder().eval()
+    assert tuple(ae.decode(torch.zeros(0, 256)).shape) == (0, 3, 64, 64)
+    u3 = v3.ConditionalUNet().eval()
+    z = torch.zeros(0, dtype=torch.long)
+    assert tuple(u3(torch.zeros(0, 256), torch.tensor([3]), z, z).shape) == (0, 256)
+    m = v4.SimpleUNet().eval()
+    assert tuple(m(torch.zeros(0, 3, 64, 64), torch.zeros(0)).shape) == (0, 3, 64, 64)
+    assert tuple(v4.DiffusionModel(m, 10, device="cpu").sample((0, 3, 32, 32)).shape) == (0, 3, 32, 32)
