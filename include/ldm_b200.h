@@ -239,7 +239,7 @@ LDM_API int ldm_generate_host(ldm_ctx* ctx, const int64_t* c_host, int batch, ui
                       uint64_t sample_offset, float* img_out_host, float* latents_out_host,
                       void* stream);
 
-/* ---- v4 / v5 pixel-space diffusion (bf16 contexts only) ----------------------------------------------
+/* ---- v4 / v5 pixel-space diffusion (bf16 = tcgen05 kernels, fp32 = strict CUDA-core path) ------------
  * ldm_pix_pack: repack SimpleUNet (v4:37-97) for the implicit-GEMM kernels and tabulate the per-stage time terms
  * time_fc_i(time_embed(t)) for t = 0..n_t-1 (v4:103-110 hoisted out of the loop).  Synchronises the stream. */
 LDM_API int ldm_pix_pack(ldm_ctx* ctx, const ldm_pix_weights* w, void* stream);

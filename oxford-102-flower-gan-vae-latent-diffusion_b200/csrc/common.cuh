@@ -359,11 +359,17 @@ struct ConvGeom {
   int B, H, W;            // input batch and spatial size
   int Cin, Cout;
   int taps;
-  int dy[9], dx[9];       // input offset of each tap
+  int dy[16], dx[16];     // input offset of each tap
   int up;                 // 1: plain conv (output H x W); 2: sub-pixel of a stride-2 transposed conv
   int pa, pb;             // sub-pixel parity (output pixel (2i+pa, 2j+pb)) when up == 2
   int nchw_out;           // 1: write (B, Cout, H, W) fp32 instead of NHWC
   int act;
+  // extensions used by the pixel path (0 = the defaults of the decoder's calls):
+  int stride;             // 2: H, W are the OUTPUT size and tap (dy, dx) of pixel (y, x) reads input (2y + dy, 2x + dx)
+  int in_pitch, out_pitch;   // channel pitch of the NHWC buffers (0: Cin / Cout)
+  int relu;               // ReLU after the bias
+  const float* post;      // per-channel term added after the activation, row n * post_stride
+  int post_stride;
 };
 int launch_conv_f32(ldm_ctx* ctx, const float* in, const float* w, const float* bias, float* out,
                     const ConvGeom& g, cudaStream_t st);

@@ -113,6 +113,8 @@ conv_f32_kernel(const float* __restrict__ in, const float* __restrict__ W, const
   te.zero();
   const int M = g.B * g.H * g.W, N = g.Cout, K = g.taps * g.Cin;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int sd = g.stride > 1 ? g.stride : 1, IH = g.H * sd, IW = g.W * sd;
+  const int ipitch = g.in_pitch ? g.in_pitch : g.Cin, opitch = g.out_pitch ? g.out_pitch : g.Cout;
   // pixel coordinates of the A rows this thread stages
   int pn[TE::kALoads], py[TE::kALoads], px[TE::kALoads];
 #pragma unroll
@@ -134,9 +136,9 @@ conv_f32_kernel(const float* __restrict__ in, const float* __restrict__ W, const
 #pragma unroll
     for (int l = 0; l < TE::kALoads; ++l) {
       const int idx = threadIdx.x + l * TE::kThreads;
-      const int y = py[l] + dy, x = px[l] + dx;
-      const bool ok = pn[l] >= 0 && y >= 0 && y < g.H && x >= 0 && x < g.W;
-      ra[l] = ok ? *reinterpret_cast<const float4*>(in + (((size_t)pn[l] * g.H + y) * g.W + x) * g.Cin + c0 + (idx & 3) * 4)
+      const int y = py[l] * sd + dy, x = px[l] * sd + dx;
+      const bool ok = pn[l] >= 0 && y >= 0 && y < IH && x >= 0 && x < IW;
+      ra[l] = ok ? *reinterpret_cast<const float4*>(in + (((size_t)pn[l] * IH + y) * IW + x) * ipitch + c0 + (idx & 3) * 4)
                  : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
@@ -171,8 +173,10 @@ conv_f32_kernel(const float* __restrict__ in, const float* __restrict__ W, const
       float v = te.acc[i][j] + (bias ? bias[co] : 0.f);
       if (g.act == LDM_ACT_SWISH) v = swishf(v);
       else if (g.act == LDM_ACT_SIGMOID) v = sigmoidf_(v);
+      if (g.relu) v = fmaxf(v, 0.f);
+      if (g.post) v += g.post[(size_t)n * g.post_stride + co];
       if (g.nchw_out) out[(((size_t)n * N + co) * OH + oy) * OW + ox] = v;
-      else out[(((size_t)n * OH + oy) * OW + ox) * N + co] = v;
+      else out[(((size_t)n * OH + oy) * OW + ox) * opitch + co] = v;
     }
   }
 }
@@ -196,7 +200,7 @@ int launch_gemm_f32(ldm_ctx* ctx, const float* A, int lda, const float* W, int M
 
 int launch_conv_f32(ldm_ctx* ctx, const float* in, const float* w, const float* bias, float* out, const ConvGeom& g,
                     cudaStream_t st) {
-  LDM_CHECK(g.Cin % BK == 0 && g.taps >= 1 && g.taps <= 9, "conv_f32: Cin %% 16 and taps in [1,9] required");
+  LDM_CHECK(g.Cin % BK == 0 && g.taps >= 1 && g.taps <= 16, "conv_f32: Cin %% 16 and taps in [1,16] required");
   const int M = g.B * g.H * g.W;
   if (g.Cout >= 64) {
     dim3 grid(ceil_div(g.Cout, 64), ceil_div(M, 64));

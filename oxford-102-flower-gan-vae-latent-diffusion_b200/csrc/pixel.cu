@@ -83,9 +83,10 @@ pix_time_terms_kernel(const float* __restrict__ t, const float* __restrict__ w0,
 // channels of group g are stored as two 4-float runs at g * 4 and C / 2 + g * 4 so that the 8 lanes of a quarter warp
 // read one contiguous 128-byte line per 16-byte load (no bank conflicts).  W % 4 == 0.
 // ------------------------------------------------------------------------------------------------------------------
+template <typename TOUT>
 __global__ void __launch_bounds__(256)
 pix_conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w /* (C, 27) */, const float* __restrict__ b,
-                   bf16* __restrict__ out, int H, int W, int C, int total_quads) {
+                   TOUT* __restrict__ out, int H, int W, int C, int total_quads) {
   extern __shared__ __align__(16) float sm[];
   float* ws = sm;             // [27][C] permuted
   float* bs = sm + C * 27;    // [C]
@@ -141,13 +142,19 @@ pix_conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w /* (
   const size_t p0 = (size_t)n * HW + (size_t)y * W + x0;
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
-    uint32_t pk[4];
+    if constexpr (sizeof(TOUT) == 4) {      // strict fp32 path
+      float4* d4 = reinterpret_cast<float4*>(out + (p0 + p) * C + g * 8);
+      d4[0] = make_float4(fmaxf(acc[p][0], 0.f), fmaxf(acc[p][1], 0.f), fmaxf(acc[p][2], 0.f), fmaxf(acc[p][3], 0.f));
+      d4[1] = make_float4(fmaxf(acc[p][4], 0.f), fmaxf(acc[p][5], 0.f), fmaxf(acc[p][6], 0.f), fmaxf(acc[p][7], 0.f));
+    } else {
+      uint32_t pk[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(acc[p][2 * j], 0.f), fmaxf(acc[p][2 * j + 1], 0.f));
-      pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(acc[p][2 * j], 0.f), fmaxf(acc[p][2 * j + 1], 0.f));
+        pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+      }
+      reinterpret_cast<uint4*>(out + (p0 + p) * C)[g] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
-    reinterpret_cast<uint4*>(out + (p0 + p) * C)[g] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
   }
 }
@@ -460,6 +467,7 @@ int pack_conv(ldm_ctx* ctx, std::vector<void*>& P, ConvLayer& L, const ldm_pix_c
   LDM_TRY(ldm_alloc_t(ctx, P, &L.w32, n));
   LDM_TRY(launch_pack_conv(ctx, c.w, L.w32, Cout, Cin, k, k, st));
   LDM_TRY(own(ctx, P, c.b, Cout, &L.b, st));
+  if (ctx->precision != LDM_PRECISION_BF16) return 0;      // strict path: fp32 weights only
   LDM_TRY(ldm_alloc_t(ctx, P, &L.w16, n));
   LDM_TRY(launch_to_bf16(ctx, L.w32, L.w16, n, st));
   if (L.bn > 128) {
@@ -478,6 +486,7 @@ int pack_convT(ldm_ctx* ctx, std::vector<void*>& P, ConvLayer& L, const ldm_pix_
   LDM_TRY(ldm_alloc_t(ctx, P, &L.w32, 4 * per));
   for (int z = 0; z < 4; ++z) LDM_TRY(launch_pack_convT(ctx, c.w, L.w32 + (size_t)z * per, Cin, Cout, z >> 1, z & 1, st));
   LDM_TRY(own(ctx, P, c.b, Cout, &L.b, st));
+  if (ctx->precision != LDM_PRECISION_BF16) return 0;
   LDM_TRY(ldm_alloc_t(ctx, P, &L.w16, 4 * per));
   LDM_TRY(launch_to_bf16(ctx, L.w32, L.w16, 4 * per, st));
   return tc_make_weight_map(ctx, L.w16, 4 * Cout, 4 * Cin, L.bn, &L.map_w);
@@ -503,7 +512,8 @@ int ensure_pix_workspace(ldm_ctx* ctx, int B, int H, int W) {
   for (void* p : M.ws) cudaFree(p);
   M.ws.clear();
   M.cap = 0;
-  const size_t c = M.base, p1 = (size_t)B * H * W, p2 = p1 / 4, p3 = p1 / 16;
+  const size_t es = ctx->precision == LDM_PRECISION_BF16 ? 1 : 2;      // strict path: the same buffers hold fp32 activations
+  const size_t c = M.base * es, p1 = (size_t)B * H * W, p2 = p1 / 4, p3 = p1 / 16;
   LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.a1, p1 * c));
   LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.cat5, p1 * 2 * c));
   LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.d1, p2 * 2 * c));
@@ -518,7 +528,7 @@ int ensure_pix_workspace(ldm_ctx* ctx, int B, int H, int W) {
   LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.x5, p2 * 2 * c));
   LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.a5, p1 * c));
   LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.x6, p1 * c));
-  LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.tsample, (size_t)B * 7 * c));
+  LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.tsample, (size_t)B * 7 * M.base));
   LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.x_state, p1 * 3));
   LDM_TRY(ldm_alloc_t(ctx, M.ws, &M.eps, p1 * 3));
   M.cap = B; M.cap_h = H; M.cap_w = W;
@@ -548,10 +558,102 @@ int conv3(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer& L, bf16* 
   return launch_conv_tc_ex(ctx, in, in_pitch, L, L.b, out, out_pitch, B, H, W, 1, 1, post, post_stride, st);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// strict fp32 path (eps within 1e-3 of the reference): the same layer sequence on the CUDA-core implicit-GEMM kernel
+// (gemm_f32.cu: conv_f32_kernel), NHWC fp32 activations in the same workspace buffers
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void pix_axpy_kernel(float* __restrict__ y, const float* __restrict__ a, const float* __restrict__ x, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __fadd_rn(y[i], __fmul_rn(__ldg(a), x[i]));
+}
+
+int conv_f32(ldm_ctx* ctx, const float* in, int in_pitch, const ConvLayer& L, const float* w, float* out, int out_pitch, int B, int H, int W,
+             int mode /* 1: 3x3, 0: 4x4 stride 2 (H, W = input size), 2: transposed, parity pa/pb */, int pa, int pb, int relu,
+             const float* post, int post_stride, cudaStream_t st) {
+  ConvGeom g = ConvGeom();
+  g.B = B; g.Cin = L.Cin; g.Cout = L.Cout; g.in_pitch = in_pitch; g.out_pitch = out_pitch; g.relu = relu; g.post = post; g.post_stride = post_stride;
+  g.up = 1;
+  if (mode == 1) {
+    g.H = H; g.W = W; g.taps = 9;
+    for (int t = 0; t < 9; ++t) { g.dy[t] = t / 3 - 1; g.dx[t] = t % 3 - 1; }
+  } else if (mode == 0) {
+    g.H = H / 2; g.W = W / 2; g.taps = 16; g.stride = 2;
+    for (int t = 0; t < 16; ++t) { g.dy[t] = t / 4 - 1; g.dx[t] = t % 4 - 1; }
+  } else {
+    g.H = H; g.W = W; g.taps = 4; g.up = 2; g.pa = pa; g.pb = pb;
+    for (int t = 0; t < 4; ++t) {
+      g.dy[t] = (t >> 1) == 0 ? 0 : (pa == 0 ? -1 : 1);
+      g.dx[t] = (t & 1) == 0 ? 0 : (pb == 0 ? -1 : 1);
+    }
+  }
+  return launch_conv_f32(ctx, in, w, L.b, out, g, st);
+}
+
+int run_forward_f32(ldm_ctx* ctx, const float* x, const float* terms, int tstride, int B, int H, int W, PixOutArgs fin, int ddpm,
+                    cudaStream_t st) {
+  PixModel& M = ctx->pix;
+  const int c = M.base, H2 = H / 2, H4 = H / 4, W2 = W / 2, W4 = W / 4, P1 = B * H * W;
+  float *a1 = (float*)M.a1, *cat5 = (float*)M.cat5, *d1 = (float*)M.d1, *a2 = (float*)M.a2, *cat4 = (float*)M.cat4, *d2 = (float*)M.d2,
+        *a3 = (float*)M.a3, *x3 = (float*)M.x3, *bt = (float*)M.bt, *x4 = (float*)M.x4, *a4 = (float*)M.a4, *x5 = (float*)M.x5,
+        *a5 = (float*)M.a5, *x6 = (float*)M.x6;
+  {
+    const long long items = (long long)(P1 / 4) * (c / 8);
+    const long long want = (items + 255) / 256;
+    const unsigned grid = (unsigned)(want < 2ll * ctx->sm_count ? want : 2ll * ctx->sm_count);
+    pix_conv_in_kernel<float><<<grid, 256, (size_t)c * 28 * sizeof(float), st>>>(x, M.in_w, M.in_b, a1, H, W, c, P1 / 4);
+    LDM_LAUNCHED(ctx);
+  }
+  const float *t1 = terms, *t2 = terms + c, *t3 = terms + 3 * c;
+  auto c3 = [&](const float* in, int ip, const ConvLayer& L, float* out, int op, int h, int w, const float* post) {
+    return conv_f32(ctx, in, ip, L, L.w32, out, op, B, h, w, 1, 0, 0, 1, post, post ? tstride : 0, st);
+  };
+  auto up = [&](const float* in, int ip, const ConvLayer& L, float* out, int op, int h, int w) {
+    const size_t per = (size_t)L.Cout * 4 * L.Cin;
+    for (int z = 0; z < 4; ++z) LDM_TRY(conv_f32(ctx, in, ip, L, L.w32 + (size_t)z * per, out, op, B, h, w, 2, z >> 1, z & 1, 0, nullptr, 0, st));
+    return 0;
+  };
+  LDM_TRY(c3(a1, c, M.c1b, cat5 + c, 2 * c, H, W, t1));
+  LDM_TRY(conv_f32(ctx, cat5 + c, 2 * c, M.down1, M.down1.w32, d1, 2 * c, B, H, W, 0, 0, 0, 0, nullptr, 0, st));
+  LDM_TRY(c3(d1, 2 * c, M.c2a, a2, 2 * c, H2, W2, nullptr));
+  LDM_TRY(c3(a2, 2 * c, M.c2b, cat4 + 2 * c, 4 * c, H2, W2, t2));
+  LDM_TRY(conv_f32(ctx, cat4 + 2 * c, 4 * c, M.down2, M.down2.w32, d2, 4 * c, B, H2, W2, 0, 0, 0, 0, nullptr, 0, st));
+  LDM_TRY(c3(d2, 4 * c, M.c3a, a3, 4 * c, H4, W4, nullptr));
+  LDM_TRY(c3(a3, 4 * c, M.c3b, x3, 4 * c, H4, W4, t3));
+  LDM_TRY(c3(x3, 4 * c, M.b0, bt, 8 * c, H4, W4, nullptr));
+  LDM_TRY(c3(bt, 8 * c, M.b2, x4, 4 * c, H4, W4, nullptr));
+  LDM_TRY(up(x4, 4 * c, M.up1, cat4, 4 * c, H4, W4));
+  LDM_TRY(c3(cat4, 4 * c, M.c4a, a4, 2 * c, H2, W2, nullptr));
+  LDM_TRY(c3(a4, 2 * c, M.c4b, x5, 2 * c, H2, W2, nullptr));
+  LDM_TRY(up(x5, 2 * c, M.up2, cat5, 2 * c, H2, W2));
+  LDM_TRY(c3(cat5, 2 * c, M.c5a, a5, c, H, W, nullptr));
+  LDM_TRY(c3(a5, c, M.c5b, x6, c, H, W, nullptr));
+  // out_conv -> eps (B, 3, H, W) [+ res_ratio * x]; the sampler then applies the posterior update
+  float* eps = ddpm ? M.eps : fin.out;
+  {
+    ConvGeom g = ConvGeom();
+    g.B = B; g.H = H; g.W = W; g.Cin = c; g.Cout = 3; g.taps = 9; g.up = 1; g.nchw_out = 1;
+    for (int t = 0; t < 9; ++t) { g.dy[t] = t / 3 - 1; g.dx[t] = t % 3 - 1; }
+    LDM_TRY(launch_conv_f32(ctx, x6, M.out_w, M.out_b, eps, g, st));
+  }
+  const size_t n3 = (size_t)P1 * 3;
+  if (M.res_ratio) {
+    pix_axpy_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(eps, M.res_ratio, x, n3);
+    LDM_LAUNCHED(ctx);
+  }
+  if (ddpm) {
+    const int total4 = (int)(n3 / 4);
+    pix_ddpm_kernel<<<ceil_div(total4, 256), 256, 0, st>>>(fin.out, eps, fin.c2, fin.sqrt_alpha, fin.sigma, fin.noise, fin.rng, fin.step,
+                                                           total4, 3 * H * W / 4);
+    LDM_LAUNCHED(ctx);
+  }
+  return 0;
+}
+
 // One forward over the workspace.  terms: (rows, 7 base) time terms, row stride tstride (0: one row for the batch).
 // fin: what out_conv does with eps.
 int run_forward(ldm_ctx* ctx, const float* x, const float* terms, int tstride, int B, int H, int W, PixOutArgs fin, int ddpm,
                 cudaStream_t st) {
+  if (ctx->precision != LDM_PRECISION_BF16) return run_forward_f32(ctx, x, terms, tstride, B, H, W, fin, ddpm, st);
   PixModel& M = ctx->pix;
   const int c = M.base, H2 = H / 2, H4 = H / 4, W2 = W / 2, W4 = W / 4;
   const int P1 = B * H * W;
@@ -567,7 +669,7 @@ int run_forward(ldm_ctx* ctx, const float* x, const float* terms, int tstride, i
     const long long items = (long long)(P1 / 4) * (c / 8);
     const long long want = (items + 255) / 256;
     const unsigned grid = (unsigned)(want < 2ll * ctx->sm_count ? want : 2ll * ctx->sm_count);
-    pix_conv_in_kernel<<<grid, 256, (size_t)c * 28 * sizeof(float), st>>>(x, M.in_w, M.in_b, M.a1, H, W, c, P1 / 4);
+    pix_conv_in_kernel<bf16><<<grid, 256, (size_t)c * 28 * sizeof(float), st>>>(x, M.in_w, M.in_b, M.a1, H, W, c, P1 / 4);
   }
   LDM_LAUNCHED(ctx);
   const float *t1 = terms, *t2 = terms + c, *t3 = terms + 3 * c;
@@ -659,15 +761,13 @@ void pix_free(ldm_ctx* ctx) {
 
 extern "C" LDM_API int ldm_pix_pack(ldm_ctx* ctx, const ldm_pix_weights* w, void* stream) {
   LDM_CHECK(ctx && w, "ldm_pix_pack: null argument");
-  LDM_CHECK(ctx->precision == LDM_PRECISION_BF16, "ldm_pix_pack: the pixel-space path runs on the bf16 tensor-core kernels only (context precision %d)",
-            ctx->precision);
   LDM_CHECK(w->in_channels == 3, "ldm_pix_pack: in_channels must be 3 (got %d)", w->in_channels);
   LDM_CHECK(w->base_channels >= 64 && w->base_channels % 64 == 0 && w->base_channels <= 256,
             "ldm_pix_pack: base_channels must be 64, 128, 192 or 256 (got %d)", w->base_channels);
   LDM_CHECK(w->time_emb_dim > 0 && w->time_emb_dim <= 4096 && w->n_t > 0, "ldm_pix_pack: bad time_emb_dim / n_t");
   cudaStream_t st = (cudaStream_t)stream;
   LDM_CUDA(cudaSetDevice(ctx->device));
-  LDM_TRY(tc_init(ctx));
+  if (ctx->precision == LDM_PRECISION_BF16) LDM_TRY(tc_init(ctx));
   LDM_CUDA(cudaDeviceSynchronize());
   pix_free(ctx);
   ctx->pix = PixModel();
@@ -690,7 +790,7 @@ extern "C" LDM_API int ldm_pix_pack(ldm_ctx* ctx, const ldm_pix_weights* w, void
   LDM_TRY(ldm_alloc_t(ctx, P, &M.in_w, (size_t)c * 27));
   LDM_TRY(launch_pack_conv(ctx, w->conv1[0].w, M.in_w, c, 3, 3, 3, st));
   LDM_TRY(own(ctx, P, w->conv1[0].b, c, &M.in_b, st));
-  if (c == 64) {
+  if (c == 64 && ctx->precision == LDM_PRECISION_BF16) {
     LDM_TRY(ldm_alloc_t(ctx, P, &M.in_w16, (size_t)64 * 64));
     pix_pack_in_tc_kernel<<<16, 256, 0, st>>>(M.in_w, M.in_w16);
     LDM_LAUNCHED(ctx);
@@ -699,7 +799,7 @@ extern "C" LDM_API int ldm_pix_pack(ldm_ctx* ctx, const ldm_pix_weights* w, void
   LDM_TRY(ldm_alloc_t(ctx, P, &M.out_w, (size_t)3 * 9 * c));
   LDM_TRY(launch_pack_conv(ctx, w->out_conv.w, M.out_w, 3, c, 3, 3, st));
   LDM_TRY(own(ctx, P, w->out_conv.b, 3, &M.out_b, st));
-  if (c == 64) {   // out_conv on the tensor cores: N padded 3 -> 16 with zero rows (conv_halo_kernel, BN = 16)
+  if (c == 64 && ctx->precision == LDM_PRECISION_BF16) {   // out_conv on the tensor cores: N padded 3 -> 16 with zero rows (conv_halo_kernel, BN = 16)
     M.out16.Cin = c; M.out16.Cout = 16; M.out16.taps = 9; M.out16.bn = 16;
     LDM_TRY(ldm_alloc_t(ctx, P, &M.out16.w16, (size_t)16 * 9 * c));
     LDM_CUDA(cudaMemsetAsync(M.out16.w16, 0, (size_t)16 * 9 * c * sizeof(bf16), st));

@@ -1,6 +1,7 @@
 """Drop-in mirror of the v4 / v5 pixel-space diffusion model (v4/model_train_test.py:37-183, v5/model_train_test.py:
 38-196): same class names, constructor arguments, method signatures and state_dict keys; the arithmetic runs in
-libldm_b200.so (ldm_pix_pack / ldm_pix_forward / ldm_pix_sample: implicit-GEMM convolutions on tcgen05, bf16).
+libldm_b200.so (ldm_pix_pack / ldm_pix_forward / ldm_pix_sample: implicit-GEMM convolutions on tcgen05 in bf16 - the
+default - or the strict fp32 CUDA-core path with `precision="fp32"`).
 
     from ldm_b200 import v4
     model = v4.SimpleUNet().to("cuda").eval()                 # v5: v4.SimpleUNet(res_ratio=True)
