@@ -9,6 +9,9 @@
 #include "epilogue.cuh"
 #include "tc_ptx.cuh"
 
+#include <cooperative_groups.h>
+#include <cstdlib>
+
 namespace {
 
 constexpr int BM = 128, BK = 64;
@@ -35,7 +38,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int nkb = args.K / BK, S = args.stages;
+  // Split-K over a thread-block cluster along z: CTA kr of KS contracts k-blocks [kr * nkb, (kr + 1) * nkb); the partial
+  // accumulators of ranks 1.. are parked in their own shared memory and folded in by rank 0 through DSMEM.  A small-M GEMM
+  // (M = 128 rows: N / BN CTAs, each streaming the whole A panel at ~44 B/clk/SM) is bound by that stream, not by MMAs.
+  const int KS = gridDim.z, kr = blockIdx.z;
+  const int nkb = args.K / BK / KS, kb0 = kr * nkb, S = args.stages;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&map_a);
@@ -63,18 +70,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int kb = 0; kb < pre; ++kb) {
         uint8_t* sa = smem + (size_t)kb * kStageBytes;
         tc::mbar_arrive_expect_tx(&full_bar[kb], kStageBytes);
-        tc::tma_load_2d(sa + kABytes, &map_w, &full_bar[kb], kb * BK, n0);
+        tc::tma_load_2d(sa + kABytes, &map_w, &full_bar[kb], (kb0 + kb) * BK, n0);
       }
       tc::pdl_wait();
-      for (int kb = 0; kb < pre; ++kb) tc::tma_load_2d(smem + (size_t)kb * kStageBytes, &map_a, &full_bar[kb], kb * BK, m0);
+      for (int kb = 0; kb < pre; ++kb) tc::tma_load_2d(smem + (size_t)kb * kStageBytes, &map_a, &full_bar[kb], (kb0 + kb) * BK, m0);
       for (int kb = pre; kb < nkb; ++kb) {
         const int s = kb % S;
         const uint32_t ph = (uint32_t)(kb / S) & 1u;
         if (!tc::mbar_wait(&empty_bar[s], ph ^ 1u, 1)) break;
         uint8_t* sa = smem + (size_t)s * kStageBytes;
         tc::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-        tc::tma_load_2d(sa, &map_a, &full_bar[s], kb * BK, m0);
-        tc::tma_load_2d(sa + kABytes, &map_w, &full_bar[s], kb * BK, n0);
+        tc::tma_load_2d(sa, &map_a, &full_bar[s], (kb0 + kb) * BK, m0);
+        tc::tma_load_2d(sa + kABytes, &map_w, &full_bar[s], (kb0 + kb) * BK, n0);
       }
     }
   } else if (warp == 1) {
@@ -98,14 +105,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else {
     // epilogue warps 2..5 own TMEM lanes [32*(warp%4), +32)
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
     tc::pdl_wait();                       // the epilogue reads residuals / state written by earlier kernels
-    tc::mbar_wait(&tmem_full_bar, 0, 3);
+    tc::mbar_wait(&tmem_full_bar, 0, 3);  // every MMA of this CTA has completed: the stage buffers are free
     tc::fence_after_sync();
+    if (kr != 0) {                        // park the partial accumulator, column-major (lanes = consecutive rows)
+      float* red = reinterpret_cast<float*>(smem);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) red[(c0 + j) * BM + q * 32 + lane] = v[j];
+      }
+    }
+  }
+  if (KS > 1) cooperative_groups::this_cluster().sync();      // partials visible cluster-wide
+  if (warp >= 2 && kr == 0) {
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 16) {
       float v[16];
       tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      for (int r = 1; r < KS; ++r) {
+        const float* rem = cooperative_groups::this_cluster().map_shared_rank(reinterpret_cast<float*>(smem), r);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += rem[(c0 + j) * BM + q * 32 + lane];
+      }
       if (row < args.M) {
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
@@ -115,6 +141,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   }
+  if (KS > 1) cooperative_groups::this_cluster().sync();      // ranks 1.. keep their shared memory alive until rank 0 has read it
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc<kTmemCols>(tmem_base);
@@ -346,14 +373,46 @@ int make_map_2d(const void* base, int rows, int cols, int ld, int box_rows, CUte
 template <int BN>
 int launch_bn(ldm_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, int M, int N, int K, const Epilogue& epi,
               cudaStream_t st) {
-  const int nkb = K / BK;
+  const int nkb_all = K / BK;
   const size_t stage_bytes = (size_t)BM * BK * 2 + (size_t)BN * BK * 2;
+  // split-K cluster (portable sizes): as many k-slices as keep >= 2 k-blocks per CTA and the grid within the SM count.
+  // Off by default: parity-green, but measured neutral to slightly slower on the M = 128 GEMMs of the v3 step (526 -> 508
+  // samples/s) - those kernels are bound by their fixed launch / prologue / first-tile latency (~8 us), not by the A stream.
+  static int splitk = -1;
+  if (splitk < 0) {
+    const char* e = getenv("LDM_GEMM_SPLITK");
+    splitk = e ? atoi(e) : 0;
+  }
+  int ks = 1;
+  const int ctas = (N / BN) * ceil_div(M, BM);
+  if (splitk)
+    for (int cand = 8; cand >= 2; cand >>= 1)
+      if (nkb_all % cand == 0 && nkb_all / cand >= 2 && ctas * cand <= ctx->sm_count) { ks = cand; break; }
+  const int nkb = nkb_all / ks;
   int stages = nkb < kMaxStages ? nkb : kMaxStages;
   while ((size_t)stages * stage_bytes > 200 * 1024) --stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  size_t smem = (size_t)stages * stage_bytes + 1024;
+  if (ks > 1 && smem < (size_t)BM * BN * 4 + 1024) smem = (size_t)BM * BN * 4 + 1024;       // room for the parked partial
   TcArgs a{M, N, K, stages};
-  dim3 grid(N / BN, ceil_div(M, BM));
-  LDM_CUDA(launch_maybe_pdl(gemm_tc_kernel<BN>, grid, kThreads, smem, st, ctx->use_pdl, ma, mw, a, epi));
+  dim3 grid(N / BN, ceil_div(M, BM), ks);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (ks > 1) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = ks;
+      ++na;
+    }
+    if (ctx->use_pdl) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    LDM_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN>, ma, mw, a, epi));
+  }
   ctx->launches++;
   LDM_CUDA(cudaGetLastError());
   return 0;
