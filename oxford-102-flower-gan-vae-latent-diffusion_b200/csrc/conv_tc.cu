@@ -713,8 +713,13 @@ int launch_bn_mt(ldm_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, con
   ConvTcArgs a = a0;
   const int nkb = a.taps * (a.Cin / BK);
   const size_t stage_bytes = (size_t)MT * BM * BK * 2 + (size_t)BN * BK * 2;
+  static int limit_kb = -1;
+  if (limit_kb < 0) {
+    const char* e = getenv("LDM_CONV_SMEM_KB");
+    limit_kb = e ? atoi(e) : 100;
+  }
   int stages = nkb < kMaxStages ? nkb : kMaxStages;
-  while (stages > 2 && (size_t)stages * stage_bytes > 100 * 1024) --stages;   // two CTAs per SM: one finishes while the other loads
+  while (stages > 2 && (size_t)stages * stage_bytes > (size_t)limit_kb * 1024) --stages;   // two CTAs per SM: one finishes while the other loads
   a.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024;
   dim3 grid(ceil_div(a.total_pix, BM * MT), a.Cout / BN, nz);
