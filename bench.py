@@ -164,8 +164,7 @@ def loop_kernel_name(eng):
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    import ldm_b200
-    from oracle import weights   # deterministic synthetic weights only (the oracle's arithmetic is not used on this arm)
+    import ldm_b200              # nothing under oracle/ is imported on this arm
 
     torch.set_grad_enabled(False)
     dev = torch.device("cuda", local_rank)
@@ -177,15 +176,11 @@ def run_ours(args, rank, world, local_rank):
 
     # random-init weights of the named architecture (ConditionalUNet + init_weights, SimpleAutoencoder())
     v3 = args.workload == "v3"
-    if v3:
-        unet = ldm_b200.v3.ConditionalUNet(precision=prec)
-        unet.load_state_dict(weights.make_unet3_state(44, "init"), strict=True)
-    else:
-        unet = ldm_b200.ConditionalUNet(precision=prec)
-        unet.load_state_dict(weights.make_unet_state(42, "init"), strict=True)
+    torch.manual_seed(42)                                                       # v2:17
+    unet = (ldm_b200.v3 if v3 else ldm_b200).ConditionalUNet(precision=prec)
+    unet.apply(ldm_b200.init_weights)                                           # v2:1346-1350 (main()'s initialisation of the denoiser)
     unet = unet.to(dev).eval()
-    ae = ldm_b200.SimpleAutoencoder(precision=prec)
-    ae.load_state_dict(weights.make_autoencoder_state(43, "init"), strict=True)
+    ae = ldm_b200.SimpleAutoencoder(precision=prec)                             # initialises itself (v2:324)
     ae = ae.to(dev).eval()
     diffusion = (ldm_b200.v3 if v3 else ldm_b200).ConditionalDenoiseDiffusion(unet, N_STEPS, dev)
     eng = unet.engine(dev, N_STEPS)
@@ -343,8 +338,7 @@ def pix_cpu_rate(batch, steps, threads=None):
 def run_pix(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from ldm_b200 import v4
-    from oracle import weights
+    from ldm_b200 import v4      # nothing under oracle/ is imported on this arm
 
     torch.set_grad_enabled(False)
     dev = torch.device("cuda", local_rank)
@@ -352,8 +346,8 @@ def run_pix(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     sampler.start()
     B, K, W = args.batch, args.steps, args.warmup
-    model = v4.SimpleUNet()
-    model.load_state_dict(weights.make_pix_state(45, "init"), strict=True)     # torch-default init statistics (v4 never re-initialises)
+    torch.manual_seed(42)
+    model = v4.SimpleUNet()                                                    # torch's default initialisation (v4 never re-initialises)
     model = model.to(dev).eval()
     diffusion = v4.DiffusionModel(model, N_STEPS, device=dev)
     eng = diffusion._engine(dev)
