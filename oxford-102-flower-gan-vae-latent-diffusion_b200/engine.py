@@ -4,6 +4,7 @@ PyTorch is used here for device memory and streams only; all arithmetic of the h
 libldm_b200.so.  One denoiser and one decoder are resident per engine; packing is redone when a
 different module, or a module whose parameters changed (tensor._version / data_ptr), is used."""
 import ctypes
+import itertools
 import os
 import threading
 
@@ -60,9 +61,23 @@ def _f32(t, device):
     return t.detach().to(device=device, dtype=torch.float32).contiguous()
 
 
+_serials = itertools.count(1)
+
+
+def _module_serial(module):
+    """A process-unique number per module OBJECT.  id(module) is not enough: CPython reuses the address of a collected
+    module for the next one, and torch's caching allocator hands the same blocks to its parameters, so (id, versions,
+    data_ptrs) of a NEW module can equal those of a dead one whose packed weights are still resident."""
+    s = module.__dict__.get("_ldm_b200_serial")
+    if s is None:
+        s = next(_serials)
+        object.__setattr__(module, "_ldm_b200_serial", s)
+    return s
+
+
 def _state_key(module, extra=()):
     ps = list(module.parameters())
-    return (id(module), tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps)) + tuple(extra)
+    return (_module_serial(module), tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps)) + tuple(extra)
 
 
 class Engine:
@@ -331,10 +346,10 @@ class Engine:
     # ------------------------------------------------------------------ conv U-Net blocks (v2:434-486)
     def _ublock(self, m, build):
         key = _state_key(m)
-        hit = self._ublocks.get(id(m))
+        hit = self._ublocks.get(_module_serial(m))
         if hit is None or hit[0] != key:
             hit = (key, build())
-            self._ublocks[id(m)] = hit
+            self._ublocks[_module_serial(m)] = hit
         return hit[1]
 
     def ublock_res_forward(self, m, x, t, c=None):

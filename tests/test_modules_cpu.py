@@ -130,3 +130,22 @@ def test_empty_batches_return_empty_tensors():
     m = v4.SimpleUNet().eval()
     assert tuple(m(torch.zeros(0, 3, 64, 64), torch.zeros(0)).shape) == (0, 3, 64, 64)
     assert tuple(v4.DiffusionModel(m, 10, device="cpu").sample((0, 3, 32, 32)).shape) == (0, 3, 32, 32)
+
+
+def test_pack_cache_key_survives_object_address_reuse():
+    """A new module that lands on the address (and parameter storage) of a collected one must not look 'already packed'."""
+    import gc
+    from ldm_b200 import engine
+    keys = set()
+    for _ in range(50):
+        m = torch.nn.Linear(4, 4)
+        keys.add(engine._state_key(m))
+        del m
+        gc.collect()
+    assert len(keys) == 50
+    m = torch.nn.Linear(4, 4)
+    k0 = engine._state_key(m)
+    assert engine._state_key(m) == k0                      # stable for an untouched module
+    with torch.no_grad():
+        m.weight.add_(1.0)
+    assert engine._state_key(m) != k0                      # in-place updates re-pack
