@@ -188,3 +188,18 @@ def test_pix_boundary_errors():
     d = v4.DiffusionModel(ok, 1000, device="cuda")
     with pytest.raises(IndexError):
         d.p_sample(torch.zeros(1, 3, 64, 64, device="cuda"), 1000)
+
+
+@pytest.mark.gpu
+def test_pix_repacks_for_every_new_module():
+    """Short-lived modules with alternating weights: a new module allocated on the address / storage of a collected one
+    must be re-packed (the engine keys its pack cache on a per-object serial, not on id())."""
+    import gc
+    for style in ["init", "perturbed"] * 4:
+        g = gold("v4", style)
+        m = _model("v4", style)
+        e = R.max_rel(m(T(g["x"]).cuda(), T(g["ta"]).cuda()).cpu(), T(g["eps_ta"]))
+        assert e < EPS_TOL["bf16"], (style, e)
+        del m
+        gc.collect()
+        torch.cuda.empty_cache() if style == "init" else None
