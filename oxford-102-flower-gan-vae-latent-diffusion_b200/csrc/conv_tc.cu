@@ -229,18 +229,9 @@ struct HaloArgs {
   const float* post;
   const float* bias;
   bf16* out;
-  int base_off_mode;       // 1: descriptor base offset = (address >> 7) & 7;  0: none
-  int debug;               // timing experiments (LDM_HALO_DEBUG): 1 = load only the first two tiles, 2 = unshifted descriptors, 4 = no stores
-  int box_rows;            // image rows per TMA operation (the halo tile is nrows / box_rows boxes)
   int stages;              // halo tiles in flight (<= kHaloStages)
   PixOutArgs fin;          // MODE 1 / 2
 };
-
-__device__ __forceinline__ uint64_t make_desc_sw128_row(uint32_t smem_addr, int base_off_mode) {
-  uint64_t d = tc::make_desc_sw128(smem_addr);
-  if (base_off_mode) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
-  return d;
-}
 
 constexpr int kHaloStages = 3;       // halo tiles in flight (one 42 KB TMA box has ~2 us of latency from a cold L2)
 constexpr int kHaloTmemStages = 4;
@@ -266,8 +257,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __shared__ float bias_s[BN], post_s[BN];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool spin = (a.debug & 32) != 0;
-#define HWAIT(bar, par, code) (spin ? tc::mbar_wait_spin(bar, par, code) : tc::mbar_wait(bar, par, code))
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&map_a);
     tc::prefetch_tmap(&map_w);
@@ -302,18 +291,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       int it = 0;
       for (int u = blockIdx.x; u < a.total_units; u += gridDim.x, ++it) {
         const int s = it % a.stages;
-        if (!HWAIT(&empty_bar[s], (uint32_t)((it / a.stages) & 1) ^ 1u, 11)) break;
+        if (!tc::mbar_wait(&empty_bar[s], (uint32_t)((it / a.stages) & 1) ^ 1u, 11)) break;
         const int n = u / a.units_per_img, s0 = (u - n * a.units_per_img) * BM, r = s0 / rowslots;
-        if ((a.debug & 1) && it >= 2) { tc::mbar_arrive(&full_bar[s]); continue; }
         tc::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)a.a_bytes);
-        for (int rr = 0; rr < a.nrows; rr += a.box_rows)
-          tc::tma_load_4d(a_s + (size_t)s * a.a_stride + (size_t)rr * rowslots * 128, &map_a, &full_bar[s], 0, -1, r - 1 + rr, n);
+        tc::tma_load_4d(a_s + (size_t)s * a.a_stride, &map_a, &full_bar[s], 0, -1, r - 1, n);
       }
     }
   } else if (warp == 1) {
     if (tc::elect_one()) {
       constexpr uint32_t idesc = tc::make_idesc_bf16(BM, BN);
-      bool ok = HWAIT(&w_bar, 0, 12);
+      bool ok = tc::mbar_wait(&w_bar, 0, 12);
       const uint32_t w_addr = tc::smem_u32(w_s);
       int it = 0;
       for (int u = blockIdx.x; u < a.total_units && ok; u += gridDim.x, ++it) {
@@ -321,14 +308,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const uint32_t ph = (uint32_t)((it / a.stages) & 1), tph = (uint32_t)((it / kTS) & 1);
         const int s0 = (u % a.units_per_img) * BM;
         const int first = s0 % rowslots + rowslots;      // tile slot of output slot 0 (the tile starts one row above)
-        ok = HWAIT(&tempty_bar[ts], tph ^ 1u, 13) && HWAIT(&full_bar[s], ph, 14);
+        ok = tc::mbar_wait(&tempty_bar[ts], tph ^ 1u, 13) && tc::mbar_wait(&full_bar[s], ph, 14);
         tc::fence_after_sync();
         const uint32_t a_addr = tc::smem_u32(a_s + (size_t)s * a.a_stride);
         const uint32_t d_tmem = tmem_base + (uint32_t)(ts * kAcc);
 #pragma unroll 1
-        for (int tap = 0; tap < ((a.debug & 8) ? NCH : 9); ++tap) {
-          const int shift = (a.debug & 2) ? 0 : first + (tap / 3 - 1) * rowslots + (tap % 3 - 1);
-          const uint64_t da = make_desc_sw128_row(a_addr + (uint32_t)shift * 128u, a.base_off_mode);
+        for (int tap = 0; tap < 9; ++tap) {
+          // row-shifted view of the SAME tile: the start address moves by whole 128-byte rows.  No descriptor base offset:
+          // on B200 the 128-byte swizzle is a function of absolute shared-memory address bits (with the base-offset field
+          // set to (address >> 7) & 7 the results are wrong; measured, see profiles/README.md)
+          const int shift = first + (tap / 3 - 1) * rowslots + (tap % 3 - 1);
+          const uint64_t da = tc::make_desc_sw128(a_addr + (uint32_t)shift * 128u);
           const uint64_t dw = tc::make_desc_sw128(w_addr + tap * kWTap);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
@@ -348,13 +338,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t ph = (uint32_t)((it / kTS) & 1);
       const int n = u / a.units_per_img, slot = (u - n * a.units_per_img) * BM + q * 32 + lane;
       const int y = slot / rowslots, cx = slot - y * rowslots;
-      const bool valid = y < a.H && cx >= 1 && cx <= a.W && !(a.debug & 4);
+      const bool valid = y < a.H && cx >= 1 && cx <= a.W;
       const int rem = y * a.W + cx - 1;
-      if (!HWAIT(&tfull_bar[s], ph, 15)) break;
+      if (!tc::mbar_wait(&tfull_bar[s], ph, 15)) break;
       tc::fence_after_sync();
       const uint32_t t_addr = tmem_base + (uint32_t)(s * kAcc) + ((uint32_t)(q * 32) << 16);
-      if (a.debug & 16) {
-      } else if (MODE == 0) {
+      if (MODE == 0) {
         bf16* dst = a.out + ((size_t)n * HW + (valid ? rem : 0)) * (size_t)a.out_pitch;
         const float* prow = (a.post && a.post_stride) ? a.post + (size_t)n * a.post_stride : nullptr;   // per-sample time terms
 #pragma unroll 1
@@ -417,7 +406,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc<kCols>(tmem_base);
-#undef HWAIT
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -828,30 +816,12 @@ int launch_conv_halo(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer
   a.a_bytes = a.nrows * a.Wp * 128;
   a.a_stride = ((a.a_bytes + 1023) & ~1023) + 1024;
   a.out_pitch = out_pitch; a.relu = relu; a.post = post; a.post_stride = post_stride; a.bias = bias; a.out = out;
-  static int base_off_mode = -1;
-  if (base_off_mode < 0) {
-    const char* e = getenv("LDM_HALO_BASE_OFFSET");
-    base_off_mode = e ? atoi(e) : 0;   // measured on B200: the swizzle is a function of the absolute shared-memory address, no base offset
-  }
-  a.base_off_mode = base_off_mode;
-  static int debug = -1;
-  if (debug < 0) {
-    const char* e = getenv("LDM_HALO_DEBUG");
-    debug = e ? atoi(e) : 0;
-  }
-  a.debug = debug;
-  static int box_rows = -1;
-  if (box_rows < 0) {
-    const char* e = getenv("LDM_HALO_BOX_ROWS");
-    box_rows = e ? atoi(e) : 0;
-  }
-  a.box_rows = (box_rows > 0 && a.nrows % box_rows == 0) ? box_rows : a.nrows;
   if (fin) a.fin = *fin;
   CUtensorMap ma;
   {
     cuuint64_t dims[4] = {(cuuint64_t)64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)in_pitch * 2, (cuuint64_t)W * in_pitch * 2, (cuuint64_t)H * W * in_pitch * 2};
-    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)a.Wp, (cuuint32_t)a.box_rows, 1};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)a.Wp, (cuuint32_t)a.nrows, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = g_encode4(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(in), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -56,14 +56,6 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int co
   return false;
 }
 
-// Same bound without the sleep back-off (latency-critical hand-overs of a persistent pipeline).
-__device__ __forceinline__ bool mbar_wait_spin(uint64_t* bar, uint32_t parity, int code) {
-  for (uint32_t it = 0; it < (1u << 26); ++it)
-    if (mbar_try_wait(bar, parity)) return true;
-  atomicCAS(&g_tc_error, 0, (code << 16) | (int)(blockIdx.x + blockIdx.y * gridDim.x));
-  return false;
-}
-
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
