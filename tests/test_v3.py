@@ -118,3 +118,25 @@ def test_v3_chain_and_larger_batches(precision):
     # out-of-range labels raise like nn.Embedding would
     with pytest.raises(IndexError):
         u(xb.cuda(), torch.tensor([1], device="cuda"), fb.cuda(), (kb + 10).cuda())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_v3_full_size_call(precision):
+    """BASELINE configs[3]: 1024 samples over 8 GPUs = one reference call of 128 rows per GPU.  Parity of that call's eps
+    against the restatement, and of 10 reverse steps from x_T with Philox noise."""
+    import ldm_b200
+    sd = weights.make_unet3_state(SEED, "init")
+    u = _unet("init", precision)
+    B = 128
+    x = torch.from_numpy(philox.normal_rows(9, 0, B, 1000))
+    f, k = torch.arange(B) % 102, (torch.arange(B) * 7) % 10
+    want = R.unet3_forward(sd, x, torch.tensor([640]), f, k)
+    got = u(x.cuda(), torch.tensor([640], device="cuda"), f.cuda(), k.cuda()).cpu()
+    assert R.max_rel(got, want) < EPS_TOL[precision], R.max_rel(got, want)
+    d = ldm_b200.v3.ConditionalDenoiseDiffusion(u, 1000, torch.device("cuda"))
+    eng = d._engine("cuda")
+    xs = x.cuda().clone()
+    eng.sample3(xs, 999, 990, f.cuda(), k.cuda(), seed=21, sample_offset=0)
+    ref = R.sample3(sd, R.schedule(1000), x, f, k, noise_fn=lambda t: torch.from_numpy(philox.normal_rows(21, 0, B, t)), t_start=999, t_end=990)
+    assert R.rel_l2(xs.cpu(), ref) < LATENT_TOL[precision], R.rel_l2(xs.cpu(), ref)
