@@ -257,7 +257,7 @@ LDM_API int ldm_pix_forward(ldm_ctx* ctx, const float* x_dev, const float* t_dev
 LDM_API int ldm_pix_sample(ldm_ctx* ctx, float* x_inout_dev, int t_start, int t_end, const float* noise_dev, uint64_t seed,
                    uint64_t sample_offset, int batch, int H, int W, int use_graph, void* stream);
 
-/* ---- conv U-Net blocks of the v2 script (bf16 contexts only; module-level operators) -------------------
+/* ---- conv U-Net blocks of the v2 script (module-level operators; bf16 = tcgen05, fp32 = strict) --------
  * *_pack copies and repacks one module's weights and returns a handle that lives until ldm_ctx_destroy.
  * ldm_ublock_res_forward  = UNetResidualBlock.forward(x, t, c) v2:475-486 (eval mode): x (B, Cin, H, W), t and c
  *   (B, d_time) embedding vectors (c may be NULL) -> out (B, Cout, H, W), all fp32 NCHW / row-major device pointers.

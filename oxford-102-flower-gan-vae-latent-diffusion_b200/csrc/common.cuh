@@ -250,6 +250,7 @@ struct UBlock {
   float *tw = nullptr, *tb = nullptr, *cw = nullptr, *cb = nullptr;       // time_emb, class_emb Linears
   ConvLayer conv1, conv2;
   DenseLayer d1, d2;              // residual 1x1 (type 1); qkv and proj 1x1 (type 2)
+  float* proj_perm = nullptr;     // fp32 contexts: proj weight with (head, head_dim)-ordered input columns
   size_t ws_elems = 0;
   bf16* buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bf16* qkv3 = nullptr;

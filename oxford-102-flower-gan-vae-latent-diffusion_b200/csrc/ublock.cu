@@ -4,7 +4,8 @@
 // path: implicit-GEMM 3x3 convolutions (conv_tc.cu) with the time / class embedding broadcast-add as the epilogue's
 // per-sample term, LayerNorm2d / GroupNorm as (scale, shift) coefficients + one fused apply pass (decoder_norm.cu), the
 // 1x1 convolutions as tcgen05 GEMMs over pixels (gemm_tc.cu) and the 4-head spatial self-attention over the H W tokens
-// as attn_tc_kernel (softmax(QK^T)V on tcgen05).  bf16 contexts only; I/O is the module's own NCHW fp32.
+// as attn_tc_kernel (softmax(QK^T)V on tcgen05).  fp32 contexts run the same sequence on the CUDA-core kernels (strict mode).
+// I/O is the module's own NCHW fp32.
 #include "common.cuh"
 
 int launch_conv_tc_ex(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer& L, const float* bias, bf16* out, int out_pitch,
@@ -26,9 +27,10 @@ namespace {
     LDM_CUDA(cudaGetLastError()); \
   } while (0)
 
-// (B, C, HW) fp32 -> (B, HW, C) bf16 through a 32 x 32 shared-memory tile
+// (B, C, HW) fp32 -> (B, HW, C) bf16 / fp32 through a 32 x 32 shared-memory tile
+template <typename T>
 __global__ void __launch_bounds__(256)
-nchw_to_nhwc_kernel(const float* __restrict__ in, bf16* __restrict__ out, int C, int HW) {
+nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int C, int HW) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -36,12 +38,13 @@ nchw_to_nhwc_kernel(const float* __restrict__ in, bf16* __restrict__ out, int C,
     tile[i][tx] = (c0 + i < C && p0 + tx < HW) ? in[((size_t)n * C + c0 + i) * HW + p0 + tx] : 0.f;
   __syncthreads();
   for (int i = ty; i < 32; i += 8)
-    if (p0 + i < HW && c0 + tx < C) out[((size_t)n * HW + p0 + i) * C + c0 + tx] = __float2bfloat16_rn(tile[tx][i]);
+    if (p0 + i < HW && c0 + tx < C) out[((size_t)n * HW + p0 + i) * C + c0 + tx] = from_f32<T>(tile[tx][i]);
 }
 
-// out (B, C, HW) fp32 = a (B, HW, C) bf16 [+ r16 (B, HW, C) bf16] [+ r32 (B, C, HW) fp32]
+// out (B, C, HW) fp32 = a (B, HW, C) [+ r16 (B, HW, C)] [+ r32 (B, C, HW) fp32]     (a, r16: bf16 or fp32)
+template <typename T>
 __global__ void __launch_bounds__(256)
-combine_nchw_kernel(const bf16* __restrict__ a, const bf16* __restrict__ r16, const float* __restrict__ r32, float* __restrict__ out,
+combine_nchw_kernel(const T* __restrict__ a, const T* __restrict__ r16, const float* __restrict__ r32, float* __restrict__ out,
                     int C, int HW) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
@@ -50,8 +53,8 @@ combine_nchw_kernel(const bf16* __restrict__ a, const bf16* __restrict__ r16, co
     float v = 0.f;
     if (p0 + i < HW && c0 + tx < C) {
       const size_t k = ((size_t)n * HW + p0 + i) * C + c0 + tx;
-      v = __bfloat162float(a[k]);
-      if (r16) v += __bfloat162float(r16[k]);
+      v = to_f32<T>(a[k]);
+      if (r16) v += to_f32<T>(r16[k]);
     }
     tile[i][tx] = v;
   }
@@ -82,18 +85,19 @@ ub_emb_kernel(const float* __restrict__ t, const float* __restrict__ c, const fl
 
 // GroupNorm(1, C) (v2:439): statistics over ALL C x HW values of a sample -> per-channel (scale, shift).  One CTA per
 // sample; sums are centred on the sample's first value.
+template <typename T>
 __global__ void __launch_bounds__(1024)
-gn1_coef_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float2* __restrict__ coef,
+gn1_coef_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float2* __restrict__ coef,
                 int HW, int C) {
   __shared__ float red[2][32];
   __shared__ float stat[2];
   const int n = blockIdx.x;
-  const bf16* base = x + (size_t)n * HW * C;
-  const float piv = __bfloat162float(base[0]);
+  const T* base = x + (size_t)n * HW * C;
+  const float piv = to_f32<T>(base[0]);
   const size_t total = (size_t)HW * C;
   float s1 = 0.f, s2 = 0.f;
   for (size_t i = threadIdx.x; i < total; i += blockDim.x) {
-    const float d = __bfloat162float(base[i]) - piv;
+    const float d = to_f32<T>(base[i]) - piv;
     s1 += d; s2 += d * d;
   }
   s1 = warp_sum(s1); s2 = warp_sum(s2);
@@ -129,6 +133,51 @@ vt_from_qkv_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ vt, int C, i
     if (c0 + i < C && p0 + tx < HW) vt[((size_t)n * C + c0 + i) * HW + p0 + tx] = tile[tx][i];
 }
 
+
+// ---- strict fp32 path (module-level parity within 1e-3): CUDA-core kernels over NHWC fp32 -----------------------------
+// LayerNorm2d coefficients: one thread per (sample, channel), two passes over the H W values of that channel
+__global__ void ln2d_coef_f32_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     float2* __restrict__ coef, int HW, int C, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int n = i / C, c = i - n * C;
+  const float* base = x + (size_t)n * HW * C + c;
+  float s = 0.f;
+  for (int p = 0; p < HW; ++p) s += base[(size_t)p * C];
+  const float mean = s / (float)HW;
+  float q = 0.f;
+  for (int p = 0; p < HW; ++p) { const float d = base[(size_t)p * C] - mean; q += d * d; }
+  const float sc = rsqrtf(q / (float)HW + 1e-5f) * gamma[c];
+  coef[i] = make_float2(sc, beta[c] - mean * sc);
+}
+
+__global__ void coef_apply_f32_kernel(const float* __restrict__ x, const float2* __restrict__ coef, float* __restrict__ out, int HW, int C,
+                                      int act, size_t total) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const size_t n = i / ((size_t)HW * C);
+  const float2 k = coef[n * C + c];
+  float v = x[i] * k.x + k.y;
+  if (act == LDM_ACT_SWISH) v = swishf(v);
+  out[i] = v;
+}
+
+// proj weight with its input columns permuted from the reference's (head_dim, head) order to (head, head_dim)
+__global__ void permute_proj_kernel(const float* __restrict__ w, float* __restrict__ out, int C, int heads) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * C) return;
+  const int o = i / C, col = i - o * C, hd = C / heads, h = col / hd, e = col - h * hd;
+  out[i] = w[(size_t)o * C + e * heads + h];
+}
+
+int conv3_f32(ldm_ctx* ctx, const float* in, const ConvLayer& L, float* out, int B, int H, int W, const float* post, cudaStream_t st) {
+  ConvGeom g = ConvGeom();
+  g.B = B; g.H = H; g.W = W; g.Cin = L.Cin; g.Cout = L.Cout; g.taps = 9; g.up = 1; g.post = post; g.post_stride = L.Cout;
+  for (int t = 0; t < 9; ++t) { g.dy[t] = t / 3 - 1; g.dx[t] = t % 3 - 1; }
+  return launch_conv_f32(ctx, in, L.w32, L.b, out, g, st);
+}
+
 int own(ldm_ctx* ctx, std::vector<void*>& pool, const float* src, size_t n, float** out, cudaStream_t st) {
   LDM_CHECK(src != nullptr, "ldm_ublock_*_pack: null weight pointer");
   LDM_TRY(ldm_alloc_t(ctx, pool, out, n));
@@ -143,6 +192,7 @@ int pack_conv3(ldm_ctx* ctx, std::vector<void*>& P, ConvLayer& L, const float* w
   LDM_TRY(ldm_alloc_t(ctx, P, &L.w32, n));
   LDM_TRY(launch_pack_conv(ctx, w, L.w32, Cout, Cin, 3, 3, st));
   LDM_TRY(own(ctx, P, b, Cout, &L.b, st));
+  if (ctx->precision != LDM_PRECISION_BF16) return 0;
   LDM_TRY(ldm_alloc_t(ctx, P, &L.w16, n));
   LDM_TRY(launch_to_bf16(ctx, L.w32, L.w16, n, st));
   return tc_make_weight_map(ctx, L.w16, Cout, 9 * Cin, L.bn, &L.map_w);
@@ -153,6 +203,7 @@ int pack_dense(ldm_ctx* ctx, std::vector<void*>& P, DenseLayer& L, const float* 
   L.N = N; L.K = K;
   LDM_TRY(own(ctx, P, w, (size_t)N * K, &L.w32, st));
   LDM_TRY(own(ctx, P, b, N, &L.b, st));
+  if (ctx->precision != LDM_PRECISION_BF16) return 0;
   LDM_TRY(ldm_alloc_t(ctx, P, &L.w16, (size_t)N * K));
   LDM_TRY(launch_to_bf16(ctx, L.w32, L.w16, (size_t)N * K, st));
   L.bn = tc_pick_bn(4096, N);
@@ -179,7 +230,6 @@ int get_block(ldm_ctx* ctx, int handle, int type, UBlock** out) {
 }
 
 int check_common(ldm_ctx* ctx, int B, int H, int W) {
-  LDM_CHECK(ctx->precision == LDM_PRECISION_BF16, "ldm_ublock_*: bf16 contexts only");
   LDM_CHECK(B > 0 && H > 0 && W > 0 && H * W >= 16 && (H * W) % 8 == 0, "ldm_ublock_*: need H * W >= 16 and a multiple of 8 (got %d x %d)", H, W);
   return 0;
 }
@@ -196,12 +246,11 @@ void ublock_free_all(ldm_ctx* ctx) {
 
 extern "C" LDM_API int ldm_ublock_res_pack(ldm_ctx* ctx, const ldm_ublock_res_weights* w, int* handle_out, void* stream) {
   LDM_CHECK(ctx && w && handle_out, "ldm_ublock_res_pack: null argument");
-  LDM_CHECK(ctx->precision == LDM_PRECISION_BF16, "ldm_ublock_res_pack: bf16 contexts only");
   LDM_CHECK(w->in_channels % 64 == 0 && w->out_channels % 64 == 0 && w->in_channels > 0 && w->out_channels > 0 && w->d_time > 0,
             "ldm_ublock_res_pack: channel counts must be multiples of 64 (%d -> %d)", w->in_channels, w->out_channels);
   cudaStream_t st = (cudaStream_t)stream;
   LDM_CUDA(cudaSetDevice(ctx->device));
-  LDM_TRY(tc_init(ctx));
+  if (ctx->precision == LDM_PRECISION_BF16) LDM_TRY(tc_init(ctx));
   ctx->ublocks.emplace_back();
   UBlock& u = ctx->ublocks.back();
   u.type = 1; u.cin = w->in_channels; u.cout = w->out_channels; u.dt = w->d_time;
@@ -237,10 +286,36 @@ extern "C" LDM_API int ldm_ublock_res_forward(ldm_ctx* ctx, int handle, const fl
   cudaStream_t st = (cudaStream_t)stream;
   LDM_CUDA(cudaSetDevice(ctx->device));
   const int HW = H * W, cm = u.cin > u.cout ? u.cin : u.cout;
-  LDM_TRY(grow(ctx, u, (size_t)B * HW * cm));
-  bf16 *xh = u.buf[0], *a = u.buf[1], *h1 = u.buf[2], *a2 = u.buf[3], *h2 = u.buf[4], *r = u.buf[5];
+  const bool f32 = ctx->precision != LDM_PRECISION_BF16;
+  LDM_TRY(grow(ctx, u, (size_t)B * HW * cm * (f32 ? 2 : 1)));
   const dim3 tg(ceil_div(HW, 32), ceil_div(u.cin, 32), B);
-  nchw_to_nhwc_kernel<<<tg, 256, 0, st>>>(x, xh, u.cin, HW);
+  const dim3 og(ceil_div(HW, 32), ceil_div(u.cout, 32), B);
+  if (f32) {
+    float *xh = (float*)u.buf[0], *a = (float*)u.buf[1], *h1 = (float*)u.buf[2], *a2 = (float*)u.buf[3], *h2 = (float*)u.buf[4],
+          *r = (float*)u.buf[5];
+    const size_t n_in = (size_t)B * HW * u.cin, n_out = (size_t)B * HW * u.cout;
+    nchw_to_nhwc_kernel<float><<<tg, 256, 0, st>>>(x, xh, u.cin, HW);
+    ln2d_coef_f32_kernel<<<ceil_div(B * u.cin, 128), 128, 0, st>>>(xh, u.n1w, u.n1b, u.coef, HW, u.cin, B * u.cin);
+    coef_apply_f32_kernel<<<(unsigned)((n_in + 255) / 256), 256, 0, st>>>(xh, u.coef, a, HW, u.cin, LDM_ACT_SWISH, n_in);
+    ub_emb_kernel<<<dim3(ceil_div(u.cout, 128), B), 128, 0, st>>>(t, c, u.tw, u.tb, u.cw, u.cb, u.post, u.cout, u.dt);
+    ctx->launches += 4;
+    LDM_TRY(conv3_f32(ctx, a, u.conv1, h1, B, H, W, u.post, st));
+    ln2d_coef_f32_kernel<<<ceil_div(B * u.cout, 128), 128, 0, st>>>(h1, u.n2w, u.n2b, u.coef, HW, u.cout, B * u.cout);
+    coef_apply_f32_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(h1, u.coef, a2, HW, u.cout, LDM_ACT_SWISH, n_out);
+    ctx->launches += 2;
+    LDM_TRY(conv3_f32(ctx, a2, u.conv2, h2, B, H, W, nullptr, st));
+    if (u.cin == u.cout) {
+      combine_nchw_kernel<float><<<og, 256, 0, st>>>(h2, nullptr, x, out, u.cout, HW);
+    } else {
+      Epilogue e; e.bias = u.d1.b; e.out_f32 = r; e.ld_of = u.cout;
+      LDM_TRY(launch_gemm_f32(ctx, xh, u.cin, u.d1.w32, B * HW, u.cout, u.cin, e, st));
+      combine_nchw_kernel<float><<<og, 256, 0, st>>>(h2, r, nullptr, out, u.cout, HW);
+    }
+    LDM_LAUNCHED(ctx);
+    return 0;
+  }
+  bf16 *xh = u.buf[0], *a = u.buf[1], *h1 = u.buf[2], *a2 = u.buf[3], *h2 = u.buf[4], *r = u.buf[5];
+  nchw_to_nhwc_kernel<bf16><<<tg, 256, 0, st>>>(x, xh, u.cin, HW);
   LDM_LAUNCHED(ctx);
   // h = conv1(act(norm1(x))) + act(time_emb(t)) [+ act(class_emb(c))]
   LDM_TRY(launch_norm_coef_bf16(ctx, xh, u.n1w, u.n1b, u.coef, B, HW, u.cin, 1, st));
@@ -253,13 +328,12 @@ extern "C" LDM_API int ldm_ublock_res_forward(ldm_ctx* ctx, int handle, const fl
   LDM_TRY(launch_coef_apply_bf16(ctx, h1, u.coef, a2, B, HW, u.cout, LDM_ACT_SWISH, st));
   LDM_TRY(launch_conv_tc_ex(ctx, a2, u.cout, u.conv2, u.conv2.b, h2, u.cout, B, H, W, 1, 0, nullptr, 0, st));
   // + residual(x): identity (the fp32 input itself) or the 1x1 convolution
-  const dim3 og(ceil_div(HW, 32), ceil_div(u.cout, 32), B);
   if (u.cin == u.cout) {
-    combine_nchw_kernel<<<og, 256, 0, st>>>(h2, nullptr, x, out, u.cout, HW);
+    combine_nchw_kernel<bf16><<<og, 256, 0, st>>>(h2, nullptr, x, out, u.cout, HW);
   } else {
     Epilogue e; e.bias = u.d1.b; e.out_bf16 = r; e.ld_ob = u.cout;
     LDM_TRY(launch_gemm_tc(ctx, xh, u.cin, B * HW, u.d1, e, st));
-    combine_nchw_kernel<<<og, 256, 0, st>>>(h2, r, nullptr, out, u.cout, HW);
+    combine_nchw_kernel<bf16><<<og, 256, 0, st>>>(h2, r, nullptr, out, u.cout, HW);
   }
   LDM_LAUNCHED(ctx);
   return 0;
@@ -267,14 +341,13 @@ extern "C" LDM_API int ldm_ublock_res_forward(ldm_ctx* ctx, int handle, const fl
 
 extern "C" LDM_API int ldm_ublock_attn_pack(ldm_ctx* ctx, const ldm_ublock_attn_weights* w, int* handle_out, void* stream) {
   LDM_CHECK(ctx && w && handle_out, "ldm_ublock_attn_pack: null argument");
-  LDM_CHECK(ctx->precision == LDM_PRECISION_BF16, "ldm_ublock_attn_pack: bf16 contexts only");
   LDM_CHECK(w->channels > 0 && w->channels % 64 == 0 && w->num_heads > 0 && w->channels % w->num_heads == 0,
             "ldm_ublock_attn_pack: channels must be a multiple of 64 and of num_heads (%d, %d heads)", w->channels, w->num_heads);
   LDM_CHECK(attn_tc_supported(w->channels / w->num_heads), "ldm_ublock_attn_pack: head_dim %d unsupported (16, 32, 64, 128)",
             w->channels / w->num_heads);
   cudaStream_t st = (cudaStream_t)stream;
   LDM_CUDA(cudaSetDevice(ctx->device));
-  LDM_TRY(tc_init(ctx));
+  if (ctx->precision == LDM_PRECISION_BF16) LDM_TRY(tc_init(ctx));
   ctx->ublocks.emplace_back();
   UBlock& u = ctx->ublocks.back();
   u.type = 2; u.cin = u.cout = w->channels; u.heads = w->num_heads;
@@ -283,6 +356,11 @@ extern "C" LDM_API int ldm_ublock_attn_pack(ldm_ctx* ctx, const ldm_ublock_attn_
   LDM_TRY(own(ctx, P, w->norm_b, u.cin, &u.n1b, st));
   LDM_TRY(pack_dense(ctx, P, u.d1, w->qkv_w, w->qkv_b, 3 * u.cin, u.cin, st));
   LDM_TRY(pack_dense(ctx, P, u.d2, w->proj_w, w->proj_b, u.cin, u.cin, st));
+  if (ctx->precision != LDM_PRECISION_BF16) {   // strict path: standard (head, head_dim) attention output, proj columns permuted
+    LDM_TRY(ldm_alloc_t(ctx, P, &u.proj_perm, (size_t)u.cin * u.cin));
+    permute_proj_kernel<<<ceil_div(u.cin * u.cin, 256), 256, 0, st>>>(u.d2.w32, u.proj_perm, u.cin, u.heads);
+    LDM_LAUNCHED(ctx);
+  }
   LDM_CUDA(cudaStreamSynchronize(st));
   *handle_out = (int)ctx->ublocks.size() - 1;
   return 0;
@@ -299,12 +377,35 @@ extern "C" LDM_API int ldm_ublock_attn_forward(ldm_ctx* ctx, int handle, const f
   cudaStream_t st = (cudaStream_t)stream;
   LDM_CUDA(cudaSetDevice(ctx->device));
   const int HW = H * W, C = u.cin, hd = C / u.heads;
-  LDM_TRY(grow(ctx, u, (size_t)B * HW * C));
-  bf16 *xh = u.buf[0], *xn = u.buf[1], *qkv = u.qkv3, *vt = u.buf[2], *att = u.buf[3], *pr = u.buf[4];
+  const bool f32 = ctx->precision != LDM_PRECISION_BF16;
+  LDM_TRY(grow(ctx, u, (size_t)B * HW * C * (f32 ? 2 : 1)));
   const dim3 tg(ceil_div(HW, 32), ceil_div(C, 32), B);
-  nchw_to_nhwc_kernel<<<tg, 256, 0, st>>>(x, xh, C, HW);
+  if (f32) {
+    float *xh = (float*)u.buf[0], *xn = (float*)u.buf[1], *qkv = (float*)u.qkv3, *att = (float*)u.buf[3], *pr = (float*)u.buf[4];
+    const size_t n = (size_t)B * HW * C;
+    nchw_to_nhwc_kernel<float><<<tg, 256, 0, st>>>(x, xh, C, HW);
+    gn1_coef_kernel<float><<<B, 1024, 0, st>>>(xh, u.n1w, u.n1b, u.coef, HW, C);
+    coef_apply_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(xh, u.coef, xn, HW, C, LDM_ACT_NONE, n);
+    ctx->launches += 3;
+    LDM_CUDA(cudaGetLastError());
+    {
+      Epilogue e; e.bias = u.d1.b; e.out_f32 = qkv; e.ld_of = 3 * C;
+      LDM_TRY(launch_gemm_f32(ctx, xn, C, u.d1.w32, B * HW, 3 * C, C, e, st));
+    }
+    for (int b = 0; b < B; ++b)      // the tokens of one sample attend to each other: one call per sample
+      LDM_TRY(launch_batch_attention<float>(ctx, qkv + (size_t)b * HW * 3 * C, att + (size_t)b * HW * C, HW, C, u.heads, st));
+    {
+      Epilogue e; e.bias = u.d2.b; e.out_f32 = pr; e.ld_of = C;
+      LDM_TRY(launch_gemm_f32(ctx, att, C, u.proj_perm, B * HW, C, C, e, st));
+    }
+    combine_nchw_kernel<float><<<tg, 256, 0, st>>>(pr, nullptr, x, out, C, HW);
+    LDM_LAUNCHED(ctx);
+    return 0;
+  }
+  bf16 *xh = u.buf[0], *xn = u.buf[1], *qkv = u.qkv3, *vt = u.buf[2], *att = u.buf[3], *pr = u.buf[4];
+  nchw_to_nhwc_kernel<bf16><<<tg, 256, 0, st>>>(x, xh, C, HW);
   LDM_LAUNCHED(ctx);
-  gn1_coef_kernel<<<B, 1024, 0, st>>>(xh, u.n1w, u.n1b, u.coef, HW, C);
+  gn1_coef_kernel<bf16><<<B, 1024, 0, st>>>(xh, u.n1w, u.n1b, u.coef, HW, C);
   LDM_LAUNCHED(ctx);
   LDM_TRY(launch_coef_apply_bf16(ctx, xh, u.coef, xn, B, HW, C, LDM_ACT_NONE, st));
   {
@@ -319,7 +420,7 @@ extern "C" LDM_API int ldm_ublock_attn_forward(ldm_ctx* ctx, int handle, const f
     Epilogue e; e.bias = u.d2.b; e.out_bf16 = pr; e.ld_ob = C;
     LDM_TRY(launch_gemm_tc(ctx, att, C, B * HW, u.d2, e, st));
   }
-  combine_nchw_kernel<<<tg, 256, 0, st>>>(pr, nullptr, x, out, C, HW);
+  combine_nchw_kernel<bf16><<<tg, 256, 0, st>>>(pr, nullptr, x, out, C, HW);
   LDM_LAUNCHED(ctx);
   return 0;
 }
