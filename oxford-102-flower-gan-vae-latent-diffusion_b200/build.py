@@ -17,9 +17,6 @@ LIB = os.path.join(HERE, "libldm_b200.so")
 SOURCES = ["api.cu", "chain.cu", "rowwise.cu", "gemm_f32.cu", "gemm_tc.cu", "conv_tc.cu", "pack.cu", "decoder.cu", "decoder_norm.cu", "pixel.cu", "ublock.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v"]
-for _k in ("LDM_CH1", "LDM_CH2"):               # accumulation chains of the chain kernel (tuning)
-    if os.environ.get(_k):
-        NVCC_FLAGS.append("-D%s=%s" % (_k, os.environ[_k]))
 if os.environ.get("LDM_CHAIN_TRACE"):          # per-CTA clock stamps inside chain_kernel (tools/chain_sweep.py)
     NVCC_FLAGS.append("-DLDM_CHAIN_TRACE")
 

@@ -333,10 +333,12 @@ static int ensure_workspace(ldm_ctx* ctx, int B) {
   LDM_TRY(ldm_alloc(ctx, P, &ctx->af_op[1], naf * op));
   if (ctx->use_chain)
   {
-    for (int j = 0; j < U.nst; ++j) LDM_TRY(ldm_alloc_t(ctx, P, &ctx->opbuf[j], (size_t)cap * U.hid[j]));
+    // + 64 rows: the last cluster of a launch writes its (up to 64-row) block unconditionally; the tensor maps stop at B
+    const size_t capc = (size_t)cap + 64;
+    for (int j = 0; j < U.nst; ++j) LDM_TRY(ldm_alloc_t(ctx, P, &ctx->opbuf[j], capc * U.hid[j]));
     for (int k = 0; k < 2; ++k) {
-      LDM_TRY(ldm_alloc_t(ctx, P, &ctx->caf[k], (size_t)cap * 3 * U.latent));
-      LDM_CUDA(cudaMemset(ctx->caf[k], 0, (size_t)cap * 3 * U.latent * sizeof(bf16)));
+      LDM_TRY(ldm_alloc_t(ctx, P, &ctx->caf[k], capc * 3 * U.latent));
+      LDM_CUDA(cudaMemset(ctx->caf[k], 0, capc * 3 * U.latent * sizeof(bf16)));
     }
   }
   if (U.variant == 3) {
@@ -797,7 +799,7 @@ extern "C" LDM_API int ldm_kernel_launch_count(ldm_ctx* ctx, uint64_t* out) {
 extern "C" LDM_API int ldm_debug_chain_trace(ldm_ctx* ctx, int step, long long* out_host, int n) {
   LDM_CHECK(ctx, "ldm_debug_chain_trace: null context");
   LDM_CUDA(cudaSetDevice(ctx->device));
-  const int total = LDM_CHAIN_CLUSTER * 2 * 64;
+  const int total = LDM_CHAIN_CLUSTER * LDM_CHAIN_TRACE_TRACKS * LDM_CHAIN_TRACE_LEN;
   if (out_host) {   // read back (and keep tracing)
     LDM_CHECK(ctx->chain_trace && n >= total, "ldm_debug_chain_trace: tracing is off or the buffer is shorter than %d", total);
     LDM_CUDA(cudaDeviceSynchronize());

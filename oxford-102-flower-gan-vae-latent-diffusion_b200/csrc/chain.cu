@@ -37,20 +37,13 @@ namespace {
 
 constexpr int CS = LDM_CHAIN_CLUSTER;   // CTAs per cluster
 constexpr int BK = 64;
-constexpr int kCtlThreads = 128;        // warp 0: weight TMA, warp 1: operand TMA, warp 2: TMEM + MMA, warp 3: spare
-constexpr uint32_t kWBytes = 128 * BK * 2;               // one weight k-block: 16 KiB
+constexpr int kCtlThreads = 128;        // warp 0: weight TMA, warp 1: operand TMA, warp 2: TMEM + MMA, warp 3: set-up
+constexpr uint32_t kWTile = 128 * BK * 2;                // one weight k-block of a tile: 16 KiB
+constexpr uint32_t kWSlotBytes = 2 * kWTile;             // a weight-ring slot carries the two weight tiles of one chunk (= 8 MMAs)
+constexpr int kMaxWSlots = 6;
+constexpr int kXSlots = 8;                               // operand ring: k-blocks of NB rows, loaded as soon as the hand-over is through
 constexpr int kSlots = CS;                               // partial-statistics slots per buffer: one per tile of a phase
-constexpr int kMaxStagesRing = 10;
-// (measured: with clean UTCHMMA issue a single accumulation chain is fastest; more chains only add TMEM loads)
-#ifndef LDM_CH1
-#define LDM_CH1 1
-#endif
-#ifndef LDM_CH2
-#define LDM_CH2 1
-#endif
-constexpr int kCh1 = LDM_CH1, kCh2 = LDM_CH2;   // chains per accumulator: single-accumulator units / dual units
-constexpr int kChains = kCh1 > 2 * kCh2 ? kCh1 : 2 * kCh2;                               // independent accumulation chains (TMEM column blocks of NB): a dependent
-                                                         // tcgen05.mma chain is latency bound (~140 cycles per MMA at N = 48), 4 chains interleave
+constexpr int kChains = 2;                               // TMEM column blocks of NB fp32 accumulators: acc1, acc2 (dual phases)
 constexpr int kTmemCols = 512;
 constexpr int kMaxXMaps = LDM_MAX_STAGES + 2;
 
@@ -59,16 +52,17 @@ template <int NW> struct Geo {
   static constexpr int NB = 16 * NW;                                   // batch rows per cluster
   static constexpr int kEpiThreads = 128 * NW;
   static constexpr int kThreads = kCtlThreads + kEpiThreads;
-  static constexpr uint32_t kXBytes = NB * BK * 2;                     // one operand k-block
-  static constexpr uint32_t kStageBytes = kWBytes + kXBytes;           // multiple of 1024
+  static constexpr uint32_t kXBytes = NB * BK * 2;                     // one operand k-block (multiple of 1024)
+  static constexpr uint32_t kXRingBytes = kXSlots * kXBytes;
   static constexpr uint32_t kSlotBytes = 2u * kSlots * NB * sizeof(float2);
   static constexpr uint32_t kGstatBytes = 2u * NW * 4u * 16u * sizeof(float2);   // per-warp partials of a row group, double-buffered
   static constexpr uint32_t kRowStatBytes = 4u * NW * 16u * sizeof(float2);      // (mean, rstd) of 16 rows per epilogue warp
   static constexpr uint32_t kPbufBytes = 128u * NB * sizeof(float);               // split-K partner's partial accumulator
   static constexpr uint32_t kAuxBytes = kSlotBytes + kGstatBytes + kRowStatBytes + kPbufBytes;
-  static constexpr int kStages = (int)((225u * 1024u - kAuxBytes) / kStageBytes) < kMaxStagesRing
-                                     ? (int)((225u * 1024u - kAuxBytes) / kStageBytes) : kMaxStagesRing;
-  static constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + kAuxBytes;
+  static constexpr int kWSlotsFit = (int)((226u * 1024u - kAuxBytes - kXRingBytes) / kWSlotBytes);
+  static constexpr int kWSlots = kWSlotsFit < kMaxWSlots ? kWSlotsFit : kMaxWSlots;
+  static constexpr size_t kSmemBytes = 1024 + (size_t)kWSlots * kWSlotBytes + kXRingBytes + kAuxBytes;
+  static_assert(kWSlots >= 2, "weight ring too small");
 };
 
 struct ChainPhase {
@@ -126,7 +120,8 @@ struct ChainParams {
   int z_col;                  // TMEM column where the eps owners park the step's noise
   int x_col;                  // TMEM column of the fp32 chain state of the eps owners
   int* err;                   // [2]: first failure code, detail
-  long long* trace;           // profiling aid: [CS][2][64] clock64 stamps of cluster 0 in step trace_step (null: off); [0]: an h-warp thread, [1]: a u-warp thread
+  long long* trace;           // profiling aid (LDM_CHAIN_TRACE builds): [CS][LDM_CHAIN_TRACE_TRACKS][LDM_CHAIN_TRACE_LEN] tagged clock64 stamps of
+                              // cluster 0 in step trace_step (null: off); tracks: 0 h-warp thread, 1 u-warp thread, 2 weight producer, 3 operand producer, 4 MMA issuer
   int trace_step;
 };
 
@@ -151,14 +146,28 @@ __device__ __forceinline__ void st_async_f4(uint32_t cluster_addr, float a, floa
   asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
                ::"r"(cluster_addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(cluster_bar) : "memory");
 }
-__device__ __forceinline__ bool try_wait_cluster(uint64_t* bar, uint32_t parity) {
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint expires)
+// instead of spinning through issue slots that the working warps of the same scheduler need
+constexpr uint32_t kWaitHintNs = 1u << 15;
+__device__ __forceinline__ bool try_wait_cta(uint32_t bar_addr, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
-      : "r"(tc::smem_u32(bar)), "r"(parity)
+      : "r"(bar_addr), "r"(parity), "r"(kWaitHintNs)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool try_wait_cluster(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity), "r"(kWaitHintNs)
       : "memory");
   return ok != 0;
 }
@@ -180,42 +189,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
       : "memory");
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
-// two 16-column loads in flight, one wait
-__device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float (&a)[16], float (&b)[16]) {
-  uint32_t r[16], s[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(ta));
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]), "=r"(s[8]),
-        "=r"(s[9]), "=r"(s[10]), "=r"(s[11]), "=r"(s[12]), "=r"(s[13]), "=r"(s[14]), "=r"(s[15])
-      : "r"(tb));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(s[i]); }
-}
-
-// out = sum of `n` accumulation chains (16 columns each, `stride` columns apart)
-__device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr, uint32_t stride, int n, float (&out)[16]) {
-  float b[16];
-  if (n == 1) {
-    tc::tmem_ld16(taddr, out);
-  } else if (n == 4) {
-    float c[16], d[16];
-    tmem_ld16x2(taddr, taddr + stride, out, b);
-    tmem_ld16x2(taddr + 2 * stride, taddr + 3 * stride, c, d);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) out[i] = (out[i] + b[i]) + (c[i] + d[i]);
-  } else {
-    tmem_ld16x2(taddr, taddr + stride, out, b);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) out[i] += b[i];
-  }
-}
-
 // Every wait in this kernel is bounded and abortable: the first timeout raises the abort flag of all CTAs of the
 // cluster, after which every wait returns at once and the kernel drains to its end (no hung GPU).
 struct Waiter {
@@ -227,31 +200,38 @@ struct Waiter {
     const uint32_t a = tc::smem_u32(const_cast<int*>(abort_flag));
     for (uint32_t r = 0; r < (uint32_t)CS; ++r) remote_st_u32(mapa_u32(a, r), 1u);
   }
-  __device__ __forceinline__ bool wait(uint64_t* bar, uint32_t parity, int code) const {
-    if (tc::mbar_try_wait(bar, parity)) return true;
-    if (aborted()) return false;
-    for (uint32_t it = 0; it < (1u << 21); ++it) {
-      if (tc::mbar_try_wait(bar, parity)) return true;
-      if (it > 256) {
-        if (aborted()) return false;
-        __nanosleep(it > 8192 ? 128 : 20);
-      }
+  // slow path: out of line, so that the fast path is one try_wait and one branch
+  __device__ __noinline__ bool wait_slow(uint32_t bar_addr, uint32_t parity, int code, int cluster) const {
+    const long long t0 = clock64();
+    for (;;) {
+      if (cluster ? try_wait_cluster(bar_addr, parity) : try_wait_cta(bar_addr, parity)) return true;
+      if (aborted()) return false;
+      if (clock64() - t0 > (4ll << 30)) break;   // ~2 s: a barrier of this kernel completes within microseconds
     }
     fail(code);
     return false;
   }
-  __device__ __forceinline__ bool wait_cluster(uint64_t* bar, uint32_t parity, int code) const {
-    if (try_wait_cluster(bar, parity)) return true;
-    if (aborted()) return false;
-    for (uint32_t it = 0; it < (1u << 21); ++it) {
-      if (try_wait_cluster(bar, parity)) return true;
-      if (it > 256) {
-        if (aborted()) return false;
-        __nanosleep(it > 8192 ? 128 : 20);
-      }
-    }
-    fail(code);
-    return false;
+  __device__ __forceinline__ bool wait(uint32_t bar_addr, uint32_t parity, int code) const {
+    if (try_wait_cta(bar_addr, parity)) return true;
+    return wait_slow(bar_addr, parity, code, 0);
+  }
+  __device__ __forceinline__ bool wait(uint64_t* bar, uint32_t parity, int code) const { return wait(tc::smem_u32(bar), parity, code); }
+  __device__ __forceinline__ bool wait_cluster(uint32_t bar_addr, uint32_t parity, int code) const {
+    if (try_wait_cluster(bar_addr, parity)) return true;
+    return wait_slow(bar_addr, parity, code, 1);
+  }
+  __device__ __forceinline__ bool wait_cluster(uint64_t* bar, uint32_t parity, int code) const { return wait_cluster(tc::smem_u32(bar), parity, code); }
+};
+
+// Tagged clock stamps of one thread (LDM_CHAIN_TRACE builds): value = clock64 | phase << 52 | tag << 56
+struct Tracer {
+  long long* buf;
+  int n;
+  bool on;
+  __device__ __forceinline__ void stamp(int tag, int p) {
+#ifdef LDM_CHAIN_TRACE
+    if (on && n < LDM_CHAIN_TRACE_LEN) buf[n++] = (clock64() & 0xFFFFFFFFFFFFFll) | ((long long)p << 52) | ((long long)tag << 56);
+#endif
   }
 };
 
@@ -338,16 +318,21 @@ __device__ __forceinline__ float2 warp_row_stats16(const float (&v)[16], int lan
   return make_float2(m, fmaxf(s2 - s1 * m, 0.0f));
 }
 
-__device__ __forceinline__ float swish_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+// v sigmoid(v) = h + h tanh(h), h = v / 2: one MUFU (tanh.approx, relative error ~2^-11, below the bf16 rounding of the result)
+__device__ __forceinline__ float swish_fast(float v) {
+  const float h = 0.5f * v;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 __device__ __forceinline__ int clamp_t(long long t, int n_t) { return (int)(t < 0 ? 0 : (t >= n_t ? n_t - 1 : t)); }
 
-// work unit of cluster rank `rank` in a phase: tile, unit-in-tile and the list of ring jobs; false: no unit.
+// work unit of cluster rank `rank` in a phase: tile, unit-in-tile and its share of the reduction; false: no unit.
 // `tail`: the extra merged phase after the last step, in which only the eps tiles work.
-// A job moves one 128 x 64 weight tile (and, unless it shares the previous job's, one operand k-block) into a ring slot:
-//   plain phase          : job i = k-block kb0 + i of [W | X]
-//   dual phase, one unit : job 2m = (W1 k-block m, X k-block m) -> accumulator 0; job 2m+1 = (W2 k-block m, same X) -> accumulator 1
-//   dual phase, two units: unit kp streams W_{kp+1} and the whole operand into its own accumulator 0
-struct Unit { int tile, kp, kb0, njobs, mode; bool is_eps; };
+//   mode 0 (plain phase)          : k-blocks [kb0, kb0 + nkb) of [W | X] -> accumulator 0
+//   mode 1 (dual phase, one unit) : every k-block against W1 (-> accumulator 0) and W2 (-> accumulator 1)
+//   mode 2 (dual phase, two units): unit kp multiplies the whole operand with W_{kp+1} into its own accumulator 0
+struct Unit { int tile, kp, kb0, nkb, mode; bool is_eps; };
 __device__ __forceinline__ bool unit_of(const ChainPhase& ph, int rank, bool tail, Unit& u) {
   const int un = rank - ph.first;
   if (un < 0 || un >= ph.tiles * ph.ks) return false;
@@ -358,7 +343,7 @@ __device__ __forceinline__ bool unit_of(const ChainPhase& ph, int rank, bool tai
   if (ph.dual) {
     u.mode = ph.ks == 1 ? 1 : 2;
     u.kb0 = 0;
-    u.njobs = ph.ks == 1 ? 2 * nkb : nkb;
+    u.nkb = nkb;
     return true;
   }
   u.mode = 0;
@@ -368,31 +353,56 @@ __device__ __forceinline__ bool unit_of(const ChainPhase& ph, int rank, bool tai
     if (u.is_eps) lo = ph.eps_kb0;
     else if (tail) return false;
   }
-  u.njobs = (nkb - lo) >> (ph.ks - 1);
-  u.kb0 = lo + u.kp * u.njobs;
+  u.nkb = (nkb - lo) >> (ph.ks - 1);
+  u.kb0 = lo + u.kp * u.nkb;
   return true;
 }
-// column of job i's weight tile in the phase's weight matrix, and of its operand k-block (-1: shares the previous job's)
-__device__ __forceinline__ void job_cols(const ChainPhase& ph, const Unit& u, int i, int& wcol, int& xcol) {
-  if (u.mode == 0) { wcol = (u.kb0 + i) * BK; xcol = ph.xcol + (u.kb0 + i) * BK; }
-  else if (u.mode == 1) { wcol = (i & 1) * ph.K + (i >> 1) * BK; xcol = (i & 1) ? -1 : (i >> 1) * BK; }
-  else { wcol = u.kp * ph.K + i * BK; xcol = i * BK; }
+
+// What the three control threads need to know about this CTA's unit of a phase, worked out ONCE per launch (the threads
+// run a long dependent instruction stream per ring slot; everything that can be hoisted out of it is).
+// A chunk is the work behind one weight-ring slot: two 128 x 64 weight tiles and 8 MMAs.
+//   mode 1      : chunk c = k-block c against W1 and W2 (one operand slot)
+//   modes 0, 2  : chunk c = k-blocks 2c, 2c + 1 of one weight matrix (two operand slots; the last chunk may hold one)
+struct __align__(16) UnitPlan {
+  int valid;        // this CTA has a unit in the phase
+  int valid_tail;   // ... and in the tail pass (eps tiles only)
+  int tile_row;     // first weight row of the tile
+  int nkb;          // operand k-blocks the unit reads
+  int mode;
+  int wcol0;        // column of the first weight tile (accumulator 0)
+  int wcol1;        // mode 1: column of W2's first tile
+  int xcol0;        // operand column of k-block 0
+};
+
+// control-thread PTX on raw shared-memory addresses (no generic -> shared conversions inside the loops)
+__device__ __forceinline__ void expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma2d_a(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
 template <int NW>
 __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __grid_constant__ ChainParams P) {
   using G = Geo<NW>;
   constexpr int NB = G::NB;
-  constexpr int S = G::kStages;
+  constexpr int S = G::kWSlots;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ring = smem;
-  float2* slots = reinterpret_cast<float2*>(ring + (size_t)S * G::kStageBytes);                          // [2][kSlots][NB]
+  uint8_t* wring = smem;                                                                                  // [S][2] weight tiles
+  uint8_t* xring = smem + (size_t)S * kWSlotBytes;                                                        // [kXSlots] operand k-blocks
+  float2* slots = reinterpret_cast<float2*>(xring + G::kXRingBytes);                                      // [2][kSlots][NB]
   float2* gstat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(slots) + G::kSlotBytes);          // [2][NW][4 warps][16 rows]
   float2* rowstat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(gstat) + G::kGstatBytes);       // [4 NW warps][16 rows]
   float4* pbuf = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(rowstat) + G::kRowStatBytes);      // [NW][4 chunks][128 rows] x 4 columns
-  __shared__ __align__(8) uint64_t full_bar[kMaxStagesRing];
-  __shared__ __align__(8) uint64_t empty_bar[kMaxStagesRing];
+  __shared__ __align__(8) uint64_t wfull_bar[kMaxWSlots];
+  __shared__ __align__(8) uint64_t wempty_bar[kMaxWSlots];
+  __shared__ __align__(8) uint64_t xfull_bar[kXSlots];
+  __shared__ __align__(8) uint64_t xempty_bar[kXSlots];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ __align__(8) uint64_t obar[2];   // phase hand-over: 16 remote arrives (one per CTA) + the local operand producer
   __shared__ __align__(8) uint64_t sbar[2];   // LayerNorm statistics: transaction barrier fed by the peers' st.async
@@ -400,6 +410,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
   __shared__ uint32_t tmem_slot;
   __shared__ int abort_flag;
   __shared__ ChainPhase sphase[LDM_CHAIN_MAX_PHASES];   // shared-memory copy: indexed constant-bank reads are slow
+  __shared__ UnitPlan splan[LDM_CHAIN_MAX_PHASES];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = blockIdx.x;                 // gridDim.x == CS: rank in cluster
@@ -409,8 +420,12 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
-      tc::mbar_init(&full_bar[s], 2);          // weight producer + operand producer (each arrive.expect_tx)
-      tc::mbar_init(&empty_bar[s], 1);
+      tc::mbar_init(&wfull_bar[s], 1);         // the weight producer's arrive.expect_tx
+      tc::mbar_init(&wempty_bar[s], 1);        // tcgen05.commit
+    }
+    for (int s = 0; s < kXSlots; ++s) {
+      tc::mbar_init(&xfull_bar[s], 1);
+      tc::mbar_init(&xempty_bar[s], 1);
     }
     tc::mbar_init(&tmem_full_bar, 1);
     tc::mbar_init(&obar[0], CS + 1);
@@ -429,6 +444,21 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&P.ph[0]);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&sphase[0]);
     for (int i = lane; i < nw; i += 32) dst[i] = src[i];
+    __syncwarp();
+    if (lane < NP) {
+      const ChainPhase& ph = sphase[lane];
+      UnitPlan pl;
+      Unit un, ut;
+      pl.valid = unit_of(ph, rank, false, un) ? 1 : 0;
+      pl.valid_tail = unit_of(ph, rank, true, ut) ? 1 : 0;
+      pl.tile_row = pl.valid ? un.tile * 128 : 0;
+      pl.nkb = pl.valid ? un.nkb : 0;
+      pl.mode = pl.valid ? un.mode : 0;
+      pl.wcol0 = pl.valid ? (un.mode == 0 ? un.kb0 * BK : (un.mode == 2 ? un.kp * ph.K : 0)) : 0;
+      pl.wcol1 = ph.K;
+      pl.xcol0 = pl.valid && un.mode == 0 ? ph.xcol + un.kb0 * BK : 0;
+      splan[lane] = pl;
+    }
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -439,53 +469,68 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
   if (warp == 0) {
     // ------------------------------------------------------------------ weight-tile producer (runs ahead of the phases)
     if (tc::elect_one()) {
-      uint32_t n = 0;
+      const uint32_t ring_a = tc::smem_u32(wring), full_a = tc::smem_u32(&wfull_bar[0]), empty_a = tc::smem_u32(&wempty_bar[0]);
+      uint32_t ws = 0, wpar = 0;
       bool ok = true;
+      Tracer TR{P.trace ? P.trace + ((size_t)rank * LDM_CHAIN_TRACE_TRACKS + 2) * LDM_CHAIN_TRACE_LEN : nullptr, 0, false};
       for (int it = 0; it <= P.n_iter && ok; ++it) {
         const bool tail = it == P.n_iter;
+        TR.on = P.trace != nullptr && blockIdx.y == 0 && it == P.trace_step;
         for (int p = 0; p < (tail ? 1 : NP) && ok; ++p) {
-          Unit un;
-          if (!unit_of(sphase[p], rank, tail, un)) continue;
-          for (int i = 0; i < un.njobs; ++i, ++n) {
-            const uint32_t s = n % S, par = (n / S) & 1u;
-            if (!W.wait(&empty_bar[s], par ^ 1u, 1)) { ok = false; break; }
-            int wcol, xcol;
-            job_cols(sphase[p], un, i, wcol, xcol);
-            tc::mbar_arrive_expect_tx(&full_bar[s], kWBytes);
-            tc::tma_load_2d(ring + (size_t)s * G::kStageBytes, &P.wmap[p], &full_bar[s], wcol, un.tile * 128);
+          const UnitPlan pl = splan[p];
+          if (!(tail ? pl.valid_tail : pl.valid)) continue;
+          const CUtensorMap* wm = &P.wmap[p];
+          const int nchunks = pl.mode == 1 ? pl.nkb : (pl.nkb + 1) >> 1;
+          const int step = pl.mode == 1 ? BK : 2 * BK;
+          int col_a = pl.wcol0, col_b = pl.mode == 1 ? pl.wcol1 : pl.wcol0 + BK;
+          for (int c = 0; c < nchunks; ++c, col_a += step, col_b += step) {
+            const bool two = pl.mode == 1 || 2 * c + 1 < pl.nkb;
+            if (!W.wait(empty_a + 8u * ws, wpar ^ 1u, 1)) { ok = false; break; }
+            const uint32_t fb = full_a + 8u * ws, dst = ring_a + ws * kWSlotBytes;
+            expect_tx_a(fb, two ? kWSlotBytes : kWTile);
+            tma2d_a(dst, wm, fb, col_a, pl.tile_row);
+            if (two) tma2d_a(dst + kWTile, wm, fb, col_b, pl.tile_row);
+            if (c == 0) TR.stamp(20, p);
+            if (c == nchunks - 1) TR.stamp(21, p);
+            if (++ws == (uint32_t)S) { ws = 0; wpar ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ operand producer: waits for the phase hand-over
+    // ------------------------------------------------------------------ operand producer: waits for the phase hand-over,
+    //                                                                    then requests EVERY k-block of the unit at once
     if (tc::elect_one()) {
-      uint32_t n = 0, gp = 0;
+      const uint32_t ring_a = tc::smem_u32(xring), full_a = tc::smem_u32(&xfull_bar[0]), empty_a = tc::smem_u32(&xempty_bar[0]);
+      uint32_t xs = 0, xpar = 0, gp = 0;
       bool ok = true;
+      Tracer TR{P.trace ? P.trace + ((size_t)rank * LDM_CHAIN_TRACE_TRACKS + 3) * LDM_CHAIN_TRACE_LEN : nullptr, 0, false};
       tc::mbar_arrive(&obar[0]);   // this thread's share of hand-overs 0 and 1
       tc::mbar_arrive(&obar[1]);
       for (int it = 0; it <= P.n_iter && ok; ++it) {
         const bool tail = it == P.n_iter;
+        TR.on = P.trace != nullptr && blockIdx.y == 0 && it == P.trace_step;
         for (int p = 0; p < (tail ? 1 : NP) && ok; ++p, ++gp) {
+          const UnitPlan pl = splan[p];
+          const CUtensorMap* xm = &P.xmaps[sphase[p].xmap + (sphase[p].xmap_alt ? (it & 1) : 0)];
           if (gp > 0) {
             const uint32_t f = gp - 1;   // hand-over that publishes this phase's operand
             if (!W.wait_cluster(&obar[f & 1u], (f >> 1) & 1u, 2)) { ok = false; break; }
+            TR.stamp(30, p);
             tc::mbar_arrive(&obar[f & 1u]);   // share of hand-over f + 2 (same barrier, next phase)
             if (!P.writer_fence) fence_proxy_async_global();   // peers' generic-proxy global writes (released above) -> async-proxy reads below
           }
-          const ChainPhase& ph = sphase[p];
-          Unit un;
-          if (!unit_of(ph, rank, tail, un)) continue;
-          const CUtensorMap* xm = &P.xmaps[ph.xmap + (ph.xmap_alt ? (it & 1) : 0)];
-          for (int i = 0; i < un.njobs; ++i, ++n) {
-            const uint32_t s = n % S, par = (n / S) & 1u;
-            if (!W.wait(&empty_bar[s], par ^ 1u, 3)) { ok = false; break; }
-            int wcol, xcol;
-            job_cols(ph, un, i, wcol, xcol);
-            if (xcol < 0) { tc::mbar_arrive(&full_bar[s]); continue; }   // this job multiplies the previous job's operand block
-            tc::mbar_arrive_expect_tx(&full_bar[s], G::kXBytes);
-            tc::tma_load_2d(ring + (size_t)s * G::kStageBytes + kWBytes, xm, &full_bar[s], xcol, row0);
+          if (!(tail ? pl.valid_tail : pl.valid)) continue;
+          int xcol = pl.xcol0;
+          for (int kb = 0; kb < pl.nkb; ++kb, xcol += BK) {
+            if (!W.wait(empty_a + 8u * xs, xpar ^ 1u, 3)) { ok = false; break; }
+            const uint32_t fb = full_a + 8u * xs;
+            expect_tx_a(fb, G::kXBytes);
+            tma2d_a(ring_a + xs * G::kXBytes, xm, fb, xcol, row0);
+            if (kb == 0) TR.stamp(32, p);
+            if (++xs == (uint32_t)kXSlots) { xs = 0; xpar ^= 1u; }
           }
+          TR.stamp(33, p);
         }
       }
     }
@@ -493,47 +538,70 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
     // ------------------------------------------------------------------ MMA issuer
     if (tc::elect_one()) {
       constexpr uint32_t idesc = tc::make_idesc_bf16(128, NB);
-      uint32_t n = 0;
+      const uint32_t wfull_a = tc::smem_u32(&wfull_bar[0]), wempty_a = tc::smem_u32(&wempty_bar[0]);
+      const uint32_t xfull_a = tc::smem_u32(&xfull_bar[0]), xempty_a = tc::smem_u32(&xempty_bar[0]);
+      const uint32_t tfull_a = tc::smem_u32(&tmem_full_bar);
+      const uint64_t wdesc0 = tc::make_desc_sw128(tc::smem_u32(wring)), xdesc0 = tc::make_desc_sw128(tc::smem_u32(xring));
+      constexpr uint64_t kWSlotD = kWSlotBytes >> 4, kWTileD = kWTile >> 4, kXD = G::kXBytes >> 4;   // descriptor start-address units (16 B)
+      const uint32_t acc0 = tmem_base, acc1 = tmem_base + (uint32_t)NB;
+      uint32_t ws = 0, wpar = 0, xs = 0, xpar = 0;
       bool ok = true;
+      Tracer TR{P.trace ? P.trace + ((size_t)rank * LDM_CHAIN_TRACE_TRACKS + 4) * LDM_CHAIN_TRACE_LEN : nullptr, 0, false};
       for (int it = 0; it <= P.n_iter && ok; ++it) {
         const bool tail = it == P.n_iter;
+        TR.on = P.trace != nullptr && blockIdx.y == 0 && it == P.trace_step;
         for (int p = 0; p < (tail ? 1 : NP) && ok; ++p) {
-          Unit un;
-          if (!unit_of(sphase[p], rank, tail, un)) continue;
-          if (un.mode == 1) {
-            // dual k-block: both weight tiles against the same operand block.  Chains 0,1: accumulator 1 (even / odd k-steps),
-            // chains 2,3: accumulator 2; consecutive MMAs never depend on each other
-            for (int i = 0; i < un.njobs; i += 2, n += 2) {
-              const uint32_t sa = n % S, pa = (n / S) & 1u, sb = (n + 1) % S, pb = ((n + 1) / S) & 1u;
-              if (!W.wait(&full_bar[sa], pa, 4) || !W.wait(&full_bar[sb], pb, 4)) { ok = false; break; }
+          const UnitPlan pl = splan[p];
+          if (!(tail ? pl.valid_tail : pl.valid)) continue;
+          if (pl.mode == 1) {
+            // dual: both weight tiles of a chunk against the same operand k-block; consecutive MMAs never depend on each other
+            for (int c = 0; c < pl.nkb; ++c) {
+              if (!W.wait(xfull_a + 8u * xs, xpar, 4) || !W.wait(wfull_a + 8u * ws, wpar, 4)) { ok = false; break; }
+              if (c == 0) TR.stamp(40, p);
+              if (c == pl.nkb / 2) TR.stamp(42, p);
               tc::fence_after_sync();
-              const uint32_t ba = tc::smem_u32(ring + (size_t)sa * G::kStageBytes), bb = tc::smem_u32(ring + (size_t)sb * G::kStageBytes);
-              const uint64_t dwa = tc::make_desc_sw128(ba), dwb = tc::make_desc_sw128(bb), dx = tc::make_desc_sw128(ba + kWBytes);
+              const uint64_t dwa = wdesc0 + (uint64_t)ws * kWSlotD, dwb = dwa + kWTileD, dx = xdesc0 + (uint64_t)xs * kXD;
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
-                const uint32_t ch = (uint32_t)(k % kCh2), acc = (uint32_t)(i != 0 || k >= kCh2);
-                tc::umma_bf16(tmem_base + ch * NB, dwa + (uint64_t)(2 * k), dx + (uint64_t)(2 * k), idesc, acc);
-                tc::umma_bf16(tmem_base + ((uint32_t)kCh2 + ch) * NB, dwb + (uint64_t)(2 * k), dx + (uint64_t)(2 * k), idesc, acc);
+                const uint32_t acc = (uint32_t)(c != 0 || k != 0);
+                tc::umma_bf16(acc0, dwa + (uint64_t)(2 * k), dx + (uint64_t)(2 * k), idesc, acc);
+                tc::umma_bf16(acc1, dwb + (uint64_t)(2 * k), dx + (uint64_t)(2 * k), idesc, acc);
               }
-              tc::umma_commit(&empty_bar[sa]);
-              tc::umma_commit(&empty_bar[sb]);
+              commit_a(wempty_a + 8u * ws);
+              commit_a(xempty_a + 8u * xs);
+              if (++ws == (uint32_t)S) { ws = 0; wpar ^= 1u; }
+              if (++xs == (uint32_t)kXSlots) { xs = 0; xpar ^= 1u; }
             }
           } else {
-            // one accumulator: k-step k of every k-block goes to chain k
-            for (int i = 0; i < un.njobs; ++i, ++n) {
-              const uint32_t s = n % S, par = (n / S) & 1u;
-              if (!W.wait(&full_bar[s], par, 4)) { ok = false; break; }
+            // one accumulator: a chunk is two consecutive k-blocks (the last chunk of an odd count holds one)
+            const int nchunks = (pl.nkb + 1) >> 1;
+            for (int c = 0; c < nchunks; ++c) {
+              const bool two = 2 * c + 1 < pl.nkb;
+              const uint32_t xs2 = xs + 1 == (uint32_t)kXSlots ? 0u : xs + 1, xpar2 = xs + 1 == (uint32_t)kXSlots ? xpar ^ 1u : xpar;
+              if (!W.wait(xfull_a + 8u * xs, xpar, 4) || (two && !W.wait(xfull_a + 8u * xs2, xpar2, 4)) || !W.wait(wfull_a + 8u * ws, wpar, 4)) { ok = false; break; }
+              if (c == 0) TR.stamp(40, p);
+              if (c == nchunks / 2) TR.stamp(42, p);
               tc::fence_after_sync();
-              const uint32_t base = tc::smem_u32(ring + (size_t)s * G::kStageBytes);
-              const uint64_t dw = tc::make_desc_sw128(base);
-              const uint64_t dx = tc::make_desc_sw128(base + kWBytes);
+              const uint64_t dwa = wdesc0 + (uint64_t)ws * kWSlotD, dxa = xdesc0 + (uint64_t)xs * kXD, dxb = xdesc0 + (uint64_t)xs2 * kXD;
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k)
-                tc::umma_bf16(tmem_base + (uint32_t)((k % kCh1) * NB), dw + (uint64_t)(2 * k), dx + (uint64_t)(2 * k), idesc, (uint32_t)(i != 0 || k >= kCh1));
-              tc::umma_commit(&empty_bar[s]);
+                tc::umma_bf16(acc0, dwa + (uint64_t)(2 * k), dxa + (uint64_t)(2 * k), idesc, (uint32_t)(c != 0 || k != 0));
+              commit_a(xempty_a + 8u * xs);
+              if (two) {
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  tc::umma_bf16(acc0, dwa + kWTileD + (uint64_t)(2 * k), dxb + (uint64_t)(2 * k), idesc, 1u);
+                commit_a(xempty_a + 8u * xs2);
+              }
+              commit_a(wempty_a + 8u * ws);
+              if (++ws == (uint32_t)S) { ws = 0; wpar ^= 1u; }
+              xs = two ? xs2 : xs;
+              xpar = two ? xpar2 : xpar;
+              if (++xs == (uint32_t)kXSlots) { xs = 0; xpar ^= 1u; }
             }
           }
-          if (ok) tc::umma_commit(&tmem_full_bar);
+          if (ok) commit_a(tfull_a);
+          TR.stamp(41, p);
         }
       }
     }
@@ -553,13 +621,8 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
     uint32_t sidx = 0;            // statistics exchanges so far (same count in every CTA)
     uint32_t sph[2] = {0, 0};     // completed phases of sbar[b] in THIS CTA
     uint32_t oidx = 0;            // hand-overs so far
-    int tr_n = 0;
-    bool tr_on = false;
-    auto stamp = [&]() {
-#ifdef LDM_CHAIN_TRACE
-      if (tr_on && tr_n < 64) P.trace[(rank * 2 + (et == 0 ? 0 : 1)) * 64 + tr_n++] = clock64();
-#endif
-    };
+    Tracer TR{P.trace ? P.trace + ((size_t)rank * LDM_CHAIN_TRACE_TRACKS + (et == 0 ? 0 : 1)) * LDM_CHAIN_TRACE_LEN : nullptr, 0, false};
+    auto stamp = [&](int tag, int p) { TR.stamp(tag, p); };
     auto epi_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(G::kEpiThreads) : "memory"); };
     auto group_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory"); };   // the 4 warps of row group g
 
@@ -659,8 +722,8 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
     for (int it = 0; it <= P.n_iter; ++it) {
       const bool tail = it == P.n_iter;
       const int par = it & 1;
-      tr_on = P.trace != nullptr && blockIdx.y == 0 && it == P.trace_step && (et == 0 || et == 64);
-      stamp();
+      TR.on = P.trace != nullptr && blockIdx.y == 0 && it == P.trace_step && (et == 0 || et == 64);
+      stamp(1, 0);
       // timestep of this iteration's forward (t_uni) and posterior coefficients of this and the previous iteration
       const int t_uni = P.sample ? P.t_start - it : (P.t_len == 1 ? clamp_t(P.t_idx[0], P.n_t) : -1);
       // unconditional loads (clamped index), patched AFTER the first wait of the iteration: no stall on their L2 latency here
@@ -681,7 +744,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
           tpar ^= 1u;
           tc::fence_after_sync();
           float pv[16];
-          tmem_ld16_sum(lane_taddr + (uint32_t)s0, (uint32_t)NB, kCh1, pv);
+          tc::tmem_ld16(lane_taddr + (uint32_t)s0, pv);
           tc::fence_before_sync();
           const uint32_t owner = (uint32_t)(ph.first + tile * ph.ks);
           const uint32_t dst = mapa_u32(tc::smem_u32(pbuf + (size_t)(g * 4) * 128 + lrow), owner);
@@ -710,16 +773,15 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
             exchange_wait(bb, ph.prev_tiles, 11);
             combine(bb, ph.prev_tiles, 64.0f);
           }
-          stamp();
+          stamp(2, p);
           W.wait(&tmem_full_bar, tpar, 5);
           tpar ^= 1u;
-          stamp();
+          stamp(3, p);
           tc::fence_after_sync();
           const float cb_prev = it > 0 ? cf_prev.x / cf_prev.y : 0.f;   // c2 / sqrt(alpha) of the previous step (forward(): 1)
           const float t_e = cb_prev * t_g;                              // the eps bias of the previous step, seen through G_0
           float a2[16];
-          const int nch = (ph.dual && ph.ks == 1) ? kCh2 : kCh1;   // chains of the (first) accumulator
-          tmem_ld16_sum(lane_taddr + (uint32_t)s0, (uint32_t)NB, nch, v);
+          tc::tmem_ld16(lane_taddr + (uint32_t)s0, v);
           if (ph.cadd_col >= 0 && !eps_tile) {
             // one association for every mode (uniform t: t_t = T[t], c = C[c_r]; per-row t: t_t = 0, c = C[c_r] + T[t_r]), so
             // that a row's result does not depend on how its timestep was passed: acc + (b + (T + C)) - e
@@ -731,7 +793,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = (v[j] + (t_b + t_t)) - t_e;
           }
-          if (ph.dual && ph.ks == 1) tmem_ld16_sum(lane_taddr + (uint32_t)(kCh2 * NB + s0), (uint32_t)NB, kCh2, a2);
+          if (ph.dual && ph.ks == 1) tc::tmem_ld16(lane_taddr + (uint32_t)(NB + s0), a2);
           tc::fence_before_sync();            // ordered before the next phase's MMAs through the hand-over
           if (ph.ks > 1) {   // the partner unit's accumulator: acc2 of a dual phase (or the other K half of a plain one)
             if (et == 0) tc::mbar_arrive_expect_tx(&pbar, G::kPbufBytes);
@@ -745,7 +807,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
               else { v[4 * c] += a.x; v[4 * c + 1] += a.y; v[4 * c + 2] += a.z; v[4 * c + 3] += a.w; }
             }
           }
-          stamp();
+          stamp(4, p);
           if (ph.dual) {
             // LayerNorm of the operand rows applied after the contraction: W2 . LN_b(h2) = r (W2' h2 - mu q) + const
             // (gamma, beta folded into W2' / the bias at pack time); (mu, r) of the 16 rows were merged before the wait
@@ -756,7 +818,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
             }
             __syncwarp();
           }
-          stamp();
+          stamp(5, p);
         }
 
         if (ph.type == LDM_PH_STAGE || ph.type == LDM_PH_MERGED) {
@@ -781,16 +843,17 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
               }
             }
             publish(b0, tile, half_row_stats8(u, lane), 16.0f, ph.first, ntile, ph.ks);
-            stamp();
+            stamp(6, p);
             exchange_wait(b0, ntile, 6);
-            stamp();
+            stamp(7, p);
             combine(b0, ntile, 64.0f);
             bf16* o = ph.out + (size_t)(row0 + s0 + hr) * ph.ld_out + f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {   // h2 = swish(LN_a(u)) + h: the next phase's operand (its LayerNorm is applied there)
               const float2 mr = rs[hr + i];
-              h2k[i] += swish_fast((u[i] - mr.x) * mr.y * ga + ba);
-              if (row0 + s0 + hr + i < P.row_end) o[(size_t)i * ph.ld_out] = __float2bfloat16_rn(h2k[i]);
+              const float a = mr.y * ga;                      // LayerNorm_a as one FMA: u a + (beta - mu a)
+              h2k[i] += swish_fast(fmaf(u[i], a, fmaf(-mr.x, a, ba)));
+              o[(size_t)i * ph.ld_out] = __float2bfloat16_rn(h2k[i]);   // rows beyond the batch land in the buffers' padding
             }
             pub_b = true;
           }
@@ -803,26 +866,26 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
             const float ga = __ldg(ph.ga + f), be = __ldg(ph.ba + f);
             publish(b0, tile, warp_row_stats16(v, lane), 32.0f, ph.first, ph.tiles, ph.ks);
             exchange_wait(b0, nparts, 8);
-            stamp();
+            stamp(11, p);
             combine(b0, nparts, 128.0f);
             const float cb_cur = cf_cur.x / cf_cur.y;
             bf16* o = P.af[par ^ 1] + (size_t)(row0 + s0) * P.ld_af + P.latent + f;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float2 mr = rs[j];
-              if (row0 + s0 + j < P.row_end) o[(size_t)j * P.ld_af] = __float2bfloat16_rn(-cb_cur * ((v[j] - mr.x) * mr.y * ga + be));
+              o[(size_t)j * P.ld_af] = __float2bfloat16_rn(-cb_cur * ((v[j] - mr.x) * mr.y * ga + be));
             }
           }
         }
 
         // ---- hand-over: this CTA's share of the phase is in global memory; tell every CTA of the cluster, then wait
         //      for all of them (the operand producer waits on the same barrier and starts the next phase's loads)
-        stamp();
+        stamp(8, p);
         if (P.writer_fence) fence_proxy_async_all();
         epi_bar();
         const uint32_t ob = oidx & 1u, opar = (oidx >> 1) & 1u;
         if (et < CS) remote_arrive(mapa_u32(obar_local[ob], (uint32_t)et));
-        stamp();
+        stamp(9, p);
 
         if (eps_tile) {
           // ---- posterior update (v2:584-592), OFF the critical path: nothing in the cluster needs x_{t-1} itself before
@@ -891,17 +954,15 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
             const float inv_sa = 1.0f / cf_cur.y;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              if (row0 + s0 + j < P.row_end) {
-                o[(size_t)j * P.ld_af] = __float2bfloat16_rn(xr[j] * inv_sa + cf_cur.z * z[j]);
-                o[(size_t)j * P.ld_af + 2 * P.latent] = __float2bfloat16_rn(-cb_cur * xr[j]);
-              }
+              o[(size_t)j * P.ld_af] = __float2bfloat16_rn(xr[j] * inv_sa + cf_cur.z * z[j]);
+              o[(size_t)j * P.ld_af + 2 * P.latent] = __float2bfloat16_rn(-cb_cur * xr[j]);
             }
           }
         }
 
         W.wait(&obar[ob], opar, 9);
         oidx++;
-        stamp();
+        stamp(10, p);
         if (pub_b) {
           // ---- background exchange, issued once the hand-over is through (the operand producer's proxy fence must not
           //      queue behind these stores): (mean, M2) of h2 over this warp's 16 features -> the tile owners of the NEXT

@@ -148,6 +148,8 @@ struct UnetModel {
 #define LDM_CHAIN_ROWS 32         // batch rows a cluster carries through the whole chain
 #define LDM_CHAIN_MAX_K 2048      // longest reduction of a phase (2 x widest hidden layer)
 #define LDM_CHAIN_MAX_PHASES (LDM_MAX_STAGES + 2)
+#define LDM_CHAIN_TRACE_TRACKS 5   // ldm_debug_chain_trace: stamped threads per CTA
+#define LDM_CHAIN_TRACE_LEN 96     // stamps per thread
 enum { LDM_PH_STAGE = 0, LDM_PH_FINAL_LN = 1, LDM_PH_MERGED = 3 };   // MERGED: stage tiles of the NEXT forward + eps tiles of the previous one
 
 struct ChainPhaseHost {
@@ -318,7 +320,7 @@ struct ldm_ctx {
   float4* coef_dev = nullptr;     // [n_steps] (c2, sqrt_alpha, sigma, 0)
   float4* coef_one = nullptr;     // one entry (1, 1, 0, 0): the 'coefficients' of a plain forward() in the chain kernel
   int* chain_err = nullptr;       // [2] first barrier timeout of the chain kernel: code, block
-  long long* chain_trace = nullptr;   // [16][64] clock stamps (ldm_debug_chain_trace), null = off
+  long long* chain_trace = nullptr;   // [CS][TRACKS][LEN] tagged clock stamps (ldm_debug_chain_trace), null = off
   int chain_trace_step = 0;
   int use_pdl = 0;
   int use_attn_tc = 1;            // v3 bf16: attention on tcgen05 (LDM_ATTN_TC=0 selects the CUDA-core kernel)

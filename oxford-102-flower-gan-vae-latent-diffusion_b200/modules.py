@@ -404,7 +404,7 @@ class UNetAttentionBlock(nn.Module):
 
     def forward(self, x):
         _require_eval(self, "UNetAttentionBlock.forward")
-        return get_engine(x.device, self.precision or "bf16").ublock_attn_forward(self, x)
+        return get_engine(x.device, self.precision).ublock_attn_forward(self, x)
 
 
 class UNetResidualBlock(nn.Module):
@@ -427,7 +427,7 @@ class UNetResidualBlock(nn.Module):
 
     def forward(self, x, t, c=None):
         _require_eval(self, "UNetResidualBlock.forward")
-        return get_engine(x.device, self.precision or "bf16").ublock_res_forward(self, x, t, c)
+        return get_engine(x.device, self.precision).ublock_res_forward(self, x, t, c)
 
 
 class SwitchSequential(nn.Sequential):

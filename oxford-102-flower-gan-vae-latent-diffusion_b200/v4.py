@@ -58,7 +58,7 @@ class SimpleUNet(nn.Module):
 
     def engine(self, device=None, n_t=None):
         device = device if device is not None else self.out_conv.weight.device
-        eng = get_engine(device, self.precision or "bf16")
+        eng = get_engine(device, self.precision)
         eng.pack_pix(self, max(self.max_timesteps, n_t or 0))
         return eng
 

@@ -42,21 +42,38 @@ for B in [int(b) for b in a.batches.split(",")]:
     eng.check_device_flags()
     print("B %4d  steps %d  %.3f ms  -> %.2f us/step  finite %s" % (B, a.steps, best, best * 1e3 / a.steps, bool(torch.isfinite(x).all())))
 
-# ---- per-CTA timeline of one reverse step (cluster 0)
+# ---- per-CTA timeline of one reverse step (cluster 0); needs an LDM_CHAIN_TRACE=1 build
 import ctypes
 import numpy as np
 from ldm_b200 import _lib
 L = _lib.lib()
 B = int(os.environ.get("TRACE_B", "48"))
+RANKS = [int(r) for r in os.environ.get("TRACE_RANKS", "0,1,4,12").split(",")]
+TRACKS, LEN, CS = 5, 96, 16
+TAG = {1: "iter", 2: "pre-acc-wait", 3: "acc-ready", 4: "acc-loaded(+partner)", 5: "dual-done", 6: "published-u", 7: "stats-u-in", 11: "stats-f-in",
+       8: "operand-written", 9: "arrive-sent", 10: "handover-done", 20: "W-first-issued", 21: "W-last-issued", 30: "X-handover-seen", 31: "X-fenced",
+       32: "X-first-issued", 33: "X-all-issued", 40: "MMA-first", 42: "MMA-half", 41: "MMA-all-issued"}
+NAME = ["h", "u", "W", "X", "M"]
 c = (torch.arange(B) % 102).to(dev)
 x = eng.randn(B, 256, 1, 0, 1000)
 _lib.check(L.ldm_debug_chain_trace(eng.ctx, 20, None, 0))
 eng.sample(x, 999, 1000 - 40, c, seed=3, use_graph=False)
-buf = np.zeros((16, 2, 64), dtype=np.int64)
+buf = np.zeros((CS, TRACKS, LEN), dtype=np.int64)
 _lib.check(L.ldm_debug_chain_trace(eng.ctx, 0, buf.ctypes.data_as(ctypes.c_void_p), buf.size))
 _lib.check(L.ldm_debug_chain_trace(eng.ctx, -1, None, 0))
-for r in range(16):
-    for w in range(2):
-        row = buf[r][w][buf[r][w] != 0]
-        if len(row) > 1:
-            print("rank %2d %s n=%2d  total %7d cyc | deltas:" % (r, "hu"[w], len(row), row[-1] - row[0]), " ".join(str(int(v)) for v in np.diff(row)))
+MASK = (1 << 52) - 1
+for r in RANKS:
+    ev = []
+    for w in range(TRACKS):
+        for v in buf[r][w]:
+            if v != 0:
+                ev.append((int(v) & MASK, w, (int(v) >> 52) & 15, (int(v) >> 56) & 255))
+    if not ev:
+        continue
+    ev.sort()
+    t0 = min(e[0] for e in ev if e[1] == 0) if any(e[1] == 0 for e in ev) else ev[0][0]
+    print("---- rank %d: %d events, step = %d cycles" % (r, len(ev), max(e[0] for e in ev if e[1] < 2) - t0))
+    last = {}
+    for t, w, p, tag in ev:
+        print("  %7d  (+%5d)  %s  p%d  %s" % (t - t0, t - last.get(w, t), NAME[w], p, TAG.get(tag, str(tag))))
+        last[w] = t
