@@ -145,6 +145,107 @@ __global__ void __launch_bounds__(32, 1) pingpong_kernel(int mode, int reps, int
   cluster_sync();
 }
 
+
+// ------------------------------------------------------------------------------------------- 4. tcgen05.mma operand paths
+// mode 0: A and B from shared memory (SS); mode 1: A from tensor memory (TS), B from shared memory; mode 2: tcgen05.cp only
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t a) {
+  uint64_t d = 0;
+  d |= (uint64_t)((a & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t idesc_bf16(int M, int N) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d), "l"(a), "l"(b), "r"(id), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t id, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d), "r"(a), "l"(b), "r"(id), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// element (r, k) of a K-major 128B-swizzled [rows x 64] bf16 tile
+__device__ __forceinline__ uint32_t sw128_off(int r, int k) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((k * 2) >> 4) ^ (r & 7)) << 4) + ((k * 2) & 15));
+}
+__global__ void __launch_bounds__(128, 1) mma_kernel(int mode, int N, int reps, long long* out, float* dout) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = base;             // A tile: 128 x 64 bf16
+  uint8_t* sb = base + 16384;     // B tile: N x 64 bf16 (N <= 256)
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tslot;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 128 * 64; i += blockDim.x) {
+    const int r = i / 64, k = i % 64;
+    *reinterpret_cast<__nv_bfloat16*>(sa + sw128_off(r, k)) = __float2bfloat16((float)(((r * 3 + k * 5) % 7) - 3));
+  }
+  for (int i = threadIdx.x; i < 256 * 64; i += blockDim.x) {
+    const int r = i / 64, k = i % 64;
+    *reinterpret_cast<__nv_bfloat16*>(sb + sw128_off(r, k)) = __float2bfloat16((float)(((r * 2 + k) % 5) - 2));
+  }
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tslot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tm = tslot;
+  const uint32_t id = idesc_bf16(128, N);
+  const uint64_t da = desc_sw128(smem_u32(sa)), db = desc_sw128(smem_u32(sb));
+  const uint32_t acc_ss = tm, acc_ts = tm + 256, wtm = tm + 480;   // 32 columns of A in TMEM
+  uint32_t par = 0;
+  if (threadIdx.x == 0) {
+    // ---- correctness: D1 = SS over 4 k-steps; A -> TMEM by tcgen05.cp; D2 = TS over 4 k-steps
+    for (int k = 0; k < 4; ++k) mma_ss(acc_ss, da + 2 * k, db + 2 * k, id, k != 0);
+    for (int k = 0; k < 4; ++k) cp_128x256b(wtm + 8 * k, da + 2 * k);
+    for (int k = 0; k < 4; ++k) mma_ts(acc_ts, wtm + 8 * k, db + 2 * k, id, k != 0);
+    commit(&bar);
+    mbar_wait(&bar, par); par ^= 1;
+    // ---- timing
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      if (mode == 0) { for (int k = 0; k < 4; ++k) mma_ss(acc_ss, da + 2 * k, db + 2 * k, id, 1); }
+      else if (mode == 1) { for (int k = 0; k < 4; ++k) mma_ts(acc_ts, wtm + 8 * k, db + 2 * k, id, 1); }
+      else if (mode == 2) { for (int k = 0; k < 4; ++k) cp_128x256b(wtm + 8 * k, da + 2 * k); }
+      else { for (int k = 0; k < 4; ++k) cp_128x256b(wtm + 8 * k, da + 2 * k); for (int k = 0; k < 4; ++k) mma_ts(acc_ts, wtm + 8 * k, db + 2 * k, id, 1); }
+    }
+    const long long t1 = clock64();
+    commit(&bar);
+    mbar_wait(&bar, par); par ^= 1;
+    out[0] = clock64() - t0;
+    out[1] = t1 - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (mode == 0 && dout) {   // dump both results of the correctness pass (first N columns): thread = lane (row)
+    const uint32_t lane_addr = tm + ((uint32_t)(warp * 32) << 16);
+    for (int c = 0; c < N; c += 8) {
+      uint32_t v[8], w[8];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(lane_addr + c));
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(lane_addr + 256 + c));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int i = 0; i < 8; ++i) {
+        dout[(size_t)threadIdx.x * 256 + c + i] = __uint_as_float(v[i]);
+        dout[(size_t)(128 + threadIdx.x) * 256 + c + i] = __uint_as_float(w[i]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm) : "memory");
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
@@ -230,6 +331,36 @@ int main() {
         printf("pingpong %s rank 0 <-> %2d: %.0f cyc round trip (%.0f one way)\n", mode == 0 ? "st.async+complete_tx" : "remote mbarrier arrive", peer,
                (double)h[0] / reps, (double)h[0] / reps / 2);
       }
+  }
+  // ---- 4. tcgen05.mma: operands from shared memory vs A from tensor memory
+  {
+    CK(cudaFuncSetAttribute(mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    float* dout;
+    CK(cudaMalloc(&dout, sizeof(float) * 256 * 256));
+    std::vector<float> hd(256 * 256);
+    for (int N : {48, 32, 64, 128, 256}) {
+      CK(cudaMemset(dout, 0, sizeof(float) * 256 * 256));
+      mma_kernel<<<1, 128, 16384 + 32768 + 1024>>>(0, N, 64, out, dout);
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(hd.data(), dout, sizeof(float) * 256 * 256, cudaMemcpyDeviceToHost));
+      int bad_ss = 0, bad_ts = 0;
+      for (int r = 0; r < 128; ++r)
+        for (int j = 0; j < N; ++j) {
+          float ref = 0.f;
+          for (int k = 0; k < 64; ++k) ref += (float)(((r * 3 + k * 5) % 7) - 3) * (float)(((j * 2 + k) % 5) - 2);
+          if (hd[(size_t)r * 256 + j] != ref) bad_ss++;
+          if (hd[(size_t)(128 + r) * 256 + j] != ref) bad_ts++;
+        }
+      printf("mma N=%3d correctness: SS mismatches %d, cp + TS mismatches %d (of %d)\n", N, bad_ss, bad_ts, 128 * N);
+      for (int mode = 0; mode < 4; ++mode) {
+        const int reps = 64;
+        mma_kernel<<<1, 128, 16384 + 32768 + 1024>>>(mode, N, reps, out, nullptr);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(h.data(), out, sizeof(long long) * 2, cudaMemcpyDeviceToHost));
+        const char* nm[4] = {"SS mma", "TS mma (A in TMEM)", "tcgen05.cp 128x256b", "cp + TS mma"};
+        printf("mma N=%3d %-22s: %.1f cyc per K=16 step (issue alone %.1f)\n", N, nm[mode], (double)h[0] / (reps * 4), (double)h[1] / (reps * 4));
+      }
+    }
   }
   return 0;
 }
