@@ -208,9 +208,10 @@ LDM_API int ldm_unet_forward(ldm_ctx* ctx, const float* x_dev, const int64_t* t_
 
 /* The posterior update of p_sample alone (v2:584-592) for a given eps:
  *   x <- (x - (1-alpha_t)/sqrt(1-alpha_bar_t) * eps) / sqrt(alpha_t) [+ sqrt(beta_t) * z if t > 0]
- * z = noise_dev if non-NULL, else Philox(seed; sample_offset + row, t) generated in-kernel. */
+ * z = noise_dev if non-NULL, else Philox(seed; sample_offset + row, t) generated in-kernel.
+ * x, eps (and noise): (batch, dim) fp32 row-major, dim a multiple of 4. */
 LDM_API int ldm_ddpm_step(ldm_ctx* ctx, float* x_inout_dev, const float* eps_dev, int t,
-                  const float* noise_dev, uint64_t seed, uint64_t sample_offset, int batch,
+                  const float* noise_dev, uint64_t seed, uint64_t sample_offset, int batch, int dim,
                   void* stream);
 
 /* Standard normals from the in-kernel Philox stream (the x_T draw of v2:595 uses step = n_steps). */
@@ -266,6 +267,8 @@ LDM_API int ldm_ublock_res_pack(ldm_ctx* ctx, const ldm_ublock_res_weights* w, i
 LDM_API int ldm_ublock_res_forward(ldm_ctx* ctx, int handle, const float* x_dev, const float* t_dev, const float* c_dev_or_null,
                            float* out_dev, int batch, int H, int W, void* stream);
 LDM_API int ldm_ublock_attn_pack(ldm_ctx* ctx, const ldm_ublock_attn_weights* w, int* handle_out, void* stream);
+/* Release one packed block (device weights + workspace); synchronises the device first.  The handle may be reused by a later pack. */
+LDM_API int ldm_ublock_free(ldm_ctx* ctx, int handle);
 LDM_API int ldm_ublock_attn_forward(ldm_ctx* ctx, int handle, const float* x_dev, float* out_dev, int batch, int H, int W,
                             void* stream);
 

@@ -4,7 +4,7 @@ ynyeh0221/Oxford-102-Flower-GAN-VAE-latent-diffusion (v2/model_train_test.py).
 The directory name carries hyphens (it is the name the build contract fixes), so import it through the
 shim at the repository root:  `import ldm_b200`.
 """
-from .engine import default_precision, get_engine, set_default_precision   # noqa: F401
+from .engine import default_precision, get_engine, invalidate, set_default_precision   # noqa: F401
 from .modules import (CALayer, ClassEmbedding, ConditionalDenoiseDiffusion, ConditionalUNet, Decoder, Encoder,  # noqa: F401
                       LayerNorm2d, ResidualBlock, SimpleAutoencoder, SpatialAttention, SwitchSequential, Swish, TimeEmbedding,
                       UNetAttentionBlock, UNetResidualBlock,
@@ -18,4 +18,4 @@ from ._lib import LIB_PATH, LdmError                                        # no
 __all__ = ["ConditionalUNet", "ConditionalDenoiseDiffusion", "SimpleAutoencoder", "Decoder", "Encoder",
            "TimeEmbedding", "ClassEmbedding", "ResidualBlock", "CALayer", "SpatialAttention", "LayerNorm2d", "Swish",
            "UNetResidualBlock", "UNetAttentionBlock", "SwitchSequential", "generate_class_samples", "generate_sharded", "shard_bounds", "init_weights", "load_autoencoder_checkpoint",
-           "get_engine", "set_default_precision", "default_precision", "LdmError", "LIB_PATH"]
+           "get_engine", "invalidate", "set_default_precision", "default_precision", "LdmError", "LIB_PATH"]

@@ -104,7 +104,7 @@ PROTOTYPES = {
     "ldm_unet3_pack": (ctypes.c_int, [_vp, ctypes.POINTER(Unet3Weights), _vp]),
     "ldm_unet3_set_conditions": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, _vp]),
     "ldm_unet_forward": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int, _vp]),
-    "ldm_ddpm_step": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, _vp]),
+    "ldm_ddpm_step": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, _vp]),
     "ldm_randn": (ctypes.c_int, [_vp, _vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
     "ldm_sample": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_uint64, ctypes.c_uint64,
                                   ctypes.c_int, ctypes.c_int, _vp]),
@@ -118,6 +118,7 @@ PROTOTYPES = {
     "ldm_ublock_res_pack": (ctypes.c_int, [_vp, ctypes.POINTER(UBlockResWeights), ctypes.POINTER(ctypes.c_int), _vp]),
     "ldm_ublock_res_forward": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
     "ldm_ublock_attn_pack": (ctypes.c_int, [_vp, ctypes.POINTER(UBlockAttnWeights), ctypes.POINTER(ctypes.c_int), _vp]),
+    "ldm_ublock_free": (ctypes.c_int, [_vp, ctypes.c_int]),
     "ldm_ublock_attn_forward": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
     "ldm_kernel_launch_count": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64)]),
     "ldm_get_info": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]),

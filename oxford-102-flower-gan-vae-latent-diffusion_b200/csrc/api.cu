@@ -647,14 +647,13 @@ extern "C" LDM_API int ldm_unet_forward(ldm_ctx* ctx, const float* x_dev, const 
 }
 
 extern "C" LDM_API int ldm_ddpm_step(ldm_ctx* ctx, float* x, const float* eps, int t, const float* noise, uint64_t seed,
-                             uint64_t sample_offset, int batch, void* stream) {
-  LDM_CHECK(ctx && x && eps && batch > 0, "ldm_ddpm_step: bad arguments");
+                             uint64_t sample_offset, int batch, int dim, void* stream) {
+  LDM_CHECK(ctx && x && eps && batch > 0 && dim > 0 && dim % 4 == 0, "ldm_ddpm_step: bad arguments (batch %d, dim %d: a positive multiple of 4)", batch, dim);
   LDM_CHECK(ctx->n_steps > 0, "ldm_ddpm_step: schedule not set");
   LDM_CHECK(t >= 0 && t < ctx->n_steps, "ldm_ddpm_step: t = %d outside [0, %d)", t, ctx->n_steps);
   LDM_CUDA(cudaSetDevice(ctx->device));
-  const int d = ctx->unet.packed ? ctx->unet.latent : 256;
   return launch_ddpm_update(ctx, x, eps, ctx->c2[t], ctx->sqrt_alpha[t], ctx->sigma[t], noise, seed, sample_offset, t,
-                            batch, d, (cudaStream_t)stream);
+                            batch, dim, (cudaStream_t)stream);
 }
 
 extern "C" LDM_API int ldm_randn(ldm_ctx* ctx, float* out, uint64_t seed, uint64_t sample_offset, int step, int batch, int dim,

@@ -2,29 +2,40 @@
 //
 //   ConditionalDenoiseDiffusion.sample / p_sample (v2:580-598) calling ConditionalUNet.forward (v2:535-561)
 //
-// Work decomposition.  Samples are independent, so a thread-block CLUSTER of 16 CTAs owns 32
-// batch rows for the WHOLE chain: all T steps run inside one launch and nothing ever crosses a cluster, so there
-// is no grid-wide synchronisation and no kernel boundary on the dependency path.  A step is a sequence of
-// "phases", one folded dense contraction each (api.cu folds every Linear that sits between two LayerNorms):
+// Work decomposition.  Samples are independent, so a thread-block CLUSTER of 16 CTAs owns NB = 16 NW
+// batch rows (32 / 48 / 64) for the WHOLE chain: all T steps run inside one launch and nothing ever crosses a cluster,
+// so there is no grid-wide synchronisation and no kernel boundary on the dependency path.  A step is FIVE "phases", one
+// folded dense contraction each (chain_pack below folds every Linear that sits between two non-linearities):
 //
-//   phase 0          x            -> [h_0 | u_0]            u_j = Linear_b,j(h_j) comes out of the SAME GEMM as h_j
-//   phase j = 1..S-1 [h2 | n]     -> [h_j | u_j]            h2 = swish(LN_a(u)) + h ; n = LN_b(h2)   (v2:546-553)
-//   phase S          [h2 | n]     -> h_S -> LN_f            (v2:554-559)
-//   phase S+1        [LN_f | x]   -> eps -> x_{t-1}         (v2:560-561, 584-592; Philox noise generated here)
+//   phase 0 (MERGED)  [x~ | -c_b LN_f(h) | -c_b x]  -> [h_0 | u_0] of the NEXT forward, and eps of the previous one
+//                                                       (eps only feeds the fp32 posterior update, off the critical path)
+//   phase j = 1..3    h2_{j-1} (raw)                 -> [h_j | u_j]       two accumulators W1 h2, W2 h2: LayerNorm_b (v2:549) is
+//                                                       applied AFTER the contraction, out = acc1 + r (acc2 - mu q)
+//   phase 4 (FINAL_LN) h2_3 (raw)                    -> h_S -> -c_b LN_f(h_S + T_f[t] + C_f[c])                 (v2:554-559)
 //
-// Inside a phase the OUTPUT FEATURES are split over the CTAs of the cluster in 128-row tiles (UMMA M = 128 rows
-// of the weight, UMMA N = the 32 batch rows), accumulators in TMEM.  Weight tiles stream from L2 through a TMA
-// ring that never waits for a phase boundary (weights do not depend on activations); the 32 x K bf16 operand is
-// exchanged through global memory (it stays in L2), copied by the epilogue warps into the 128-byte-swizzled
-// K-major layout the UMMA shared-memory descriptor expects.  LayerNorm needs whole-row statistics: every warp
-// publishes per-row partial (mean, M2) pairs into the shared memory of its peers (DSMEM) and the partials are
-// merged with Chan's formula.  The cluster-wide rendezvous is an mbarrier in every CTA that the 16 CTAs
-// arrive on remotely (release/acquire at cluster scope): only the epilogue warps take part, so the TMA and
-// MMA warps keep running ahead.
+//   u_j = Linear_b,j(h_j) comes out of the SAME contraction as h_j; h2 = swish(LN_a(u)) + h (v2:546-548) is the epilogue.
 //
-//   warp 0    : TMA producer of weight tiles (all steps, all phases of this CTA, 5-stage ring)
-//   warp 1    : TMEM allocator + tcgen05.mma issuer
-//   warps 2-5 : operand copy, epilogue (tables, LayerNorm, Swish, residual, DDPM update), cluster rendezvous
+// Inside a phase the OUTPUT FEATURES are split over the CTAs in 128-row weight tiles (UMMA M = 128 weight rows, N = NB
+// batch rows, fp32 accumulators in TMEM); phases with few tiles and a long reduction give each accumulator / K half to its
+// own CTA ("units", ks = 2) and the helper ships its accumulator to the tile owner with st.async.
+//
+// Data movement.  Weights (11 MB bf16, L2 resident) stream through a ring of 32 KiB slots (two tiles = 8 MMAs per slot) that
+// runs ahead of the phases.  The NB x K bf16 operand of a phase is written to global memory by the producing CTAs, handed
+// over with one release / acquire round on a cluster mbarrier (16 remote arrives per CTA), and TMA-loaded into an operand
+// ring of 8 k-block slots: every k-block of the unit is requested the moment the hand-over is through.  LayerNorm needs
+// whole-row statistics: per-row (mean, M2) partials travel as 8-byte st.async into the peers' shared memory (completion on
+// a transaction mbarrier) and are merged with Chan's formula; the statistics of h2 travel in the BACKGROUND to the next
+// phase's tile owners.  Measured limits that shape all this (tools/ubench.cu): TMA inbound 51.7 B/clk per
+// SM whatever the grid, DSMEM bulk copies 15.5 B/clk per SM (so operands cannot be broadcast through DSMEM), one
+// tcgen05.mma of M = 128, N <= 128 every 74 clocks whether A comes from shared memory or from TMEM.
+//
+//   warp 0    : TMA producer of weight tiles (elected thread; per-launch unit plans, no per-slot address arithmetic)
+//   warp 1    : operand producer: waits for the phase hand-over, requests the unit's k-blocks
+//   warp 2    : TMEM allocator + tcgen05.mma issuer
+//   warp 3    : set-up (phase table and unit plans into shared memory)
+//   warps 4.. : 4 NW epilogue warps: tables, LayerNorm, Swish, residual, statistics exchange, operand stores, hand-over,
+//               posterior update (eps owners)
+// Every wait is a hardware-suspended mbarrier try_wait, bounded by a clock and abortable by any CTA of the cluster.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>

@@ -1,5 +1,6 @@
 // Philox4x32-10 + Box-Muller: device side of the noise stream specified in oracle/philox.py
-// (tests/test_gpu_philox.py checks this file against that spec).
+// (tests/test_philox_spec.py pins the spec with known answers; tests/test_gpu_parity.py compares the in-kernel draws of
+// ldm_randn / the chain with it).
 //   key = (seed lo, seed hi); counter = (quad, sample lo, step, sample hi)
 //   r0..r3 -> u(r) = ((r >> 8) + 0.5) * 2^-24 ; (z0, z1) = sqrt(-2 ln u(r0)) (cos, sin)(2 pi u(r1)), same for (r2, r3)
 #pragma once
@@ -19,7 +20,9 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 }
 
 __device__ __forceinline__ float philox_u01(uint32_t r) {
-  return ((float)(r >> 8) + 0.5f) * 5.9604644775390625e-08f;  // 2^-24; exact in fp32
+  // (k + 0.5) 2^-24 needs 25 significant bits once k = r >> 8 reaches 2^23: the add then rounds to even (one fp32 rounding,
+  // at most 2^-25 away from the float64 spec of oracle/philox.py; u may reach 1.0f, for which the radius is 0)
+  return ((float)(r >> 8) + 0.5f) * 5.9604644775390625e-08f;
 }
 
 // four standard normals for elements [4*quad, 4*quad+4) of global sample `sample` at `step`

@@ -236,12 +236,33 @@ int check_common(ldm_ctx* ctx, int B, int H, int W) {
 
 }  // namespace
 
+static void ublock_release(UBlock& u) {
+  for (void* p : u.ws) cudaFree(p);
+  for (void* p : u.allocs) cudaFree(p);
+  u = UBlock();      // type 0: a free slot
+}
+
 void ublock_free_all(ldm_ctx* ctx) {
-  for (UBlock& u : ctx->ublocks) {
-    for (void* p : u.ws) cudaFree(p);
-    for (void* p : u.allocs) cudaFree(p);
-  }
+  for (UBlock& u : ctx->ublocks) ublock_release(u);
   ctx->ublocks.clear();
+}
+
+// a finished block goes into the first free slot (handles of released blocks are reused), or at the end
+static int ublock_store(ldm_ctx* ctx, UBlock& u) {
+  for (size_t i = 0; i < ctx->ublocks.size(); ++i)
+    if (ctx->ublocks[i].type == 0) { ctx->ublocks[i] = u; return (int)i; }
+  ctx->ublocks.push_back(u);
+  return (int)ctx->ublocks.size() - 1;
+}
+
+// Release the packed weights and the workspace of one conv U-Net block; its handle may be handed out again.
+extern "C" LDM_API int ldm_ublock_free(ldm_ctx* ctx, int handle) {
+  LDM_CHECK(ctx, "ldm_ublock_free: null context");
+  LDM_CHECK(handle >= 0 && handle < (int)ctx->ublocks.size() && ctx->ublocks[handle].type != 0, "ldm_ublock_free: bad handle %d", handle);
+  LDM_CUDA(cudaSetDevice(ctx->device));
+  LDM_CUDA(cudaDeviceSynchronize());      // no kernel of this context may still read the block
+  ublock_release(ctx->ublocks[handle]);
+  return 0;
 }
 
 extern "C" LDM_API int ldm_ublock_res_pack(ldm_ctx* ctx, const ldm_ublock_res_weights* w, int* handle_out, void* stream) {
@@ -251,10 +272,10 @@ extern "C" LDM_API int ldm_ublock_res_pack(ldm_ctx* ctx, const ldm_ublock_res_we
   cudaStream_t st = (cudaStream_t)stream;
   LDM_CUDA(cudaSetDevice(ctx->device));
   if (ctx->precision == LDM_PRECISION_BF16) LDM_TRY(tc_init(ctx));
-  ctx->ublocks.emplace_back();
-  UBlock& u = ctx->ublocks.back();
+  UBlock u;
   u.type = 1; u.cin = w->in_channels; u.cout = w->out_channels; u.dt = w->d_time;
   auto& P = u.allocs;
+  auto body = [&]() -> int {
   LDM_TRY(own(ctx, P, w->norm1_w, u.cin, &u.n1w, st));
   LDM_TRY(own(ctx, P, w->norm1_b, u.cin, &u.n1b, st));
   LDM_TRY(own(ctx, P, w->norm2_w, u.cout, &u.n2w, st));
@@ -270,7 +291,11 @@ extern "C" LDM_API int ldm_ublock_res_pack(ldm_ctx* ctx, const ldm_ublock_res_we
     LDM_TRY(pack_dense(ctx, P, u.d1, w->res_w, w->res_b, u.cout, u.cin, st));
   }
   LDM_CUDA(cudaStreamSynchronize(st));
-  *handle_out = (int)ctx->ublocks.size() - 1;
+  return 0;
+  };
+  const int rc = body();
+  if (rc != 0) { cudaStreamSynchronize(st); ublock_release(u); return rc; }   // a pack that fails midway leaves nothing behind
+  *handle_out = ublock_store(ctx, u);
   return 0;
 }
 
@@ -348,10 +373,10 @@ extern "C" LDM_API int ldm_ublock_attn_pack(ldm_ctx* ctx, const ldm_ublock_attn_
   cudaStream_t st = (cudaStream_t)stream;
   LDM_CUDA(cudaSetDevice(ctx->device));
   if (ctx->precision == LDM_PRECISION_BF16) LDM_TRY(tc_init(ctx));
-  ctx->ublocks.emplace_back();
-  UBlock& u = ctx->ublocks.back();
+  UBlock u;
   u.type = 2; u.cin = u.cout = w->channels; u.heads = w->num_heads;
   auto& P = u.allocs;
+  auto body = [&]() -> int {
   LDM_TRY(own(ctx, P, w->norm_w, u.cin, &u.n1w, st));
   LDM_TRY(own(ctx, P, w->norm_b, u.cin, &u.n1b, st));
   LDM_TRY(pack_dense(ctx, P, u.d1, w->qkv_w, w->qkv_b, 3 * u.cin, u.cin, st));
@@ -362,7 +387,11 @@ extern "C" LDM_API int ldm_ublock_attn_pack(ldm_ctx* ctx, const ldm_ublock_attn_
     LDM_LAUNCHED(ctx);
   }
   LDM_CUDA(cudaStreamSynchronize(st));
-  *handle_out = (int)ctx->ublocks.size() - 1;
+  return 0;
+  };
+  const int rc = body();
+  if (rc != 0) { cudaStreamSynchronize(st); ublock_release(u); return rc; }
+  *handle_out = ublock_store(ctx, u);
   return 0;
 }
 

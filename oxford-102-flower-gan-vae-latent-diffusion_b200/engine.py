@@ -7,6 +7,7 @@ import ctypes
 import itertools
 import os
 import threading
+import weakref
 
 import torch
 
@@ -62,22 +63,35 @@ def _f32(t, device):
 
 
 _serials = itertools.count(1)
+_serial_of = weakref.WeakKeyDictionary()      # module object -> serial; not an attribute, so copy.deepcopy / pickle do not carry it
 
 
 def _module_serial(module):
     """A process-unique number per module OBJECT.  id(module) is not enough: CPython reuses the address of a collected
     module for the next one, and torch's caching allocator hands the same blocks to its parameters, so (id, versions,
     data_ptrs) of a NEW module can equal those of a dead one whose packed weights are still resident."""
-    s = module.__dict__.get("_ldm_b200_serial")
+    s = _serial_of.get(module)
     if s is None:
-        s = next(_serials)
-        object.__setattr__(module, "_ldm_b200_serial", s)
+        s = _serial_of[module] = next(_serials)
     return s
 
 
 def _state_key(module, extra=()):
+    """What a pack is valid for: the module object, and the version counter and storage of every parameter.  In-place
+    edits through autograd-visible ops (`p.add_()`, `p.copy_()`, optimizer steps, load_state_dict) bump `_version` and
+    re-pack on the next call.  Edits made through `p.data` (`p.data.mul_()`, EMA updates written that way) and edits of
+    BUFFERS do NOT change this key: call `Engine.invalidate(module)` (or `ldm_b200.invalidate(module)`) after them."""
     ps = list(module.parameters())
     return (_module_serial(module), tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps)) + tuple(extra)
+
+
+def invalidate(module=None):
+    """Forget the packed copy of `module` (or of everything) in every engine: the next call re-packs from the module's
+    current tensors.  Needed only after weight edits that bypass the version counter (see _state_key)."""
+    with _lock:
+        engines = list(_engines.values())
+    for eng in engines:
+        eng.invalidate(module)
 
 
 class Engine:
@@ -91,7 +105,7 @@ class Engine:
         self._sched_key = None
         self._cls_key = None
         self._pix_key = None
-        self._ublocks = {}      # id(module) -> (state key, handle)
+        self._ublocks = {}      # module serial -> (state key, handle)
 
     def __del__(self):
         try:
@@ -99,6 +113,18 @@ class Engine:
                 lib().ldm_ctx_destroy(self.ctx)
         except Exception:
             pass
+
+    def invalidate(self, module=None):
+        """Drop the packed state of `module` (None: of every module) so that its next use re-packs."""
+        ser = None if module is None else _module_serial(module)
+        for attr in ("_unet_key", "_dec_key", "_pix_key"):
+            k = getattr(self, attr)
+            if k is not None and (ser is None or k[0] == ser):
+                setattr(self, attr, None)
+                if attr == "_unet_key":
+                    self._cls_key = None
+        for s in [s for s in self._ublocks if ser is None or s == ser]:
+            self._ublock_release(s)
 
     # ------------------------------------------------------------------ helpers
     def stream(self):
@@ -274,8 +300,15 @@ class Engine:
         return out
 
     def ddpm_step(self, x, eps, t, noise=None, seed=0, sample_offset=0):
+        """In-place posterior update of x (B, D) for a given eps (v2:584-592)."""
+        for name, v in (("x", x), ("eps", eps), ("noise", noise)):
+            if v is None:
+                continue
+            if not (v.is_cuda and v.device == self.device and v.dtype == torch.float32 and v.is_contiguous() and v.dim() == 2
+                    and tuple(v.shape) == tuple(x.shape)):
+                raise ValueError("ddpm_step: %s must be a contiguous fp32 (B, D) tensor on %s with the shape of x" % (name, self.device))
         check(lib().ldm_ddpm_step(self.ctx, _ptr(x), _ptr(eps), int(t), _ptr(noise) if noise is not None else None,
-                                  seed, sample_offset, x.shape[0], self.stream()), "ldm_ddpm_step")
+                                  seed, sample_offset, x.shape[0], x.shape[1], self.stream()), "ldm_ddpm_step")
         return x
 
     def randn(self, batch, dim, seed, sample_offset, step):
@@ -344,12 +377,24 @@ class Engine:
         return x
 
     # ------------------------------------------------------------------ conv U-Net blocks (v2:434-486)
+    def _ublock_release(self, serial):
+        hit = self._ublocks.pop(serial, None)
+        if hit is not None and self.ctx:
+            lib().ldm_ublock_free(self.ctx, hit[1])       # best effort: the context frees whatever is left when it dies
+
     def _ublock(self, m, build):
-        key = _state_key(m)
-        hit = self._ublocks.get(_module_serial(m))
+        """Handle of the packed block of module `m`: re-packed (the old device copy released) when its weights changed,
+        released when the module is collected."""
+        key, ser = _state_key(m), _module_serial(m)
+        hit = self._ublocks.get(ser)
         if hit is None or hit[0] != key:
+            if hit is not None:
+                self._ublock_release(ser)
+            else:
+                me = weakref.ref(self)
+                weakref.finalize(m, lambda: me() is not None and me()._ublock_release(ser))
             hit = (key, build())
-            self._ublocks[_module_serial(m)] = hit
+            self._ublocks[ser] = hit
         return hit[1]
 
     def ublock_res_forward(self, m, x, t, c=None):

@@ -169,6 +169,8 @@ class ConditionalDenoiseDiffusion:
         x = xt.detach().to(device=eng.device, dtype=torch.float32).clone(memory_format=torch.contiguous_format)
         if noise is not None:
             noise = noise.reshape(1, *x.shape)
+        if c is not None and c.numel() and (int(c.min()) < 0 or int(c.max()) >= self.eps_model.num_classes):
+            raise IndexError("class label out of range [0, %d)" % self.eps_model.num_classes)     # what nn.Embedding raises
         eng.sample(x, ti, ti, c, noise=noise, seed=_fresh_seed() if seed is None else int(seed),
                    sample_offset=int(sample_offset), use_graph=False)
         return x

@@ -111,6 +111,7 @@ class ConditionalDenoiseDiffusion:
             noise = noise.reshape(1, *x.shape)
         eng.sample3(x, ti, ti, flower_label, color_label, noise=noise, seed=_fresh_seed() if seed is None else int(seed),
                     sample_offset=int(sample_offset), use_graph=False)
+        eng.check_device_flags(self.eps_model.num_classes)      # out-of-range labels raise here, not in a later unrelated call
         return x
 
     def sample(self, shape, device, flower_label, color_label, *, seed=None, sample_offset=0, x_T=None, noise=None,
@@ -120,6 +121,8 @@ class ConditionalDenoiseDiffusion:
         B, D = int(shape[0]), int(shape[1])
         if D != self.eps_model.latent_dim:
             raise ValueError("shape[1] must be latent_dim=%d" % self.eps_model.latent_dim)
+        if B == 0:
+            return torch.empty((0, D), device=device, dtype=torch.float32)
         eng = self._engine(device)
         seed = _fresh_seed() if seed is None else int(seed)
         if x_T is None:

@@ -149,3 +149,55 @@ def test_pack_cache_key_survives_object_address_reuse():
     with torch.no_grad():
         m.weight.add_(1.0)
     assert engine._state_key(m) != k0                      # in-place updates re-pack
+
+
+def test_default_precision_reaches_every_mirror(monkeypatch):
+    """set_default_precision() / LDM_B200_PRECISION select the engine of EVERY mirror whose `precision` was left unset
+    (v4.SimpleUNet and the conv U-Net blocks used to fall back to bf16 on their own)."""
+    import ldm_b200
+    from ldm_b200 import engine, modules, v4
+    seen = []
+
+    class Stop(Exception):
+        pass
+
+    def fake(device, precision=None):
+        seen.append(precision or engine.default_precision())
+        raise Stop
+
+    for mod in (modules, v4):
+        monkeypatch.setattr(mod, "get_engine", fake)
+    engine.set_default_precision("fp32")
+    try:
+        for call in (lambda: v4.SimpleUNet().eval().engine(torch.device("cuda", 0)),
+                     lambda: ldm_b200.UNetAttentionBlock(64).eval()(torch.zeros(1, 64, 4, 4, device="meta")),
+                     lambda: ldm_b200.UNetResidualBlock(64, 64).eval()(torch.zeros(1, 64, 4, 4, device="meta"), torch.zeros(1, 256)),
+                     lambda: v4.SimpleUNet(precision="bf16").eval().engine(torch.device("cuda", 0))):
+            with pytest.raises(Stop):
+                call()
+    finally:
+        engine.set_default_precision(None)
+    assert seen == ["fp32", "fp32", "fp32", "bf16"]
+
+
+def test_pack_serial_is_not_inherited_by_copies_and_invalidate_forgets():
+    import copy
+    from ldm_b200 import engine
+    m = torch.nn.Linear(4, 4)
+    k = engine._state_key(m)
+    assert "_ldm_b200_serial" not in m.__dict__                    # kept outside the module: deepcopy / pickle cannot carry it
+    m2 = copy.deepcopy(m)
+    assert engine._state_key(m2)[0] != k[0]
+    with torch.no_grad():
+        m.weight.data.mul_(2.0)                                    # an edit through .data does not bump the version counter ...
+    assert engine._state_key(m) == k
+
+    class E(engine.Engine):                                        # ... which is what invalidate() is for (no context needed here)
+        def __init__(self):
+            self.ctx = None
+            self._unet_key, self._dec_key, self._pix_key, self._cls_key, self._ublocks = k, ("other",), None, 1, {}
+    e = E()
+    e.invalidate(m)
+    assert e._unet_key is None and e._cls_key is None and e._dec_key == ("other",)
+    e.invalidate()
+    assert e._dec_key is None

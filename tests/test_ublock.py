@@ -108,3 +108,55 @@ def test_switch_sequential_and_long_sequences():
     want = R.unet_attention_block(sd_a, "", R.unet_residual_block(sd_r, "", x, t, c))
     got = seq(x.cuda(), t.cuda(), c.cuda()).cpu()
     assert R.max_rel(got, want) < EPS_TOL["bf16"], R.max_rel(got, want)
+
+
+@pytest.mark.gpu
+def test_block_handles_are_released_and_reused():
+    """Re-packs (changed weights, .data edits + invalidate, collected modules) release the previous device copy: the
+    context's handle table stays at the number of LIVE blocks instead of growing with every pack."""
+    import gc
+    import ldm_b200
+    from ldm_b200 import engine
+    sd = weights.make_state(weights.ublock_attn_spec(128), 47, "perturbed")
+    x = T(G["attn_128_x"]).cuda()
+    eng = engine.get_engine(torch.device("cuda", 0), "bf16")
+    eng.invalidate()
+    gc.collect()
+    base = len(eng._ublocks)
+    handles = set()
+    for i in range(6):
+        m = ldm_b200.UNetAttentionBlock(128, precision="bf16")
+        m.load_state_dict(sd, strict=True)
+        m = m.cuda().eval()
+        y0 = m(x)
+        assert R.max_rel(y0.cpu(), T(G["attn_128_y"])) < EPS_TOL["bf16"]
+        with torch.no_grad():
+            m.proj.weight.mul_(0.5)                                   # version bump: re-pack in place of the old handle
+        y1 = m(x)
+        assert not torch.equal(y0, y1)
+        m.proj.weight.data.mul_(2.0)                                  # .data edit: invisible until invalidate()
+        assert torch.equal(m(x), y1)
+        ldm_b200.invalidate(m)
+        assert R.max_rel(m(x).cpu(), T(G["attn_128_y"])) < EPS_TOL["bf16"]
+        handles.add(eng._ublocks[engine._module_serial(m)][1])
+        assert len(eng._ublocks) == base + 1
+        del m
+        gc.collect()
+        assert len(eng._ublocks) == base                              # the finalizer released the collected module's block
+    assert len(handles) <= 2, handles                                 # freed slots are handed out again
+
+
+@pytest.mark.gpu
+def test_ddpm_step_validates_its_operands():
+    import ldm_b200
+    from ldm_b200 import engine
+    eng = engine.get_engine(torch.device("cuda", 0), "fp32")
+    d = ldm_b200.ConditionalDenoiseDiffusion(ldm_b200.ConditionalUNet(precision="fp32").cuda().eval(), 1000, torch.device("cuda"))
+    eng.set_schedule(*d._host_schedule)
+    x, eps, z = torch.randn(5, 192, device="cuda"), torch.randn(5, 192, device="cuda"), torch.randn(5, 192, device="cuda")
+    want = R.ddpm_update(R.schedule(1000), x.cpu(), eps.cpu(), 321, z.cpu())
+    got = eng.ddpm_step(x.clone(), eps, 321, noise=z)                 # any row width (a multiple of 4), not only latent_dim
+    assert torch.equal(got.cpu(), want)
+    for bad in (eps[:, :100], eps.double(), eps.cpu(), eps.t().contiguous().t()):
+        with pytest.raises(ValueError):
+            eng.ddpm_step(x.clone(), bad, 321, noise=z)
