@@ -239,6 +239,10 @@ LDM_API int ldm_decode(ldm_ctx* ctx, const float* z_dev, float* img_out_dev, int
 LDM_API int ldm_generate_host(ldm_ctx* ctx, const int64_t* c_host, int batch, uint64_t seed,
                       uint64_t sample_offset, float* img_out_host, float* latents_out_host,
                       void* stream);
+/* The same for the v3 multi-conditional denoiser (v3:860-893 then decode): `flower_host`, `color_host` are batch int64
+ * labels each; the batch is ONE reference call (its rows are coupled through the cross-batch attention, v3:832). */
+LDM_API int ldm_generate3_host(ldm_ctx* ctx, const int64_t* flower_host, const int64_t* color_host, int batch, uint64_t seed,
+                       uint64_t sample_offset, float* img_out_host, float* latents_out_host, void* stream);
 
 /* ---- v4 / v5 pixel-space diffusion (bf16 = tcgen05 kernels, fp32 = strict CUDA-core path) ------------
  * ldm_pix_pack: repack SimpleUNet (v4:37-97) for the implicit-GEMM kernels and tabulate the per-stage time terms
@@ -276,11 +280,20 @@ LDM_API int ldm_ublock_attn_forward(ldm_ctx* ctx, int handle, const float* x_dev
 LDM_API int ldm_kernel_launch_count(ldm_ctx* ctx, uint64_t* out); /* kernels launched (graph nodes count per replay) */
 LDM_API int ldm_get_info(ldm_ctx* ctx, const char* key, double* out);
 
-/* Profiling aid for the persistent loop kernel: ldm_debug_chain_trace(ctx, step, NULL, 0) arms a per-CTA clock64()
- * timeline of reverse step `step` of the next ldm_sample (cluster 0 only; step < 0 switches it off);
- * ldm_debug_chain_trace(ctx, 0, out_host, n >= 16*64) synchronises and copies the stamps out: row = rank of the
- * CTA in its cluster, entries = stamps in program order (0 = unused). */
+/* Profiling aid for the persistent loop kernel (libraries built with LDM_CHAIN_TRACE): ldm_debug_chain_trace(ctx, step,
+ * NULL, 0) arms a clock64() timeline of reverse step `step` of the next ldm_sample (cluster 0 only; step < 0 switches it
+ * off); ldm_debug_chain_trace(ctx, 0, out_host, n >= 16 * 5 * 96) synchronises and copies the stamps out as
+ * [cluster rank][track][stamp]: tracks = two epilogue threads, weight producer, operand producer, MMA issuer;
+ * stamp = clock | phase << 52 | tag << 56, in program order (0 = unused).  tools/chain_sweep.py decodes it. */
 LDM_API int ldm_debug_chain_trace(ldm_ctx* ctx, int step, long long* out_host, int n);
+
+/* Per-launch device times of everything the context launches on `stream` (eager launches only: nothing is recorded
+ * while a graph is captured or replayed).  ldm_debug_ktrace(ctx, 1, stream, ...) starts a trace (CUDA event after every
+ * kernel launch); ldm_debug_ktrace(ctx, 0, NULL, names, names_cap, ms, n_cap, &n) stops it, synchronises and returns the
+ * n kernel names (newline separated, in launch order) and the milliseconds from the previous mark to the mark after
+ * each kernel.  This is how bench.py fills `roofline_kernels` (CUDA events, not a profiler). */
+LDM_API int ldm_debug_ktrace(ldm_ctx* ctx, int start, void* stream, char* names_out, int names_cap, float* ms_out, int n_cap,
+                     int* n_out);
 
 #ifdef __cplusplus
 }

@@ -111,6 +111,7 @@ PROTOTYPES = {
     "ldm_decoder_pack": (ctypes.c_int, [_vp, ctypes.POINTER(DecoderWeights), _vp]),
     "ldm_decode": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, _vp]),
     "ldm_generate_host": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, _vp, _vp, _vp]),
+    "ldm_generate3_host": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, _vp, _vp, _vp]),
     "ldm_pix_pack": (ctypes.c_int, [_vp, ctypes.POINTER(PixWeights), _vp]),
     "ldm_pix_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
     "ldm_pix_sample": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_uint64, ctypes.c_uint64,
@@ -123,6 +124,7 @@ PROTOTYPES = {
     "ldm_kernel_launch_count": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64)]),
     "ldm_get_info": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]),
     "ldm_debug_chain_trace": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int]),
+    "ldm_debug_ktrace": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_char_p, ctypes.c_int, _vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
 }
 
 _lib = None

@@ -134,6 +134,8 @@ extern "C" LDM_API int ldm_ctx_destroy(ldm_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   drop_graphs(ctx);
+  for (auto& m : ctx->kt_marks) cudaEventDestroy(m.second);
+  ctx->kt_marks.clear();
   free_pool(ctx->allocs);
   free_pool(ctx->ws_allocs);
   free_pool(ctx->dec_allocs);
@@ -786,6 +788,43 @@ extern "C" LDM_API int ldm_generate_host(ldm_ctx* ctx, const int64_t* c_host, in
   return 0;
 }
 
+// v3 (v3:860-893 + decode): host (flower, color) labels in, host images out, one call.  The 2 x batch labels are staged in
+// c_stage; the chain runs as one call of `batch` rows (the rows of a v3 call are coupled through the attention).
+extern "C" LDM_API int ldm_generate3_host(ldm_ctx* ctx, const int64_t* flower_host, const int64_t* color_host, int batch, uint64_t seed,
+                                          uint64_t sample_offset, float* img_out_host, float* latents_out_host, void* stream) {
+  LDM_CHECK(ctx && flower_host && color_host && img_out_host && batch > 0, "ldm_generate3_host: bad arguments");
+  LDM_CHECK(ctx->n_steps > 0 && ctx->unet.packed && ctx->unet.variant == 3 && ctx->dec.packed,
+            "ldm_generate3_host: schedule, v3 denoiser and decoder must be set first");
+  cudaStream_t st = (cudaStream_t)stream;
+  LDM_CUDA(cudaSetDevice(ctx->device));
+  LDM_TRY(ensure_workspace(ctx, batch));
+  if (2 * batch > ctx->host_cap) {
+    cudaDeviceSynchronize();
+    free_pool(ctx->stage_allocs);
+    LDM_TRY(ldm_alloc_t(ctx, ctx->stage_allocs, &ctx->c_stage, (size_t)2 * batch));
+    LDM_TRY(ldm_alloc_t(ctx, ctx->stage_allocs, &ctx->img_stage, (size_t)2 * batch * 3 * 64 * 64));
+    ctx->host_cap = 2 * batch;
+  }
+  LDM_CUDA(cudaMemcpyAsync(ctx->c_stage, flower_host, (size_t)batch * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  LDM_CUDA(cudaMemcpyAsync(ctx->c_stage + batch, color_host, (size_t)batch * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  LDM_TRY(ldm_unet3_set_conditions(ctx, ctx->c_stage, ctx->c_stage + batch, batch, st));
+  LDM_TRY(launch_randn(ctx, ctx->x_state, seed, sample_offset, ctx->n_steps, batch, ctx->unet.latent, st));   // v3:889
+  LDM_TRY(ldm_sample(ctx, ctx->x_state, ctx->n_steps - 1, 0, nullptr, seed, sample_offset, batch, 1, st));
+  LDM_TRY(decoder_run_impl(ctx, ctx->x_state, ctx->img_stage, batch, st));
+  LDM_CUDA(cudaMemcpyAsync(img_out_host, ctx->img_stage, (size_t)batch * 3 * 64 * 64 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (latents_out_host)
+    LDM_CUDA(cudaMemcpyAsync(latents_out_host, ctx->x_state, (size_t)batch * ctx->unet.latent * sizeof(float), cudaMemcpyDeviceToHost, st));
+  LDM_CUDA(cudaStreamSynchronize(st));
+  int flags = 0;
+  LDM_CUDA(cudaMemcpy(&flags, ctx->dev_flags, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flags & 1) {
+    cudaMemset(ctx->dev_flags, 0, sizeof(int));
+    ldm_set_error("ldm_generate3_host: flower / colour label out of range");
+    return -2;
+  }
+  return 0;
+}
+
 // -------------------------------------------------------------------------------------------------
 // introspection
 // -------------------------------------------------------------------------------------------------
@@ -815,6 +854,43 @@ extern "C" LDM_API int ldm_debug_chain_trace(ldm_ctx* ctx, int step, long long* 
   LDM_CUDA(cudaMemset(ctx->chain_trace, 0, sizeof(long long) * total));
   ctx->chain_trace_step = step;
   drop_graphs(ctx);
+  return 0;
+}
+
+extern "C" LDM_API int ldm_debug_ktrace(ldm_ctx* ctx, int start, void* stream, char* names_out, int names_cap, float* ms_out,
+                                        int n_cap, int* n_out) {
+  LDM_CHECK(ctx, "ldm_debug_ktrace: null context");
+  LDM_CUDA(cudaSetDevice(ctx->device));
+  auto drop = [&]() {
+    for (auto& m : ctx->kt_marks) cudaEventDestroy(m.second);
+    ctx->kt_marks.clear();
+  };
+  if (start) {
+    drop();
+    ctx->kt_stream = (cudaStream_t)stream;
+    ctx->kt_on = true;
+    ldm_kmark(ctx, "start");
+    return 0;
+  }
+  ctx->kt_on = false;
+  LDM_CHECK(names_out && ms_out && n_out && names_cap > 0 && n_cap > 0, "ldm_debug_ktrace: output buffers missing");
+  LDM_CHECK(!ctx->kt_marks.empty(), "ldm_debug_ktrace: no trace was started");
+  LDM_CUDA(cudaEventSynchronize(ctx->kt_marks.back().second));
+  int n = 0;
+  size_t pos = 0;
+  for (size_t i = 1; i < ctx->kt_marks.size() && n < n_cap; ++i) {
+    const std::string& nm = ctx->kt_marks[i].first;
+    if (pos + nm.size() + 2 > (size_t)names_cap) break;
+    float ms = 0.f;
+    LDM_CUDA(cudaEventElapsedTime(&ms, ctx->kt_marks[i - 1].second, ctx->kt_marks[i].second));
+    memcpy(names_out + pos, nm.data(), nm.size());
+    pos += nm.size();
+    names_out[pos++] = '\n';
+    ms_out[n++] = ms;
+  }
+  names_out[pos] = 0;
+  *n_out = n;
+  drop();
   return 0;
 }
 

@@ -74,6 +74,11 @@ template <int NW> struct Geo {
   static constexpr int kWSlots = kWSlotsFit < kMaxWSlots ? kWSlotsFit : kMaxWSlots;
   static constexpr size_t kSmemBytes = 1024 + (size_t)kWSlots * kWSlotBytes + kXRingBytes + kAuxBytes;
   static_assert(kWSlots >= 2, "weight ring too small");
+  // Per-sample additive terms (class-table rows; per-row timesteps of forward()): with 168 registers per thread (NW = 2)
+  // they are re-fetched from the L2-resident tables in every phase's preamble, which saves their TMEM read (the
+  // accumulator loads of an epilogue run at 64 B/clk per SM); at NW >= 3 (128 registers or fewer) holding 16 more values
+  // across the waits spills, and they stay parked in TMEM columns for the whole launch (measured: 38.5 vs 37.0 us / step)
+  static constexpr bool kCaddInTmem = NW >= 3;
 };
 
 struct ChainPhase {
@@ -92,7 +97,8 @@ struct ChainPhase {
   int xmap;            // index of the operand's tensor map (+ 1 on odd steps when xmap_alt)
   int xmap_alt;        // 1: the operand alternates between xmap and xmap + 1 with the step parity ([LN_f(h) | x])
   int xcol;            // first column of the operand inside that buffer
-  int cadd_col;        // TMEM column of this phase's per-sample additive term (-1: none)
+  int cadd_col;        // >= 0: the phase has a per-sample additive term (class table row; per-row timestep of forward()), parked at
+                       // this TMEM column when Geo::kCaddInTmem; -1: none
   int nst_tiles;       // MERGED: tiles [0, nst_tiles) are stage tiles, the rest finish eps
   int eps_kb0;         // MERGED: first k-block the eps tiles read (they skip the x~ block)
   const float* g0b;    // MERGED: G_0 . b_fin (tile order)
@@ -422,6 +428,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
   __shared__ int abort_flag;
   __shared__ ChainPhase sphase[LDM_CHAIN_MAX_PHASES];   // shared-memory copy: indexed constant-bank reads are slow
   __shared__ UnitPlan splan[LDM_CHAIN_MAX_PHASES];
+  __shared__ int scls[64], strow[64];                   // class / clamped per-row timestep of the cluster's rows (-1: no term)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = blockIdx.x;                 // gridDim.x == CS: rank in cluster
@@ -455,6 +462,12 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&P.ph[0]);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&sphase[0]);
     for (int i = lane; i < nw; i += 32) dst[i] = src[i];
+    for (int j = lane; j < NB; j += 32) {
+      const int r = row0 + j;
+      const bool ok = r < P.row_end;
+      scls[j] = ok && P.cls ? P.cls[r] : -1;
+      strow[j] = ok && !P.sample && P.t_len != 1 ? clamp_t(P.t_idx[r], P.n_t) : -1;
+    }
     __syncwarp();
     if (lane < NP) {
       const ChainPhase& ph = sphase[lane];
@@ -476,7 +489,6 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
   tc::fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
   cluster_sync_all();   // every CTA's barriers exist before any remote arrive / store
-
   if (warp == 0) {
     // ------------------------------------------------------------------ weight-tile producer (runs ahead of the phases)
     if (tc::elect_one()) {
@@ -689,9 +701,9 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
       __syncwarp();
     };
 
-    // ---- per-sample additive terms (class tables; per-sample timesteps of forward()) live in TMEM for the whole chain
-    {
-      const bool per_row_t = !P.sample && P.t_len != 1;
+    const bool per_row_t = !P.sample && P.t_len != 1;
+    if constexpr (G::kCaddInTmem) {
+      // ---- per-sample additive terms live in TMEM for the whole chain (Geo::kCaddInTmem)
       for (int p = 0; p < NP; ++p) {
         const ChainPhase& ph = sphase[p];
         Unit un;
@@ -700,12 +712,10 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
         float c[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int r = row0 + s0 + j;
+          const int ci = scls[s0 + j], ti = strow[s0 + j];
           float a = 0.f;
-          if (r < P.row_end) {
-            if (ph.tab_c && P.cls) a += __ldg(ph.tab_c + (size_t)P.cls[r] * ph.rows + grow);
-            if (ph.tab_t && per_row_t) a += __ldg(ph.tab_t + (size_t)clamp_t(P.t_idx[r], P.n_t) * ph.rows + grow);
-          }
+          if (ph.tab_c && ci >= 0) a += __ldg(ph.tab_c + (size_t)ci * ph.rows + grow);
+          if (ph.tab_t && per_row_t && ti >= 0) a += __ldg(ph.tab_t + (size_t)ti * ph.rows + grow);
           c[j] = a;
         }
         tmem_st16(lane_taddr + (uint32_t)(ph.cadd_col + s0), c);
@@ -777,6 +787,30 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
             if (ph.type == LDM_PH_MERGED) t_g = __ldg(ph.g0b + grow);
             if (ph.dual) t_q = __ldg(ph.q + grow);
           }
+          const bool has_c = ph.cadd_col >= 0 && !eps_tile;
+          float cadd[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) cadd[j] = 0.f;
+          if (has_c && !G::kCaddInTmem) {
+            // 16 independent L2 loads per table, issued back to back (indices from shared memory; a missing term reads
+            // row 0 and is multiplied by zero): their latency hides under the accumulator wait
+            if (ph.tab_c) {
+              const float* tc_ = ph.tab_c + grow;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int ci = scls[s0 + j];
+                cadd[j] = 0.f + (ci >= 0 ? 1.f : 0.f) * __ldg(tc_ + (size_t)(ci >= 0 ? ci : 0) * ph.rows);
+              }
+            }
+            if (ph.tab_t && per_row_t) {
+              const float* tt_ = ph.tab_t + grow;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int ti = strow[s0 + j];
+                cadd[j] += (ti >= 0 ? 1.f : 0.f) * __ldg(tt_ + (size_t)(ti >= 0 ? ti : 0) * ph.rows);
+              }
+            }
+          }
           if (ph.dual) {
             // (mu, r) of the operand rows: the previous phase's background statistics exchange lands while the tensor core
             // is still busy with this phase; merged here, used after the accumulator wait
@@ -793,13 +827,12 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
           const float t_e = cb_prev * t_g;                              // the eps bias of the previous step, seen through G_0
           float a2[16];
           tc::tmem_ld16(lane_taddr + (uint32_t)s0, v);
-          if (ph.cadd_col >= 0 && !eps_tile) {
+          if (has_c) {
             // one association for every mode (uniform t: t_t = T[t], c = C[c_r]; per-row t: t_t = 0, c = C[c_r] + T[t_r]), so
             // that a row's result does not depend on how its timestep was passed: acc + (b + (T + C)) - e
-            float c[16];
-            tc::tmem_ld16(lane_taddr + (uint32_t)(ph.cadd_col + s0), c);
+            if constexpr (G::kCaddInTmem) tc::tmem_ld16(lane_taddr + (uint32_t)(ph.cadd_col + s0), cadd);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = (v[j] + (t_b + (t_t + c[j]))) - t_e;
+            for (int j = 0; j < 16; ++j) v[j] = (v[j] + (t_b + (t_t + cadd[j]))) - t_e;
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = (v[j] + (t_b + t_t)) - t_e;
@@ -1050,11 +1083,6 @@ __global__ void pack_fill_kernel(float* __restrict__ p, float v, int n) {
   if (i < n) p[i] = v;
 }
 
-#define LDM_LAUNCHED(ctx)             \
-  do {                                \
-    (ctx)->launches++;                \
-    LDM_CUDA(cudaGetLastError());     \
-  } while (0)
 
 int mm(ldm_ctx* ctx, const float* A, int lda, const float* B, int ldb, int transB, float* C, int ldc, int M, int N, int K,
        cudaStream_t st) {
@@ -1146,7 +1174,7 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
   for (void* p : C.allocs) cudaFree(p);
   C = ChainModel();
   const int nst = U.nst, L = U.latent;
-  LDM_CHECK(nst + 1 <= LDM_CHAIN_MAX_PHASES && kChains * 48 + (nst + 3) * 48 <= kTmemCols, "chain: too many stages (%d) for the TMEM-resident per-sample terms", nst);
+  LDM_CHECK(nst + 1 <= LDM_CHAIN_MAX_PHASES && nst <= 5, "chain: more stages (%d) than the persistent kernel is validated for: the per-layer path takes over", nst);
   LDM_CHECK(L % 128 == 0 && L / 128 <= kSlots, "chain: latent_dim %d unsupported", L);
   for (int i = 0; i < nst; ++i)
     LDM_CHECK(U.hid[i] % 64 == 0 && U.hid[i] / 64 <= CS && U.hid[i] / 64 <= kSlots, "chain: hidden dim %d unsupported", U.hid[i]);
@@ -1325,7 +1353,7 @@ static int chain_pick_nw(int B, int n_phases) {
   int best = 0, best_waves = 1 << 30;
   if (const char* f = getenv("LDM_CHAIN_NW")) { const int nw = atoi(f); if (nw >= 2 && nw <= 4 && g_chain_clusters[nw] >= 1) return nw; }
   for (int nw = 2; nw <= 4; ++nw) {
-    if ((kChains + n_phases + 2) * 16 * nw > kTmemCols) continue;   // accumulators + per-sample terms + parked noise + state must fit the TMEM columns
+    if ((kChains + 2 + (nw >= 3 ? n_phases : 0)) * 16 * nw > kTmemCols) continue;   // accumulators + parked noise + state (+ per-sample terms) must fit the TMEM columns
     if (g_chain_clusters[nw] < 1) continue;
     const int waves = ceil_div(ceil_div(B, 16 * nw), g_chain_clusters[nw]);
     if (waves < best_waves) { best_waves = waves; best = nw; }
@@ -1347,7 +1375,6 @@ int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const
   ChainParams P;
   memset(&P, 0, sizeof(P));
   const int nst = U.nst, L = U.latent;
-  LDM_CHECK(kChains * NB + (C.n_phases + 2) * NB <= kTmemCols, "chain: %d phases x %d rows exceed the TMEM columns", C.n_phases, NB);
   LDM_CHECK(nst + 2 <= kMaxXMaps, "chain: too many stages");
   // stage the first merged operand: [x | 0 | 0] (the stage tiles see G_0 x; the eps tiles have nothing to finish yet)
   LDM_TRY(launch_load_x<bf16>(ctx, x, ctx->caf[0], 3 * L, B, L, st));
@@ -1357,7 +1384,7 @@ int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const
   LDM_TRY(tc_make_act_map(ctx->caf[1], B, 3 * L, 3 * L, NB, &P.xmaps[1]));
   for (int j = 0; j < nst; ++j) LDM_TRY(tc_make_act_map(ctx->opbuf[j], B, U.hid[j], U.hid[j], NB, &P.xmaps[2 + j]));
   for (int j = nst; j < kMaxXMaps - 2; ++j) P.xmaps[2 + j] = P.xmaps[0];
-  int cadd = kChains * NB;
+  int cadd = (kChains + 2) * NB;      // TMEM: accumulators, parked noise, chain state, then the per-sample terms (NW >= 3)
   for (int j = 0; j < C.n_phases; ++j) {
     const ChainPhaseHost& H = C.ph[j];
     ChainPhase& D = P.ph[j];
@@ -1368,7 +1395,7 @@ int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const
     D.prev_tiles = j == 0 ? 0 : (j == 1 ? C.ph[0].nst_tiles : C.ph[j - 1].tiles);
     D.bias = H.bias; D.tab_t = H.tab_t; D.tab_c = ctx->has_cls ? H.tab_c : nullptr;
     D.cadd_col = -1;
-    if (H.tab_t) { D.cadd_col = cadd; cadd += NB; }
+    if (H.tab_t) { D.cadd_col = nw >= 3 ? cadd : 0; cadd += nw >= 3 ? NB : 0; }
     if (j < nst) { D.ga = U.ln_a_w[j]; D.ba = U.ln_a_b[j]; D.gb = U.ln_b_w[j]; D.bb = U.ln_b_b[j]; }
     else { D.ga = U.ln_f_w; D.ba = U.ln_f_b; }
     if (j == 0) { D.xmap = 0; D.xmap_alt = 1; D.xcol = 0; }
@@ -1376,10 +1403,10 @@ int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const
     if (j < nst) { D.out = ctx->opbuf[j]; D.ld_out = U.hid[j]; }
   }
   for (int j = C.n_phases; j < LDM_CHAIN_MAX_PHASES; ++j) P.wmap[j] = C.ph[0].map;
-  P.z_col = cadd;
-  P.x_col = cadd + NB;
+  P.z_col = kChains * NB;
+  P.x_col = kChains * NB + NB;
   { const char* wf = getenv("LDM_CHAIN_WRITER_FENCE"); P.writer_fence = wf ? atoi(wf) : 0; }
-  LDM_CHECK(cadd + 2 * NB <= kTmemCols, "chain: TMEM columns exhausted (%d phases x %d rows)", C.n_phases, NB);
+  LDM_CHECK(cadd <= kTmemCols, "chain: TMEM columns exhausted (%d phases x %d rows)", C.n_phases, NB);
   P.n_phases = C.n_phases;
   P.B = B; P.row_begin = 0; P.row_end = B;
   P.n_iter = n_iter; P.t_start = t_start; P.sample = sample; P.latent = L; P.n_t = U.n_t;
@@ -1399,5 +1426,6 @@ int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const
   else rc = launch_variant<4>(P, nclusters, st);
   LDM_TRY(rc);
   ctx->launches++;
+  ldm_kmark(ctx, "chain_kernel");
   return 0;
 }

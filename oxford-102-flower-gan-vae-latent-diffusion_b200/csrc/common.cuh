@@ -324,7 +324,34 @@ struct ldm_ctx {
   int chain_trace_step = 0;
   int use_pdl = 0;
   int use_attn_tc = 1;            // v3 bf16: attention on tcgen05 (LDM_ATTN_TC=0 selects the CUDA-core kernel)
+  // per-launch timing (ldm_debug_ktrace): one CUDA event after every kernel launch on kt_stream while kt_on
+  bool kt_on = false;
+  cudaStream_t kt_stream = nullptr;
+  std::vector<std::pair<std::string, cudaEvent_t>> kt_marks;
 };
+
+// Called right after a kernel launch: with tracing on, an event on the traced stream closes the interval of that kernel
+// (kernels of a stream run back to back, so mark[i] - mark[i-1] is kernel i plus whatever gap precedes it).
+static inline void ldm_kmark(ldm_ctx* ctx, const char* name) {
+  if (!ctx->kt_on || ctx->capturing) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, ctx->kt_stream);
+  ctx->kt_marks.emplace_back(name, e);
+}
+
+#define LDM_LAUNCHED_AS(ctx, name)    \
+  do {                                \
+    (ctx)->launches++;                \
+    ldm_kmark((ctx), name);           \
+    LDM_CUDA(cudaGetLastError());     \
+  } while (0)
+#define LDM_LAUNCHED(ctx)             \
+  do {                                \
+    (ctx)->launches++;                \
+    ldm_kmark((ctx), __func__);       \
+    LDM_CUDA(cudaGetLastError());     \
+  } while (0)
 
 // Launch with programmatic dependent launch (PDL): the grid may start while its predecessor in the stream drains, runs its
 // prologue (barrier init, TMEM allocation, descriptor prefetch, resident weights) and blocks in griddepcontrol.wait until

@@ -713,6 +713,7 @@ int launch_bn_mt(ldm_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, con
   dim3 grid(ceil_div(a.total_pix, BM * MT), a.Cout / BN, nz);
   LDM_CUDA(launch_maybe_pdl(conv_tc_kernel<BN, MT>, grid, kThreads, smem, st, ctx->use_pdl, ma, mw, a));
   ctx->launches++;
+  ldm_kmark(ctx, "conv_tc");
   LDM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -847,6 +848,7 @@ int launch_conv_halo(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer
   else if (ddpm) LDM_CUDA(launch_maybe_pdl(conv_halo_kernel<16, 2, 2>, dim3(grid), kThreads, smem, st, ctx->use_pdl, ma, L.map_w, a));
   else LDM_CUDA(launch_maybe_pdl(conv_halo_kernel<16, 1, 2>, dim3(grid), kThreads, smem, st, ctx->use_pdl, ma, L.map_w, a));
   ctx->launches++;
+  ldm_kmark(ctx, "conv_halo");
   LDM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -911,6 +913,7 @@ int launch_conv_halo_stream(ldm_ctx* ctx, const bf16* in, int in_pitch, const Co
   if (L.Cout == 64) LDM_CUDA(launch_maybe_pdl(conv_halo_stream_kernel<64>, dim3(grid), kThreads, smem, st, ctx->use_pdl, ma, map_w, a));
   else LDM_CUDA(launch_maybe_pdl(conv_halo_stream_kernel<128>, dim3(grid), kThreads, smem, st, ctx->use_pdl, ma, map_w, a));
   ctx->launches++;
+  ldm_kmark(ctx, "conv_halo_stream");
   LDM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -920,6 +923,7 @@ int launch_conv_out3(ldm_ctx* ctx, const bf16* in, const float* w, const float* 
   const int total = B * H * W;
   conv_out3_kernel<<<ceil_div(total, 256), 256, 0, st>>>(in, w, bias, out, H, W, total);
   ctx->launches++;
+  ldm_kmark(ctx, "conv_out3");
   LDM_CUDA(cudaGetLastError());
   return 0;
 }

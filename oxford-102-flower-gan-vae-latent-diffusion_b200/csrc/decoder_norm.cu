@@ -343,11 +343,6 @@ sa_apply_bf16_kernel(const bf16* __restrict__ x, const float2* __restrict__ coef
 
 }  // namespace
 
-#define LDM_LAUNCHED(ctx)         \
-  do {                            \
-    (ctx)->launches++;            \
-    LDM_CUDA(cudaGetLastError()); \
-  } while (0)
 
 template <typename T>
 int launch_inorm_stats(ldm_ctx* ctx, const T* x, float* stats, int B, int HW, int C, int group, cudaStream_t st) {

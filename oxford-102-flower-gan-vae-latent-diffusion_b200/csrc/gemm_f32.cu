@@ -194,6 +194,7 @@ int launch_gemm_f32(ldm_ctx* ctx, const float* A, int lda, const float* W, int M
     gemm_f32_kernel<64, 64><<<grid, TileEngine<64, 64>::kThreads, 0, st>>>(A, lda, W, M, N, K, epi);
   }
   ctx->launches++;
+  ldm_kmark(ctx, "gemm_f32");
   LDM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -210,6 +211,7 @@ int launch_conv_f32(ldm_ctx* ctx, const float* in, const float* w, const float* 
     conv_f32_kernel<64, 32><<<grid, TileEngine<64, 32>::kThreads, 0, st>>>(in, w, bias, out, g);
   }
   ctx->launches++;
+  ldm_kmark(ctx, "conv_f32");
   LDM_CUDA(cudaGetLastError());
   return 0;
 }

@@ -414,6 +414,7 @@ int launch_bn(ldm_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, int M,
     LDM_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN>, ma, mw, a, epi));
   }
   ctx->launches++;
+  ldm_kmark(ctx, "gemm_tc");
   LDM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -460,6 +461,7 @@ int launch_attn_prep(ldm_ctx* ctx, const float* qkv, bf16* qk, bf16* vt, int row
   const int n = rows * 3 * d;
   LDM_CUDA(launch_maybe_pdl(attn_prep_kernel, dim3(ceil_div(n, 256)), 256, 0, st, ctx->use_pdl, qkv, qk, vt, rows, d, ldv));
   ctx->launches++;
+  ldm_kmark(ctx, "attn_prep");
   LDM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -475,6 +477,7 @@ static int launch_attn_hd(ldm_ctx* ctx, const CUtensorMap& mqk, const CUtensorMa
   }
   LDM_CUDA(launch_maybe_pdl(attn_tc_kernel<HD>, dim3(ceil_div(a.L, 128), a.heads, batches), kThreads, smem, st, ctx->use_pdl, mqk, mvt, a));
   ctx->launches++;
+  ldm_kmark(ctx, "attn_tc");
   LDM_CUDA(cudaGetLastError());
   return 0;
 }

@@ -79,11 +79,6 @@ __global__ void pack_convT_kernel(const float* __restrict__ w, float* __restrict
 
 }  // namespace
 
-#define LDM_LAUNCHED(ctx)         \
-  do {                            \
-    (ctx)->launches++;            \
-    LDM_CUDA(cudaGetLastError()); \
-  } while (0)
 
 int launch_pack_matmul_nn(ldm_ctx* ctx, const float* A, const float* B, float* C, int M, int N, int K, cudaStream_t st) {
   matmul_nn_kernel<<<dim3(ceil_div(N, 128), M), 128, 0, st>>>(A, B, C, M, N, K);

@@ -35,11 +35,6 @@ int launch_conv_halo(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer
 namespace {
 
 #define HW_MULT4(H, W) ((((H) * (W)) & 3) == 0)
-#define LDM_LAUNCHED(ctx)         \
-  do {                            \
-    (ctx)->launches++;            \
-    LDM_CUDA(cudaGetLastError()); \
-  } while (0)
 
 // ------------------------------------------------------------------------------------------------------------------
 // time terms: out[row] = [time_fc1 | time_fc2 | time_fc3](Linear2(relu(Linear1(t))))     (v4:103-110)
@@ -496,7 +491,7 @@ int launch_time_terms(ldm_ctx* ctx, const float* t, float* out, int rows, cudaSt
   PixModel& M = ctx->pix;
   pix_time_terms_kernel<<<rows, 128, 2 * M.temb * sizeof(float), st>>>(t, M.te0_w, M.te0_b, M.te2_w, M.te2_b, M.tfc_w[0], M.tfc_b[0],
                                                                          M.tfc_w[1], M.tfc_b[1], M.tfc_w[2], M.tfc_b[2], out, M.temb, M.base);
-  LDM_LAUNCHED(ctx);
+  LDM_LAUNCHED_AS(ctx, "pix_time_terms");
   return 0;
 }
 
@@ -601,7 +596,7 @@ int run_forward_f32(ldm_ctx* ctx, const float* x, const float* terms, int tstrid
     const long long want = (items + 255) / 256;
     const unsigned grid = (unsigned)(want < 2ll * ctx->sm_count ? want : 2ll * ctx->sm_count);
     pix_conv_in_kernel<float><<<grid, 256, (size_t)c * 28 * sizeof(float), st>>>(x, M.in_w, M.in_b, a1, H, W, c, P1 / 4);
-    LDM_LAUNCHED(ctx);
+    LDM_LAUNCHED_AS(ctx, "pix_conv_in");
   }
   const float *t1 = terms, *t2 = terms + c, *t3 = terms + 3 * c;
   auto c3 = [&](const float* in, int ip, const ConvLayer& L, float* out, int op, int h, int w, const float* post) {
@@ -638,13 +633,13 @@ int run_forward_f32(ldm_ctx* ctx, const float* x, const float* terms, int tstrid
   const size_t n3 = (size_t)P1 * 3;
   if (M.res_ratio) {
     pix_axpy_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(eps, M.res_ratio, x, n3);
-    LDM_LAUNCHED(ctx);
+    LDM_LAUNCHED_AS(ctx, "pix_axpy");
   }
   if (ddpm) {
     const int total4 = (int)(n3 / 4);
     pix_ddpm_kernel<<<ceil_div(total4, 256), 256, 0, st>>>(fin.out, eps, fin.c2, fin.sqrt_alpha, fin.sigma, fin.noise, fin.rng, fin.step,
                                                            total4, 3 * H * W / 4);
-    LDM_LAUNCHED(ctx);
+    LDM_LAUNCHED_AS(ctx, "pix_ddpm");
   }
   return 0;
 }
@@ -671,7 +666,7 @@ int run_forward(ldm_ctx* ctx, const float* x, const float* terms, int tstride, i
     const unsigned grid = (unsigned)(want < 2ll * ctx->sm_count ? want : 2ll * ctx->sm_count);
     pix_conv_in_kernel<bf16><<<grid, 256, (size_t)c * 28 * sizeof(float), st>>>(x, M.in_w, M.in_b, M.a1, H, W, c, P1 / 4);
   }
-  LDM_LAUNCHED(ctx);
+  LDM_LAUNCHED_AS(ctx, "pix_conv_in");
   const float *t1 = terms, *t2 = terms + c, *t3 = terms + 3 * c;
   // encoder (v4:113-122); x1 -> cat5[:, c:2c], x2 -> cat4[:, 2c:4c]
   LDM_TRY(conv3(ctx, M.a1, c, M.c1b, M.cat5 + c, 2 * c, B, H, W, t1, tstride, st));
@@ -704,7 +699,7 @@ int run_forward(ldm_ctx* ctx, const float* x, const float* terms, int tstride, i
       const int total4 = P1 * 3 / 4;
       pix_ddpm_kernel<<<ceil_div(total4, 256), 256, 0, st>>>(fin.out, M.eps, fin.c2, fin.sqrt_alpha, fin.sigma, fin.noise, fin.rng,
                                                              fin.step, total4, 3 * H * W / 4);
-      LDM_LAUNCHED(ctx);
+      LDM_LAUNCHED_AS(ctx, "pix_ddpm");
     }
     return 0;
   }
@@ -717,7 +712,7 @@ int run_forward(ldm_ctx* ctx, const float* x, const float* terms, int tstride, i
     if (ddpm) pix_conv_out_kernel<1><<<ceil_div(P1, 128), 128, smem, st>>>(fin);
     else pix_conv_out_kernel<0><<<ceil_div(P1, 128), 128, smem, st>>>(fin);
   }
-  LDM_LAUNCHED(ctx);
+  LDM_LAUNCHED_AS(ctx, "pix_conv_out");
   return 0;
 }
 
@@ -793,7 +788,7 @@ extern "C" LDM_API int ldm_pix_pack(ldm_ctx* ctx, const ldm_pix_weights* w, void
   if (c == 64 && ctx->precision == LDM_PRECISION_BF16) {
     LDM_TRY(ldm_alloc_t(ctx, P, &M.in_w16, (size_t)64 * 64));
     pix_pack_in_tc_kernel<<<16, 256, 0, st>>>(M.in_w, M.in_w16);
-    LDM_LAUNCHED(ctx);
+    LDM_LAUNCHED_AS(ctx, "pix_pack_in_tc");
     LDM_TRY(tc_make_weight_map(ctx, M.in_w16, 64, 64, 64, &M.in_map));
   }
   LDM_TRY(ldm_alloc_t(ctx, P, &M.out_w, (size_t)3 * 9 * c));

@@ -325,11 +325,6 @@ int dispatch_nv4(int d, F&& f) {
 
 }  // namespace
 
-#define LDM_LAUNCHED(ctx)                      \
-  do {                                         \
-    (ctx)->launches++;                         \
-    LDM_CUDA(cudaGetLastError());              \
-  } while (0)
 
 template <typename TOP>
 int launch_stage_mid(ldm_ctx* ctx, const float* u, const float* h, const float* ga, const float* ba,

@@ -21,11 +21,6 @@ int launch_coef_apply_bf16(ldm_ctx* ctx, const bf16* x, const float2* coef, bf16
 
 namespace {
 
-#define LDM_LAUNCHED(ctx)         \
-  do {                            \
-    (ctx)->launches++;            \
-    LDM_CUDA(cudaGetLastError()); \
-  } while (0)
 
 // (B, C, HW) fp32 -> (B, HW, C) bf16 / fp32 through a 32 x 32 shared-memory tile
 template <typename T>

@@ -140,6 +140,18 @@ class Engine:
         check(lib().ldm_kernel_launch_count(self.ctx, ctypes.byref(out)), "ldm_kernel_launch_count")
         return out.value
 
+    def ktrace_start(self):
+        """Start recording a CUDA event after every kernel this context launches eagerly on the current stream."""
+        check(lib().ldm_debug_ktrace(self.ctx, 1, self.stream(), None, 0, None, 0, None), "ldm_debug_ktrace")
+
+    def ktrace_stop(self, max_kernels=8192):
+        """-> [(kernel name, milliseconds)] in launch order since ktrace_start()."""
+        names = ctypes.create_string_buffer(64 * max_kernels)
+        ms = (ctypes.c_float * max_kernels)()
+        n = ctypes.c_int()
+        check(lib().ldm_debug_ktrace(self.ctx, 0, None, names, len(names), ms, max_kernels, ctypes.byref(n)), "ldm_debug_ktrace")
+        return list(zip(names.value.decode().split("\n")[:n.value], [float(ms[i]) for i in range(n.value)]))
+
     def check_device_flags(self, num_classes=None):
         """Raise like the reference's nn.Embedding / tensor indexing would on a bad index."""
         f = int(self.info("device_flags"))
@@ -484,4 +496,12 @@ class Engine:
         lp = _ptr(latents_host) if latents_host is not None else None
         check(lib().ldm_generate_host(self.ctx, cp, B, seed, sample_offset, _ptr(img_host), lp, self.stream()),
               "ldm_generate_host")
+        return img_host
+
+    def generate3_host(self, flower_host, color_host, img_host, latents_host=None, seed=0, sample_offset=0):
+        """v3: host (flower, color) labels in, host images out, one call (ldm_generate3_host)."""
+        B = img_host.shape[0]
+        lp = _ptr(latents_host) if latents_host is not None else None
+        check(lib().ldm_generate3_host(self.ctx, _ptr(flower_host), _ptr(color_host), B, seed, sample_offset, _ptr(img_host), lp,
+                                       self.stream()), "ldm_generate3_host")
         return img_host

@@ -1,0 +1,51 @@
+"""Race proxy for the hand-rolled mbarrier / st.async / DSMEM / TMA protocols (compute-sanitizer is closed on the GPU pool,
+profiles/r02_sanitizer_closed.txt): identical inputs must give bit-identical outputs on every repetition, and no bounded
+wait may have timed out."""
+import pytest
+import torch
+
+from oracle import weights
+from tests._util import make_unet
+
+torch.set_grad_enabled(False)
+pytestmark = pytest.mark.gpu
+
+
+def test_chain_kernel_is_bit_stable_over_repetitions():
+    import ldm_b200
+    u = make_unet("init", "bf16")
+    d = ldm_b200.ConditionalDenoiseDiffusion(u, 1000, torch.device("cuda"))
+    eng = u.engine(torch.device("cuda"), 1000)
+    eng.set_schedule(*d._host_schedule)
+    for B in (256, 33, 100):                      # 6 x 48 rows with a ragged last cluster; one partial cluster; 32-row clusters
+        c = (torch.arange(B) % 102).cuda()
+        x_T = eng.randn(B, 256, 5, 0, 1000)
+        ref = None
+        for rep in range(8):
+            x = x_T.clone()
+            eng.sample(x, 999, 800, c, seed=5, use_graph=False)
+            eng.check_device_flags()
+            assert torch.isfinite(x).all()
+            ref = x if ref is None else ref
+            assert torch.equal(x, ref), (B, rep)
+
+
+def test_attention_and_halo_kernels_are_bit_stable_over_repetitions():
+    from ldm_b200 import v3, v4
+    u3 = v3.ConditionalUNet(precision="bf16")
+    u3.load_state_dict(weights.make_unet3_state(44, "init"))
+    u3 = u3.cuda().eval()
+    B = 300                                        # three query / key tiles of attn_tc_kernel
+    x = torch.randn(B, 256, device="cuda")
+    f, k = torch.arange(B, device="cuda") % 102, torch.arange(B, device="cuda") % 10
+    ref = u3(x, torch.tensor([77], device="cuda"), f, k)
+    for rep in range(10):
+        assert torch.equal(u3(x, torch.tensor([77], device="cuda"), f, k), ref), rep
+    m = v4.SimpleUNet()
+    m.load_state_dict(weights.make_pix_state(45, "init"))
+    m = m.cuda().eval()
+    xi, t = torch.randn(8, 3, 64, 64, device="cuda"), torch.arange(8, device="cuda") * 100.0
+    ref = m(xi, t)
+    for rep in range(10):
+        assert torch.equal(m(xi, t), ref), rep
+    u3.engine(torch.device("cuda"), 1000).check_device_flags()
