@@ -12,7 +12,7 @@ Prints ONE JSON line (rank 0).  Besides the base contract the v2 line carries
 
   roofline          the dominant kernel (chain_kernel), CUDA-event timed; `traffic` from the sidecar the profiling
                     script writes (profiles/*chain_traffic.json), never a constant in this file
-  roofline_kernels  every kernel of one traced pass (chain + the 39 decoder launches): {name, what, bound, flop | bytes,
+  roofline_kernels  every kernel of one traced pass (chain + the 42 decoder launches): {name, what, bound, flop | bytes,
                     us, achieved, peak, frac}; tensor-bound ones against the measured bf16 peak, memory-bound ones
                     (norm / gating / LayerNorm passes) as GB/s against the measured HBM copy bandwidth.  Timed with a
                     CUDA event after every launch (ldm_debug_ktrace), not under a profiler
@@ -205,7 +205,7 @@ def run_reference_arm(args, rank):
 # per-kernel records (roofline_kernels)
 # ------------------------------------------------------------------------------------------------------
 def decoder_kernel_table(B):
-    """The 39 launches of one bf16 decode of B latents, in launch order (csrc/decoder.cu: decode_chunk_bf16):
+    """The 42 launches of one bf16 decode of B latents, in launch order (csrc/decoder.cu: decode_chunk_bf16):
     (trace name, what, bound, flop or bytes).  Memory-bound passes: algorithmic bytes = tensors read + written once."""
     t = []
     E = lambda C, H: B * H * H * C      # elements of an NHWC activation
@@ -223,15 +223,16 @@ def decoder_kernel_table(B):
               ("conv_tc", "res%d.conv2 3x3" % C, "tensor", conv),
               ("launch_norm_coef_bf16", "res%d.ln2 statistics" % C, "hbm", n * 2),
               ("launch_sa_map_bf16", "res%d channel gate + spatial mean/max map" % C, "hbm", n * 2),
-              ("launch_sa_apply_bf16", "res%d ln2 * CA * SA(7x7) + x, Swish" % C, "hbm", n * 6)]
+              ("launch_sa_gate", "res%d sigmoid(conv7x7(map))" % C, "hbm", B * H * H * 12),
+              ("launch_sa_apply_bf16", "res%d ln2 * CA * SA gate + x, Swish" % C, "hbm", n * 6)]
         no = E(C // 2, 2 * H)
         t += [("conv_tc", "up ConvT(4,2,1) %d->%d @%dx%d" % (C, C // 2, 2 * H, 2 * H), "tensor", 2 * no * 4 * C),
               ("launch_norm_coef_bf16", "up GroupNorm statistics", "hbm", no * 2),
               ("launch_coef_apply_bf16", "up GroupNorm apply + Swish", "hbm", no * 4)]
     n = E(32, 64)
-    t += [("conv_tc", "final_conv.0 3x3 64->32 @64x64", "tensor", 2 * n * 9 * 64),
-          ("launch_inorm_stats", "final GroupNorm(8,32) statistics", "hbm", n * 2),
-          ("launch_norm_apply", "final GroupNorm apply + Swish", "hbm", n * 4),
+    t += [("conv_halo", "final_conv.0 3x3 64->32 @64x64 (halo kernel)", "tensor", 2 * n * 9 * 64),
+          ("launch_norm_coef_bf16", "final GroupNorm(8,32) statistics", "hbm", n * 2),
+          ("launch_coef_apply_bf16", "final GroupNorm apply + Swish", "hbm", n * 4),
           ("conv_out3", "final_conv.3 3x3 32->3 + Sigmoid (CUDA cores)", "hbm", n * 2 + B * 3 * 4096 * 4)]
     return t
 
@@ -435,7 +436,7 @@ def run_latent(workload, B, K, W, prec, rank, world, local_rank, sampler, with_c
             recs.append({"name": "chain_kernel", "what": "1000 reverse steps, fused posterior update", "bound": "tensor", "flop": loop_flops,
                          "us": ck[-1][1] * 1000.0, "achieved": loop_flops / s / 1e12, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": loop_flops / s / 1e12 / pk["bf16_sustained"]})
-        dec_trace = trace[len(trace) - len(decoder_kernel_table(B)):] if len(trace) >= 39 else trace
+        dec_trace = trace[len(trace) - len(decoder_kernel_table(B)):] if len(trace) >= len(decoder_kernel_table(B)) else trace
         drecs, ok = kernel_records(dec_trace, decoder_kernel_table(B), pk)
         line["roofline_kernels"] = recs + drecs
         line["roofline_kernels_info"] = {"timing": "CUDA event after every launch of one untimed eager pass (ldm_debug_ktrace); us includes the gap to the previous kernel",

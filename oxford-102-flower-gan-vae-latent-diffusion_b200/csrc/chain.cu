@@ -647,6 +647,13 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
     Tracer TR{P.trace ? P.trace + ((size_t)rank * LDM_CHAIN_TRACE_TRACKS + (et == 0 ? 0 : 1)) * LDM_CHAIN_TRACE_LEN : nullptr, 0, false};
     auto stamp = [&](int tag, int p) { TR.stamp(tag, p); };
     auto epi_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(G::kEpiThreads) : "memory"); };
+    // Every epilogue warp needs the same barrier: ONE warp polls the mbarrier, the others block in a named barrier (bar.sync
+    // costs no issue slots, a polling warp does; measured: try_wait returns within ~45 clocks whatever the suspend hint, and
+    // twelve polling warps took 12 % of the SM's issue slots away from the MMA / TMA threads and from each other)
+    auto epi_wait = [&](uint64_t* bar, uint32_t parity, int code) {
+      if (warp == 4) W.wait(bar, parity, code);
+      asm volatile("bar.sync 8, %0;" ::"n"(G::kEpiThreads) : "memory");
+    };
     auto group_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory"); };   // the 4 warps of row group g
 
     // Statistics exchange, sender side.  Lane l holds (mean, M2) of group row (l >> 1) over `cnt` features of this
@@ -670,7 +677,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
     // wait until the partials of all `nparts` tiles for all NB rows have landed in buffer `buf`
     auto exchange_wait = [&](uint32_t buf, int nparts, int code) {
       if (et == 0) tc::mbar_arrive_expect_tx(&sbar[buf], (uint32_t)nparts * NB * (uint32_t)sizeof(float2));
-      W.wait(&sbar[buf], sph[buf] & 1u, code);
+      epi_wait(&sbar[buf], sph[buf] & 1u, code);
       sph[buf]++;
     };
     // receiver side: merge the `nparts` per-tile partials (`cnt` features each) into (mean, rstd) of the warp's 16
@@ -761,7 +768,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
         const int tile = has_unit ? un.tile : 0;
         const int grow = tile * 128 + lrow;
         if (partner) {
-          W.wait(&tmem_full_bar, tpar, 5);
+          epi_wait(&tmem_full_bar, tpar, 5);
           tpar ^= 1u;
           tc::fence_after_sync();
           float pv[16];
@@ -819,7 +826,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
             combine(bb, ph.prev_tiles, 64.0f);
           }
           stamp(2, p);
-          W.wait(&tmem_full_bar, tpar, 5);
+          epi_wait(&tmem_full_bar, tpar, 5);
           tpar ^= 1u;
           stamp(3, p);
           tc::fence_after_sync();
@@ -841,7 +848,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
           tc::fence_before_sync();            // ordered before the next phase's MMAs through the hand-over
           if (ph.ks > 1) {   // the partner unit's accumulator: acc2 of a dual phase (or the other K half of a plain one)
             if (et == 0) tc::mbar_arrive_expect_tx(&pbar, G::kPbufBytes);
-            W.wait(&pbar, ppar, 10);
+            epi_wait(&pbar, ppar, 10);
             ppar ^= 1u;
             const float4* pp = pbuf + (size_t)(g * 4) * 128 + lrow;
 #pragma unroll
@@ -1004,7 +1011,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
           }
         }
 
-        W.wait(&obar[ob], opar, 9);
+        epi_wait(&obar[ob], opar, 9);
         oidx++;
         stamp(10, p);
         if (pub_b) {

@@ -296,7 +296,9 @@ struct ldm_ctx {
   std::vector<void*> dec_allocs;
   void *d_a = nullptr, *d_b = nullptr, *d_c = nullptr;  // ping-pong activation buffers (operand-typed, NHWC)
   float *d_f0 = nullptr, *d_f1 = nullptr;               // fp32 scratch (raw conv outputs, fc rows)
-  float *d_stats = nullptr, *d_gap = nullptr, *d_ca = nullptr, *d_map = nullptr;
+  float *d_stats = nullptr, *d_gap = nullptr, *d_ca = nullptr, *d_map = nullptr, *d_gate = nullptr;
+  float2* d_part = nullptr;       // norm_coef: per-split partial sums
+  int* d_cnt = nullptr;           // norm_coef: per (sample, channel block) tickets
   float* z_tmp = nullptr;
   bf16 *d_zb = nullptr, *d_h1b = nullptr;               // bf16 operands of Decoder.fc (tensor-core path)
   // generate_host staging

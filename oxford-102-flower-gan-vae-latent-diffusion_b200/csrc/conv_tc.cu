@@ -585,41 +585,65 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
 }
 
 // final_conv[3] + Sigmoid (v2:277-278): Conv2d(32, 3, 3, padding 1) over NHWC bf16 -> NCHW fp32.  N = 3 output
-// channels is no tensor-core shape: one thread per pixel on the CUDA cores, weights in shared memory.
+// channels is no tensor-core shape: one thread per pixel on the CUDA cores.  A CTA owns an 8 x 32 pixel tile: its
+// 10 x 34 halo is loaded ONCE with coalesced 16-byte reads into shared memory, channel-octet major ([4][340] uint4), so
+// that the 32 lanes of a warp (32 neighbouring pixels) read consecutive 16-byte words for every tap (the direct
+// per-thread global reads of the first version walked 64-byte strides through L1: 576 wavefronts per warp instead of 144).
+constexpr int kO3TW = 32, kO3TH = 16, kO3HW = kO3TW + 2, kO3HH = kO3TH + 2, kO3HP = kO3HW * kO3HH;
 __global__ void __launch_bounds__(256)
 conv_out3_kernel(const bf16* __restrict__ in, const float* __restrict__ w /* (3, 9*32) */, const float* __restrict__ bias,
-                 float* __restrict__ out, int H, int W, int total_pix) {
-  __shared__ float ws[3 * 288];
-  for (int i = threadIdx.x; i < 3 * 288; i += 256) ws[i] = w[i];
+                 float* __restrict__ out, int H, int W) {
+  __shared__ float4 ws[3 * 72];          // 16-byte broadcast reads of the weights
+  __shared__ uint4 tile[4][kO3HP];       // 16 x 32 pixels + halo, channel-octet major
+  for (int i = threadIdx.x; i < 3 * 288; i += 256) reinterpret_cast<float*>(ws)[i] = w[i];
+  const int n = blockIdx.z, y0 = blockIdx.y * kO3TH, x0 = blockIdx.x * kO3TW, HW = H * W;
+  const uint4* src = reinterpret_cast<const uint4*>(in + (size_t)n * HW * 32);
+  for (int i = threadIdx.x; i < 4 * kO3HP; i += 256) {
+    const int hp = i >> 2, j = i & 3, hy = hp / kO3HW, hx = hp - hy * kO3HW;
+    const int yy = y0 + hy - 1, xx = x0 + hx - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);     // zero padding
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(src + ((size_t)yy * W + xx) * 4 + j);
+    tile[j][hp] = v;
+  }
   __syncthreads();
-  const int p = blockIdx.x * 256 + threadIdx.x;
-  if (p >= total_pix) return;
-  const int HW = H * W, n = p / HW, rem = p - n * HW, y = rem / W, x = rem - y * W;
-  float acc0 = bias[0], acc1 = bias[1], acc2 = bias[2];
+  // every thread finishes TWO pixels (rows ty and ty + 8 of the tile): each weight word read from shared memory feeds both
+  const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
+  float acc[2][3];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) { acc[r][0] = bias[0]; acc[r][1] = bias[1]; acc[r][2] = bias[2]; }
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
-    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-    const uint4* src = reinterpret_cast<const uint4*>(in + ((size_t)n * HW + (size_t)yy * W + xx) * 32);
+    const int hp = (ty + tap / 3) * kO3HW + tx + tap % 3;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint4 u = __ldg(src + j);
-      const uint32_t wd[4] = {u.x, u.y, u.z, u.w};
+      const int k4 = tap * 8 + j * 2;      // float4 index of channel j * 8 of this tap
+      const float4 a0 = ws[k4], a1 = ws[k4 + 1], b0 = ws[72 + k4], b1 = ws[72 + k4 + 1], c0 = ws[144 + k4], c1 = ws[144 + k4 + 1];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&wd[e]);
-        const float f0 = __low2float(h2), f1 = __high2float(h2);
-        const int ci = j * 8 + e * 2, k = tap * 32 + ci;
-        acc0 += f0 * ws[k] + f1 * ws[k + 1];
-        acc1 += f0 * ws[288 + k] + f1 * ws[288 + k + 1];
-        acc2 += f0 * ws[576 + k] + f1 * ws[576 + k + 1];
+      for (int r = 0; r < 2; ++r) {
+        const uint4 u = tile[j][hp + r * 8 * kO3HW];
+        const uint32_t wd[4] = {u.x, u.y, u.z, u.w};
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&wd[e]);
+          f[2 * e] = __low2float(h2); f[2 * e + 1] = __high2float(h2);
+        }
+        acc[r][0] += f[0] * a0.x + f[1] * a0.y + f[2] * a0.z + f[3] * a0.w + f[4] * a1.x + f[5] * a1.y + f[6] * a1.z + f[7] * a1.w;
+        acc[r][1] += f[0] * b0.x + f[1] * b0.y + f[2] * b0.z + f[3] * b0.w + f[4] * b1.x + f[5] * b1.y + f[6] * b1.z + f[7] * b1.w;
+        acc[r][2] += f[0] * c0.x + f[1] * c0.y + f[2] * c0.z + f[3] * c0.w + f[4] * c1.x + f[5] * c1.y + f[6] * c1.z + f[7] * c1.w;
       }
     }
   }
-  float* o = out + (size_t)n * 3 * HW + rem;
-  o[0] = sigmoidf_(acc0);
-  o[HW] = sigmoidf_(acc1);
-  o[2 * HW] = sigmoidf_(acc2);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int y = y0 + ty + 8 * r, x = x0 + tx;
+    if (y < H && x < W) {
+      float* o = out + (size_t)n * 3 * HW + (size_t)y * W + x;
+      o[0] = sigmoidf_(acc[r][0]);
+      o[HW] = sigmoidf_(acc[r][1]);
+      o[2 * HW] = sigmoidf_(acc[r][2]);
+    }
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -789,7 +813,7 @@ int launch_conv_tc(ldm_ctx* ctx, const bf16* in, const ConvLayer& L, const float
 // 3x3 convolution, Cin = 64, through conv_halo_kernel.  L.map_w: (Cout rows, 9 * 64), box (64, Cout); Cout = 64 (bf16
 // NHWC output) or 16 (out_conv of the pixel path: fin != nullptr, rows 3..15 of the packed weight are zero).
 int conv_halo_supported(int H, int W, int Cin, int Cout) {
-  if (Cin != 64 || (Cout != 64 && Cout != 16) || W < 30 || W + 2 > 256) return 0;
+  if (Cin != 64 || (Cout != 64 && Cout != 32 && Cout != 16) || W < 30 || W + 2 > 256) return 0;
   const int Wp = W + 2, nrows = (Wp - 1 + 128 + Wp - 1) / Wp + 2;
   const size_t a_stride = (((size_t)nrows * Wp * 128 + 1023) & ~(size_t)1023) + 1024;
   const size_t smem = (((size_t)9 * Cout * 128 + 1023) & ~(size_t)1023) + 1024 + kHaloStages * a_stride + 1024;
@@ -805,6 +829,7 @@ int launch_conv_halo(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer
   static bool attr_set = false;
   if (!attr_set) {
     LDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<64, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
+    LDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<32, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
     LDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<16, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
     LDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<16, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
     attr_set = true;
@@ -844,7 +869,9 @@ int launch_conv_halo(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer
   const size_t smem = (((size_t)9 * L.Cout * 128 + 1023) & ~(size_t)1023) + 1024 + a.stages * (size_t)a.a_stride + 1024;
   const int slots = pair ? 2 * ctx->sm_count : ctx->sm_count;
   const int grid = a.total_units < slots ? a.total_units : slots;
-  if (!fin) LDM_CUDA(launch_maybe_pdl(conv_halo_kernel<64, 0, 1>, dim3(grid), kThreads, smem, st, ctx->use_pdl, ma, L.map_w, a));
+  LDM_CHECK(fin ? L.Cout == 16 : (L.Cout == 64 || L.Cout == 32), "conv_halo: %d output channels in this mode", L.Cout);
+  if (!fin && L.Cout == 32) LDM_CUDA(launch_maybe_pdl(conv_halo_kernel<32, 0, 1>, dim3(grid), kThreads, smem, st, ctx->use_pdl, ma, L.map_w, a));
+  else if (!fin) LDM_CUDA(launch_maybe_pdl(conv_halo_kernel<64, 0, 1>, dim3(grid), kThreads, smem, st, ctx->use_pdl, ma, L.map_w, a));
   else if (ddpm) LDM_CUDA(launch_maybe_pdl(conv_halo_kernel<16, 2, 2>, dim3(grid), kThreads, smem, st, ctx->use_pdl, ma, L.map_w, a));
   else LDM_CUDA(launch_maybe_pdl(conv_halo_kernel<16, 1, 2>, dim3(grid), kThreads, smem, st, ctx->use_pdl, ma, L.map_w, a));
   ctx->launches++;
@@ -920,8 +947,7 @@ int launch_conv_halo_stream(ldm_ctx* ctx, const bf16* in, int in_pitch, const Co
 
 int launch_conv_out3(ldm_ctx* ctx, const bf16* in, const float* w, const float* bias, float* out, int B, int H, int W,
                      cudaStream_t st) {
-  const int total = B * H * W;
-  conv_out3_kernel<<<ceil_div(total, 256), 256, 0, st>>>(in, w, bias, out, H, W, total);
+  conv_out3_kernel<<<dim3(ceil_div(W, kO3TW), ceil_div(H, kO3TH), B), 256, 0, st>>>(in, w, bias, out, H, W);
   ctx->launches++;
   ldm_kmark(ctx, "conv_out3");
   LDM_CUDA(cudaGetLastError());

@@ -3,19 +3,23 @@
 // four sub-pixel 2x2-tap convolutions; LayerNorm2d / GroupNorm / CALayer / SpatialAttention are the
 // memory-bound kernels of decoder_norm.cu.
 #include "common.cuh"
+#include "pix_out.cuh"
 
 int tc_pick_bn(int M, int N);
 int conv_tc_pick_bn(int Cout);
 int launch_conv_tc(ldm_ctx* ctx, const bf16* in, const ConvLayer& L, const float* bias, bf16* out, int B, int H, int W,
                    int up, cudaStream_t st);
-int launch_norm_coef_bf16(ldm_ctx* ctx, const bf16* x, const float* gamma, const float* beta, float2* coef, int B, int HW,
-                          int C, int group, cudaStream_t st);
+int launch_norm_coef_bf16_ws(ldm_ctx* ctx, const bf16* x, const float* gamma, const float* beta, float2* coef, int B, int HW,
+                             int C, int group, float2* part, int* cnt, cudaStream_t st);
 int launch_coef_apply_bf16(ldm_ctx* ctx, const bf16* x, const float2* coef, bf16* out, int B, int HW, int C, int act,
                            cudaStream_t st);
 int launch_sa_map_bf16(ldm_ctx* ctx, const bf16* x, const float2* coef, const float* ca, float* map, int B, int HW, int C,
                        cudaStream_t st);
 int launch_sa_apply_bf16(ldm_ctx* ctx, const bf16* x, const float2* coef, const float* ca, const float* map,
-                         const float* sa_w, const bf16* resid, bf16* out, int B, int H, int C, cudaStream_t st);
+                         const float* sa_w, const bf16* resid, bf16* out, float* gate, int B, int H, int C, cudaStream_t st);
+int launch_conv_halo(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer& L, const float* bias, bf16* out, int out_pitch,
+                     int B, int H, int W, int relu, const float* post, int post_stride, const PixOutArgs* fin, int ddpm,
+                     cudaStream_t st);
 int launch_conv_out3(ldm_ctx* ctx, const bf16* in, const float* w, const float* bias, float* out, int B, int H, int W,
                      cudaStream_t st);
 
@@ -73,6 +77,10 @@ int ensure_dec_workspace(ldm_ctx* ctx, int B) {
   LDM_TRY(ldm_alloc_t(ctx, P, &ctx->d_gap, (size_t)B * 512));
   LDM_TRY(ldm_alloc_t(ctx, P, &ctx->d_ca, (size_t)B * 512));
   LDM_TRY(ldm_alloc_t(ctx, P, &ctx->d_map, (size_t)B * 1024 * 2));
+  LDM_TRY(ldm_alloc_t(ctx, P, &ctx->d_gate, (size_t)B * 1024));
+  LDM_TRY(ldm_alloc_t(ctx, P, &ctx->d_part, (size_t)B * 1024));          // norm_coef pixel-split partial sums
+  LDM_TRY(ldm_alloc_t(ctx, P, &ctx->d_cnt, (size_t)B * 16));             // ... and their tickets (left zero by every launch)
+  LDM_CUDA(cudaMemset(ctx->d_cnt, 0, (size_t)B * 16 * sizeof(int)));
   LDM_TRY(ldm_alloc_t(ctx, P, &ctx->d_zb, (size_t)B * 256 + 64));
   LDM_TRY(ldm_alloc_t(ctx, P, &ctx->d_h1b, (size_t)B * 512));
   ctx->act_maps.clear();   // descriptors over the old workspace are stale
@@ -151,14 +159,14 @@ int res_block_bf16(ldm_ctx* ctx, const ResBlockModel& R, int B, const bf16* X, b
   const int C = R.C, H = R.HW, P = H * H;
   float2* coef = reinterpret_cast<float2*>(ctx->d_stats);
   LDM_TRY(launch_conv_tc(ctx, X, R.conv1, R.conv1.b, Y, B, H, H, 1, st));                              // conv1
-  LDM_TRY(launch_norm_coef_bf16(ctx, Y, R.ln1_w, R.ln1_b, coef, B, P, C, 1, st));                       // ln1 as (scale, shift)
+  LDM_TRY(launch_norm_coef_bf16_ws(ctx, Y, R.ln1_w, R.ln1_b, coef, B, P, C, 1, ctx->d_part, ctx->d_cnt, st));   // ln1 as (scale, shift)
   LDM_TRY(launch_coef_apply_bf16(ctx, Y, coef, OUT, B, P, C, LDM_ACT_SWISH, st));                       // swish(ln1(.))
   LDM_TRY(launch_conv_tc(ctx, OUT, R.conv2, R.conv2.b, Y, B, H, H, 1, st));                             // conv2
-  LDM_TRY(launch_norm_coef_bf16(ctx, Y, R.ln2_w, R.ln2_b, coef, B, P, C, 1, st));                       // ln2 as (scale, shift)
+  LDM_TRY(launch_norm_coef_bf16_ws(ctx, Y, R.ln2_w, R.ln2_b, coef, B, P, C, 1, ctx->d_part, ctx->d_cnt, st));   // ln2 as (scale, shift)
   // CALayer (v2:64-67): the average pool of an instance-normalised map is its beta, so the channel gate is a
   // per-channel constant computed at pack time (ca_const), the same for every sample
   LDM_TRY(launch_sa_map_bf16(ctx, Y, coef, R.ca_const, ctx->d_map, B, P, C, st));
-  LDM_TRY(launch_sa_apply_bf16(ctx, Y, coef, R.ca_const, ctx->d_map, R.sa_w, X, OUT, B, H, C, st));
+  LDM_TRY(launch_sa_apply_bf16(ctx, Y, coef, R.ca_const, ctx->d_map, R.sa_w, X, OUT, ctx->d_gate, B, H, C, st));
   return 0;
 }
 
@@ -167,7 +175,7 @@ int up_block_bf16(ldm_ctx* ctx, const DecoderModel& D, int idx, int B, int H, in
   const int Cout = Cin / 2, P = 4 * H * H;
   LDM_TRY(launch_conv_tc(ctx, X, D.up[idx][0], D.up_b[idx], Y, B, H, H, 2, st));   // four sub-pixel parities, one launch
   float2* coef = reinterpret_cast<float2*>(ctx->d_stats);
-  LDM_TRY(launch_norm_coef_bf16(ctx, Y, D.up_gn_w[idx], D.up_gn_b[idx], coef, B, P, Cout, 8, st));
+  LDM_TRY(launch_norm_coef_bf16_ws(ctx, Y, D.up_gn_w[idx], D.up_gn_b[idx], coef, B, P, Cout, 8, ctx->d_part, ctx->d_cnt, st));
   LDM_TRY(launch_coef_apply_bf16(ctx, Y, coef, OUT, B, P, Cout, LDM_ACT_SWISH, st));
   return 0;
 }
@@ -191,9 +199,12 @@ int decode_chunk_bf16(ldm_ctx* ctx, const float* z, float* img, int B, cudaStrea
   LDM_TRY(res_block_bf16(ctx, D.res[2], B, A, Bf, C, st));
   LDM_TRY(up_block_bf16(ctx, D, 2, B, 32, 128, C, Bf, A, st));
   // final_conv (v2:272-278)
-  LDM_TRY(launch_conv_tc(ctx, A, D.fin0, D.fin0.b, Bf, B, 64, 64, 1, st));
-  LDM_TRY(launch_inorm_stats<bf16>(ctx, Bf, ctx->d_stats, B, 4096, 32, 4, st));
-  LDM_TRY(launch_norm_apply<bf16>(ctx, Bf, ctx->d_stats, D.fin_gn_w, D.fin_gn_b, C, B, 4096, 32, 4, LDM_ACT_SWISH, st));
+  // 64 -> 32 at 64 x 64: the halo kernel (weights resident, every pixel tile loaded once with its halo) instead of nine
+  // re-loaded taps per tile
+  LDM_TRY(launch_conv_halo(ctx, A, 64, D.fin0, D.fin0.b, Bf, 32, B, 64, 64, 0, nullptr, 0, nullptr, 0, st));
+  float2* coef = reinterpret_cast<float2*>(ctx->d_stats);
+  LDM_TRY(launch_norm_coef_bf16_ws(ctx, Bf, D.fin_gn_w, D.fin_gn_b, coef, B, 4096, 32, 4, ctx->d_part, ctx->d_cnt, st));   // GroupNorm(8, 32)
+  LDM_TRY(launch_coef_apply_bf16(ctx, Bf, coef, C, B, 4096, 32, LDM_ACT_SWISH, st));
   LDM_TRY(launch_conv_out3(ctx, C, D.fin3.w32, D.fin3.b, img, B, 64, 64, st));
   return 0;
 }

@@ -195,43 +195,82 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// One CTA per (sample, 64-channel block): threads = 8 channel-octets x 32 pixel lanes.  Writes, per channel,
-// scale = rstd * gamma and shift = beta - mean * scale of its normalisation group (cg channels x HW pixels; cg | 8),
-// so that the consumers apply LayerNorm2d / GroupNorm as one FMA.  Sums are centred on the first pixel of the
-// channel to keep the single pass free of cancellation.
+// One CTA per (sample, CB-channel block, pixel split): threads = CB / 8 channel-octets x 2048 / CB pixel lanes, four 16-byte
+// loads in flight per thread.  With S > 1 splits every CTA leaves its per-channel partial sums (centred on the sample's
+// first pixel, so they add) in `part`; the last CTA of a (sample, block) to finish, by ticket, adds them IN SPLIT ORDER
+// (deterministic) and writes the coefficients.  `cnt` must be zero on entry and is left zero.
+template <int CB>
 __global__ void __launch_bounds__(256)
-norm_coef_bf16_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                      float2* __restrict__ coef, int HW, int C, int cg) {
-  __shared__ float s1[32][65], s2[32][65];
-  const int n = blockIdx.y, c0 = blockIdx.x * 64, oct = threadIdx.x & 7, pl = threadIdx.x >> 3;
+norm_coef2_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  float2* __restrict__ coef, int HW, int C, int cg, float2* __restrict__ part, int* __restrict__ cnt, int S) {
+  constexpr int OCT = CB / 8, PL = 256 / OCT;
+  __shared__ float s1[PL][CB + 1], s2[PL][CB + 1];
+  __shared__ int s_last;
+  const int n = blockIdx.y, cb = blockIdx.x, c0 = cb * CB, sp = blockIdx.z;
+  const int oct = threadIdx.x % OCT, pl = threadIdx.x / OCT;
   const bf16* base = x + (size_t)n * HW * C + c0 + oct * 8;
   float piv[8], a[8], b[8];
   unpack8(__ldg(reinterpret_cast<const uint4*>(base)), piv);
 #pragma unroll
   for (int e = 0; e < 8; ++e) { a[e] = 0.f; b[e] = 0.f; }
-  for (int p = pl; p < HW; p += 32) {
+  const int per = HW / S, p_hi = (sp + 1) * per;
+  int p = sp * per + pl;
+  for (; p + 3 * PL < p_hi; p += 4 * PL) {
+    uint4 u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u[i] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(p + i * PL) * C));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float f[8];
+      unpack8(u[i], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = f[e] - piv[e]; a[e] += d; b[e] = fmaf(d, d, b[e]); }
+    }
+  }
+  for (; p < p_hi; p += PL) {
     float f[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(base + (size_t)p * C)), f);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { const float d = f[e] - piv[e]; a[e] += d; b[e] += d * d; }
+    for (int e = 0; e < 8; ++e) { const float d = f[e] - piv[e]; a[e] += d; b[e] = fmaf(d, d, b[e]); }
   }
 #pragma unroll
   for (int e = 0; e < 8; ++e) { s1[pl][oct * 8 + e] = a[e]; s2[pl][oct * 8 + e] = b[e]; }
   __syncthreads();
-  if (threadIdx.x < 64) {
-    const int c = threadIdx.x;
-    float t1 = 0.f, t2 = 0.f;
+  float t1 = 0.f, t2 = 0.f;
+  if (threadIdx.x < CB) {
 #pragma unroll 8
-    for (int i = 0; i < 32; ++i) { t1 += s1[i][c]; t2 += s2[i][c]; }
+    for (int i = 0; i < PL; ++i) { t1 += s1[i][threadIdx.x]; t2 += s2[i][threadIdx.x]; }
+  }
+  if (S > 1) {
+    float2* mine = part + (((size_t)n * gridDim.x + cb) * S) * CB;
+    if (threadIdx.x < CB) mine[(size_t)sp * CB + threadIdx.x] = make_float2(t1, t2);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int ticket = atomicAdd(&cnt[n * gridDim.x + cb], 1);
+      s_last = ticket == S - 1;
+      if (s_last) cnt[n * gridDim.x + cb] = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < CB) {
+      t1 = 0.f; t2 = 0.f;
+      for (int i = 0; i < S; ++i) { const float2 v = __ldcg(mine + (size_t)i * CB + threadIdx.x); t1 += v.x; t2 += v.y; }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < CB) {
+    const int c = threadIdx.x;
     // per-channel (mean, M2), then merge the cg channels of the group (Chan et al.)
     const float inv = 1.0f / (float)HW;
     const float pv = __bfloat162float(x[(size_t)n * HW * C + c0 + c]);
     const float dm = t1 * inv;
-    float mean = pv + dm, m2 = fmaxf(t2 - t1 * dm, 0.f);
-    s1[0][c] = mean; s2[0][c] = m2;
+    s1[0][c] = pv + dm;
+    s2[0][c] = fmaxf(t2 - t1 * dm, 0.f);
   }
   __syncthreads();
-  if (threadIdx.x < 64) {
+  if (threadIdx.x < CB) {
     const int c = threadIdx.x, g0 = (c / cg) * cg;
     float gm = 0.f;
     for (int i = 0; i < cg; ++i) gm += s1[0][g0 + i];
@@ -265,79 +304,138 @@ coef_apply_bf16_kernel(const bf16* __restrict__ x, const float2* __restrict__ co
 }
 
 // SpatialAttention input (v2:76-78): per pixel, mean and max over channels of z = ca[c] * (x * scale + shift).
-// C/8 lanes per pixel (C = 128: 16 lanes, two pixels per warp; C >= 256: a whole warp, several octets per lane).
+// A warp walks `run` consecutive pixels of ONE sample: LPP = min(32, C / 8) lanes share a pixel (NO = C / (8 LPP) channel
+// octets per lane), 32 / LPP pixels side by side; the lane's (ca * scale, ca * shift) stay in registers for the whole run.
+template <int NO>
 __global__ void __launch_bounds__(256)
-sa_map_bf16_kernel(const bf16* __restrict__ x, const float2* __restrict__ coef, const float* __restrict__ ca,
-                   float* __restrict__ map, int HW, int C, int npix) {
-  const int lpp = C >= 256 ? 32 : C / 8;                 // lanes per pixel
-  const int ppw = 32 / lpp;                              // pixels per warp
+sa_map2_kernel(const bf16* __restrict__ x, const float2* __restrict__ coef, const float* __restrict__ ca,
+               float* __restrict__ map, int HW, int C, int npix, int run) {
+  const int lpp = C / (8 * NO) < 32 ? C / (8 * NO) : 32, ppw = 32 / lpp;
   const int lane = threadIdx.x & 31, wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int pix = wid * ppw + lane / lpp, sub = lane % lpp;
-  float s = 0.f, m = -INFINITY;
-  if (pix < npix) {
-    const int n = pix / HW;
-    const bf16* row = x + (size_t)pix * C;
-    const float2* cf = coef + (size_t)n * C;
-    for (int c = sub * 8; c < C; c += lpp * 8) {
-      float f[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(row + c)), f);
+  const int first = wid * run;
+  if (first >= npix) return;
+  const int n = first / HW, sub = lane % lpp, pj = lane / lpp;
+  float A[NO][8], Bv[NO][8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float2 k = __ldg(cf + c + e);
-        const float z = __ldg(ca + c + e) * (f[e] * k.x + k.y);
-        s += z;
-        m = fmaxf(m, z);
-      }
+  for (int o = 0; o < NO; ++o) {
+    const int c = (sub + o * lpp) * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float2 k = __ldg(coef + (size_t)n * C + c + e);
+      const float g = __ldg(ca + c + e);
+      A[o][e] = g * k.x; Bv[o][e] = g * k.y;
     }
   }
-  for (int o = lpp >> 1; o > 0; o >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  }
-  if (pix < npix && sub == 0) {
-    map[(size_t)pix * 2 + 0] = s / (float)C;
-    map[(size_t)pix * 2 + 1] = m;
+  const float inv_c = 1.0f / (float)C;
+  for (int i = 0; i < run; i += 2 * ppw) {       // two pixel groups per iteration: two independent 16-byte loads in flight
+    uint4 u[2][NO];
+    int pix[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      pix[h] = first + i + h * ppw + pj;
+      const bool ok = i + h * ppw < run && pix[h] < npix;
+      pix[h] = ok ? pix[h] : -1;
+#pragma unroll
+      for (int o = 0; o < NO; ++o)
+        u[h][o] = ok ? __ldg(reinterpret_cast<const uint4*>(x + (size_t)pix[h] * C + (sub + o * lpp) * 8)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float s = 0.f, m = -INFINITY;
+#pragma unroll
+      for (int o = 0; o < NO; ++o) {
+        float f[8];
+        unpack8(u[h][o], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float z = fmaf(f[e], A[o][e], Bv[o][e]); s += z; m = fmaxf(m, z); }
+      }
+      for (int o = lpp >> 1; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      }
+      if (pix[h] >= 0 && sub == 0) *reinterpret_cast<float2*>(map + (size_t)pix[h] * 2) = make_float2(s * inv_c, m);
+    }
   }
 }
 
-// out = swish(z * sigmoid(conv7x7(map)) + resid)   (v2:79-81 then v2:176-177), same lane layout as sa_map
+// gate = sigmoid(conv7x7([mean, max] map)) (v2:79-80): one thread per pixel; the map of a sample is a few KiB (L1 / L2)
 __global__ void __launch_bounds__(256)
-sa_apply_bf16_kernel(const bf16* __restrict__ x, const float2* __restrict__ coef, const float* __restrict__ ca,
-                     const float* __restrict__ map, const float* __restrict__ sa_w, const bf16* __restrict__ resid,
-                     bf16* __restrict__ out, int H, int C, int npix) {
-  const int lpp = C >= 256 ? 32 : C / 8;
-  const int ppw = 32 / lpp;
-  const int lane = threadIdx.x & 31, wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int pix = wid * ppw + lane / lpp, sub = lane % lpp;
-  const int HW = H * H;
-  const bool ok = pix < npix;
-  const int n = ok ? pix / HW : 0, rem = ok ? pix - n * HW : 0, y = rem / H, xx = rem - y * H;
+sa_gate_kernel(const float* __restrict__ map, const float* __restrict__ sa_w, float* __restrict__ gate, int H, int npix) {
+  __shared__ float w[98];
+  if (threadIdx.x < 98) w[threadIdx.x] = sa_w[threadIdx.x];
+  __syncthreads();
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const int HW = H * H, n = pix / HW, rem = pix - n * HW, y = rem / H, xx = rem - y * H;
+  const float2* mp = reinterpret_cast<const float2*>(map) + (size_t)n * HW;
   float a = 0.f;
-  if (ok) {
-    for (int t = sub; t < 98; t += lpp) {
-      const int ch = t / 49, k = t - ch * 49, ky = k / 7, kx = k - ky * 7;
-      const int yy = y + ky - 3, xq = xx + kx - 3;
-      if (yy >= 0 && yy < H && xq >= 0 && xq < H) a += __ldg(sa_w + t) * __ldg(map + ((size_t)n * HW + yy * H + xq) * 2 + ch);
+  for (int ky = 0; ky < 7; ++ky) {
+    const int yy = y + ky - 3;
+    if (yy < 0 || yy >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 7; ++kx) {
+      const int xq = xx + kx - 3;
+      if (xq < 0 || xq >= H) continue;
+      const float2 v = __ldg(mp + yy * H + xq);
+      a = fmaf(w[ky * 7 + kx], v.x, a);
+      a = fmaf(w[49 + ky * 7 + kx], v.y, a);
     }
   }
-  for (int o = lpp >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-  if (!ok) return;
-  const float gate = sigmoidf_(a);
-  const bf16* row = x + (size_t)pix * C;
-  const bf16* rr = resid + (size_t)pix * C;
-  bf16* orow = out + (size_t)pix * C;
-  const float2* cf = coef + (size_t)n * C;
-  for (int c = sub * 8; c < C; c += lpp * 8) {
-    float f[8], r[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(row + c)), f);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(rr + c)), r);
+  gate[pix] = sigmoidf_(a);
+}
+
+// out = swish(z * gate + resid)   (v2:81 then v2:176-177), same lane layout as sa_map2
+template <int NO>
+__global__ void __launch_bounds__(256)
+sa_apply2_kernel(const bf16* __restrict__ x, const float2* __restrict__ coef, const float* __restrict__ ca,
+                 const float* __restrict__ gate, const bf16* __restrict__ resid, bf16* __restrict__ out, int HW, int C, int npix,
+                 int run) {
+  const int lpp = C / (8 * NO) < 32 ? C / (8 * NO) : 32, ppw = 32 / lpp;
+  const int lane = threadIdx.x & 31, wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int first = wid * run;
+  if (first >= npix) return;
+  const int n = first / HW, sub = lane % lpp, pj = lane / lpp;
+  float A[NO][8], Bv[NO][8];
+#pragma unroll
+  for (int o = 0; o < NO; ++o) {
+    const int c = (sub + o * lpp) * 8;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float2 k = __ldg(cf + c + e);
-      const float z = __ldg(ca + c + e) * (f[e] * k.x + k.y);
-      f[e] = swishf(z * gate + r[e]);
+      const float2 k = __ldg(coef + (size_t)n * C + c + e);
+      const float g = __ldg(ca + c + e);
+      A[o][e] = g * k.x; Bv[o][e] = g * k.y;
     }
-    *reinterpret_cast<uint4*>(orow + c) = pack8(f);
+  }
+  for (int i = 0; i < run; i += 2 * ppw) {
+    uint4 u[2][NO], r[2][NO];
+    float gt[2];
+    int pix[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      pix[h] = first + i + h * ppw + pj;
+      const bool ok = i + h * ppw < run && pix[h] < npix;
+      pix[h] = ok ? pix[h] : -1;
+      gt[h] = ok ? __ldg(gate + pix[h]) : 0.f;
+#pragma unroll
+      for (int o = 0; o < NO; ++o) {
+        const size_t off = (size_t)(ok ? pix[h] : 0) * C + (sub + o * lpp) * 8;
+        u[h][o] = ok ? __ldg(reinterpret_cast<const uint4*>(x + off)) : make_uint4(0, 0, 0, 0);
+        r[h][o] = ok ? __ldg(reinterpret_cast<const uint4*>(resid + off)) : make_uint4(0, 0, 0, 0);
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (pix[h] < 0) continue;
+#pragma unroll
+      for (int o = 0; o < NO; ++o) {
+        float f[8], rr[8];
+        unpack8(u[h][o], f);
+        unpack8(r[h][o], rr);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = swishf(fmaf(fmaf(f[e], A[o][e], Bv[o][e]), gt[h], rr[e]));
+        *reinterpret_cast<uint4*>(out + (size_t)pix[h] * C + (sub + o * lpp) * 8) = pack8(f);
+      }
+    }
   }
 }
 
@@ -393,14 +491,30 @@ int launch_sa_apply(ldm_ctx* ctx, const T* x, const float* stats, const float* g
 
 
 // ---- bf16 fast path launchers
-int launch_norm_coef_bf16(ldm_ctx* ctx, const bf16* x, const float* gamma, const float* beta, float2* coef, int B, int HW,
-                          int C, int group, cudaStream_t st) {
+// splits of the pixel range so that a few CTAs per SM are in flight: power of two, >= 4 pixels per thread
+static int norm_splits(int blocks, int HW, int pl, int C) {
+  int s = 1;
+  while (blocks * s < 1184 && HW / (2 * s) >= 4 * pl && 2 * s * C <= 1024 && s < 16) s *= 2;
+  return s;
+}
+// `part` (B x 1024 float2) and `cnt` (B x 16 ints, zero) enable the pixel splits; without them one CTA walks the whole sample
+int launch_norm_coef_bf16_ws(ldm_ctx* ctx, const bf16* x, const float* gamma, const float* beta, float2* coef, int B, int HW,
+                             int C, int group, float2* part, int* cnt, cudaStream_t st) {
   LDM_CHECK(C % 64 == 0 || C == 32, "norm_coef: C must be 32 or a multiple of 64 (C=%d)", C);
   LDM_CHECK(group == 1 || group == 2 || group == 4 || group == 8, "norm_coef: group size %d unsupported", group);
-  LDM_CHECK(C % 64 == 0, "norm_coef: C %% 64 == 0 required on the vector path (C=%d)", C);
-  norm_coef_bf16_kernel<<<dim3(C / 64, B), 256, 0, st>>>(x, gamma, beta, coef, HW, C, group);
-  LDM_LAUNCHED(ctx);
+  if (C == 32) {
+    const int S = part && cnt ? norm_splits(B, HW, 64, C) : 1;
+    norm_coef2_kernel<32><<<dim3(1, B, S), 256, 0, st>>>(x, gamma, beta, coef, HW, C, group, part, cnt, S);
+  } else {
+    const int S = part && cnt && C / 64 <= 16 ? norm_splits(B * (C / 64), HW, 32, C) : 1;
+    norm_coef2_kernel<64><<<dim3(C / 64, B, S), 256, 0, st>>>(x, gamma, beta, coef, HW, C, group, part, cnt, S);
+  }
+  LDM_LAUNCHED_AS(ctx, "launch_norm_coef_bf16");
   return 0;
+}
+int launch_norm_coef_bf16(ldm_ctx* ctx, const bf16* x, const float* gamma, const float* beta, float2* coef, int B, int HW,
+                          int C, int group, cudaStream_t st) {
+  return launch_norm_coef_bf16_ws(ctx, x, gamma, beta, coef, B, HW, C, group, nullptr, nullptr, st);
 }
 int launch_coef_apply_bf16(ldm_ctx* ctx, const bf16* x, const float2* coef, bf16* out, int B, int HW, int C, int act,
                            cudaStream_t st) {
@@ -409,20 +523,35 @@ int launch_coef_apply_bf16(ldm_ctx* ctx, const bf16* x, const float2* coef, bf16
   LDM_LAUNCHED(ctx);
   return 0;
 }
+// pixels a warp walks: a power of two dividing HW (one sample per warp), a multiple of 2 ppw, short enough that the grid
+// holds a few thousand warps (a small map with 512 channels would otherwise run on 64 CTAs)
+static int sa_run(int npix, int HW, int ppw) {
+  int run = 32;
+  while (run > HW || (run > 2 * ppw && npix / run < 4096)) run >>= 1;
+  return run < 2 * ppw ? 2 * ppw : run;
+}
 int launch_sa_map_bf16(ldm_ctx* ctx, const bf16* x, const float2* coef, const float* ca, float* map, int B, int HW, int C,
                        cudaStream_t st) {
-  LDM_CHECK(C % 64 == 0, "sa_map: C %% 64 == 0 required");
-  const int npix = B * HW, lpp = C >= 256 ? 32 : C / 8, ppw = 32 / lpp;
-  const int warps = ceil_div(npix, ppw);
-  sa_map_bf16_kernel<<<ceil_div(warps, 8), 256, 0, st>>>(x, coef, ca, map, HW, C, npix);
+  LDM_CHECK(C % 64 == 0 && C <= 512 && HW % 4 == 0, "sa_map: C %% 64 == 0, C <= 512 and HW %% 4 == 0 required (C=%d, HW=%d)", C, HW);
+  const int npix = B * HW, no = C > 256 ? 2 : 1, lpp = C / (8 * no) < 32 ? C / (8 * no) : 32;
+  const int run = sa_run(npix, HW, 32 / lpp), warps = ceil_div(npix, run);
+  LDM_CHECK(HW % run == 0, "sa_map: HW (%d) must be a multiple of the warp run (%d)", HW, run);
+  if (no == 2) sa_map2_kernel<2><<<ceil_div(warps, 8), 256, 0, st>>>(x, coef, ca, map, HW, C, npix, run);
+  else sa_map2_kernel<1><<<ceil_div(warps, 8), 256, 0, st>>>(x, coef, ca, map, HW, C, npix, run);
   LDM_LAUNCHED(ctx);
   return 0;
 }
+// gate: (B, H, H) scratch of the spatial-attention gate
 int launch_sa_apply_bf16(ldm_ctx* ctx, const bf16* x, const float2* coef, const float* ca, const float* map,
-                         const float* sa_w, const bf16* resid, bf16* out, int B, int H, int C, cudaStream_t st) {
-  const int npix = B * H * H, lpp = C >= 256 ? 32 : C / 8, ppw = 32 / lpp;
-  const int warps = ceil_div(npix, ppw);
-  sa_apply_bf16_kernel<<<ceil_div(warps, 8), 256, 0, st>>>(x, coef, ca, map, sa_w, resid, out, H, C, npix);
+                         const float* sa_w, const bf16* resid, bf16* out, float* gate, int B, int H, int C, cudaStream_t st) {
+  LDM_CHECK(C % 64 == 0 && C <= 512, "sa_apply: C %% 64 == 0 and C <= 512 required (C=%d)", C);
+  const int HW = H * H, npix = B * HW, no = C > 256 ? 2 : 1, lpp = C / (8 * no) < 32 ? C / (8 * no) : 32;
+  const int run = sa_run(npix, HW, 32 / lpp), warps = ceil_div(npix, run);
+  LDM_CHECK(HW % run == 0, "sa_apply: HW (%d) must be a multiple of the warp run (%d)", HW, run);
+  sa_gate_kernel<<<ceil_div(npix, 256), 256, 0, st>>>(map, sa_w, gate, H, npix);
+  LDM_LAUNCHED_AS(ctx, "launch_sa_gate");
+  if (no == 2) sa_apply2_kernel<2><<<ceil_div(warps, 8), 256, 0, st>>>(x, coef, ca, gate, resid, out, HW, C, npix, run);
+  else sa_apply2_kernel<1><<<ceil_div(warps, 8), 256, 0, st>>>(x, coef, ca, gate, resid, out, HW, C, npix, run);
   LDM_LAUNCHED(ctx);
   return 0;
 }

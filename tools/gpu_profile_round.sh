@@ -1,12 +1,13 @@
 #!/bin/bash
 # Evidence for the round: plain bench, then the ncu launch list of the SAME command, then --set full captures of the
 # dominant kernel (chain_kernel) and of the first decoder convolutions.  Usage: bash tools/gpu_profile_round.sh <tag>
+# Afterwards, here: python tools/ncu_traffic.py gpurun_out/<tag>_chain_full.ncu-rep profiles/<tag>_chain_traffic.json
 TAG=${1:-rXX}
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu --no-secondary"
 $CMD > gpurun_out/${TAG}_bench_plain.log 2>&1 || { echo "plain bench failed"; tail -5 gpurun_out/${TAG}_bench_plain.log; exit 1; }
-tail -1 gpurun_out/${TAG}_bench_plain.log | cut -c1-400
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches_bench.csv $CMD > gpurun_out/ncu1.log 2>&1
+tail -1 gpurun_out/${TAG}_bench_plain.log | cut -c1-300
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${TAG}_launches_bench.csv $CMD > gpurun_out/ncu1.log 2>&1
 echo "launch list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:chain_kernel -c 1 -f -o gpurun_out/${TAG}_chain_full $CMD > gpurun_out/ncu2.log 2>&1
 echo "chain full rc=$?"
