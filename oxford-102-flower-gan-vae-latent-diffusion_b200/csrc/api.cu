@@ -109,10 +109,13 @@ extern "C" LDM_API int ldm_ctx_create(ldm_ctx** out, int device, int precision) 
   if (r == 0) r = (int)cudaMemset(ctx->chain_err, 0, 2 * sizeof(int));
   if (r == 0) r = ldm_alloc_t(ctx, ctx->allocs, &ctx->coef_one, 1);
   if (r == 0) { const float4 one = make_float4(1.f, 1.f, 0.f, 0.f); r = (int)cudaMemcpy(ctx->coef_one, &one, sizeof(one), cudaMemcpyHostToDevice); }
-  if (r == 0 && precision == LDM_PRECISION_BF16) {
-    // the persistent cluster kernel is the bf16 denoiser; LDM_CHAIN=0 selects the one-kernel-per-layer sequence
+  {
+    // The persistent cluster kernel is the denoiser of both modes: bf16 operands (2e-2), or, in the strict mode, bf16
+    // (hi, lo) splits of weights and operands with the three products hi.hi + hi.lo + lo.hi on the tensor cores (1e-3).
+    // LDM_CHAIN=0 selects the one-kernel-per-layer sequence (strict mode: fp32 FMA on the CUDA cores).
     const char* ch = getenv("LDM_CHAIN");
-    ctx->chain_enabled = ch ? atoi(ch) : 1;
+    if (r == 0 && precision != LDM_PRECISION_BF16) r = tc_init(ctx);
+    ctx->chain_enabled = r == 0 ? (ch ? atoi(ch) : 1) : 0;
     if (ctx->chain_enabled && chain_init(ctx) != 0) ctx->chain_enabled = 0;   // ldm_last_error() keeps the reason
     ctx->use_chain = ctx->chain_enabled;
   }
@@ -335,12 +338,13 @@ static int ensure_workspace(ldm_ctx* ctx, int B) {
   LDM_TRY(ldm_alloc(ctx, P, &ctx->af_op[1], naf * op));
   if (ctx->use_chain)
   {
-    // + 64 rows: the last cluster of a launch writes its (up to 64-row) block unconditionally; the tensor maps stop at B
-    const size_t capc = (size_t)cap + 64;
-    for (int j = 0; j < U.nst; ++j) LDM_TRY(ldm_alloc_t(ctx, P, &ctx->opbuf[j], capc * U.hid[j]));
+    // + 64 rows: the last cluster of a launch writes its (up to 64-row) block unconditionally; the tensor maps stop at B.
+    // Strict mode: every operand row is its (hi, lo, hi) thirds.
+    const size_t capc = (size_t)cap + 64, mult = ctx->precision == LDM_PRECISION_BF16 ? 1 : 3;
+    for (int j = 0; j < U.nst; ++j) LDM_TRY(ldm_alloc_t(ctx, P, &ctx->opbuf[j], capc * U.hid[j] * mult));
     for (int k = 0; k < 2; ++k) {
-      LDM_TRY(ldm_alloc_t(ctx, P, &ctx->caf[k], capc * 3 * U.latent));
-      LDM_CUDA(cudaMemset(ctx->caf[k], 0, capc * 3 * U.latent * sizeof(bf16)));
+      LDM_TRY(ldm_alloc_t(ctx, P, &ctx->caf[k], capc * 3 * U.latent * mult));
+      LDM_CUDA(cudaMemset(ctx->caf[k], 0, capc * 3 * U.latent * mult * sizeof(bf16)));
     }
   }
   if (U.variant == 3) {
@@ -644,6 +648,7 @@ extern "C" LDM_API int ldm_unet_forward(ldm_ctx* ctx, const float* x_dev, const 
     if (ctx->use_chain) return launch_chain(ctx, batch, 1, 0, 0, t_dev, t_len, const_cast<float*>(x_dev), eps_out_dev, nullptr, st);
     return denoise<bf16>(ctx, batch, 0, md, st);
   }
+  if (ctx->use_chain) return launch_chain(ctx, batch, 1, 0, 0, t_dev, t_len, const_cast<float*>(x_dev), eps_out_dev, nullptr, st);
   LDM_TRY(stage_x<float>(ctx, x_dev, batch, 0, st));
   return denoise<float>(ctx, batch, 0, md, st);
 }
@@ -671,7 +676,7 @@ extern "C" LDM_API int ldm_randn(ldm_ctx* ctx, float* out, uint64_t seed, uint64
 static int run_chain(ldm_ctx* ctx, int B, int t_start, int t_end, const float* noise, cudaStream_t st) {
   // x lives in ctx->x_state; its operand copy must already be staged in af_op[0]
   const size_t slab = (size_t)B * ctx->unet.latent;
-  if (ctx->precision == LDM_PRECISION_BF16 && ctx->use_chain)   // the whole loop is one persistent kernel
+  if (ctx->use_chain)   // the whole loop is one persistent kernel (both precisions)
     return launch_chain(ctx, B, t_start - t_end + 1, t_start, 1, nullptr, 1, ctx->x_state, nullptr, noise, st);
   for (int t = t_start, j = 0; t >= t_end; --t, ++j) {
     StepMode md; md.sample = 1; md.t = t; md.x = ctx->x_state;

@@ -107,7 +107,8 @@ struct ChainPhase {
   const float* tab_c;  // [ncls, rows] tile order (null: none)
   const float *ga, *ba, *gb, *bb;   // LayerNorm affine parameters, natural feature order
   bf16* out;           // operand this phase produces (stage phases)
-  int ld_out;
+  int ld_out;          // its pitch; with ChainParams::split the row is [hi | lo | hi], each `wout` wide
+  int wout;
 };
 
 struct ChainParams {
@@ -133,6 +134,8 @@ struct ChainParams {
   const float4* coef_or_one;  // sample: coef; forward(): one entry (1, 1, 0, 0)
   bf16* af[2];                // (B, ld_af): [x~ | -c_b LN_f(h) | -c_b x] operand of the merged phase, double-buffered over steps
   int ld_af;
+  int split;                  // strict mode: every operand is stored as bf16 (hi, lo, hi) thirds against weights (hi, hi, lo): the
+                              // three-term split hi.hi + hi.lo + lo.hi keeps ~16 bits of the fp32 product on the bf16 tensor cores
   int writer_fence;           // 1: every writer thread issues fence.proxy.async before the hand-over; 0: the operand producer does
   int z_col;                  // TMEM column where the eps owners park the step's noise
   int x_col;                  // TMEM column of the fp32 chain state of the eps owners
@@ -341,6 +344,19 @@ __device__ __forceinline__ float swish_fast(float v) {
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
   return fmaf(h, t, h);
+}
+__device__ __forceinline__ float swish_precise(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+// bf16 (hi, lo) parts of an fp32 value: v = hi + lo up to 2^-17 relative
+__device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+// operand store: one bf16, or the (hi, lo, hi) thirds `w` columns apart
+__device__ __forceinline__ void store_operand(bf16* o, float v, int split, int w) {
+  if (!split) { *o = __float2bfloat16_rn(v); return; }
+  bf16 hi, lo;
+  split_bf16(v, hi, lo);
+  o[0] = hi; o[w] = lo; o[2 * w] = hi;
 }
 __device__ __forceinline__ int clamp_t(long long t, int n_t) { return (int)(t < 0 ? 0 : (t >= n_t ? n_t - 1 : t)); }
 
@@ -903,8 +919,9 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
             for (int i = 0; i < 8; ++i) {   // h2 = swish(LN_a(u)) + h: the next phase's operand (its LayerNorm is applied there)
               const float2 mr = rs[hr + i];
               const float a = mr.y * ga;                      // LayerNorm_a as one FMA: u a + (beta - mu a)
-              h2k[i] += swish_fast(fmaf(u[i], a, fmaf(-mr.x, a, ba)));
-              o[(size_t)i * ph.ld_out] = __float2bfloat16_rn(h2k[i]);   // rows beyond the batch land in the buffers' padding
+              const float pre = fmaf(u[i], a, fmaf(-mr.x, a, ba));
+              h2k[i] += P.split ? swish_precise(pre) : swish_fast(pre);
+              store_operand(o + (size_t)i * ph.ld_out, h2k[i], P.split, ph.wout);   // rows beyond the batch land in the buffers' padding
             }
             pub_b = true;
           }
@@ -924,7 +941,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float2 mr = rs[j];
-              o[(size_t)j * P.ld_af] = __float2bfloat16_rn(-cb_cur * ((v[j] - mr.x) * mr.y * ga + be));
+              store_operand(o + (size_t)j * P.ld_af, -cb_cur * ((v[j] - mr.x) * mr.y * ga + be), P.split, 3 * P.latent);
             }
           }
         }
@@ -1005,8 +1022,8 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
             const float inv_sa = 1.0f / cf_cur.y;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              o[(size_t)j * P.ld_af] = __float2bfloat16_rn(xr[j] * inv_sa + cf_cur.z * z[j]);
-              o[(size_t)j * P.ld_af + 2 * P.latent] = __float2bfloat16_rn(-cb_cur * xr[j]);
+              store_operand(o + (size_t)j * P.ld_af, xr[j] * inv_sa + cf_cur.z * z[j], P.split, 3 * P.latent);
+              store_operand(o + (size_t)j * P.ld_af + 2 * P.latent, -cb_cur * xr[j], P.split, 3 * P.latent);
             }
           }
         }
@@ -1069,6 +1086,25 @@ __global__ void pack_rows_bf16_kernel(const float* __restrict__ src, bf16* __res
   if (i >= (size_t)rows * K) return;
   const int rt = (int)(i / K), k = (int)(i % K);
   dst[i] = __float2bfloat16_rn(src[(size_t)tile_src_row(rt, d, stage, nsr) * K + k]);
+}
+// strict mode: each accumulator block of Kp columns becomes [hi | hi | lo] (3 Kp columns), against operands stored as [hi | lo | hi]
+__global__ void pack_rows_split_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int rows, int K, int Kp, int d, int stage, int nsr) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * K) return;
+  const int rt = (int)(i / K), k = (int)(i % K), a = k / Kp, kk = k - a * Kp;
+  const float v = src[(size_t)tile_src_row(rt, d, stage, nsr) * K + k];
+  const bf16 hi = __float2bfloat16_rn(v), lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  bf16* o = dst + (size_t)rt * 3 * K + (size_t)a * 3 * Kp + kk;
+  o[0] = hi; o[Kp] = hi; o[2 * Kp] = lo;
+}
+// first merged operand of a launch: [x | 0 | 0] (bf16), or its (hi, lo, hi) thirds in strict mode
+__global__ void chain_stage_x_kernel(const float* __restrict__ x, bf16* __restrict__ dst, int B, int L, int split) {
+  const int W3 = 3 * L, ld = split ? 3 * W3 : W3;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * W3) return;
+  const int r = (int)(i / W3), c = (int)(i % W3);
+  const float v = c < L ? x[(size_t)r * L + c] : 0.f;
+  store_operand(dst + (size_t)r * ld + c, v, split, W3);
 }
 // tables: dst[t][rt] = src[t][src_row(rt)]
 __global__ void pack_cols_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int rows, int d, int stage, int nsr) {
@@ -1181,6 +1217,7 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
   for (void* p : C.allocs) cudaFree(p);
   C = ChainModel();
   const int nst = U.nst, L = U.latent;
+  const int split = ctx->precision == LDM_PRECISION_FP32 ? 1 : 0;   // strict mode: three-term bf16 split (see ChainParams::split)
   LDM_CHECK(nst + 1 <= LDM_CHAIN_MAX_PHASES && nst <= 5, "chain: more stages (%d) than the persistent kernel is validated for: the per-layer path takes over", nst);
   LDM_CHECK(L % 128 == 0 && L / 128 <= kSlots, "chain: latent_dim %d unsupported", L);
   for (int i = 0; i < nst; ++i)
@@ -1228,7 +1265,7 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
         LDM_TRY(mm(ctx, U.tab_c[0], d, U.block[0].w32, d, 1, Cn + d, rows, U.ncls, d, d, st));
         H.type = LDM_PH_MERGED;
         H.nst_tiles = nsr / 128;
-        H.eps_kb0 = L / BK;
+        H.eps_kb0 = split ? 0 : L / BK;   // strict mode: the x~ block recurs in every third of the operand (its eps weights are zero)
       } else {
         // Operand: raw h2 of stage i = j-1 (dp wide).  With n = LN_b(h2) = r Gamma (h2 - mu) + beta (v2:549) and the folded
         // L = 1 attention A n + a (v2:550-552), h_{j} = D (h2 + A n + a) + b_d (v2:553) becomes
@@ -1271,14 +1308,16 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
         H.type = last ? LDM_PH_FINAL_LN : LDM_PH_STAGE;
       }
       LDM_CHECK(rows % 128 == 0 && K % BK == 0 && rows / 128 <= CS, "chain: phase %d shape (%d x %d) unsupported", j, rows, K);
-      H.K = H.dual ? K / 2 : K; H.rows = rows; H.tiles = rows / 128; H.d = d;
+      const int Kp = H.dual ? K / 2 : K, mult = split ? 3 : 1;      // per-accumulator reduction length, natural and as the kernel sees it
+      H.K = Kp * mult; H.rows = rows; H.tiles = rows / 128; H.d = d;
       // two units per tile when few tiles carry a long reduction: one per accumulator (dual) / one per K half (plain)
       H.ks = (K >= 1024 && H.tiles * 2 <= CS && (K / BK) % 2 == 0 && !getenv("LDM_CHAIN_NO_SPLITK")) ? 2 : 1;
-      LDM_TRY(ldm_alloc_t(ctx, PA, &H.w, (size_t)rows * K));
+      LDM_TRY(ldm_alloc_t(ctx, PA, &H.w, (size_t)rows * K * mult));
       LDM_TRY(ldm_alloc_t(ctx, PA, &H.bias, (size_t)rows));
       {
         const size_t n = (size_t)rows * K;
-        pack_rows_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Gn, H.w, rows, K, d, stage, nsr);
+        if (split) pack_rows_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Gn, H.w, rows, K, Kp, d, stage, nsr);
+        else pack_rows_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Gn, H.w, rows, K, d, stage, nsr);
         LDM_LAUNCHED(ctx);
         pack_cols_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(bn, H.bias, 1, rows, d, stage, nsr);
         LDM_LAUNCHED(ctx);
@@ -1303,7 +1342,7 @@ int chain_pack(ldm_ctx* ctx, cudaStream_t st) {
         pack_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Cn, H.tab_c, U.ncls, rows, d, stage, nsr);
         LDM_LAUNCHED(ctx);
       }
-      LDM_TRY(tc_make_weight_map(ctx, H.w, rows, K, 128, &H.map));   // box = 128 rows x 64 k
+      LDM_TRY(tc_make_weight_map(ctx, H.w, rows, K * mult, 128, &H.map));   // box = 128 rows x 64 k
       LDM_CUDA(cudaStreamSynchronize(st));
       free_tmp();
     }
@@ -1384,12 +1423,16 @@ int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const
   const int nst = U.nst, L = U.latent;
   LDM_CHECK(nst + 2 <= kMaxXMaps, "chain: too many stages");
   // stage the first merged operand: [x | 0 | 0] (the stage tiles see G_0 x; the eps tiles have nothing to finish yet)
-  LDM_TRY(launch_load_x<bf16>(ctx, x, ctx->caf[0], 3 * L, B, L, st));
-  LDM_CUDA(cudaMemset2DAsync(ctx->caf[0] + L, (size_t)3 * L * sizeof(bf16), 0, (size_t)2 * L * sizeof(bf16), (size_t)B, st));
+  const int split = ctx->precision == LDM_PRECISION_FP32 ? 1 : 0, mult = split ? 3 : 1;
+  {
+    const size_t n = (size_t)B * 3 * L;
+    chain_stage_x_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, ctx->caf[0], B, L, split);
+    LDM_LAUNCHED_AS(ctx, "chain_stage_x");
+  }
   // operand descriptors: rows beyond the batch are zero-filled by the TMA unit
-  LDM_TRY(tc_make_act_map(ctx->caf[0], B, 3 * L, 3 * L, NB, &P.xmaps[0]));
-  LDM_TRY(tc_make_act_map(ctx->caf[1], B, 3 * L, 3 * L, NB, &P.xmaps[1]));
-  for (int j = 0; j < nst; ++j) LDM_TRY(tc_make_act_map(ctx->opbuf[j], B, U.hid[j], U.hid[j], NB, &P.xmaps[2 + j]));
+  LDM_TRY(tc_make_act_map(ctx->caf[0], B, 3 * L * mult, 3 * L * mult, NB, &P.xmaps[0]));
+  LDM_TRY(tc_make_act_map(ctx->caf[1], B, 3 * L * mult, 3 * L * mult, NB, &P.xmaps[1]));
+  for (int j = 0; j < nst; ++j) LDM_TRY(tc_make_act_map(ctx->opbuf[j], B, U.hid[j] * mult, U.hid[j] * mult, NB, &P.xmaps[2 + j]));
   for (int j = nst; j < kMaxXMaps - 2; ++j) P.xmaps[2 + j] = P.xmaps[0];
   int cadd = (kChains + 2) * NB;      // TMEM: accumulators, parked noise, chain state, then the per-sample terms (NW >= 3)
   for (int j = 0; j < C.n_phases; ++j) {
@@ -1407,7 +1450,7 @@ int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const
     else { D.ga = U.ln_f_w; D.ba = U.ln_f_b; }
     if (j == 0) { D.xmap = 0; D.xmap_alt = 1; D.xcol = 0; }
     else { D.xmap = 2 + (j - 1); D.xmap_alt = 0; D.xcol = 0; }
-    if (j < nst) { D.out = ctx->opbuf[j]; D.ld_out = U.hid[j]; }
+    if (j < nst) { D.out = ctx->opbuf[j]; D.ld_out = U.hid[j] * mult; D.wout = U.hid[j]; }
   }
   for (int j = C.n_phases; j < LDM_CHAIN_MAX_PHASES; ++j) P.wmap[j] = C.ph[0].map;
   P.z_col = kChains * NB;
@@ -1422,7 +1465,7 @@ int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const
   P.x = x; P.eps_out = eps_out; P.noise = noise; P.rng = ctx->rng_dev;
   P.coef = ctx->coef_dev;
   P.coef_or_one = sample ? ctx->coef_dev : ctx->coef_one;
-  P.af[0] = ctx->caf[0]; P.af[1] = ctx->caf[1]; P.ld_af = 3 * L;
+  P.af[0] = ctx->caf[0]; P.af[1] = ctx->caf[1]; P.ld_af = 3 * L * mult; P.split = split;
   P.err = ctx->chain_err;
   P.trace = ctx->chain_trace;
   P.trace_step = ctx->chain_trace_step;
