@@ -185,6 +185,7 @@ struct ConvLayer {       // implicit GEMM: out[pix, co] = sum_{tap, ci} in[pix +
 struct ResBlockModel {
   int C = 0, HW = 0;     // channels, spatial side
   ConvLayer conv1, conv2;
+  ConvLayer conv1s, conv2s;   // strict mode: (hi, hi, lo) bf16 split of the weights, Cin = 3 C (tensor-core path of the fp32 context)
   float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
   float *ca_w0, *ca_w2;  // (C/8, C), (C, C/8)
   float* sa_w;           // (2, 7, 7)
@@ -202,6 +203,8 @@ struct DecoderModel {
   float *up_b[3], *up_gn_w[3], *up_gn_b[3];
   ConvLayer fin0, fin3;
   float *fin_gn_w, *fin_gn_b;
+  ConvLayer ups[3], fin0s;   // strict mode: split weights of the stacked ConvTranspose parities and of final_conv.0 (Cin = 3 C)
+  bool strict_tc = false;    // the fp32 context runs its convolutions as three-term bf16 products on the tensor cores
 };
 
 struct GraphKey {
@@ -301,6 +304,7 @@ struct ldm_ctx {
   int* d_cnt = nullptr;           // norm_coef: per (sample, channel block) tickets
   float* z_tmp = nullptr;
   bf16 *d_zb = nullptr, *d_h1b = nullptr;               // bf16 operands of Decoder.fc (tensor-core path)
+  bf16* d_split = nullptr;                               // strict mode: (hi, lo, hi) bf16 thirds of the fp32 input of a convolution
   // generate_host staging
   int64_t* c_stage = nullptr;     // device staging of the labels copied from the host
   float* img_stage = nullptr;     // device images before the copy back

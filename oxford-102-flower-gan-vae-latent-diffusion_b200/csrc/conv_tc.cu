@@ -42,6 +42,7 @@ struct ConvTcArgs {
   int post_stride;     // 0: one row for the whole batch
   const float* bias;
   bf16* out;        // (B, up*H, up*W, out_pitch), already offset to the first output channel
+  float* out32;     // strict mode: fp32 output instead (same indexing, pitch in floats); `out` is then unused
 };
 
 // MT = pixel tiles per CTA (1 or 2): with MT = 2 a weight tile fetched from L2 feeds two 128-pixel tiles (two TMEM
@@ -167,6 +168,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       op = ((size_t)n * (2 * a.H) + (size_t)(2 * y + pa)) * (size_t)(2 * a.W) + (size_t)(2 * x + pb);
     }
     bf16* dst = a.out + op * (size_t)a.out_pitch + nc0;
+    float* dst32 = a.out32 ? a.out32 + op * (size_t)a.out_pitch + nc0 : nullptr;
     const float* prow = a.post ? a.post + (size_t)(valid ? p / HW : 0) * a.post_stride + nc0 : nullptr;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -186,14 +188,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
           }
         }
+        if (dst32) {
+          float4* d4 = reinterpret_cast<float4*>(dst32 + c0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-          pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+          for (int j = 0; j < 4; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+          d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
-        uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
-        d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       }
     }
     }
@@ -768,13 +776,13 @@ int conv_tc_pick_bn(int Cout) { return Cout >= 256 ? 256 : Cout; }
 
 // in: (B, H, W, Cin of pitch in_pitch) bf16; out: (B, up*H, up*W, Cout of pitch out_pitch) bf16 (mode 0: (B, H/2, W/2, .)).
 // L.w16 / L.map_w: (nz * Cout, taps * Cin), box (64, bn).  mode = ConvTcArgs::up.
-int launch_conv_tc_ex(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer& L, const float* bias, bf16* out, int out_pitch,
-                      int B, int H, int W, int mode, int relu, const float* post, int post_stride, cudaStream_t st) {
+static int conv_tc_launch(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer& L, const float* bias, bf16* out, float* out32,
+                          int out_pitch, int B, int H, int W, int mode, int relu, const float* post, int post_stride, cudaStream_t st) {
   LDM_TRY(conv_init(ctx));
   LDM_CHECK(L.w16 != nullptr, "conv_tc: layer not packed for the tensor-core path");
   LDM_CHECK(L.Cin % BK == 0, "conv_tc: Cin %% 64 == 0 required (Cin=%d)", L.Cin);
   LDM_CHECK((mode == 1 && L.taps == 9) || (mode == 2 && L.taps == 4) || (mode == 0 && L.taps == 16), "conv_tc: unsupported taps/mode combination");
-  LDM_CHECK(out_pitch % 8 == 0 && ((uintptr_t)out & 15) == 0, "conv_tc: output must be 16-byte aligned (pitch %d)", out_pitch);
+  LDM_CHECK(out_pitch % 8 == 0 && (((uintptr_t)out | (uintptr_t)out32) & 15) == 0, "conv_tc: output must be 16-byte aligned (pitch %d)", out_pitch);
   CUtensorMap ma;
   ConvTcArgs a;
   if (mode == 0) {
@@ -786,7 +794,7 @@ int launch_conv_tc_ex(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLaye
   }
   a.Cin = L.Cin; a.Cout = L.Cout; a.taps = L.taps; a.up = mode; a.total_pix = B * a.H * a.W; a.stages = 0;
   a.in_pitch = in_pitch; a.out_pitch = out_pitch; a.relu = relu; a.post = post; a.post_stride = post_stride;
-  a.bias = bias; a.out = out;
+  a.bias = bias; a.out = out; a.out32 = out32;
   const int nz = mode == 2 ? 4 : 1;
   int bn = L.bn ? L.bn : conv_tc_pick_bn(L.Cout);
   const CUtensorMap* mw = &L.map_w;
@@ -802,6 +810,18 @@ int launch_conv_tc_ex(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLaye
   }
   ldm_set_error("conv_tc: unsupported Cout %d", L.Cout);
   return -1;
+}
+
+int launch_conv_tc_ex(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer& L, const float* bias, bf16* out, int out_pitch,
+                      int B, int H, int W, int mode, int relu, const float* post, int post_stride, cudaStream_t st) {
+  return conv_tc_launch(ctx, in, in_pitch, L, bias, out, nullptr, out_pitch, B, H, W, mode, relu, post, post_stride, st);
+}
+
+// Strict mode: `in` holds the (hi, lo, hi) bf16 thirds of an fp32 activation (3 C channels per pixel), L the matching
+// (hi, hi, lo) split of the weights (L.Cin = 3 C): the three-term product on the bf16 tensor cores, fp32 NHWC output.
+int launch_conv_tc_f32out(ldm_ctx* ctx, const bf16* in, const ConvLayer& L, const float* bias, float* out32, int B, int H, int W,
+                          int up, cudaStream_t st) {
+  return conv_tc_launch(ctx, in, L.Cin, L, bias, nullptr, out32, L.Cout, B, H, W, up, 0, nullptr, 0, st);
 }
 
 int launch_conv_tc(ldm_ctx* ctx, const bf16* in, const ConvLayer& L, const float* bias, bf16* out, int B, int H, int W,

@@ -20,6 +20,10 @@ int launch_sa_apply_bf16(ldm_ctx* ctx, const bf16* x, const float2* coef, const 
 int launch_conv_halo(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer& L, const float* bias, bf16* out, int out_pitch,
                      int B, int H, int W, int relu, const float* post, int post_stride, const PixOutArgs* fin, int ddpm,
                      cudaStream_t st);
+int launch_conv_tc_f32out(ldm_ctx* ctx, const bf16* in, const ConvLayer& L, const float* bias, float* out32, int B, int H, int W,
+                          int up, cudaStream_t st);
+int launch_split3(ldm_ctx* ctx, const float* x, bf16* out, size_t npix, int C, cudaStream_t st);
+int launch_pack_conv_split(ldm_ctx* ctx, const float* w, bf16* out, int rows, int taps, int Cin, cudaStream_t st);
 int launch_conv_out3(ldm_ctx* ctx, const bf16* in, const float* w, const float* bias, float* out, int B, int H, int W,
                      cudaStream_t st);
 
@@ -62,7 +66,8 @@ void convT_geom(ConvGeom& g, int B, int H, int Cin, int Cout, int pa, int pb) {
 }
 
 int ensure_dec_workspace(ldm_ctx* ctx, int B) {
-  if (B <= ctx->dec_cap) return 0;
+  if (B <= ctx->dec_cap && (!ctx->dec.strict_tc || ctx->d_split)) return 0;
+  if (B < ctx->dec_cap) B = ctx->dec_cap;
   cudaDeviceSynchronize();
   for (void* p : ctx->dec_allocs) cudaFree(p);
   ctx->dec_allocs.clear();
@@ -83,20 +88,30 @@ int ensure_dec_workspace(ldm_ctx* ctx, int B) {
   LDM_CUDA(cudaMemset(ctx->d_cnt, 0, (size_t)B * 16 * sizeof(int)));
   LDM_TRY(ldm_alloc_t(ctx, P, &ctx->d_zb, (size_t)B * 256 + 64));
   LDM_TRY(ldm_alloc_t(ctx, P, &ctx->d_h1b, (size_t)B * 512));
+  if (ctx->dec.strict_tc) LDM_TRY(ldm_alloc_t(ctx, P, &ctx->d_split, act * 3));   // (hi, lo, hi) thirds of the largest convolution input
   ctx->act_maps.clear();   // descriptors over the old workspace are stale
   ctx->dec_cap = B;
   return 0;
 }
 
 // ResidualBlock.forward (v2:170-178): x in `X`, result in `OUT`, scratch `Y` (raw conv outputs)
+// strict-mode convolution: fp32 NHWC in -> (hi, lo, hi) bf16 thirds -> three-term product on the tensor cores -> fp32 NHWC out
+int conv_strict(ldm_ctx* ctx, const float* X, const ConvLayer& Ls, const float* bias, float* Y, int B, int H, int up, cudaStream_t st) {
+  LDM_TRY(launch_split3(ctx, X, ctx->d_split, (size_t)B * H * H, Ls.Cin / 3, st));
+  return launch_conv_tc_f32out(ctx, ctx->d_split, Ls, bias, Y, B, H, H, up, st);
+}
+
 int res_block_f32(ldm_ctx* ctx, const ResBlockModel& R, int B, const float* X, float* Y, float* OUT, cudaStream_t st) {
   const int C = R.C, H = R.HW, P = H * H;
+  const bool tc = ctx->dec.strict_tc;
   ConvGeom g;
   conv3_geom(g, B, H, C, C);
-  LDM_TRY(launch_conv_f32(ctx, X, R.conv1.w32, R.conv1.b, Y, g, st));                                   // conv1
+  if (tc) LDM_TRY(conv_strict(ctx, X, R.conv1s, R.conv1.b, Y, B, H, 1, st));
+  else LDM_TRY(launch_conv_f32(ctx, X, R.conv1.w32, R.conv1.b, Y, g, st));                              // conv1
   LDM_TRY(launch_inorm_stats<float>(ctx, Y, ctx->d_stats, B, P, C, 1, st));                              // ln1 statistics
   LDM_TRY(launch_norm_apply<float>(ctx, Y, ctx->d_stats, R.ln1_w, R.ln1_b, OUT, B, P, C, 1, LDM_ACT_SWISH, st));  // swish(ln1(.))
-  LDM_TRY(launch_conv_f32(ctx, OUT, R.conv2.w32, R.conv2.b, Y, g, st));                                  // conv2
+  if (tc) LDM_TRY(conv_strict(ctx, OUT, R.conv2s, R.conv2.b, Y, B, H, 1, st));
+  else LDM_TRY(launch_conv_f32(ctx, OUT, R.conv2.w32, R.conv2.b, Y, g, st));                             // conv2
   LDM_TRY(launch_inorm_stats<float>(ctx, Y, ctx->d_stats, B, P, C, 1, st));                              // ln2 statistics
   LDM_TRY(launch_gap_norm<float>(ctx, Y, ctx->d_stats, R.ln2_w, R.ln2_b, ctx->d_gap, B, P, C, st));      // CALayer avg_pool
   LDM_TRY(launch_ca_mlp(ctx, ctx->d_gap, R.ca_w0, R.ca_w2, ctx->d_ca, B, C, st));                        // CALayer conv_du
@@ -109,12 +124,16 @@ int res_block_f32(ldm_ctx* ctx, const ResBlockModel& R, int B, const float* X, f
 int up_block_f32(ldm_ctx* ctx, const DecoderModel& D, int idx, int B, int H, int Cin, const float* X, float* Y, float* OUT,
                  cudaStream_t st) {
   const int Cout = Cin / 2;
-  for (int pa = 0; pa < 2; ++pa)
-    for (int pb = 0; pb < 2; ++pb) {
-      ConvGeom g;
-      convT_geom(g, B, H, Cin, Cout, pa, pb);
-      LDM_TRY(launch_conv_f32(ctx, X, D.up[idx][pa * 2 + pb].w32, D.up_b[idx], Y, g, st));
-    }
+  if (D.strict_tc) {
+    LDM_TRY(conv_strict(ctx, X, D.ups[idx], D.up_b[idx], Y, B, H, 2, st));   // four sub-pixel parities, one launch
+  } else {
+    for (int pa = 0; pa < 2; ++pa)
+      for (int pb = 0; pb < 2; ++pb) {
+        ConvGeom g;
+        convT_geom(g, B, H, Cin, Cout, pa, pb);
+        LDM_TRY(launch_conv_f32(ctx, X, D.up[idx][pa * 2 + pb].w32, D.up_b[idx], Y, g, st));
+      }
+  }
   const int P = 4 * H * H;
   LDM_TRY(launch_inorm_stats<float>(ctx, Y, ctx->d_stats, B, P, Cout, 8, st));
   LDM_TRY(launch_norm_apply<float>(ctx, Y, ctx->d_stats, D.up_gn_w[idx], D.up_gn_b[idx], OUT, B, P, Cout, 8, LDM_ACT_SWISH, st));
@@ -142,7 +161,8 @@ int decode_chunk_f32(ldm_ctx* ctx, const float* z, float* img, int B, cudaStream
   // final_conv (v2:272-278): conv 64->32, GroupNorm(8, 32), Swish, conv 32->3, Sigmoid; output NCHW
   ConvGeom g;
   conv3_geom(g, B, 64, 64, 32);
-  LDM_TRY(launch_conv_f32(ctx, A, D.fin0.w32, D.fin0.b, Bf, g, st));
+  if (D.strict_tc) LDM_TRY(conv_strict(ctx, A, D.fin0s, D.fin0.b, Bf, B, 64, 1, st));
+  else LDM_TRY(launch_conv_f32(ctx, A, D.fin0.w32, D.fin0.b, Bf, g, st));
   LDM_TRY(launch_inorm_stats<float>(ctx, Bf, ctx->d_stats, B, 4096, 32, 4, st));
   LDM_TRY(launch_norm_apply<float>(ctx, Bf, ctx->d_stats, D.fin_gn_w, D.fin_gn_b, C, B, 4096, 32, 4, LDM_ACT_SWISH, st));
   conv3_geom(g, B, 64, 32, 3);
@@ -300,6 +320,34 @@ int decoder_pack_impl(ldm_ctx* ctx, const ldm_decoder_weights* w, cudaStream_t s
       LDM_TRY(tc_make_weight_map(ctx, U0.w16, 4 * U0.Cout, 4 * U0.Cin, conv_tc_pick_bn(U0.Cout), &U0.map_w));
     }
     LDM_TRY(conv_bf16(ctx, P, D.fin0, st));
+  }
+  if (ctx->precision != LDM_PRECISION_BF16) {
+    // strict mode: the 3x3 / transposed convolutions as three-term bf16 products on the tensor cores (LDM_DEC_F32=1 keeps
+    // them on the CUDA cores); split weights: per tap [hi | hi | lo] of the Cin columns
+    const char* e = getenv("LDM_DEC_F32");
+    D.strict_tc = !(e && atoi(e));
+    if (D.strict_tc) {
+      auto split_layer = [&](const ConvLayer& L, ConvLayer& S) -> int {
+        S = ConvLayer();
+        S.Cin = 3 * L.Cin; S.Cout = L.Cout; S.taps = L.taps; S.b = L.b;
+        LDM_TRY(ldm_alloc_t(ctx, P, &S.w16, (size_t)L.Cout * L.taps * S.Cin));
+        LDM_TRY(launch_pack_conv_split(ctx, L.w32, S.w16, L.Cout, L.taps, L.Cin, st));
+        return tc_make_weight_map(ctx, S.w16, S.Cout, S.taps * S.Cin, conv_tc_pick_bn(S.Cout), &S.map_w);
+      };
+      for (int i = 0; i < 3; ++i) {
+        LDM_TRY(split_layer(D.res[i].conv1, D.res[i].conv1s));
+        LDM_TRY(split_layer(D.res[i].conv2, D.res[i].conv2s));
+        const ConvLayer& U0 = D.up[i][0];
+        ConvLayer& S = D.ups[i];
+        S = ConvLayer();
+        S.Cin = 3 * U0.Cin; S.Cout = U0.Cout; S.taps = 4;
+        const size_t per = (size_t)U0.Cout * 4 * S.Cin;
+        LDM_TRY(ldm_alloc_t(ctx, P, &S.w16, 4 * per));
+        for (int z = 0; z < 4; ++z) LDM_TRY(launch_pack_conv_split(ctx, D.up[i][z].w32, S.w16 + (size_t)z * per, U0.Cout, 4, U0.Cin, st));
+        LDM_TRY(tc_make_weight_map(ctx, S.w16, 4 * S.Cout, 4 * S.Cin, conv_tc_pick_bn(S.Cout), &S.map_w));
+      }
+      LDM_TRY(split_layer(D.fin0, D.fin0s));
+    }
   }
   LDM_CUDA(cudaStreamSynchronize(st));
   D.packed = true;

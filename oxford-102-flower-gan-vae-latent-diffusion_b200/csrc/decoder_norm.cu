@@ -556,6 +556,54 @@ int launch_sa_apply_bf16(ldm_ctx* ctx, const bf16* x, const float2* coef, const 
   return 0;
 }
 
+// fp32 NHWC (npix, C) -> bf16 (npix, 3 C) = [hi | lo | hi] per pixel: the operand of a strict-mode convolution
+__global__ void __launch_bounds__(256)
+split3_kernel(const float* __restrict__ x, bf16* __restrict__ out, size_t total4, int C4) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const size_t pix = i / C4;
+  const int c4 = (int)(i - pix * C4);
+  const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+  const float f[4] = {v.x, v.y, v.z, v.w};
+  __nv_bfloat162 hi[2], lo[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const bf16 h0 = __float2bfloat16_rn(f[2 * e]), h1 = __float2bfloat16_rn(f[2 * e + 1]);
+    hi[e] = __halves2bfloat162(h0, h1);
+    lo[e] = __halves2bfloat162(__float2bfloat16_rn(f[2 * e] - __bfloat162float(h0)), __float2bfloat16_rn(f[2 * e + 1] - __bfloat162float(h1)));
+  }
+  const uint2 H = make_uint2(*reinterpret_cast<uint32_t*>(&hi[0]), *reinterpret_cast<uint32_t*>(&hi[1]));
+  const uint2 Lo = make_uint2(*reinterpret_cast<uint32_t*>(&lo[0]), *reinterpret_cast<uint32_t*>(&lo[1]));
+  bf16* o = out + pix * (size_t)(12 * C4) + (size_t)c4 * 4;
+  *reinterpret_cast<uint2*>(o) = H;
+  *reinterpret_cast<uint2*>(o + 4 * C4) = Lo;
+  *reinterpret_cast<uint2*>(o + 8 * C4) = H;
+}
+int launch_split3(ldm_ctx* ctx, const float* x, bf16* out, size_t npix, int C, cudaStream_t st) {
+  LDM_CHECK(C % 4 == 0, "split3: C %% 4 == 0 required");
+  const size_t total4 = npix * (size_t)(C / 4);
+  split3_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(x, out, total4, C / 4);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+// (rows, taps * Cin) fp32 -> (rows, taps * 3 Cin) bf16: per tap [hi | hi | lo]
+__global__ void pack_conv_split_kernel(const float* __restrict__ w, bf16* __restrict__ out, size_t total, int Cin) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const size_t rt = i / Cin;            // (row, tap)
+  const int ci = (int)(i - rt * Cin);
+  const float v = w[i];
+  const bf16 hi = __float2bfloat16_rn(v), lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  bf16* o = out + rt * (size_t)(3 * Cin) + ci;
+  o[0] = hi; o[Cin] = hi; o[2 * Cin] = lo;
+}
+int launch_pack_conv_split(ldm_ctx* ctx, const float* w, bf16* out, int rows, int taps, int Cin, cudaStream_t st) {
+  const size_t total = (size_t)rows * taps * Cin;
+  pack_conv_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, out, total, Cin);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+
 #define INST(T)                                                                                                        \
   template int launch_inorm_stats<T>(ldm_ctx*, const T*, float*, int, int, int, int, cudaStream_t);                    \
   template int launch_norm_apply<T>(ldm_ctx*, const T*, const float*, const float*, const float*, T*, int, int, int,  \
