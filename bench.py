@@ -416,6 +416,7 @@ def run_latent(workload, B, K, W, prec, rank, world, local_rank, sampler, with_c
                    "l2": "flushed (256 MiB write) between timed iterations", "weights": "random-init (seeded), eval mode"},
         "e2e": {"value": total * K / t_e2e, "unit": "samples/s", "h2d_bytes_per_step": B * (16 if v3 else 8), "d2h_bytes_per_step": B * IMG_BYTES},
         "gpu_launches": int(launches),
+        "ms_per_iter": [round(s.elapsed_time(e), 3) for s, m, e in ev],      # this rank's timed iterations (CUDA events)
         "clocks": clocks_of(sampler, t_win0, t_win1),
         "roofline": {"bound": "tensor", "kernel": loop_kernel_name(eng, B),
                      "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
