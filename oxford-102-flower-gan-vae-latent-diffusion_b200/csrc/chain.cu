@@ -681,7 +681,9 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
     auto publish = [&](uint32_t buf, int tile, float2 st, float cnt, int first, int ntiles, int ks) {
       float2* gs = gstat + ((size_t)buf * NW + g) * 64;
       if ((lane & 1) == 0) gs[q * 16 + (lane >> 1)] = st;
+      stamp(13, 0);
       group_bar();
+      stamp(14, 0);
       const float2 p0 = gs[xrow], p1 = gs[16 + xrow], p2 = gs[32 + xrow], p3 = gs[48 + xrow];
       const float mean = 0.25f * ((p0.x + p1.x) + (p2.x + p3.x));
       const float d0 = p0.x - mean, d1 = p1.x - mean, d2 = p2.x - mean, d3 = p3.x - mean;
@@ -909,11 +911,14 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
                 u[i] = lo ? recv : v[8 + i];
               }
             }
-            publish(b0, tile, half_row_stats8(u, lane), 16.0f, ph.first, ntile, ph.ks);
+            stamp(12, p);
+            const float2 ust = half_row_stats8(u, lane);
+            publish(b0, tile, ust, 16.0f, ph.first, ntile, ph.ks);
             stamp(6, p);
             exchange_wait(b0, ntile, 6);
             stamp(7, p);
             combine(b0, ntile, 64.0f);
+            stamp(15, p);
             bf16* o = ph.out + (size_t)(row0 + s0 + hr) * ph.ld_out + f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {   // h2 = swish(LN_a(u)) + h: the next phase's operand (its LayerNorm is applied there)

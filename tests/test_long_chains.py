@@ -187,3 +187,67 @@ def test_generate_class_samples_and_sharded_entry(tmp_path):
     classes = torch.full((n,), 33)
     imgs3, lat3, (lo, hi) = sharding.generate_sharded(ae, d, classes, seed=11)
     assert (lo, hi) == (0, n) and torch.equal(lat3, lat) and torch.equal(imgs3, imgs)
+
+
+@pytest.mark.gpu
+def test_v3_host_entry_and_kernel_trace():
+    """ldm_generate3_host (host labels in, host images out) equals sample + decode; ldm_debug_ktrace lists the launches."""
+    import ldm_b200
+    u = ldm_b200.v3.ConditionalUNet(precision="bf16")
+    u.load_state_dict(weights.make_unet3_state(V3_SEED, "init"), strict=True)
+    u = u.to("cuda").eval()
+    ae = make_autoencoder("init", "bf16")
+    d = ldm_b200.v3.ConditionalDenoiseDiffusion(u, 60, torch.device("cuda"))
+    eng = d._engine("cuda")
+    eng.pack_decoder(ae.decoder)
+    B = 10
+    f, k = (torch.arange(B) * 11) % 102, torch.arange(B) % 10
+    img = torch.empty(B, 3, 64, 64).pin_memory()
+    lat = torch.empty(B, 256).pin_memory()
+    eng.generate3_host(f.pin_memory(), k.pin_memory(), img, lat, seed=9, sample_offset=0)
+    x0 = d.sample((B, 256), torch.device("cuda"), f.cuda(), k.cuda(), seed=9, sample_offset=0)
+    assert torch.equal(lat, x0.cpu())
+    eng.ktrace_start()
+    ref = ae.decode(x0)
+    trace = eng.ktrace_stop()
+    assert torch.equal(img, ref.cpu())
+    names = [n for n, _ in trace]
+    assert len(trace) == 42 and names[0] == "launch_load_x" and names[-1] == "conv_out3" and names.count("conv_tc") == 9 and names.count("conv_halo") == 1
+    assert all(0.0 < ms < 50.0 for _, ms in trace)
+    with pytest.raises(ldm_b200.LdmError):
+        eng.generate3_host((f + 200).pin_memory(), k.pin_memory(), img, None, seed=9)      # flower label out of range
+
+
+@pytest.mark.gpu
+def test_strict_cuda_core_paths_in_a_fresh_process():
+    """The strict mode runs the three-term bf16 split on the tensor cores by default; LDM_CHAIN=0 and LDM_DEC_F32=1 select the
+    fp32 CUDA-core kernels (gemm_f32 / conv_f32), kept as the independent cross-check: both must meet the strict tolerances,
+    and agree with each other far inside them."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import numpy as np, torch
+from oracle import restate as R
+from tests._util import EPS_TOL, IMAGE_TOL, T, make_autoencoder, make_unet
+torch.set_grad_enabled(False)
+g = np.load("tests/golden/v2_perturbed.npz")
+u = make_unet("perturbed", "fp32")
+eng = u.engine("cuda", 1000)
+x, c = T(g["fwd_x"]).cuda(), T(g["fwd_c"]).cuda()
+eps = u(x, torch.tensor([500], device="cuda"), c).cpu()
+img = make_autoencoder("perturbed", "fp32").decode(T(g["dec_z"]).cuda()).cpu()
+print("RESULT", int(eng.info("chain")), R.max_rel(eps, T(g["fwd_eps_t500"])), float((img - T(g["dec_img"])).abs().max()))
+np.save("%s", np.concatenate([eps.numpy().ravel(), img.numpy().ravel()]))
+"""
+    outs = {}
+    for name, env_extra in (("tc", {}), ("cuda_cores", {"LDM_CHAIN": "0", "LDM_DEC_F32": "1"})):
+        path = os.path.join(root, "gpurun_out", "strict_%s.npy" % name) if os.path.isdir(os.path.join(root, "gpurun_out")) else "/tmp/strict_%s.npy" % name
+        env = dict(os.environ, PYTHONPATH=root, **env_extra)
+        r = subprocess.run([sys.executable, "-c", code % path], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "RESULT" in r.stdout, r.stdout + r.stderr
+        chain, e_eps, e_img = r.stdout.split("RESULT")[1].split()[:3]
+        assert int(chain) == (1 if name == "tc" else 0)
+        assert float(e_eps) < EPS_TOL["fp32"] and float(e_img) < IMAGE_TOL["fp32"], (name, e_eps, e_img)
+        outs[name] = np.load(path)
+    assert float(np.abs(outs["tc"] - outs["cuda_cores"]).max() / np.abs(outs["cuda_cores"]).max()) < 1e-4

@@ -51,7 +51,7 @@ B = int(os.environ.get("TRACE_B", "48"))
 RANKS = [int(r) for r in os.environ.get("TRACE_RANKS", "0,1,4,12").split(",")]
 TRACKS, LEN, CS = 5, 96, 16
 TAG = {1: "iter", 2: "pre-acc-wait", 3: "acc-ready", 4: "acc-loaded(+partner)", 5: "dual-done", 6: "published-u", 7: "stats-u-in", 11: "stats-f-in",
-       8: "operand-written", 9: "arrive-sent", 10: "handover-done", 20: "W-first-issued", 21: "W-last-issued", 30: "X-handover-seen", 31: "X-fenced",
+       12: "traded", 13: "stats-done", 14: "group-bar", 15: "combined", 8: "operand-written", 9: "arrive-sent", 10: "handover-done", 20: "W-first-issued", 21: "W-last-issued", 30: "X-handover-seen", 31: "X-fenced",
        32: "X-first-issued", 33: "X-all-issued", 40: "MMA-first", 42: "MMA-half", 41: "MMA-all-issued"}
 NAME = ["h", "u", "W", "X", "M"]
 c = (torch.arange(B) % 102).to(dev)
