@@ -253,6 +253,7 @@ def pix_kernel_table(B):
 
 def kernel_records(trace, table, pk, anchor=None):
     """Zip a traced launch list with the expected table; a name mismatch degrades to time-only records."""
+    trace = [("conv_tc" if n == "conv_tc_pair" else n, ms) for n, ms in trace]   # the 2-CTA variant of the same convolution
     names = [n for n, _ in trace]
     start = 0
     if anchor is not None:
@@ -287,11 +288,24 @@ def summarize_hbm(recs):
 # ------------------------------------------------------------------------------------------------------
 # GPU arm: v2 (headline) and v3 latent workloads
 # ------------------------------------------------------------------------------------------------------
+V2_NOTE = ("the loop is a chain of 5 dependent contractions per step x 1000 steps inside 16-CTA clusters: each phase is "
+           "bounded by one tcgen05.mma of M=128, N<=128 per 67-74 clocks (240 per step and CTA), by the TMA issue rate of its "
+           "producer threads and by two cluster-wide exchanges (LayerNorm statistics, operand hand-over), not by the "
+           "tensor pipe's peak (DESIGN.md 5.1, tools/ubench.cu); the decoder convolutions are the tensor-bound kernels")
+V3_NOTE = ("the rows of a v3 call are coupled by the cross-batch attention, so the call is one grid: 19 dependent phases per step, "
+           "each paying a grid-wide barrier (~1.5-2 us: write drain, one atomic, one poll) and ~1.2 us of first-tile latency "
+           "before ~1-3 us of work (DESIGN.md 8.1, tools/v3loop_trace.py); the tensor pipe is idle most of the step")
+
+
 def loop_kernel_name(eng, nb):
     if int(eng.info("chain")):
         return ("chain_kernel: the whole 1000-step loop is ONE persistent launch (16-CTA clusters, 5 dependent tcgen05 "
                 "contractions per step, TMA operands, DSMEM statistics)")
-    return "sampling loop (one CUDA-graph launch = 1000 steps x %d kernels)" % int(eng.info("launches_per_step"))
+    n = int(eng.info("launches_per_step"))
+    if n == 0:   # v3: unet3_loop_kernel
+        return ("unet3_loop_kernel: the whole 1000-step loop is ONE persistent launch (128 co-resident CTAs, 19 phases per step "
+                "separated by grid-wide barriers: folded tcgen05 contractions, LayerNorm rows, one attention head per CTA)")
+    return "sampling loop (one CUDA-graph launch = 1000 steps x %d kernels)" % n
 
 
 def run_latent(workload, B, K, W, prec, rank, world, local_rank, sampler, with_cpu, with_kernels, label):
@@ -423,10 +437,7 @@ def run_latent(workload, B, K, W, prec, rank, world, local_rank, sampler, with_c
                      "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": pk["src"], "ms_per_launch": loop_s * 1000.0,
                      "algorithmic_flop_per_launch": loop_flops,
-                     "note": "the loop is a chain of 5 dependent contractions per step x 1000 steps inside 16-CTA clusters: each phase is "
-                             "bounded by one tcgen05.mma of M=128, N<=128 per 74 clocks (240 per step and CTA), by 51.7 B/clk of TMA "
-                             "inbound per SM and by two cluster-wide exchanges (LayerNorm statistics, operand hand-over), not by the "
-                             "tensor pipe's peak (DESIGN.md 5.1, tools/ubench.cu); the decoder convolutions are the tensor-bound kernels"},
+                     "note": V3_NOTE if v3 else V2_NOTE},
         "decode": {"ms": dec_s * 1000.0, "tflops": FLOP_DECODE_PER_SAMPLE * B / dec_s / 1e12 if dec_s > 0 else None},
     }
     if trace is not None and prec == "bf16":

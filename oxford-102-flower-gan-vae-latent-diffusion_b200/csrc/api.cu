@@ -146,6 +146,7 @@ extern "C" LDM_API int ldm_ctx_destroy(ldm_ctx* ctx) {
   free_pool(ctx->dec.allocs);
   free_pool(ctx->stage_allocs);
   free_pool(ctx->chain.allocs);
+  v3loop_free(ctx);
   pix_free(ctx);
   ublock_free_all(ctx);
   if (ctx->coef_dev) cudaFree(ctx->coef_dev);
@@ -211,6 +212,7 @@ extern "C" LDM_API int ldm_unet_pack(ldm_ctx* ctx, const ldm_unet_weights* w, vo
   LDM_CHECK(w->n_t >= 1 && w->num_classes >= 1 && w->sinusoid, "ldm_unet_pack: sinusoid table missing");
   cudaDeviceSynchronize();
   drop_graphs(ctx);
+  v3loop_free(ctx);
   free_pool(U.allocs);
   U = UnetModel();
   U.latent = w->latent_dim; U.tdim = w->time_dim; U.ncls = w->num_classes; U.nst = nst; U.n_t = w->n_t;
@@ -481,6 +483,7 @@ extern "C" LDM_API int ldm_unet3_pack(ldm_ctx* ctx, const ldm_unet3_weights* w, 
   ctx->batch_cls = -1;
   ctx->has_cls = false;
   U.packed = true;
+  LDM_TRY(v3loop_pack(ctx, st));   // the whole loop as one persistent kernel where the architecture allows (v3loop.cu)
   return 0;
 }
 
@@ -643,6 +646,8 @@ extern "C" LDM_API int ldm_unet_forward(ldm_ctx* ctx, const float* x_dev, const 
   LDM_TRY(check_classes_match(ctx, batch));
   LDM_TRY(launch_check_t(ctx, t_dev, t_len, ctx->unet.n_t, ctx->dev_flags, st));
   StepMode md; md.t_idx = t_dev; md.t_len = t_len; md.eps_out = eps_out_dev;
+  if (v3loop_supported(ctx, batch))
+    return launch_v3loop(ctx, batch, 1, 0, 0, t_dev, t_len, const_cast<float*>(x_dev), eps_out_dev, nullptr, st);
   if (ctx->precision == LDM_PRECISION_BF16) {
     LDM_TRY(stage_x<bf16>(ctx, x_dev, batch, 0, st));
     if (ctx->use_chain) return launch_chain(ctx, batch, 1, 0, 0, t_dev, t_len, const_cast<float*>(x_dev), eps_out_dev, nullptr, st);
@@ -678,6 +683,8 @@ static int run_chain(ldm_ctx* ctx, int B, int t_start, int t_end, const float* n
   const size_t slab = (size_t)B * ctx->unet.latent;
   if (ctx->use_chain)   // the whole loop is one persistent kernel (both precisions)
     return launch_chain(ctx, B, t_start - t_end + 1, t_start, 1, nullptr, 1, ctx->x_state, nullptr, noise, st);
+  if (v3loop_supported(ctx, B))   // v3: one persistent kernel for the whole loop (the rows of a call are coupled: one grid)
+    return launch_v3loop(ctx, B, t_start - t_end + 1, t_start, 1, nullptr, 1, ctx->x_state, nullptr, noise, st);
   for (int t = t_start, j = 0; t >= t_end; --t, ++j) {
     StepMode md; md.sample = 1; md.t = t; md.x = ctx->x_state;
     md.noise = noise ? noise + (size_t)j * slab : nullptr;
@@ -910,7 +917,7 @@ extern "C" LDM_API int ldm_get_info(ldm_ctx* ctx, const char* key, double* out) 
   if (!strcmp(key, "chain_max_clusters")) { *out = ctx->chain_max_clusters; return 0; }
   if (!strcmp(key, "chain_peak_bytes_per_step")) { *out = ctx->chain.peak_bytes_per_step; return 0; }
   if (!strcmp(key, "launches_per_step")) {
-    if (ctx->use_chain) { *out = 0.0; return 0; }                // the loop is one launch
+    if (ctx->use_chain || (ctx->v3loop && ctx->use_v3loop)) { *out = 0.0; return 0; }   // the loop is one launch
     *out = ctx->unet.packed ? 3.0 + (ctx->unet.variant == 3 ? 6.0 : 4.0) * ctx->unet.nst : 0.0;   // G0, (G1, R1, G2[, A, G2b], G3) x stages, R_f, G_f
     return 0;
   }
@@ -930,6 +937,7 @@ extern "C" LDM_API int ldm_get_info(ldm_ctx* ctx, const char* key, double* out) 
       LDM_CUDA(cudaMemcpy(ce, ctx->chain_err, sizeof(ce), cudaMemcpyDeviceToHost));
       if (ce[0]) { f = (ce[0] << 16) | (ce[1] & 0xFFFF); LDM_CUDA(cudaMemset(ctx->chain_err, 0, sizeof(ce))); }
     }
+    if (!f) LDM_TRY(v3loop_error(ctx, &f));
     *out = f;
     return 0;
   }

@@ -329,6 +329,9 @@ struct ldm_ctx {
   long long* chain_trace = nullptr;   // [CS][TRACKS][LEN] tagged clock stamps (ldm_debug_chain_trace), null = off
   int chain_trace_step = 0;
   int use_pdl = 0;
+  // persistent kernel of the v3 loop (v3loop.cu): folded phase list + workspace, null when the architecture is not covered
+  void* v3loop = nullptr;
+  int use_v3loop = 1;             // LDM_V3LOOP=0 keeps v3 on the per-layer path
   int use_attn_tc = 1;            // v3 bf16: attention on tcgen05 (LDM_ATTN_TC=0 selects the CUDA-core kernel)
   // per-launch timing (ldm_debug_ktrace): one CUDA event after every kernel launch on kt_stream while kt_on
   bool kt_on = false;
@@ -375,6 +378,14 @@ static inline cudaError_t launch_maybe_pdl(Kern kern, dim3 grid, int threads, si
 
 __device__ __forceinline__ void ldm_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void ldm_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// v3loop.cu
+int v3loop_pack(ldm_ctx* ctx, cudaStream_t st);
+void v3loop_free(ldm_ctx* ctx);
+int v3loop_supported(ldm_ctx* ctx, int B);
+int v3loop_error(ldm_ctx* ctx, int* out);
+int launch_v3loop(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const int64_t* t_idx, int t_len, float* x, float* eps_out,
+                  const float* noise, cudaStream_t st);
 
 // memory helpers (api.cu)
 int ldm_alloc(ldm_ctx* ctx, std::vector<void*>& pool, void** out, size_t bytes);

@@ -592,6 +592,183 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   if (warp == 1) tc::tmem_dealloc<kTS * BN>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// conv_tc_pair_kernel: the 256-channel output tile as a 2-CTA MMA (tcgen05 cta_group::2, thread-block cluster of two).
+// One tcgen05.mma of M = 128 reads its operands from shared memory at 64 B/clk (measured, tools/ubench.cu): a
+// 128 x 256 x 16 tile step needs 4 KB of pixels + 8 KB of weights = 192 clocks against 128 clocks of tensor time.  A CTA
+// pair computes 256 pixels x 256 channels per instruction: each CTA holds ITS 128 pixels (A) and HALF of the weight tile
+// (B rows [128 r, 128 r + 128)), i.e. 4 KB + 4 KB per step = the tensor rate, and each weight byte is fetched from L2 once
+// per pair.  Both CTAs run the TMA producer (cp.async.bulk.tensor ... cta_group::2, completing on the LEADER's barrier);
+// the leader's elected thread issues the MMAs; tcgen05.commit multicasts the slot release and the accumulator-ready signal
+// to both CTAs; each CTA's epilogue warps read their own TMEM (their 128 pixels x 256 channels).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pair_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void pair_sync() { asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address: the even (leader) CTA of the pair
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(tc::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(tc::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma2_load_5d(void* dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(tc::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+               ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {   // arrives on `bar` of BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(tc::smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 2)
+conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const ConvTcArgs a) {
+  constexpr int BN = 256, HALF = 128;
+  constexpr uint32_t kABytes = BM * BK * 2, kWBytes = HALF * BK * 2, kStageBytes = kABytes + kWBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];      // used in the leader only: both CTAs' loads complete on it
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float bias_s[BN];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = pair_rank();
+  const int m0 = blockIdx.x * BM, nc0 = blockIdx.y * BN, z = blockIdx.z;
+  const int pa = z >> 1, pb = z & 1;
+  const int HW = a.H * a.W;
+  const int cblocks = a.Cin / BK;
+  const int nkb = a.taps * cblocks, S = a.stages;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&map_a);
+    tc::prefetch_tmap(&map_w);
+    for (int s = 0; s < S; ++s) {
+      tc::mbar_init(&full_bar[s], 1);
+      tc::mbar_init(&empty_bar[s], 1);
+    }
+    tc::mbar_init(&tmem_full_bar, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&tmem_slot)), "n"(BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < BN; i += 128) bias_s[i] = a.bias ? a.bias[nc0 + i] : 0.f;
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  pair_sync();              // the peer's barriers exist before any remote completion / multicast commit reaches them
+  tc::fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      const int tn0 = m0 / HW, ty0 = (m0 - tn0 * HW) / a.W;
+      const int wrow = z * a.Cout + nc0 + (int)rank * HALF;      // this CTA's half of the weight tile
+      int tap = 0, cb = 0;
+      for (int kb = 0; kb < nkb; ++kb, ++cb) {
+        const int s = kb % S;
+        const uint32_t ph = (uint32_t)(kb / S) & 1u;
+        if (!tc::mbar_wait(&empty_bar[s], ph ^ 1u, 1)) break;
+        if (cb == cblocks) { cb = 0; ++tap; }
+        uint8_t* sa = smem + (size_t)s * kStageBytes;
+        const uint32_t fb = tc::smem_u32(&full_bar[s]) & kPeerMask;      // the leader's barrier
+        if (rank == 0) tc::mbar_arrive_expect_tx(&full_bar[s], 2 * kStageBytes);
+        if (a.up == 0) {
+          const int ky = tap >> 2, kx = tap & 3;
+          const int dy = ky == 0 ? -1 : (ky == 3 ? 1 : 0), dx = kx == 0 ? -1 : (kx == 3 ? 1 : 0);
+          const int py = (ky == 0 || ky == 2) ? 1 : 0, px = (kx == 0 || kx == 2) ? 1 : 0;
+          tma2_load_5d(sa, &map_a, fb, px * a.in_pitch + cb * BK, dx, py, ty0 + dy, tn0);
+        } else {
+          int dy, dx;
+          if (a.up == 1) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
+          else { dy = (tap >> 1) == 0 ? 0 : (pa == 0 ? -1 : 1); dx = (tap & 1) == 0 ? 0 : (pb == 0 ? -1 : 1); }
+          tma2_load_4d(sa, &map_a, fb, cb * BK, dx, ty0 + dy, tn0);
+        }
+        tma2_load_2d(sa + kABytes, &map_w, fb, tap * a.Cin + cb * BK, wrow);
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && tc::elect_one()) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16(2 * BM, BN);
+      bool ok = true;
+      for (int kb = 0; kb < nkb && ok; ++kb) {
+        const int s = kb % S;
+        const uint32_t ph = (uint32_t)(kb / S) & 1u;
+        ok = tc::mbar_wait(&full_bar[s], ph, 2);
+        tc::fence_after_sync();
+        const uint32_t a_addr = tc::smem_u32(smem + (size_t)s * kStageBytes);
+        const uint64_t da = tc::make_desc_sw128(a_addr), dw = tc::make_desc_sw128(a_addr + kABytes);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          umma2_bf16(tmem_base, da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+        umma2_commit_both(&empty_bar[s]);
+      }
+      umma2_commit_both(&tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    tc::mbar_wait(&tmem_full_bar, 0, 3);
+    tc::fence_after_sync();
+    const int p = m0 + q * 32 + lane;
+    const bool valid = p < a.total_pix;
+    size_t op = (size_t)p;
+    if (a.up == 2) {
+      const int n = p / HW, rem = p - n * HW, y = rem / a.W, x = rem - y * a.W;
+      op = ((size_t)n * (2 * a.H) + (size_t)(2 * y + pa)) * (size_t)(2 * a.W) + (size_t)(2 * x + pb);
+    }
+    bf16* dst = a.out + op * (size_t)a.out_pitch + nc0;
+    float* dst32 = a.out32 ? a.out32 + op * (size_t)a.out_pitch + nc0 : nullptr;
+    const float* prow = a.post ? a.post + (size_t)(valid ? p / HW : 0) * a.post_stride + nc0 : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      float v[16];
+      tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          v[j] += bias_s[c0 + j];
+          if (a.relu) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (prow) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(prow + c0) + j);
+            v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
+          }
+        }
+        if (dst32) {
+          float4* d4 = reinterpret_cast<float4*>(dst32 + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+          d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  pair_sync();              // neither CTA frees TMEM / leaves while its peer's MMAs or commits may still address it
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+}
+
 // final_conv[3] + Sigmoid (v2:277-278): Conv2d(32, 3, 3, padding 1) over NHWC bf16 -> NCHW fp32.  N = 3 output
 // channels is no tensor-core shape: one thread per pixel on the CUDA cores.  A CTA owns an 8 x 32 pixel tile: its
 // 10 x 34 halo is loaded ONCE with coalesced 16-byte reads into shared memory, channel-octet major ([4][340] uint4), so
@@ -759,6 +936,43 @@ int conv_mt2() {
   return v;
 }
 
+int conv_pair() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LDM_CONV_PAIR");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
+// 256-channel tiles as CTA pairs (conv_tc_pair_kernel): `mw128` is the weight map with a 128-row box
+int launch_pair(ldm_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw128, const ConvTcArgs& a0, int nz, cudaStream_t st) {
+  ConvTcArgs a = a0;
+  const int nkb = a.taps * (a.Cin / BK);
+  const size_t stage_bytes = (size_t)BM * BK * 2 + (size_t)128 * BK * 2;
+  static int want = -1;
+  if (want < 0) {
+    const char* e = getenv("LDM_CONV_PAIR_STAGES");
+    want = e ? atoi(e) : 3;            // 3 x 32 KB: two CTAs per SM (one pair's epilogue under the other pair's main loop)
+    if (want < 2) want = 2;
+    if (want > 6) want = 6;
+  }
+  int stages = nkb < want ? nkb : want;
+  a.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  static bool attr = false;
+  if (!attr) {
+    LDM_CUDA(cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  dim3 grid(ceil_div(a.total_pix, BM), a.Cout / 256, nz);      // grid.x even (checked by the caller): __cluster_dims__(2, 1, 1)
+  conv_tc_pair_kernel<<<grid, kThreads, smem, st>>>(ma, mw128, a);
+  ctx->launches++;
+  ldm_kmark(ctx, "conv_tc_pair");
+  LDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int BN>
 int launch_bn(ldm_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, const ConvTcArgs& a, int nz, cudaStream_t st) {
   // two pixel tiles per CTA where that still leaves >= 1.5 CTAs per SM (64 / 128-channel tiles only: TMEM and
@@ -802,6 +1016,8 @@ static int conv_tc_launch(ldm_ctx* ctx, const bf16* in, int in_pitch, const Conv
     bn = L.bn_alt;      // fewer tiles than SMs: halve the tile (measured: 128 tiles of 256 channels 33 us -> 256 tiles of 128 channels 24 us)
     mw = &L.map_w_alt;
   }
+  if (bn == 256 && conv_pair() && L.bn_alt == 128 && ceil_div(a.total_pix, BM) % 2 == 0)
+    return launch_pair(ctx, ma, L.map_w_alt, a, nz, st);      // 2-CTA MMA: 256 pixels x 256 channels per CTA pair
   switch (bn) {
     case 32: return launch_bn<32>(ctx, ma, *mw, a, nz, st);
     case 64: return launch_bn<64>(ctx, ma, *mw, a, nz, st);

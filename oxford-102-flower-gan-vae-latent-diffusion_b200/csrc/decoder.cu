@@ -240,7 +240,12 @@ int conv_bf16(ldm_ctx* ctx, std::vector<void*>& pool, ConvLayer& L, cudaStream_t
   const size_t n = (size_t)L.Cout * L.taps * L.Cin;
   LDM_TRY(ldm_alloc_t(ctx, pool, &L.w16, n));
   LDM_TRY(launch_to_bf16(ctx, L.w32, L.w16, n, st));
-  return tc_make_weight_map(ctx, L.w16, L.Cout, L.taps * L.Cin, conv_tc_pick_bn(L.Cout), &L.map_w);
+  LDM_TRY(tc_make_weight_map(ctx, L.w16, L.Cout, L.taps * L.Cin, conv_tc_pick_bn(L.Cout), &L.map_w));
+  if (L.Cout % 256 == 0) {      // 128-row box: each CTA of a pair loads half of a 256-channel tile (conv_tc_pair_kernel)
+    L.bn_alt = 128;
+    LDM_TRY(tc_make_weight_map(ctx, L.w16, L.Cout, L.taps * L.Cin, 128, &L.map_w_alt));
+  }
+  return 0;
 }
 
 }  // namespace
@@ -318,6 +323,10 @@ int decoder_pack_impl(ldm_ctx* ctx, const ldm_decoder_weights* w, cudaStream_t s
       LDM_TRY(ldm_alloc_t(ctx, P, &U0.w16, 4 * per));
       for (int z = 0; z < 4; ++z) LDM_TRY(launch_to_bf16(ctx, D.up[i][z].w32, U0.w16 + (size_t)z * per, per, st));
       LDM_TRY(tc_make_weight_map(ctx, U0.w16, 4 * U0.Cout, 4 * U0.Cin, conv_tc_pick_bn(U0.Cout), &U0.map_w));
+      if (U0.Cout % 256 == 0) {
+        U0.bn_alt = 128;
+        LDM_TRY(tc_make_weight_map(ctx, U0.w16, 4 * U0.Cout, 4 * U0.Cin, 128, &U0.map_w_alt));
+      }
     }
     LDM_TRY(conv_bf16(ctx, P, D.fin0, st));
   }
@@ -332,7 +341,12 @@ int decoder_pack_impl(ldm_ctx* ctx, const ldm_decoder_weights* w, cudaStream_t s
         S.Cin = 3 * L.Cin; S.Cout = L.Cout; S.taps = L.taps; S.b = L.b;
         LDM_TRY(ldm_alloc_t(ctx, P, &S.w16, (size_t)L.Cout * L.taps * S.Cin));
         LDM_TRY(launch_pack_conv_split(ctx, L.w32, S.w16, L.Cout, L.taps, L.Cin, st));
-        return tc_make_weight_map(ctx, S.w16, S.Cout, S.taps * S.Cin, conv_tc_pick_bn(S.Cout), &S.map_w);
+        LDM_TRY(tc_make_weight_map(ctx, S.w16, S.Cout, S.taps * S.Cin, conv_tc_pick_bn(S.Cout), &S.map_w));
+        if (S.Cout % 256 == 0) {
+          S.bn_alt = 128;
+          LDM_TRY(tc_make_weight_map(ctx, S.w16, S.Cout, S.taps * S.Cin, 128, &S.map_w_alt));
+        }
+        return 0;
       };
       for (int i = 0; i < 3; ++i) {
         LDM_TRY(split_layer(D.res[i].conv1, D.res[i].conv1s));
@@ -345,6 +359,10 @@ int decoder_pack_impl(ldm_ctx* ctx, const ldm_decoder_weights* w, cudaStream_t s
         LDM_TRY(ldm_alloc_t(ctx, P, &S.w16, 4 * per));
         for (int z = 0; z < 4; ++z) LDM_TRY(launch_pack_conv_split(ctx, D.up[i][z].w32, S.w16 + (size_t)z * per, U0.Cout, 4, U0.Cin, st));
         LDM_TRY(tc_make_weight_map(ctx, S.w16, 4 * S.Cout, 4 * S.Cin, conv_tc_pick_bn(S.Cout), &S.map_w));
+        if (S.Cout % 256 == 0) {
+          S.bn_alt = 128;
+          LDM_TRY(tc_make_weight_map(ctx, S.w16, 4 * S.Cout, 4 * S.Cin, 128, &S.map_w_alt));
+        }
       }
       LDM_TRY(split_layer(D.fin0, D.fin0s));
     }

@@ -532,6 +532,25 @@ int tc_error_reset() {
   return 0;
 }
 
+// The same matrix as a 3-D tensor (64 columns, rows, cols / 64 k-blocks): one box = `kblocks` consecutive 64-column tiles of
+// box_rows rows, which land as consecutive swizzled tiles in shared memory (one TMA instruction for several k-blocks)
+int tc_make_kblock_map(const void* base, int rows, int cols, int ld, int box_rows, int kblocks, CUtensorMap* out) {
+  LDM_CHECK(g_encode != nullptr, "tensor-core path not initialised (cuTensorMapEncodeTiled unavailable)");
+  LDM_CHECK(((uintptr_t)base & 15) == 0 && (ld * 2) % 16 == 0 && cols % BK == 0, "TMA needs 16-byte aligned base and pitch, whole k-blocks");
+  cuuint64_t dims[3] = {(cuuint64_t)BK, (cuuint64_t)rows, (cuuint64_t)(cols / BK)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)BK * 2};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, (cuuint32_t)kblocks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ldm_set_error("cuTensorMapEncodeTiled (k-block map) failed: CUresult %d (rows=%d cols=%d ld=%d box_rows=%d x %d)", (int)r, rows, cols, ld, box_rows, kblocks);
+    return (int)r;
+  }
+  return 0;
+}
+
 // 2-D bf16 activation (rows, cols) with row pitch ld, box (box_rows, 64 columns), 128-byte swizzle; rows read past
 // `rows` are zero-filled
 int tc_make_act_map(const void* base, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {

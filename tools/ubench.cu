@@ -249,6 +249,54 @@ __global__ void __launch_bounds__(128, 1) mma_kernel(int mode, int N, int reps, 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+
+// ------------------------------------------------------------------------------------------- 5. tcgen05.mma issue patterns
+// SS MMAs of shape M x N x 16 rotating over `nacc` independent accumulators (column blocks of TMEM) and, with `nab` > 1,
+// over distinct A k-slices: is the 74-clock floor of a small-N MMA a per-accumulator dependency or operand delivery?
+__global__ void __launch_bounds__(128, 1) mma_rot_kernel(int M, int N, int nacc, int reps, long long* out) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = base;
+  uint8_t* sb = base + 16384;
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tslot;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(base)[i] = 0x3f803f80u;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tslot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tm = tslot;
+  const uint32_t id = idesc_bf16(M, N);
+  const uint64_t da = desc_sw128(smem_u32(sa)), db = desc_sw128(smem_u32(sb));
+  const uint32_t stride = (uint32_t)(512 / nacc);
+  if (threadIdx.x == 0) {
+    for (int j = 0; j < nacc; ++j) mma_ss(tm + j * stride, da, db, id, 0);
+    commit(&bar);
+    mbar_wait(&bar, 0);
+    const long long t0 = clock64();
+    int j = 0;
+    for (int r = 0; r < reps; ++r)
+      for (int k = 0; k < 4; ++k) {
+        mma_ss(tm + j * stride, da + 2 * k, db + 2 * k, id, 1);
+        j = j + 1 == nacc ? 0 : j + 1;
+      }
+    const long long t1 = clock64();
+    commit(&bar);
+    mbar_wait(&bar, 1);
+    out[0] = clock64() - t0;
+    out[1] = t1 - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm) : "memory");
+}
+
 int main() {
   CK(cudaSetDevice(0));
   cudaDeviceProp prop;
@@ -361,6 +409,20 @@ int main() {
         printf("mma N=%3d %-22s: %.1f cyc per K=16 step (issue alone %.1f)\n", N, nm[mode], (double)h[0] / (reps * 4), (double)h[1] / (reps * 4));
       }
     }
+  }
+  // ---- 5. issue patterns: rotating accumulators, M = 64
+  {
+    CK(cudaFuncSetAttribute(mma_rot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    for (int M : {128, 64})
+      for (int N : {48, 64, 128, 256})
+        for (int nacc : {1, 2, 4}) {
+          if (N * nacc > 512) continue;
+          if (M == 64 && (N % 8)) continue;
+          mma_rot_kernel<<<1, 128, 16384 + 32768 + 1024>>>(M, N, nacc, 64, out);
+          CK(cudaDeviceSynchronize());
+          CK(cudaMemcpy(h.data(), out, sizeof(long long) * 2, cudaMemcpyDeviceToHost));
+          printf("mma-rot M=%3d N=%3d accumulators %d: %.1f cyc per K=16 step (issue alone %.1f)\n", M, N, nacc, (double)h[0] / 256, (double)h[1] / 256);
+        }
   }
   return 0;
 }
