@@ -140,3 +140,85 @@ def test_v3_full_size_call(precision):
     eng.sample3(xs, 999, 990, f.cuda(), k.cuda(), seed=21, sample_offset=0)
     ref = R.sample3(sd, R.schedule(1000), x, f, k, noise_fn=lambda t: torch.from_numpy(philox.normal_rows(21, 0, B, t)), t_start=999, t_end=990)
     assert R.rel_l2(xs.cpu(), ref) < LATENT_TOL[precision], R.rel_l2(xs.cpu(), ref)
+
+
+# ----------------------------------------------------------------------------- GPU: the persistent loop kernel (v3loop.cu)
+@pytest.mark.gpu
+def test_v3_loop_kernel_is_the_bf16_path_and_agrees_with_the_per_layer_sequence():
+    """bf16 calls of up to 128 rows run unet3_loop_kernel (ONE launch for the whole chain, no graph); LDM_V3LOOP=0 selects the
+    per-layer sequence (27 launches per step).  Both must reproduce the restatement's chain, and agree with each other."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import numpy as np, torch
+import ldm_b200
+from oracle import philox, weights
+torch.set_grad_enabled(False)
+u = ldm_b200.v3.ConditionalUNet(precision="bf16")
+u.load_state_dict(weights.make_unet3_state(44, "perturbed"), strict=True)
+u = u.to("cuda").eval()
+d = ldm_b200.v3.ConditionalDenoiseDiffusion(u, 1000, torch.device("cuda"))
+eng = d._engine("cuda")
+B = 32
+x = torch.from_numpy(philox.normal_rows(3, 0, B, 1000)).cuda()
+f, k = (torch.arange(B) * 5 %% 102).cuda(), (torch.arange(B) %% 10).cuda()
+eng.ktrace_start()
+eng.sample3(x, 999, 960, f, k, seed=17, sample_offset=0, use_graph=False)
+names = [n for n, _ in eng.ktrace_stop()]
+print("RESULT", int(eng.info("launches_per_step")), len(names), names[-1])
+np.save("%s", x.cpu().numpy())
+"""
+    outs = {}
+    for name, env_extra in (("loop", {}), ("layers", {"LDM_V3LOOP": "0"})):
+        path = os.path.join(root, "gpurun_out", "v3_%s.npy" % name) if os.path.isdir(os.path.join(root, "gpurun_out")) else "/tmp/v3_%s.npy" % name
+        env = dict(os.environ, PYTHONPATH=root, **env_extra)
+        r = subprocess.run([sys.executable, "-c", code % path], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "RESULT" in r.stdout, r.stdout + r.stderr
+        per_step, n_launches, last = r.stdout.split("RESULT")[1].split()[:3]
+        if name == "loop":
+            assert int(per_step) == 0 and int(n_launches) <= 8 and last == "unet3_loop", r.stdout
+        else:
+            assert int(per_step) == 27 and int(n_launches) >= 40 * 27, r.stdout
+        outs[name] = torch.from_numpy(np.load(path))
+    sd = weights.make_unet3_state(SEED, "perturbed")
+    B = 32
+    x = torch.from_numpy(philox.normal_rows(3, 0, B, 1000))
+    f, k = torch.arange(B) * 5 % 102, torch.arange(B) % 10
+    ref = R.sample3(sd, R.schedule(1000), x, f, k, noise_fn=lambda t: torch.from_numpy(philox.normal_rows(17, 0, B, t)), t_start=999, t_end=960)
+    for name in outs:
+        assert R.rel_l2(outs[name], ref) < LATENT_TOL["bf16"], (name, R.rel_l2(outs[name], ref))
+    assert R.rel_l2(outs["loop"], outs["layers"]) < LATENT_TOL["bf16"]
+
+
+@pytest.mark.gpu
+def test_v3_loop_kernel_other_architecture_and_ragged_calls():
+    """A non-default architecture the loop kernel covers (head widths 16 and 32, 128-wide latent, three stages) at ragged call
+    sizes, single and per-row timesteps, against the restatement; one the kernel does not cover falls back to the layers."""
+    import ldm_b200
+    kw = dict(latent_dim=128, hidden_dims=[128, 256, 128, 128], time_emb_dim=256, num_classes=7, num_colors=3)
+    sd = weights.make_state(weights.unet3_spec(latent_dim=128, hidden=kw["hidden_dims"], temb=256, num_classes=7, num_colors=3), 5, "perturbed")
+    u = ldm_b200.v3.ConditionalUNet(precision="bf16", **kw)
+    u.load_state_dict(sd, strict=True)
+    u = u.to("cuda").eval()
+    torch.manual_seed(11)
+    for B in (1, 5, 127, 128):
+        x, f, k = torch.randn(B, 128) * 1.5, torch.randint(0, 7, (B,)), torch.randint(0, 3, (B,))
+        t1 = torch.tensor([613])
+        got = u(x.cuda(), t1.cuda(), f.cuda(), k.cuda()).cpu()
+        assert R.max_rel(got, R.unet3_forward(sd, x, t1, f, k)) < EPS_TOL["bf16"], B
+        tb = torch.randint(0, 1000, (B,))
+        got = u(x.cuda(), tb.cuda(), f.cuda(), k.cuda()).cpu()
+        assert R.max_rel(got, R.unet3_forward(sd, x, tb, f, k)) < EPS_TOL["bf16"], B
+    eng = ldm_b200.get_engine(torch.device("cuda"), "bf16")
+    assert int(eng.info("launches_per_step")) == 0          # the loop kernel took these calls
+    # head width 48 is outside the tensor-core attention: per-layer sequence, same answers
+    kw2 = dict(latent_dim=128, hidden_dims=[128, 384, 128], time_emb_dim=256, num_classes=7, num_colors=3)
+    sd2 = weights.make_state(weights.unet3_spec(latent_dim=128, hidden=kw2["hidden_dims"], temb=256, num_classes=7, num_colors=3), 6, "perturbed")
+    u2 = ldm_b200.v3.ConditionalUNet(precision="bf16", **kw2)
+    u2.load_state_dict(sd2, strict=True)
+    u2 = u2.to("cuda").eval()
+    x, f, k = torch.randn(9, 128), torch.randint(0, 7, (9,)), torch.randint(0, 3, (9,))
+    got = u2(x.cuda(), torch.tensor([5], device="cuda"), f.cuda(), k.cuda()).cpu()
+    assert R.max_rel(got, R.unet3_forward(sd2, x, torch.tensor([5]), f, k)) < EPS_TOL["bf16"]
+    assert int(eng.info("launches_per_step")) > 0
