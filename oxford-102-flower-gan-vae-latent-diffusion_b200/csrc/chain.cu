@@ -52,6 +52,7 @@ constexpr int kCtlThreads = 128;        // warp 0: weight TMA, warp 1: operand T
 constexpr uint32_t kWTile = 128 * BK * 2;                // one weight k-block of a tile: 16 KiB
 constexpr uint32_t kWSlotBytes = 2 * kWTile;             // a weight-ring slot carries the two weight tiles of one chunk (= 8 MMAs)
 constexpr int kMaxWSlots = 6;
+constexpr int kXGroup = 4;                               // operand k-blocks per grouped TMA box (kXSlots % kXGroup == 0)
 constexpr int kXSlots = 8;                               // operand ring: k-blocks of NB rows, loaded as soon as the hand-over is through
 constexpr int kSlots = CS;                               // partial-statistics slots per buffer: one per tile of a phase
 constexpr int kChains = 2;                               // TMEM column blocks of NB fp32 accumulators: acc1, acc2 (dual phases)
@@ -114,6 +115,8 @@ struct ChainPhase {
 struct ChainParams {
   CUtensorMap wmap[LDM_CHAIN_MAX_PHASES];
   CUtensorMap xmaps[kMaxXMaps];   // [0], [1]: af[0], af[1]; [2 + j]: opbuf[j]
+  CUtensorMap xmaps4[kMaxXMaps];  // the same operands as (64, rows, k-block) tensors: one box = kXGroup consecutive k-blocks
+  int xgroup;                     // 1: operand k-blocks are requested kXGroup at a time where the ring position allows
   ChainPhase ph[LDM_CHAIN_MAX_PHASES];
   int n_phases;
   int B;                      // rows of the whole batch (leading dimension of `noise` slabs)
@@ -407,6 +410,15 @@ struct __align__(16) UnitPlan {
   int xcol0;        // operand column of k-block 0
 };
 
+// k-blocks the operand producer requests with one box at ring slot xs when `rem` k-blocks of the unit remain (the MMA issuer
+// applies the same rule).  Measured at B = 256: groups of 4 take 5.4 % off the step, the whole ring (8) in one box only 3 % - the
+// first MMA of a phase waits for the first box to land.
+__device__ __forceinline__ int x_group(int enabled, uint32_t xs, int rem) {
+  if (!enabled) return 1;
+  if ((xs % kXGroup) == 0 && rem >= kXGroup) return kXGroup;
+  return 1;
+}
+
 // control-thread PTX on raw shared-memory addresses (no generic -> shared conversions inside the loops)
 __device__ __forceinline__ void expect_tx_a(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -414,6 +426,10 @@ __device__ __forceinline__ void expect_tx_a(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void tma2d_a(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma3d_a(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void commit_a(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -471,6 +487,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
     tc::fence_barrier_init();
     for (int p = 0; p < NP; ++p) tc::prefetch_tmap(&P.wmap[p]);
     for (int p = 0; p < kMaxXMaps; ++p) tc::prefetch_tmap(&P.xmaps[p]);
+    for (int p = 0; p < kMaxXMaps; ++p) tc::prefetch_tmap(&P.xmaps4[p]);
   }
   if (warp == 2) tc::tmem_alloc<kTmemCols>(&tmem_slot);
   if (warp == 3) {
@@ -560,13 +577,29 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
             if (!P.writer_fence) fence_proxy_async_global();   // peers' generic-proxy global writes (released above) -> async-proxy reads below
           }
           if (!(tail ? pl.valid_tail : pl.valid)) continue;
+          const CUtensorMap* xm4 = &P.xmaps4[sphase[p].xmap + (sphase[p].xmap_alt ? (it & 1) : 0)];
           int xcol = pl.xcol0;
-          for (int kb = 0; kb < pl.nkb; ++kb, xcol += BK) {
-            if (!W.wait(empty_a + 8u * xs, xpar ^ 1u, 3)) { ok = false; break; }
+          for (int kb = 0; kb < pl.nkb;) {
             const uint32_t fb = full_a + 8u * xs;
+            const int grp = x_group(P.xgroup, xs, pl.nkb - kb);
+            if (grp > 1) {
+              // `grp` k-blocks as ONE box: the TMA unit spends ~150 clocks per instruction plus ~1.3 per 128-byte row, so a
+              // 6 KB box per k-block held the first MMAs of a phase back.  The slots of a ring round are freed in order: the
+              // last slot of the group is the one to wait for.  The group completes on its first slot's barrier; the other
+              // slots' barriers are not used in this round (the MMA issuer keeps one parity bit per barrier).
+              if (!W.wait(empty_a + 8u * (xs + grp - 1), xpar ^ 1u, 3)) { ok = false; break; }
+              expect_tx_a(fb, (uint32_t)grp * G::kXBytes);
+              tma3d_a(ring_a + xs * G::kXBytes, xm4, fb, 0, row0, xcol / BK);
+              if (kb == 0) TR.stamp(32, p);
+              kb += grp; xcol += grp * BK; xs += grp;
+              if (xs == (uint32_t)kXSlots) { xs = 0; xpar ^= 1u; }
+              continue;
+            }
+            if (!W.wait(empty_a + 8u * xs, xpar ^ 1u, 3)) { ok = false; break; }
             expect_tx_a(fb, G::kXBytes);
             tma2d_a(ring_a + xs * G::kXBytes, xm, fb, xcol, row0);
             if (kb == 0) TR.stamp(32, p);
+            ++kb; xcol += BK;
             if (++xs == (uint32_t)kXSlots) { xs = 0; xpar ^= 1u; }
           }
           TR.stamp(33, p);
@@ -584,6 +617,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
       constexpr uint64_t kWSlotD = kWSlotBytes >> 4, kWTileD = kWTile >> 4, kXD = G::kXBytes >> 4;   // descriptor start-address units (16 B)
       const uint32_t acc0 = tmem_base, acc1 = tmem_base + (uint32_t)NB;
       uint32_t ws = 0, wpar = 0, xs = 0, xpar = 0;
+      uint32_t xfpar = 0;       // bit s: parity of the next phase of operand barrier s (a barrier is only used by the first slot of a group)
       bool ok = true;
       Tracer TR{P.trace ? P.trace + ((size_t)rank * LDM_CHAIN_TRACE_TRACKS + 4) * LDM_CHAIN_TRACE_LEN : nullptr, 0, false};
       for (int it = 0; it <= P.n_iter && ok; ++it) {
@@ -594,8 +628,15 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
           if (!(tail ? pl.valid_tail : pl.valid)) continue;
           if (pl.mode == 1) {
             // dual: both weight tiles of a chunk against the same operand k-block; consecutive MMAs never depend on each other
+            int grp = 0;      // k-blocks of the current operand group that are still to come (their barrier is the group's first)
             for (int c = 0; c < pl.nkb; ++c) {
-              if (!W.wait(xfull_a + 8u * xs, xpar, 4) || !W.wait(wfull_a + 8u * ws, wpar, 4)) { ok = false; break; }
+              if (grp == 0) {
+                if (!W.wait(xfull_a + 8u * xs, (xfpar >> xs) & 1u, 4)) { ok = false; break; }
+                xfpar ^= 1u << xs;
+                grp = x_group(P.xgroup, xs, pl.nkb - c);
+              }
+              --grp;
+              if (!W.wait(wfull_a + 8u * ws, wpar, 4)) { ok = false; break; }
               if (c == 0) TR.stamp(40, p);
               if (c == pl.nkb / 2) TR.stamp(42, p);
               tc::fence_after_sync();
@@ -614,10 +655,25 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
           } else {
             // one accumulator: a chunk is two consecutive k-blocks (the last chunk of an odd count holds one)
             const int nchunks = (pl.nkb + 1) >> 1;
+            int grp = 0;
             for (int c = 0; c < nchunks; ++c) {
               const bool two = 2 * c + 1 < pl.nkb;
               const uint32_t xs2 = xs + 1 == (uint32_t)kXSlots ? 0u : xs + 1, xpar2 = xs + 1 == (uint32_t)kXSlots ? xpar ^ 1u : xpar;
-              if (!W.wait(xfull_a + 8u * xs, xpar, 4) || (two && !W.wait(xfull_a + 8u * xs2, xpar2, 4)) || !W.wait(wfull_a + 8u * ws, wpar, 4)) { ok = false; break; }
+              if (grp == 0) {
+                if (!W.wait(xfull_a + 8u * xs, (xfpar >> xs) & 1u, 4)) { ok = false; break; }
+                xfpar ^= 1u << xs;
+                grp = x_group(P.xgroup, xs, pl.nkb - 2 * c);
+              }
+              --grp;
+              if (two) {
+                if (grp == 0) {
+                  if (!W.wait(xfull_a + 8u * xs2, (xfpar >> xs2) & 1u, 4)) { ok = false; break; }
+                  xfpar ^= 1u << xs2;
+                  grp = x_group(P.xgroup, xs2, pl.nkb - (2 * c + 1));
+                }
+                --grp;
+              }
+              if (!W.wait(wfull_a + 8u * ws, wpar, 4)) { ok = false; break; }
               if (c == 0) TR.stamp(40, p);
               if (c == nchunks / 2) TR.stamp(42, p);
               tc::fence_after_sync();
@@ -1214,6 +1270,7 @@ int launch_variant(const ChainParams& P, int nclusters, cudaStream_t st) {
 }  // namespace
 
 int tc_make_act_map(const void* base, int rows, int cols, int ld, int box_rows, CUtensorMap* out);
+int tc_make_kblock_map(const void* base, int rows, int cols, int ld, int box_rows, int kblocks, CUtensorMap* out);
 
 // Can 16-CTA clusters of this kernel be scheduled on this device?  (called once per context)
 int chain_init(ldm_ctx* ctx) {
@@ -1454,6 +1511,11 @@ int launch_chain(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const
   LDM_TRY(tc_make_act_map(ctx->caf[1], B, 3 * L * mult, 3 * L * mult, NB, &P.xmaps[1]));
   for (int j = 0; j < nst; ++j) LDM_TRY(tc_make_act_map(ctx->opbuf[j], B, U.hid[j] * mult, U.hid[j] * mult, NB, &P.xmaps[2 + j]));
   for (int j = nst; j < kMaxXMaps - 2; ++j) P.xmaps[2 + j] = P.xmaps[0];
+  LDM_TRY(tc_make_kblock_map(ctx->caf[0], B, 3 * L * mult, 3 * L * mult, NB, kXGroup, &P.xmaps4[0]));
+  LDM_TRY(tc_make_kblock_map(ctx->caf[1], B, 3 * L * mult, 3 * L * mult, NB, kXGroup, &P.xmaps4[1]));
+  for (int j = 0; j < nst; ++j) LDM_TRY(tc_make_kblock_map(ctx->opbuf[j], B, U.hid[j] * mult, U.hid[j] * mult, NB, kXGroup, &P.xmaps4[2 + j]));
+  for (int j = nst; j < kMaxXMaps - 2; ++j) P.xmaps4[2 + j] = P.xmaps4[0];
+  { const char* xg = getenv("LDM_CHAIN_XGROUP"); P.xgroup = xg ? atoi(xg) : 1; }
   int cadd = (kChains + 2) * NB;      // TMEM: accumulators, parked noise, chain state, then the per-sample terms (NW >= 3)
   for (int j = 0; j < C.n_phases; ++j) {
     const ChainPhaseHost& H = C.ph[j];
