@@ -1128,7 +1128,16 @@ int launch_v3loop(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, cons
     LDM_CUDA(cudaMemsetAsync(trace, 0, trace_n * sizeof(long long), st));
     P.trace = trace;
   }
-  unet3_loop_kernel<<<M->grid, kThreads, M->smem, st>>>(P);
+  {
+    // cooperative launch: the grid barrier needs every CTA resident at once, also when other work shares the device
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(M->grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = M->smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    LDM_CUDA(cudaLaunchKernelEx(&cfg, unet3_loop_kernel, P));
+  }
   LDM_LAUNCHED_AS(ctx, "unet3_loop");
   if (trace) {   // per phase of step 1: this CTA's work, then its wait at the barrier (ns), for a few CTAs
     std::vector<long long> h(trace_n);
