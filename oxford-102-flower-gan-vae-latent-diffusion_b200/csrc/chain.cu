@@ -569,6 +569,14 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
         for (int p = 0; p < (tail ? 1 : NP) && ok; ++p, ++gp) {
           const UnitPlan pl = splan[p];
           const CUtensorMap* xm = &P.xmaps[sphase[p].xmap + (sphase[p].xmap_alt ? (it & 1) : 0)];
+          // the first request of the phase is armed BEFORE the hand-over is awaited (slot free, bytes expected): after it only
+          // the proxy fence and the TMA instruction stand between the hand-over and the first operand bytes
+          const bool valid = tail ? pl.valid_tail : pl.valid;
+          const int grp0 = valid ? x_group(P.xgroup, xs, pl.nkb) : 0;
+          if (grp0 > 0) {
+            if (!W.wait(empty_a + 8u * (xs + grp0 - 1), xpar ^ 1u, 3)) { ok = false; break; }
+            expect_tx_a(full_a + 8u * xs, (uint32_t)grp0 * G::kXBytes);
+          }
           if (gp > 0) {
             const uint32_t f = gp - 1;   // hand-over that publishes this phase's operand
             if (!W.wait_cluster(&obar[f & 1u], (f >> 1) & 1u, 2)) { ok = false; break; }
@@ -582,21 +590,26 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) chain_kernel(const __gri
           for (int kb = 0; kb < pl.nkb;) {
             const uint32_t fb = full_a + 8u * xs;
             const int grp = x_group(P.xgroup, xs, pl.nkb - kb);
+            const bool armed = kb == 0;      // the unit's first request: see above
             if (grp > 1) {
               // `grp` k-blocks as ONE box: the TMA unit spends ~150 clocks per instruction plus ~1.3 per 128-byte row, so a
               // 6 KB box per k-block held the first MMAs of a phase back.  The slots of a ring round are freed in order: the
               // last slot of the group is the one to wait for.  The group completes on its first slot's barrier; the other
               // slots' barriers are not used in this round (the MMA issuer keeps one parity bit per barrier).
-              if (!W.wait(empty_a + 8u * (xs + grp - 1), xpar ^ 1u, 3)) { ok = false; break; }
-              expect_tx_a(fb, (uint32_t)grp * G::kXBytes);
+              if (!armed) {
+                if (!W.wait(empty_a + 8u * (xs + grp - 1), xpar ^ 1u, 3)) { ok = false; break; }
+                expect_tx_a(fb, (uint32_t)grp * G::kXBytes);
+              }
               tma3d_a(ring_a + xs * G::kXBytes, xm4, fb, 0, row0, xcol / BK);
               if (kb == 0) TR.stamp(32, p);
               kb += grp; xcol += grp * BK; xs += grp;
               if (xs == (uint32_t)kXSlots) { xs = 0; xpar ^= 1u; }
               continue;
             }
-            if (!W.wait(empty_a + 8u * xs, xpar ^ 1u, 3)) { ok = false; break; }
-            expect_tx_a(fb, G::kXBytes);
+            if (!armed) {
+              if (!W.wait(empty_a + 8u * xs, xpar ^ 1u, 3)) { ok = false; break; }
+              expect_tx_a(fb, G::kXBytes);
+            }
             tma2d_a(ring_a + xs * G::kXBytes, xm, fb, xcol, row0);
             if (kb == 0) TR.stamp(32, p);
             ++kb; xcol += BK;
