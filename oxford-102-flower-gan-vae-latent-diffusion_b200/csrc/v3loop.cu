@@ -11,7 +11,7 @@
 //   GEMM  [h_i | u_i] = in . [Wh ; Wb Wh]^T + tables     in = x (i = 0) or [h2_{i-1} | a_{i-1}]; Wh = [W_down | W_down W_o]
 //                                                         folds out_proj, the residual and the down projection of the
 //                                                         previous stage with this stage's block Linear (v3:818-825,838-841)
-//   MID   h2 = swish(LN_a(u)) + h ; n = LN_b(h2)          one warp per row (v3:826-830)
+//   MID   h2 = swish(LN_a(u)) + h ; n = LN_b(h2)          one row per CTA, 128 threads (v3:826-830)
 //   GEMM  [Q | K | V] = in_proj(n)                         epilogue writes [Q | K] row-major and V transposed (v3:832)
 //   ATTN  a = softmax(Q K^T / sqrt(hd)) V                  one CTA per head: S and O in TMEM (v3:832-836)
 //
@@ -19,13 +19,16 @@
 //
 // A GEMM phase is M = 128 rows x N outputs, cut into 32-column tiles and, for the long reductions, into k-parts whose fp32
 // partials are added by the following row phase (fixed order: deterministic).  Work item j of a phase goes to CTA j mod G.
-//   warp 0    : TMA producer.  The ring of 8 x (128 x 64 operand tile + 32 x 64 weight tile) runs across phases; the weight
-//               tiles of a phase's first item are requested BEFORE the barrier that precedes it (weights do not depend on
-//               activations), the operand tiles right after
-//   warp 1    : tcgen05.mma issuer (UMMA 128 x 32 x 16, fp32 accumulator in TMEM)
-//   warps 2-5 : epilogue (epilogue.cuh, shared with gemm_tc.cu), row phases, softmax
-// Activations produced inside the kernel are read with ld.global.cg or by TMA (L2), never through L1.
-// Every wait is bounded; a timeout raises an abort flag that drains the whole grid.
+//   warp 0    : TMA producer.  The ring of 4 stages x two k-blocks (one 3-D box for the 128 x 128 operand tile, one for the
+//               32 x 128 weight tile: a cp.async.bulk.tensor costs ~150 clocks of the TMA unit plus ~1.3 per 128-byte row) runs
+//               across phases; it also stages the NEXT phase's descriptor in shared memory (the kernel parameters are reached
+//               through generic loads) and runs the grid barrier
+//   warp 1    : tcgen05.mma issuer (UMMA 128 x 32 x 16, fp32 accumulator in TMEM); during a barrier it requests the weight
+//               tiles of the next phase's first item (weights do not depend on activations), off the barrier's path
+//   warps 2-5 : epilogue (one TMEM load per tile, additive rows requested before the accumulator wait), row phases, softmax,
+//               the step's Philox draws (CTAs without a head, last attention phase)
+// Activations produced inside the kernel are read with ld.global.cg or by TMA (L2), never through L1.  The kernel is
+// launched cooperatively (every CTA resident).  Every wait is bounded; a timeout raises an abort flag that drains the grid.
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
