@@ -49,3 +49,27 @@ def test_attention_and_halo_kernels_are_bit_stable_over_repetitions():
     for rep in range(10):
         assert torch.equal(m(xi, t), ref), rep
     u3.engine(torch.device("cuda"), 1000).check_device_flags()
+
+
+def test_v3_loop_kernel_is_bit_stable_over_repetitions():
+    """unet3_loop_kernel: 19 grid-wide barriers per step between generic-proxy stores and TMA reads; any missing release /
+    acquire / proxy fence would show up as run-to-run differences."""
+    from ldm_b200 import v3
+    u3 = v3.ConditionalUNet(precision="bf16")
+    u3.load_state_dict(weights.make_unet3_state(44, "perturbed"))
+    u3 = u3.cuda().eval()
+    d = v3.ConditionalDenoiseDiffusion(u3, 1000, torch.device("cuda"))
+    eng = d._engine("cuda")
+    for B in (128, 37):
+        f, k = torch.arange(B, device="cuda") % 102, torch.arange(B, device="cuda") % 10
+        x_T = eng.randn(B, 256, 7, 0, 1000)
+        ref = None
+        for rep in range(8):
+            x = x_T.clone()
+            eng.sample3(x, 999, 900, f, k, seed=7, sample_offset=0, use_graph=False)
+            assert torch.isfinite(x).all()
+            ref = x if ref is None else ref
+            assert torch.equal(x, ref), (B, rep)
+        assert int(eng.info("launches_per_step")) == 0
+        eng.check_device_flags(u3.num_classes)
+    assert int(eng.info("tc_error")) == 0
