@@ -302,6 +302,44 @@ coef_apply_bf16_kernel(const bf16* __restrict__ x, const float2* __restrict__ co
   }
   reinterpret_cast<uint4*>(out)[i] = pack8(f);
 }
+// The same for power-of-two channel counts with HW C / 8 a multiple of 1024 (every layer of the decoder): blockIdx.y = sample,
+// a thread keeps its channel octet (256 is a multiple of C / 8), fetches the octet's coefficients once and streams FOUR
+// 16-byte loads per iteration (independent, issued before the first use); 32-bit index arithmetic, no division.
+constexpr int kCaUnroll = 4;
+__global__ void __launch_bounds__(256)
+coef_apply_bf16_stream_kernel(const bf16* __restrict__ x, const float2* __restrict__ coef, bf16* __restrict__ out, int HWC8, int C8,
+                              int act, int iters) {
+  const int n = blockIdx.y, c8 = threadIdx.x & (C8 - 1);
+  const uint4* xi = reinterpret_cast<const uint4*>(x) + (size_t)n * HWC8;
+  uint4* xo = reinterpret_cast<uint4*>(out) + (size_t)n * HWC8;
+  float sc[8], sh[8];
+  {
+    const float4* cf = reinterpret_cast<const float4*>(coef + ((size_t)n * C8 + c8) * 8);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float4 k = __ldg(cf + e);
+      sc[2 * e] = k.x; sh[2 * e] = k.y; sc[2 * e + 1] = k.z; sh[2 * e + 1] = k.w;
+    }
+  }
+  int i = blockIdx.x * (256 * kCaUnroll * iters) + threadIdx.x;
+  for (int it = 0; it < iters; ++it, i += 256 * kCaUnroll) {
+    uint4 u[kCaUnroll];
+#pragma unroll
+    for (int j = 0; j < kCaUnroll; ++j) u[j] = __ldcs(xi + i + 256 * j);
+#pragma unroll
+    for (int j = 0; j < kCaUnroll; ++j) {
+      float f[8];
+      unpack8(u[j], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float v = f[e] * sc[e] + sh[e];
+        if (act == LDM_ACT_SWISH) v = swishf(v);
+        f[e] = v;
+      }
+      xo[i + 256 * j] = pack8(f);
+    }
+  }
+}
 
 // SpatialAttention input (v2:76-78): per pixel, mean and max over channels of z = ca[c] * (x * scale + shift).
 // A warp walks `run` consecutive pixels of ONE sample: LPP = min(32, C / 8) lanes share a pixel (NO = C / (8 LPP) channel
@@ -519,7 +557,15 @@ int launch_norm_coef_bf16(ldm_ctx* ctx, const bf16* x, const float* gamma, const
 int launch_coef_apply_bf16(ldm_ctx* ctx, const bf16* x, const float2* coef, bf16* out, int B, int HW, int C, int act,
                            cudaStream_t st) {
   const size_t total8 = (size_t)B * HW * C / 8;
-  coef_apply_bf16_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(x, coef, out, HW * C / 8, C / 8, act, total8);
+  const int C8 = C / 8, HWC8 = HW * C8;
+  if (C8 >= 1 && C8 <= 256 && (C8 & (C8 - 1)) == 0 && HWC8 % (256 * kCaUnroll) == 0 && B <= 65535) {
+    const int chunks = HWC8 / (256 * kCaUnroll);
+    int iters = 1;      // enough blocks to fill the machine a few times over, long enough per thread to amortise the coefficient fetch
+    while (iters < 8 && chunks % (2 * iters) == 0 && (long long)(chunks / (2 * iters)) * B >= 4ll * ctx->sm_count) iters *= 2;
+    coef_apply_bf16_stream_kernel<<<dim3(chunks / iters, B), 256, 0, st>>>(x, coef, out, HWC8, C8, act, iters);
+  } else {
+    coef_apply_bf16_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(x, coef, out, HWC8, C8, act, total8);
+  }
   LDM_LAUNCHED(ctx);
   return 0;
 }
