@@ -914,7 +914,9 @@ int v3loop_pack(ldm_ctx* ctx, cudaStream_t st) {
 
   V3Loop* M = new V3Loop();
   ctx->v3loop = M;
-  auto fail = [&](int r) { v3loop_free(ctx); return r; };
+  std::vector<void*> tmp;      // fp32 staging of the folds, released before returning (also on failure)
+  auto done_tmp = [&]() { cudaStreamSynchronize(st); for (void* p : tmp) cudaFree(p); tmp.clear(); };
+  auto fail = [&](int r) { done_tmp(); v3loop_free(ctx); return r; };
 #define V3_TRY(x) do { int r_ = (x); if (r_ != 0) return fail(r_); } while (0)
   M->nst = nst;
   M->smem = kRingBytes + 1024;
@@ -936,8 +938,6 @@ int v3loop_pack(ldm_ctx* ctx, cudaStream_t st) {
   }
   auto& A = M->allocs;
   const int dmax = U.dmax, L = U.latent;
-  std::vector<void*> tmp;
-  auto done_tmp = [&]() { for (void* p : tmp) cudaFree(p); tmp.clear(); };
   auto alloc_z = [&](void** out, size_t bytes) -> int {
     LDM_TRY(ldm_alloc(ctx, A, out, bytes));
     LDM_CUDA(cudaMemsetAsync(*out, 0, bytes, st));
