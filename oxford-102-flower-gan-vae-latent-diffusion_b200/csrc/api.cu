@@ -646,8 +646,10 @@ extern "C" LDM_API int ldm_unet_forward(ldm_ctx* ctx, const float* x_dev, const 
   LDM_TRY(check_classes_match(ctx, batch));
   LDM_TRY(launch_check_t(ctx, t_dev, t_len, ctx->unet.n_t, ctx->dev_flags, st));
   StepMode md; md.t_idx = t_dev; md.t_len = t_len; md.eps_out = eps_out_dev;
-  if (v3loop_supported(ctx, batch))
-    return launch_v3loop(ctx, batch, 1, 0, 0, t_dev, t_len, const_cast<float*>(x_dev), eps_out_dev, nullptr, st);
+  if (v3loop_supported(ctx, batch)) {
+    const int r = launch_v3loop(ctx, batch, 1, 0, 0, t_dev, t_len, const_cast<float*>(x_dev), eps_out_dev, nullptr, st);
+    if (r != LDM_V3LOOP_UNAVAILABLE) return r;
+  }
   if (ctx->precision == LDM_PRECISION_BF16) {
     LDM_TRY(stage_x<bf16>(ctx, x_dev, batch, 0, st));
     if (ctx->use_chain) return launch_chain(ctx, batch, 1, 0, 0, t_dev, t_len, const_cast<float*>(x_dev), eps_out_dev, nullptr, st);
@@ -683,8 +685,10 @@ static int run_chain(ldm_ctx* ctx, int B, int t_start, int t_end, const float* n
   const size_t slab = (size_t)B * ctx->unet.latent;
   if (ctx->use_chain)   // the whole loop is one persistent kernel (both precisions)
     return launch_chain(ctx, B, t_start - t_end + 1, t_start, 1, nullptr, 1, ctx->x_state, nullptr, noise, st);
-  if (v3loop_supported(ctx, B))   // v3: one persistent kernel for the whole loop (the rows of a call are coupled: one grid)
-    return launch_v3loop(ctx, B, t_start - t_end + 1, t_start, 1, nullptr, 1, ctx->x_state, nullptr, noise, st);
+  if (v3loop_supported(ctx, B)) {   // v3: one persistent kernel for the whole loop (the rows of a call are coupled: one grid)
+    const int r = launch_v3loop(ctx, B, t_start - t_end + 1, t_start, 1, nullptr, 1, ctx->x_state, nullptr, noise, st);
+    if (r != LDM_V3LOOP_UNAVAILABLE) return r;
+  }
   for (int t = t_start, j = 0; t >= t_end; --t, ++j) {
     StepMode md; md.sample = 1; md.t = t; md.x = ctx->x_state;
     md.noise = noise ? noise + (size_t)j * slab : nullptr;

@@ -384,6 +384,7 @@ int v3loop_pack(ldm_ctx* ctx, cudaStream_t st);
 void v3loop_free(ldm_ctx* ctx);
 int v3loop_supported(ldm_ctx* ctx, int B);
 int v3loop_error(ldm_ctx* ctx, int* out);
+#define LDM_V3LOOP_UNAVAILABLE (-77)      // launch_v3loop: the grid cannot be co-resident; the caller takes the per-layer path
 int launch_v3loop(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, const int64_t* t_idx, int t_len, float* x, float* eps_out,
                   const float* noise, cudaStream_t st);
 

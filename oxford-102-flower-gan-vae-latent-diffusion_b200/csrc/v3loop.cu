@@ -1139,7 +1139,13 @@ int launch_v3loop(ldm_ctx* ctx, int B, int n_iter, int t_start, int sample, cons
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    LDM_CUDA(cudaLaunchKernelEx(&cfg, unet3_loop_kernel, P));
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, unet3_loop_kernel, P);
+    if (le == cudaErrorCooperativeLaunchTooLarge) {      // the device cannot hold the grid at once (shared / partitioned GPU):
+      (void)cudaGetLastError();                          // this context runs v3 through the per-layer sequence from now on
+      ctx->use_v3loop = 0;
+      return LDM_V3LOOP_UNAVAILABLE;
+    }
+    LDM_CUDA(le);
   }
   LDM_LAUNCHED_AS(ctx, "unet3_loop");
   if (trace) {   // per phase of step 1: this CTA's work, then its wait at the barrier (ns), for a few CTAs
