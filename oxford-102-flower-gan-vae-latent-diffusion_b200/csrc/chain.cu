@@ -22,7 +22,9 @@
 // Data movement.  Weights (11 MB bf16, L2 resident) stream through a ring of 32 KiB slots (two tiles = 8 MMAs per slot) that
 // runs ahead of the phases.  The NB x K bf16 operand of a phase is written to global memory by the producing CTAs, handed
 // over with one release / acquire round on a cluster mbarrier (16 remote arrives per CTA), and TMA-loaded into an operand
-// ring of 8 k-block slots: every k-block of the unit is requested the moment the hand-over is through.  LayerNorm needs
+// ring of 8 k-block slots: every k-block of the unit is requested the moment the hand-over is through, four k-blocks per TMA
+// instruction (a cp.async.bulk.tensor costs the TMA unit ~150 clocks plus ~1.3 per 128-byte row; the first request is armed
+// before the hand-over wait).  LayerNorm needs
 // whole-row statistics: per-row (mean, M2) partials travel as 8-byte st.async into the peers' shared memory (completion on
 // a transaction mbarrier) and are merged with Chan's formula; the statistics of h2 travel in the BACKGROUND to the next
 // phase's tile owners.  Measured limits that shape all this (tools/ubench.cu): TMA inbound 51.7 B/clk per
