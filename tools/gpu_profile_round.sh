@@ -11,6 +11,6 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --c
 echo "launch list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:chain_kernel -c 1 -f -o gpurun_out/${TAG}_chain_full $CMD > gpurun_out/ncu2.log 2>&1
 echo "chain full rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -c 2 -f -o gpurun_out/${TAG}_conv_full $CMD > gpurun_out/ncu3.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc -c 2 -f -o gpurun_out/${TAG}_conv_full $CMD > gpurun_out/ncu3.log 2>&1
 echo "conv full rc=$?"
 ls -la gpurun_out/*.ncu-rep
