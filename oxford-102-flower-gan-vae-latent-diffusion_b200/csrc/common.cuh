@@ -107,6 +107,9 @@ struct Epilogue {
   const float* noise = nullptr;     // explicit (M, N) draws or null -> Philox
   const unsigned long long* rng = nullptr;  // device {seed, sample_offset}: read at run time so a captured graph replays with new seeds
   int step = 0;
+  // plain `bias + fp32 store` epilogues of wide outputs (Decoder.fc[3]): the tile is staged in shared memory and written row by
+  // row, 512 contiguous bytes per warp instruction, instead of 32 rows x 16 bytes (gemm_tc_kernel only; needs out_f32)
+  int stage_f32 = 0;
 };
 
 // ---------------------------------------------------------------------------------------------

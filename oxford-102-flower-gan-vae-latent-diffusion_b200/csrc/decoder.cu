@@ -208,7 +208,7 @@ int decode_chunk_bf16(ldm_ctx* ctx, const float* z, float* img, int B, cudaStrea
     Epilogue e; e.bias = D.fc0.b; e.out_f32 = ctx->d_f0; e.ld_of = 512;
     LDM_TRY(launch_gemm_tc(ctx, ctx->d_zb, D.latent, B, D.fc0, e, st));
     LDM_TRY(launch_row_ln<bf16>(ctx, ctx->d_f0, 512, D.fc1_w, D.fc1_b, LDM_ACT_SWISH, ctx->d_h1b, 512, B, 512, st));
-    Epilogue e2; e2.bias = D.fc3.b; e2.out_f32 = (float*)ctx->d_b; e2.ld_of = 32768;
+    Epilogue e2; e2.bias = D.fc3.b; e2.out_f32 = (float*)ctx->d_b; e2.ld_of = 32768; e2.stage_f32 = 1;
     LDM_TRY(launch_gemm_tc(ctx, ctx->d_h1b, 512, B, D.fc3, e2, st));
     LDM_TRY(launch_row_ln<bf16>(ctx, (const float*)ctx->d_b, 32768, D.fc4_w, D.fc4_b, LDM_ACT_SWISH, A, 32768, B, 32768, st));
   }

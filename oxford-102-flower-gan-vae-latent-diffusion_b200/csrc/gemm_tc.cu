@@ -120,7 +120,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   }
   if (KS > 1) cooperative_groups::this_cluster().sync();      // partials visible cluster-wide
-  if (warp >= 2 && kr == 0) {
+  if (warp >= 2 && kr == 0 && epi.stage_f32 && KS == 1) {
+    // bias + fp32 store through shared memory (the ring is free: every MMA has completed).  Row pitch BN * 4 + 16 bytes:
+    // the 16-byte accesses of a quarter-warp fall into distinct banks both when a lane writes its own row and when a warp
+    // reads one row.
+    const int q = warp & 3;
+    constexpr int kPitch = BN * 4 + 16;
+    uint8_t* stg = smem;
+    uint8_t* mine = stg + (size_t)(q * 32 + lane) * kPitch;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      float v[16];
+      tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        float4 b = epi.bias ? *reinterpret_cast<const float4*>(epi.bias + n0 + c0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(mine + (size_t)(c0 + j) * 4) = make_float4(v[j] + b.x, v[j + 1] + b.y, v[j + 2] + b.z, v[j + 3] + b.w);
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int r = q; r < BM; r += 4) {
+      const int row = m0 + r;
+      if (row >= args.M) break;
+      const uint8_t* src = stg + (size_t)r * kPitch;
+      float* dst = epi.out_f32 + (size_t)row * epi.ld_of + n0;
+      for (int c = lane; c < BN / 4; c += 32) reinterpret_cast<float4*>(dst)[c] = *reinterpret_cast<const float4*>(src + (size_t)c * 16);
+    }
+  } else if (warp >= 2 && kr == 0) {
     const int q = warp & 3;
     const int row = m0 + q * 32 + lane;
 #pragma unroll 1
@@ -391,8 +417,11 @@ int launch_bn(ldm_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, int M,
   const int nkb = nkb_all / ks;
   int stages = nkb < kMaxStages ? nkb : kMaxStages;
   while ((size_t)stages * stage_bytes > 200 * 1024) --stages;
+  if (epi.stage_f32)      // store-bound GEMM: two CTAs per SM, one writes its tile while the other runs its main loop
+    while (stages > 2 && (size_t)stages * stage_bytes > 100 * 1024) --stages;
   size_t smem = (size_t)stages * stage_bytes + 1024;
   if (ks > 1 && smem < (size_t)BM * BN * 4 + 1024) smem = (size_t)BM * BN * 4 + 1024;       // room for the parked partial
+  if (epi.stage_f32 && smem < (size_t)BM * (BN * 4 + 16) + 1024) smem = (size_t)BM * (BN * 4 + 16) + 1024;      // ... or for the staged output tile
   TcArgs a{M, N, K, stages};
   dim3 grid(N / BN, ceil_div(M, BM), ks);
   {
