@@ -12,7 +12,7 @@ Prints ONE JSON line (rank 0).  Besides the base contract the v2 line carries
 
   roofline          the dominant kernel (chain_kernel), CUDA-event timed; `traffic` from the sidecar the profiling
                     script writes (profiles/*chain_traffic.json), never a constant in this file
-  roofline_kernels  every kernel of one traced pass (chain + the 42 decoder launches): {name, what, bound, flop | bytes,
+  roofline_kernels  every kernel of one traced pass (chain + the 41 decoder launches): {name, what, bound, flop | bytes,
                     us, achieved, peak, frac}; tensor-bound ones against the measured bf16 peak, memory-bound ones
                     (norm / gating / LayerNorm passes) as GB/s against the measured HBM copy bandwidth.  Timed with a
                     CUDA event after every launch (ldm_debug_ktrace), not under a profiler
@@ -205,7 +205,7 @@ def run_reference_arm(args, rank):
 # per-kernel records (roofline_kernels)
 # ------------------------------------------------------------------------------------------------------
 def decoder_kernel_table(B):
-    """The 42 launches of one bf16 decode of B latents, in launch order (csrc/decoder.cu: decode_chunk_bf16):
+    """The 41 launches of one bf16 decode of B latents, in launch order (csrc/decoder.cu: decode_chunk_bf16):
     (trace name, what, bound, flop or bytes).  Memory-bound passes: algorithmic bytes = tensors read + written once."""
     t = []
     E = lambda C, H: B * H * H * C      # elements of an NHWC activation
@@ -232,8 +232,8 @@ def decoder_kernel_table(B):
     n = E(32, 64)
     t += [("conv_halo", "final_conv.0 3x3 64->32 @64x64 (halo kernel)", "tensor", 2 * n * 9 * 64),
           ("launch_norm_coef_bf16", "final GroupNorm(8,32) statistics", "hbm", n * 2),
-          ("launch_coef_apply_bf16", "final GroupNorm apply + Swish", "hbm", n * 4),
-          ("conv_out3", "final_conv.3 3x3 32->3 + Sigmoid (CUDA cores)", "hbm", n * 2 + B * 3 * 4096 * 4)]
+          ("final_gn_conv3", "final GroupNorm apply + Swish + final_conv.3 3x3 32->3 + Sigmoid (one pass, mma.sync)", "hbm",
+           n * 2 + B * 3 * 4096 * 4)]
     return t
 
 

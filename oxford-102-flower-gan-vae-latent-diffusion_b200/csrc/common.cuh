@@ -205,6 +205,7 @@ struct DecoderModel {
   ConvLayer up[3][4];    // 4 sub-pixel parities (a*2+b), each 4 taps
   float *up_b[3], *up_gn_w[3], *up_gn_b[3];
   ConvLayer fin0, fin3;
+  uint32_t* fin3_frag = nullptr;   // bf16 path: mma.sync B fragments of final_conv.3 (final_w_frag_kernel)
   float *fin_gn_w, *fin_gn_b;
   ConvLayer ups[3], fin0s;   // strict mode: split weights of the stacked ConvTranspose parities and of final_conv.0 (Cin = 3 C)
   bool strict_tc = false;    // the fp32 context runs its convolutions as three-term bf16 products on the tensor cores

@@ -26,6 +26,9 @@ int launch_split3(ldm_ctx* ctx, const float* x, bf16* out, size_t npix, int C, c
 int launch_pack_conv_split(ldm_ctx* ctx, const float* w, bf16* out, int rows, int taps, int Cin, cudaStream_t st);
 int launch_conv_out3(ldm_ctx* ctx, const bf16* in, const float* w, const float* bias, float* out, int B, int H, int W,
                      cudaStream_t st);
+int launch_final_gn_conv3(ldm_ctx* ctx, const bf16* x, const float2* coef, const uint32_t* wf, const float* bias, float* out, int B,
+                          int H, int W, cudaStream_t st);
+int launch_final_w_frag(ldm_ctx* ctx, const float* w, uint32_t* wf, cudaStream_t st);
 
 namespace {
 
@@ -224,6 +227,9 @@ int decode_chunk_bf16(ldm_ctx* ctx, const float* z, float* img, int B, cudaStrea
   LDM_TRY(launch_conv_halo(ctx, A, 64, D.fin0, D.fin0.b, Bf, 32, B, 64, 64, 0, nullptr, 0, nullptr, 0, st));
   float2* coef = reinterpret_cast<float2*>(ctx->d_stats);
   LDM_TRY(launch_norm_coef_bf16_ws(ctx, Bf, D.fin_gn_w, D.fin_gn_b, coef, B, 4096, 32, 4, ctx->d_part, ctx->d_cnt, st));   // GroupNorm(8, 32)
+  // GroupNorm apply + Swish + final_conv.3 + Sigmoid as ONE pass (LDM_DEC_FUSE_OUT=0: the two-kernel sequence)
+  static const bool fuse_out = !(getenv("LDM_DEC_FUSE_OUT") && atoi(getenv("LDM_DEC_FUSE_OUT")) == 0);
+  if (fuse_out) return launch_final_gn_conv3(ctx, Bf, coef, D.fin3_frag, D.fin3.b, img, B, 64, 64, st);
   LDM_TRY(launch_coef_apply_bf16(ctx, Bf, coef, C, B, 4096, 32, LDM_ACT_SWISH, st));
   LDM_TRY(launch_conv_out3(ctx, C, D.fin3.w32, D.fin3.b, img, B, 64, 64, st));
   return 0;
@@ -329,6 +335,8 @@ int decoder_pack_impl(ldm_ctx* ctx, const ldm_decoder_weights* w, cudaStream_t s
       }
     }
     LDM_TRY(conv_bf16(ctx, P, D.fin0, st));
+    LDM_TRY(ldm_alloc_t(ctx, P, &D.fin3_frag, (size_t)36 * 32));
+    LDM_TRY(launch_final_w_frag(ctx, D.fin3.w32, D.fin3_frag, st));
   }
   if (ctx->precision != LDM_PRECISION_BF16) {
     // strict mode: the 3x3 / transposed convolutions as three-term bf16 products on the tensor cores (LDM_DEC_F32=1 keeps

@@ -2,6 +2,8 @@
 // LayerNorm2d / GroupNorm statistics and application (v2:144-156, v2:257,263,269,274), the CALayer
 // squeeze-excite (v2:53-67) and SpatialAttention gating fused with the residual add + Swish of
 // ResidualBlock.forward (v2:69-81,170-178).
+#include <limits.h>
+
 #include "common.cuh"
 
 namespace {
@@ -647,6 +649,147 @@ int launch_pack_conv_split(ldm_ctx* ctx, const float* w, bf16* out, int rows, in
   const size_t total = (size_t)rows * taps * Cin;
   pack_conv_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, out, total, Cin);
   LDM_LAUNCHED(ctx);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// final_conv[1..4] as ONE pass (v2:274-278): GroupNorm(8, 32) apply + Swish -> Conv2d(32, 3, 3, padding 1) -> Sigmoid,
+// raw conv output NHWC bf16 (B, H, W, 32) in, NCHW fp32 image out.  The separate apply pass re-wrote and re-read the
+// 67 MB tensor, and the one-thread-per-pixel convolution behind it sat on the fp32 FMA rate (2 592 FMA per pixel = 73 us
+// per 256 images on 148 SMs).  Here a CTA normalises a 16 x 32 pixel tile with its halo WHILE loading it (the zero
+// padding applies to the activated tensor: out-of-image slots stay 0), keeps it in shared memory channel-octet major
+// (an 8-pixel x 8-channel ldmatrix tile is 128 contiguous bytes for every tap shift) and runs the convolution as
+// warp-level mma.sync m16n8k16 (rows = 16 neighbouring pixels, k = 16 channels of one tap).  N = 3 is no tcgen05 shape
+// (at N = 16 its rate is set by the 4 KB pixel operand per MMA, no better than this).  The weights stay at fp32 precision as
+// a bf16 (hi, lo) pair that shares ONE MMA: columns 0-2 of the n = 8 tile are the hi parts of the three output channels,
+// columns 3-5 the lo parts, and the epilogue adds column c + 3 to column c.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kF3TW = 32, kF3TH = 16, kF3HW = kF3TW + 2, kF3HH = kF3TH + 2, kF3HP = kF3HW * kF3HH;
+constexpr int kF3Frag = 9 * 2 * 2;     // B fragments: [tap][k half][b0 | b1], one 32-bit word per lane each
+__global__ void __launch_bounds__(256, 3)
+final_gn_conv3_kernel(const bf16* __restrict__ x, const float2* __restrict__ coef, const uint32_t* __restrict__ wf /* [36][32] */,
+                      const float* __restrict__ bias, float* __restrict__ out, int H, int W) {
+  __shared__ uint4 tile[4][kF3HP];                // activated halo tile, [channel octet][slot]
+  const int n = blockIdx.z, y0 = blockIdx.y * kF3TH, x0 = blockIdx.x * kF3TW, HW = H * W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // ---- weight fragments (final_w_frag_kernel, pack time) straight into registers: 36 independent coalesced loads
+  uint32_t bfr[kF3Frag];
+#pragma unroll
+  for (int f = 0; f < kF3Frag; ++f) bfr[f] = __ldg(wf + f * 32 + lane);
+  // ---- halo tile: GroupNorm apply + Swish on the way in (the arithmetic of coef_apply_bf16_stream_kernel)
+  {
+    const int j = threadIdx.x & 3;      // channel octet of this thread (256 is a multiple of 4)
+    float sc[8], sh[8];
+    const float4* cf = reinterpret_cast<const float4*>(coef + (size_t)n * 32 + j * 8);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float4 k = __ldg(cf + e);
+      sc[2 * e] = k.x; sh[2 * e] = k.y; sc[2 * e + 1] = k.z; sh[2 * e + 1] = k.w;
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)n * HW * 32);
+    // 4 * 612 = 2448 sixteen-byte words: ten per thread (the last one partial), five loads in flight at a time
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint4 u[5];
+      int hpv[5];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const int i = threadIdx.x + (half * 5 + q) * 256;
+        const int hp = i >> 2, hy = hp / kF3HW, hx = hp - hy * kF3HW;
+        const int yy = y0 + hy - 1, xx = x0 + hx - 1;
+        const bool in = i < 4 * kF3HP && yy >= 0 && yy < H && xx >= 0 && xx < W;
+        hpv[q] = i < 4 * kF3HP ? (in ? hp : -1 - hp) : INT_MIN;
+        u[q] = in ? __ldcs(src + ((size_t)yy * W + xx) * 4 + j) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        if (hpv[q] == INT_MIN) continue;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (hpv[q] >= 0) {
+          float f[8];
+          unpack8(u[q], f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {      // swish with the two-instruction division: this pass is issue-bound, not memory-bound
+            const float a = f[e] * sc[e] + sh[e];
+            f[e] = __fdividef(a, 1.0f + __expf(-a));
+          }
+          v = pack8(f);
+        }
+        tile[j][hpv[q] >= 0 ? hpv[q] : -1 - hpv[q]] = v;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- warp `warp` finishes tile rows 2 warp, 2 warp + 1: four m16 tiles (row, x half)
+  float acc[4][4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f; }
+  const int lm = lane >> 3, lr = lane & 7;     // ldmatrix: this lane supplies row lr of 8 x 8 matrix lm
+  const uint32_t tile_a = (uint32_t)__cvta_generic_to_shared(&tile[0][0]);
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+    for (int kc = 0; kc < 2; ++kc) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int slot0 = (2 * warp + (m >> 1) + tap / 3) * kF3HW + (m & 1) * 16 + tap % 3;
+        const uint32_t addr = tile_a + (uint32_t)(((2 * kc + (lm >> 1)) * kF3HP + slot0 + (lm & 1) * 8 + lr) * 16);
+        uint32_t a0, a1, a2, a3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr));
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                     : "+f"(acc[m][0]), "+f"(acc[m][1]), "+f"(acc[m][2]), "+f"(acc[m][3])
+                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bfr[(tap * 2 + kc) * 2]), "r"(bfr[(tap * 2 + kc) * 2 + 1]));
+      }
+    }
+  }
+  // ---- accumulator fragment: (row g, columns 2t, 2t + 1) and (row g + 8, ...); channel c = column c (hi) + column c + 3 (lo).
+  //      Lane t of a quad ends up with channel t of its two pixels (t = 3: idle).
+  const int g = lane >> 2, t = lane & 3, qb = lane & ~3;
+  const float bs = t < 3 ? __ldg(bias + t) : 0.f;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int y = y0 + 2 * warp + (m >> 1);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float ce = acc[m][2 * h], co = acc[m][2 * h + 1];
+      const float c0 = __shfl_sync(0xffffffffu, ce, qb), c1 = __shfl_sync(0xffffffffu, co, qb);
+      const float c2 = __shfl_sync(0xffffffffu, ce, qb + 1), c3 = __shfl_sync(0xffffffffu, co, qb + 1);
+      const float c4 = __shfl_sync(0xffffffffu, ce, qb + 2), c5 = __shfl_sync(0xffffffffu, co, qb + 2);
+      const float v = t == 0 ? c0 + c3 : (t == 1 ? c1 + c4 : c2 + c5);
+      const int xq = x0 + (m & 1) * 16 + g + 8 * h;
+      if (t < 3 && y < H && xq < W) out[(size_t)n * 3 * HW + (size_t)t * HW + (size_t)y * W + xq] = sigmoidf_(v + bs);
+    }
+  }
+}
+// B fragments of the 3 x (9 * 32) fp32 weights for final_gn_conv3_kernel: [tap][k half][b0 | b1][lane]; lane (g = lane / 4,
+// t = lane % 4) holds column g, rows k = 2t, 2t + 1 (b0) and k = 2t + 8, 2t + 9 (b1): g < 3 the bf16 hi part of output
+// channel g, 3 <= g < 6 the lo part (w - hi) of channel g - 3, zero above
+__global__ void final_w_frag_kernel(const float* __restrict__ w, uint32_t* __restrict__ wf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kF3Frag * 32) return;
+  const int l = i & 31, f = i >> 5, reg = f & 1, kc = (f >> 1) & 1, tap = f >> 2;
+  const int g = l >> 2, t = l & 3;
+  uint32_t v = 0;
+  if (g < 6) {
+    const float* wp = w + (size_t)(g % 3) * 288 + tap * 32 + kc * 16 + reg * 8 + 2 * t;
+    const float w0 = wp[0], w1 = wp[1];
+    bf16 h0 = __float2bfloat16_rn(w0), h1 = __float2bfloat16_rn(w1);
+    if (g >= 3) { h0 = __float2bfloat16_rn(w0 - __bfloat162float(h0)); h1 = __float2bfloat16_rn(w1 - __bfloat162float(h1)); }
+    __nv_bfloat162 h2 = __halves2bfloat162(h0, h1);
+    v = *reinterpret_cast<uint32_t*>(&h2);
+  }
+  wf[i] = v;
+}
+int launch_final_w_frag(ldm_ctx* ctx, const float* w, uint32_t* wf, cudaStream_t st) {
+  final_w_frag_kernel<<<ceil_div(kF3Frag * 32, 256), 256, 0, st>>>(w, wf);
+  LDM_LAUNCHED(ctx);
+  return 0;
+}
+int launch_final_gn_conv3(ldm_ctx* ctx, const bf16* x, const float2* coef, const uint32_t* wf, const float* bias, float* out, int B,
+                          int H, int W, cudaStream_t st) {
+  LDM_CHECK(((uintptr_t)x & 15) == 0 && wf != nullptr, "final_gn_conv3: input must be 16-byte aligned, weights packed");
+  final_gn_conv3_kernel<<<dim3(ceil_div(W, kF3TW), ceil_div(H, kF3TH), B), 256, 0, st>>>(x, coef, wf, bias, out, H, W);
+  LDM_LAUNCHED_AS(ctx, "final_gn_conv3");
   return 0;
 }
 
