@@ -122,7 +122,7 @@ extern "C" LDM_API int ldm_ctx_create(ldm_ctx** out, int device, int precision) 
   const char* atc = getenv("LDM_ATTN_TC");
   ctx->use_attn_tc = atc ? atoi(atc) : 1;
   const char* pdl = getenv("LDM_PDL");
-  ctx->use_pdl = pdl ? atoi(pdl) : 0;
+  ctx->use_pdl = pdl ? atoi(pdl) : 1;      // programmatic dependent launch of the decoder / pixel-path kernels (LDM_PDL=0: plain stream order)
   if (r != 0) {
     free_pool(ctx->allocs);
     delete ctx;

@@ -178,6 +178,8 @@ sa_apply_kernel(const T* __restrict__ x, const float* __restrict__ stats, const 
 // ---------------------------------------------------------------------------------------------------------------
 // bf16 fast path: 16-byte (8-channel) accesses, one pass statistics, (scale, shift) precomputed per (sample, channel)
 // ---------------------------------------------------------------------------------------------------------------
+// Every kernel of the bf16 path starts with ldm_pdl_wait(): launched through launch_maybe_pdl, the grid may be scheduled while
+// its predecessor in the stream drains and blocks there until the predecessor's writes are visible (a no-op for a plain launch).
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -205,6 +207,7 @@ template <int CB>
 __global__ void __launch_bounds__(256)
 norm_coef2_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                   float2* __restrict__ coef, int HW, int C, int cg, float2* __restrict__ part, int* __restrict__ cnt, int S) {
+  ldm_pdl_wait();
   constexpr int OCT = CB / 8, PL = 256 / OCT;
   __shared__ float s1[PL][CB + 1], s2[PL][CB + 1];
   __shared__ int s_last;
@@ -289,6 +292,7 @@ norm_coef2_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, c
 __global__ void __launch_bounds__(256)
 coef_apply_bf16_kernel(const bf16* __restrict__ x, const float2* __restrict__ coef, bf16* __restrict__ out, int HWC8, int C8,
                        int act, size_t total8) {
+  ldm_pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total8) return;
   const int n = (int)(i / HWC8), c8 = (int)(i % C8);
@@ -311,6 +315,7 @@ constexpr int kCaUnroll = 4;
 __global__ void __launch_bounds__(256)
 coef_apply_bf16_stream_kernel(const bf16* __restrict__ x, const float2* __restrict__ coef, bf16* __restrict__ out, int HWC8, int C8,
                               int act, int iters) {
+  ldm_pdl_wait();
   const int n = blockIdx.y, c8 = threadIdx.x & (C8 - 1);
   const uint4* xi = reinterpret_cast<const uint4*>(x) + (size_t)n * HWC8;
   uint4* xo = reinterpret_cast<uint4*>(out) + (size_t)n * HWC8;
@@ -350,6 +355,7 @@ template <int NO>
 __global__ void __launch_bounds__(256)
 sa_map2_kernel(const bf16* __restrict__ x, const float2* __restrict__ coef, const float* __restrict__ ca,
                float* __restrict__ map, int HW, int C, int npix, int run) {
+  ldm_pdl_wait();
   const int lpp = C / (8 * NO) < 32 ? C / (8 * NO) : 32, ppw = 32 / lpp;
   const int lane = threadIdx.x & 31, wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int first = wid * run;
@@ -401,6 +407,7 @@ sa_map2_kernel(const bf16* __restrict__ x, const float2* __restrict__ coef, cons
 // gate = sigmoid(conv7x7([mean, max] map)) (v2:79-80): one thread per pixel; the map of a sample is a few KiB (L1 / L2)
 __global__ void __launch_bounds__(256)
 sa_gate_kernel(const float* __restrict__ map, const float* __restrict__ sa_w, float* __restrict__ gate, int H, int npix) {
+  ldm_pdl_wait();
   __shared__ float w[98];
   if (threadIdx.x < 98) w[threadIdx.x] = sa_w[threadIdx.x];
   __syncthreads();
@@ -430,6 +437,7 @@ __global__ void __launch_bounds__(256)
 sa_apply2_kernel(const bf16* __restrict__ x, const float2* __restrict__ coef, const float* __restrict__ ca,
                  const float* __restrict__ gate, const bf16* __restrict__ resid, bf16* __restrict__ out, int HW, int C, int npix,
                  int run) {
+  ldm_pdl_wait();
   const int lpp = C / (8 * NO) < 32 ? C / (8 * NO) : 32, ppw = 32 / lpp;
   const int lane = threadIdx.x & 31, wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int first = wid * run;
@@ -544,10 +552,10 @@ int launch_norm_coef_bf16_ws(ldm_ctx* ctx, const bf16* x, const float* gamma, co
   LDM_CHECK(group == 1 || group == 2 || group == 4 || group == 8, "norm_coef: group size %d unsupported", group);
   if (C == 32) {
     const int S = part && cnt ? norm_splits(B, HW, 64, C) : 1;
-    norm_coef2_kernel<32><<<dim3(1, B, S), 256, 0, st>>>(x, gamma, beta, coef, HW, C, group, part, cnt, S);
+    LDM_CUDA(launch_maybe_pdl(norm_coef2_kernel<32>, dim3(1, B, S), 256, 0, st, ctx->use_pdl, x, gamma, beta, coef, HW, C, group, part, cnt, S));
   } else {
     const int S = part && cnt && C / 64 <= 16 ? norm_splits(B * (C / 64), HW, 32, C) : 1;
-    norm_coef2_kernel<64><<<dim3(C / 64, B, S), 256, 0, st>>>(x, gamma, beta, coef, HW, C, group, part, cnt, S);
+    LDM_CUDA(launch_maybe_pdl(norm_coef2_kernel<64>, dim3(C / 64, B, S), 256, 0, st, ctx->use_pdl, x, gamma, beta, coef, HW, C, group, part, cnt, S));
   }
   LDM_LAUNCHED_AS(ctx, "launch_norm_coef_bf16");
   return 0;
@@ -564,9 +572,9 @@ int launch_coef_apply_bf16(ldm_ctx* ctx, const bf16* x, const float2* coef, bf16
     const int chunks = HWC8 / (256 * kCaUnroll);
     int iters = 1;      // enough blocks to fill the machine a few times over, long enough per thread to amortise the coefficient fetch
     while (iters < 8 && chunks % (2 * iters) == 0 && (long long)(chunks / (2 * iters)) * B >= 4ll * ctx->sm_count) iters *= 2;
-    coef_apply_bf16_stream_kernel<<<dim3(chunks / iters, B), 256, 0, st>>>(x, coef, out, HWC8, C8, act, iters);
+    LDM_CUDA(launch_maybe_pdl(coef_apply_bf16_stream_kernel, dim3(chunks / iters, B), 256, 0, st, ctx->use_pdl, x, coef, out, HWC8, C8, act, iters));
   } else {
-    coef_apply_bf16_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(x, coef, out, HWC8, C8, act, total8);
+    LDM_CUDA(launch_maybe_pdl(coef_apply_bf16_kernel, dim3((unsigned)((total8 + 255) / 256)), 256, 0, st, ctx->use_pdl, x, coef, out, HWC8, C8, act, total8));
   }
   LDM_LAUNCHED(ctx);
   return 0;
@@ -584,8 +592,8 @@ int launch_sa_map_bf16(ldm_ctx* ctx, const bf16* x, const float2* coef, const fl
   const int npix = B * HW, no = C > 256 ? 2 : 1, lpp = C / (8 * no) < 32 ? C / (8 * no) : 32;
   const int run = sa_run(npix, HW, 32 / lpp), warps = ceil_div(npix, run);
   LDM_CHECK(HW % run == 0, "sa_map: HW (%d) must be a multiple of the warp run (%d)", HW, run);
-  if (no == 2) sa_map2_kernel<2><<<ceil_div(warps, 8), 256, 0, st>>>(x, coef, ca, map, HW, C, npix, run);
-  else sa_map2_kernel<1><<<ceil_div(warps, 8), 256, 0, st>>>(x, coef, ca, map, HW, C, npix, run);
+  if (no == 2) LDM_CUDA(launch_maybe_pdl(sa_map2_kernel<2>, dim3(ceil_div(warps, 8)), 256, 0, st, ctx->use_pdl, x, coef, ca, map, HW, C, npix, run));
+  else LDM_CUDA(launch_maybe_pdl(sa_map2_kernel<1>, dim3(ceil_div(warps, 8)), 256, 0, st, ctx->use_pdl, x, coef, ca, map, HW, C, npix, run));
   LDM_LAUNCHED(ctx);
   return 0;
 }
@@ -596,10 +604,10 @@ int launch_sa_apply_bf16(ldm_ctx* ctx, const bf16* x, const float2* coef, const 
   const int HW = H * H, npix = B * HW, no = C > 256 ? 2 : 1, lpp = C / (8 * no) < 32 ? C / (8 * no) : 32;
   const int run = sa_run(npix, HW, 32 / lpp), warps = ceil_div(npix, run);
   LDM_CHECK(HW % run == 0, "sa_apply: HW (%d) must be a multiple of the warp run (%d)", HW, run);
-  sa_gate_kernel<<<ceil_div(npix, 256), 256, 0, st>>>(map, sa_w, gate, H, npix);
+  LDM_CUDA(launch_maybe_pdl(sa_gate_kernel, dim3(ceil_div(npix, 256)), 256, 0, st, ctx->use_pdl, map, sa_w, gate, H, npix));
   LDM_LAUNCHED_AS(ctx, "launch_sa_gate");
-  if (no == 2) sa_apply2_kernel<2><<<ceil_div(warps, 8), 256, 0, st>>>(x, coef, ca, gate, resid, out, HW, C, npix, run);
-  else sa_apply2_kernel<1><<<ceil_div(warps, 8), 256, 0, st>>>(x, coef, ca, gate, resid, out, HW, C, npix, run);
+  if (no == 2) LDM_CUDA(launch_maybe_pdl(sa_apply2_kernel<2>, dim3(ceil_div(warps, 8)), 256, 0, st, ctx->use_pdl, x, coef, ca, (const float*)gate, resid, out, HW, C, npix, run));
+  else LDM_CUDA(launch_maybe_pdl(sa_apply2_kernel<1>, dim3(ceil_div(warps, 8)), 256, 0, st, ctx->use_pdl, x, coef, ca, (const float*)gate, resid, out, HW, C, npix, run));
   LDM_LAUNCHED(ctx);
   return 0;
 }
@@ -676,6 +684,7 @@ final_gn_conv3_kernel(const bf16* __restrict__ x, const float2* __restrict__ coe
   uint32_t bfr[kF3Frag];
 #pragma unroll
   for (int f = 0; f < kF3Frag; ++f) bfr[f] = __ldg(wf + f * 32 + lane);
+  ldm_pdl_wait();      // the fragments are pack-time constants: fetched before the predecessor's results are awaited
   // ---- halo tile: GroupNorm apply + Swish on the way in (the arithmetic of coef_apply_bf16_stream_kernel)
   {
     const int j = threadIdx.x & 3;      // channel octet of this thread (256 is a multiple of 4)
@@ -788,7 +797,7 @@ int launch_final_w_frag(ldm_ctx* ctx, const float* w, uint32_t* wf, cudaStream_t
 int launch_final_gn_conv3(ldm_ctx* ctx, const bf16* x, const float2* coef, const uint32_t* wf, const float* bias, float* out, int B,
                           int H, int W, cudaStream_t st) {
   LDM_CHECK(((uintptr_t)x & 15) == 0 && wf != nullptr, "final_gn_conv3: input must be 16-byte aligned, weights packed");
-  final_gn_conv3_kernel<<<dim3(ceil_div(W, kF3TW), ceil_div(H, kF3TH), B), 256, 0, st>>>(x, coef, wf, bias, out, H, W);
+  LDM_CUDA(launch_maybe_pdl(final_gn_conv3_kernel, dim3(ceil_div(W, kF3TW), ceil_div(H, kF3TH), B), 256, 0, st, ctx->use_pdl, x, coef, wf, bias, out, H, W));
   LDM_LAUNCHED_AS(ctx, "final_gn_conv3");
   return 0;
 }

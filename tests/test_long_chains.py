@@ -212,7 +212,7 @@ def test_v3_host_entry_and_kernel_trace():
     trace = eng.ktrace_stop()
     assert torch.equal(img, ref.cpu())
     names = [n for n, _ in trace]
-    assert len(trace) == 42 and names[0] == "launch_load_x" and names[-1] == "conv_out3" and names.count("conv_tc") == 9 and names.count("conv_halo") == 1
+    assert len(trace) == 41 and names[0] == "launch_load_x" and names[-1] == "final_gn_conv3" and names.count("conv_tc") == 9 and names.count("conv_halo") == 1
     assert all(0.0 < ms < 50.0 for _, ms in trace)
     with pytest.raises(ldm_b200.LdmError):
         eng.generate3_host((f + 200).pin_memory(), k.pin_memory(), img, None, seed=9)      # flower label out of range
