@@ -383,6 +383,7 @@ static inline cudaError_t launch_maybe_pdl(Kern kern, dim3 grid, int threads, si
 __device__ __forceinline__ void ldm_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void ldm_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+
 // v3loop.cu
 int v3loop_pack(ldm_ctx* ctx, cudaStream_t st);
 void v3loop_free(ldm_ctx* ctx);

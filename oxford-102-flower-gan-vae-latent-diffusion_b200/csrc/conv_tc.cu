@@ -668,6 +668,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   pair_sync();              // the peer's barriers exist before any remote completion / multicast commit reaches them
   tc::fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
+  tc::pdl_wait();           // everything above overlaps the previous kernel's tail (no-op without the PDL launch attribute)
 
   if (warp == 0) {
     if (tc::elect_one()) {
@@ -966,7 +967,7 @@ int launch_pair(ldm_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw128, c
     attr = true;
   }
   dim3 grid(ceil_div(a.total_pix, BM), a.Cout / 256, nz);      // grid.x even (checked by the caller): __cluster_dims__(2, 1, 1)
-  conv_tc_pair_kernel<<<grid, kThreads, smem, st>>>(ma, mw128, a);
+  LDM_CUDA(launch_maybe_pdl(conv_tc_pair_kernel, grid, kThreads, smem, st, ctx->use_pdl, ma, mw128, a));
   ctx->launches++;
   ldm_kmark(ctx, "conv_tc_pair");
   LDM_CUDA(cudaGetLastError());

@@ -120,6 +120,7 @@ row_ln_big_kernel(const float* __restrict__ in, int ld_in, const float* __restri
   const float4* ip = reinterpret_cast<const float4*>(in + (size_t)row * ld_in);
   const int n4 = d >> 2;
   float s = 0.f;
+  ldm_pdl_wait();
   for (int q = tid; q < n4; q += 256) { float4 v = ip[q]; s += (v.x + v.y) + (v.z + v.w); }
   s = warp_sum(s);
   if (lane == 0) red[wid] = s;
@@ -357,7 +358,7 @@ int launch_row_ln(ldm_ctx* ctx, const float* in, int ld_in, const float* g, cons
       return 0;
     });
   } else {
-    row_ln_big_kernel<TOP><<<M, 256, 0, st>>>(in, ld_in, g, b, act, out, ld_out, d);
+    LDM_CUDA(launch_maybe_pdl(row_ln_big_kernel<TOP>, dim3(M), 256, 0, st, ctx->use_pdl, in, ld_in, g, b, act, out, ld_out, d));
   }
   LDM_LAUNCHED(ctx);
   return 0;
