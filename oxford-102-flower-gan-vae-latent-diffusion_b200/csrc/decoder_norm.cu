@@ -539,10 +539,13 @@ int launch_sa_apply(ldm_ctx* ctx, const T* x, const float* stats, const float* g
 
 
 // ---- bf16 fast path launchers
-// splits of the pixel range so that a few CTAs per SM are in flight: power of two, >= 4 pixels per thread
+// splits of the pixel range: power of two, >= 4 pixels per thread, until two CTAs per SM exist.  Measured over the ten statistics
+// passes of a 256-image decode (LDM_NORM_BLOCKS): 296 blocks 1.424 ms per decode, 592: 1.434, 1184: 1.474, 2368: 1.503, no
+// splits: 1.455 - the ticket / partial-sum epilogue of a split costs more than the extra CTAs bring
 static int norm_splits(int blocks, int HW, int pl, int C) {
+  static const int want = getenv("LDM_NORM_BLOCKS") ? atoi(getenv("LDM_NORM_BLOCKS")) : 296;
   int s = 1;
-  while (blocks * s < 1184 && HW / (2 * s) >= 4 * pl && 2 * s * C <= 1024 && s < 16) s *= 2;
+  while (blocks * s < want && HW / (2 * s) >= 4 * pl && 2 * s * C <= 1024 && s < 16) s *= 2;
   return s;
 }
 // `part` (B x 1024 float2) and `cnt` (B x 16 ints, zero) enable the pixel splits; without them one CTA walks the whole sample
