@@ -417,6 +417,164 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// convt_halo_kernel<BN, KB>: one output parity (pa, pb) of ConvTranspose2d(4, 2, 1) with Cin = 64 KB, Cout = BN, in the halo
+// scheme: a persistent CTA keeps the parity's 4 taps x KB weight tiles resident (64 KB at BN = 64, KB = 2) and loads every
+// 128-slot pixel run ONCE with its halo (one box per 64-channel block), the four taps (0 | -1 or +1 per axis) being row /
+// column shifts of that tile.  Measured (256 images): 152 -> 108 us; one ring slot per 64-channel tile (five slots) and two
+// alternating accumulators changed nothing - about 105 clocks per MMA remain, as in conv_halo_kernel.  conv_tc_kernel reloads the pixel tile for every tap and the weight tile for every pixel tile:
+// 160 - 192 KB of operands per 128 x 64 outputs against 2.1 k tensor clocks, which bound up1 (128 -> 64 at 64 x 64) at a
+// third of the tensor rate.  blockIdx.y = parity; units are strided over blockIdx.x.
+// ------------------------------------------------------------------------------------------------------------------
+struct ConvTHaloArgs {
+  int H, W, Wp;            // input grid; Wp = W + 2
+  int units_per_img, total_units;
+  int a_bytes, a_stride;   // one 64-channel halo tile; tile pitch (1024-aligned plus one guard KB)
+  int Cin, Cout, out_pitch, relu;
+  const float* bias;
+  bf16* out;               // (B, 2H, 2W, out_pitch)
+  int stages;
+};
+constexpr int kCtStagesMax = 3;
+
+template <int BN, int KB>
+__global__ void __launch_bounds__(kThreads, 1)
+convt_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const ConvTHaloArgs a) {
+  constexpr uint32_t kWTap = BN * BK * 2, kWBytes = 4 * KB * kWTap;
+  constexpr int kTS = 4;                       // accumulator stages: the epilogue of unit j runs under the MMAs of j + 1 .. j + 3
+  constexpr int kCols = kTS * BN <= 256 ? 256 : 512;
+  static_assert(kTS * BN <= 512, "TMEM budget");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w_s = smem;
+  uint8_t* a_s = smem + kWBytes + 1024;        // one guard KB: tap (-1, -1) of slot 0 reads 128 bytes in front of a tile
+  __shared__ __align__(8) uint64_t full_bar[kCtStagesMax], empty_bar[kCtStagesMax], tfull_bar[kTS], tempty_bar[kTS], w_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float bias_s[BN];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int z = blockIdx.y, pa = z >> 1, pb = z & 1;
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&map_a);
+    tc::prefetch_tmap(&map_w);
+    for (int s = 0; s < kCtStagesMax; ++s) {
+      tc::mbar_init(&full_bar[s], 1);
+      tc::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < kTS; ++s) {
+      tc::mbar_init(&tfull_bar[s], 1);
+      tc::mbar_init(&tempty_bar[s], 4);
+    }
+    tc::mbar_init(&w_bar, 1);
+    tc::fence_barrier_init();
+    tc::mbar_arrive_expect_tx(&w_bar, kWBytes);      // weights do not depend on the previous kernel: fetched before the PDL wait
+    for (int t = 0; t < 4; ++t)
+      for (int cb = 0; cb < KB; ++cb)
+        tc::tma_load_2d(w_s + (t * KB + cb) * kWTap, &map_w, &w_bar, t * a.Cin + cb * BK, z * a.Cout);
+  }
+  if (warp == 1) tc::tmem_alloc<kCols>(&tmem_slot);
+  if (warp >= 2)
+    for (int i = threadIdx.x - 64; i < BN; i += 128) bias_s[i] = a.bias ? a.bias[i] : 0.f;
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  const int rowslots = a.Wp;
+  const uint32_t stage_pitch = (uint32_t)(KB * a.a_stride);
+  tc::pdl_wait();
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      int it = 0;
+      for (int u = blockIdx.x; u < a.total_units; u += gridDim.x, ++it) {
+        const int s = it % a.stages;
+        if (!tc::mbar_wait(&empty_bar[s], (uint32_t)((it / a.stages) & 1) ^ 1u, 11)) break;
+        const int n = u / a.units_per_img, s0 = (u - n * a.units_per_img) * BM, r = s0 / rowslots;
+        tc::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(KB * a.a_bytes));
+        for (int cb = 0; cb < KB; ++cb)
+          tc::tma_load_4d(a_s + (size_t)s * stage_pitch + (size_t)cb * a.a_stride, &map_a, &full_bar[s], cb * BK, -1, r - 1, n);
+      }
+    }
+  } else if (warp == 1) {
+    if (tc::elect_one()) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16(BM, BN);
+      bool ok = tc::mbar_wait(&w_bar, 0, 12);
+      const uint32_t w_addr = tc::smem_u32(w_s);
+      int it = 0;
+      for (int u = blockIdx.x; u < a.total_units && ok; u += gridDim.x, ++it) {
+        const int s = it % a.stages, ts = it % kTS;
+        const uint32_t ph = (uint32_t)((it / a.stages) & 1), tph = (uint32_t)((it / kTS) & 1);
+        const int s0 = (u % a.units_per_img) * BM;
+        const int first = s0 % rowslots + rowslots;      // tile slot of output slot 0 (the tile starts one row above)
+        ok = tc::mbar_wait(&tempty_bar[ts], tph ^ 1u, 13) && tc::mbar_wait(&full_bar[s], ph, 14);
+        tc::fence_after_sync();
+        const uint32_t a_addr = tc::smem_u32(a_s + (size_t)s * stage_pitch);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ts * BN);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          // tap t of parity (pa, pb): offset 0 or (-1 | +1) per axis - a row / column shift of the SAME tile (conv_halo_kernel);
+          // tap-major, channel blocks inside: the summation order of conv_tc_kernel, so both kernels give the same bits
+          const int dy = (t >> 1) == 0 ? 0 : (pa == 0 ? -1 : 1), dx = (t & 1) == 0 ? 0 : (pb == 0 ? -1 : 1);
+          const int shift = first + dy * rowslots + dx;
+#pragma unroll
+          for (int cb = 0; cb < KB; ++cb) {
+            const uint64_t da = tc::make_desc_sw128(a_addr + (uint32_t)(cb * a.a_stride) + (uint32_t)shift * 128u);
+            const uint64_t dw = tc::make_desc_sw128(w_addr + (uint32_t)(t * KB + cb) * kWTap);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              tc::umma_bf16(d_tmem, da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc, (uint32_t)((t | cb | k) != 0));
+          }
+        }
+        tc::umma_commit(&empty_bar[s]);
+        tc::umma_commit(&tfull_bar[ts]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int H2 = 2 * a.H, W2 = 2 * a.W;
+    int it = 0;
+    for (int u = blockIdx.x; u < a.total_units; u += gridDim.x, ++it) {
+      const int s = it % kTS;
+      const uint32_t ph = (uint32_t)((it / kTS) & 1);
+      const int n = u / a.units_per_img, slot = (u - n * a.units_per_img) * BM + q * 32 + lane;
+      const int y = slot / rowslots, cx = slot - y * rowslots;
+      const bool valid = y < a.H && cx >= 1 && cx <= a.W;
+      if (!tc::mbar_wait(&tfull_bar[s], ph, 15)) break;
+      tc::fence_after_sync();
+      const uint32_t t_addr = tmem_base + (uint32_t)(s * BN) + ((uint32_t)(q * 32) << 16);
+      const size_t op = valid ? ((size_t)n * H2 + (size_t)(2 * y + pa)) * (size_t)W2 + (size_t)(2 * (cx - 1) + pb) : 0;
+      bf16* dst = a.out + op * (size_t)a.out_pitch;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(t_addr + (uint32_t)c0, v);
+        if (valid) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            v[j] += bias_s[c0 + j];
+            if (a.relu) v[j] = fmaxf(v[j], 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+          d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty_bar[s]);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<kCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // conv_halo_stream_kernel<BN>: the halo scheme for Cin = 64 * KB > 64, where the nine weight tiles of every 64-channel
 // block no longer fit next to the pixel tiles.  Pixel tiles keep the halo layout (ONE box per (unit, channel block)
 // instead of nine), the weight tiles (BN x 64, one per (channel block, tap)) stream through their own TMA ring in
@@ -1113,6 +1271,68 @@ int launch_conv_halo(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer
   else LDM_CUDA(launch_maybe_pdl(conv_halo_kernel<16, 1, 2>, dim3(grid), kThreads, smem, st, ctx->use_pdl, ma, L.map_w, a));
   ctx->launches++;
   ldm_kmark(ctx, "conv_halo");
+  LDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ConvTranspose2d(4, 2, 1) with Cin = 128, Cout = 64 through convt_halo_kernel (the four parities as blockIdx.y).  L: the stacked
+// sub-pixel weights of decoder.cu / pixel.cu ((4 Cout) rows, 4 taps x Cin columns), L.map_w boxed (64, 64).
+static int convt_halo_plan(int H, int W, int Cin, int Cout, ConvTHaloArgs* a, size_t* smem) {
+  if (Cin != 128 || Cout != 64 || W < 30 || W + 2 > 256) return 0;
+  const int Wp = W + 2, nrows = (Wp - 1 + 128 + Wp - 1) / Wp + 2;
+  if (nrows > 256) return 0;
+  const int a_bytes = nrows * Wp * 128, a_stride = ((a_bytes + 1023) & ~1023) + 1024, KB = Cin / 64;
+  const size_t fixed = (size_t)4 * KB * Cout * 128 + 1024 + 1024;
+  int stages = (int)((220 * 1024 - fixed) / ((size_t)KB * a_stride));
+  if (stages > kCtStagesMax) stages = kCtStagesMax;
+  if (stages < 2) return 0;
+  if (a) {
+    a->H = H; a->W = W; a->Wp = Wp;
+    a->units_per_img = ceil_div(H * Wp, BM);
+    a->a_bytes = a_bytes; a->a_stride = a_stride; a->Cin = Cin; a->Cout = Cout; a->stages = stages;
+  }
+  if (smem) *smem = fixed + (size_t)stages * KB * a_stride;
+  return 1;
+}
+int convt_halo_supported(int H, int W, int Cin, int Cout) {
+  static const bool on = !(getenv("LDM_CONVT_HALO") && atoi(getenv("LDM_CONVT_HALO")) == 0);
+  return on && convt_halo_plan(H, W, Cin, Cout, nullptr, nullptr);
+}
+int launch_convt_halo(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer& L, const float* bias, bf16* out, int out_pitch,
+                      int B, int H, int W, int relu, cudaStream_t st) {
+  LDM_TRY(conv_init(ctx));
+  ConvTHaloArgs a = {};
+  size_t smem = 0;
+  LDM_CHECK(convt_halo_plan(H, W, L.Cin, L.Cout, &a, &smem), "convt_halo: unsupported shape (H=%d W=%d Cin=%d Cout=%d)", H, W, L.Cin, L.Cout);
+  LDM_CHECK(L.taps == 4 && L.w16 != nullptr && ((uintptr_t)in & 15) == 0 && in_pitch % 8 == 0 && out_pitch % 8 == 0,
+            "convt_halo: packed sub-pixel weights and 16-byte aligned buffers required");
+  static bool attr_set = false;
+  if (!attr_set) {
+    LDM_CUDA(cudaFuncSetAttribute(convt_halo_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
+    attr_set = true;
+  }
+  a.total_units = B * a.units_per_img;
+  a.out_pitch = out_pitch; a.relu = relu; a.bias = bias; a.out = out;
+  CUtensorMap ma;
+  {
+    const int nrows = a.a_bytes / (a.Wp * 128);
+    cuuint64_t dims[4] = {(cuuint64_t)L.Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)in_pitch * 2, (cuuint64_t)W * in_pitch * 2, (cuuint64_t)H * W * in_pitch * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)a.Wp, (cuuint32_t)nrows, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode4(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(in), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      ldm_set_error("cuTensorMapEncodeTiled (convt halo box %d x %d) failed: CUresult %d", a.Wp, nrows, (int)r);
+      return (int)r;
+    }
+  }
+  const int per = ctx->sm_count / 4 < 1 ? 1 : ctx->sm_count / 4;      // one CTA per SM, the parities side by side
+  const int gx = a.total_units < per ? a.total_units : per;
+  LDM_CUDA(launch_maybe_pdl(convt_halo_kernel<64, 2>, dim3(gx, 4), kThreads, smem, st, ctx->use_pdl, ma, L.map_w, a));
+  ctx->launches++;
+  ldm_kmark(ctx, "conv_tc");      // keeps the per-kernel tables of bench.py: the same layer on another kernel
   LDM_CUDA(cudaGetLastError());
   return 0;
 }

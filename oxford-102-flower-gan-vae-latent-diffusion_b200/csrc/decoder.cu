@@ -29,6 +29,9 @@ int launch_conv_out3(ldm_ctx* ctx, const bf16* in, const float* w, const float* 
 int launch_final_gn_conv3(ldm_ctx* ctx, const bf16* x, const float2* coef, const uint32_t* wf, const float* bias, float* out, int B,
                           int H, int W, cudaStream_t st);
 int launch_final_w_frag(ldm_ctx* ctx, const float* w, uint32_t* wf, cudaStream_t st);
+int convt_halo_supported(int H, int W, int Cin, int Cout);
+int launch_convt_halo(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer& L, const float* bias, bf16* out, int out_pitch,
+                      int B, int H, int W, int relu, cudaStream_t st);
 
 namespace {
 
@@ -196,7 +199,10 @@ int res_block_bf16(ldm_ctx* ctx, const ResBlockModel& R, int B, const bf16* X, b
 int up_block_bf16(ldm_ctx* ctx, const DecoderModel& D, int idx, int B, int H, int Cin, const bf16* X, bf16* Y, bf16* OUT,
                   cudaStream_t st) {
   const int Cout = Cin / 2, P = 4 * H * H;
-  LDM_TRY(launch_conv_tc(ctx, X, D.up[idx][0], D.up_b[idx], Y, B, H, H, 2, st));   // four sub-pixel parities, one launch
+  if (convt_halo_supported(H, H, Cin, Cout))      // up1 (128 -> 64 at 64 x 64): resident weights, every pixel run loaded once
+    LDM_TRY(launch_convt_halo(ctx, X, Cin, D.up[idx][0], D.up_b[idx], Y, Cout, B, H, H, 0, st));
+  else
+    LDM_TRY(launch_conv_tc(ctx, X, D.up[idx][0], D.up_b[idx], Y, B, H, H, 2, st));   // four sub-pixel parities, one launch
   float2* coef = reinterpret_cast<float2*>(ctx->d_stats);
   LDM_TRY(launch_norm_coef_bf16_ws(ctx, Y, D.up_gn_w[idx], D.up_gn_b[idx], coef, B, P, Cout, 8, ctx->d_part, ctx->d_cnt, st));
   LDM_TRY(launch_coef_apply_bf16(ctx, Y, coef, OUT, B, P, Cout, LDM_ACT_SWISH, st));

@@ -20,6 +20,9 @@
 
 #include <cstdlib>
 
+int convt_halo_supported(int H, int W, int Cin, int Cout);
+int launch_convt_halo(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer& L, const float* bias, bf16* out, int out_pitch,
+                      int B, int H, int W, int relu, cudaStream_t st);
 int launch_conv_tc_ex(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer& L, const float* bias, bf16* out, int out_pitch,
                       int B, int H, int W, int mode, int relu, const float* post, int post_stride, cudaStream_t st);
 int tc_make_weight_map(ldm_ctx* ctx, const bf16* w, int N, int K, int bn, CUtensorMap* out);
@@ -683,7 +686,10 @@ int run_forward(ldm_ctx* ctx, const float* x, const float* terms, int tstride, i
   LDM_TRY(launch_conv_tc_ex(ctx, M.x4, 4 * c, M.up1, M.up1.b, M.cat4, 4 * c, B, H4, W4, 2, 0, nullptr, 0, st));
   LDM_TRY(conv3(ctx, M.cat4, 4 * c, M.c4a, M.a4, 2 * c, B, H2, W2, nullptr, 0, st));
   LDM_TRY(conv3(ctx, M.a4, 2 * c, M.c4b, M.x5, 2 * c, B, H2, W2, nullptr, 0, st));
-  LDM_TRY(launch_conv_tc_ex(ctx, M.x5, 2 * c, M.up2, M.up2.b, M.cat5, 2 * c, B, H2, W2, 2, 0, nullptr, 0, st));
+  if (convt_halo_supported(H2, W2, 2 * c, c) && M.up2.bn == 64)      // 128 -> 64: resident weights, every pixel run loaded once
+    LDM_TRY(launch_convt_halo(ctx, M.x5, 2 * c, M.up2, M.up2.b, M.cat5, 2 * c, B, H2, W2, 0, st));
+  else
+    LDM_TRY(launch_conv_tc_ex(ctx, M.x5, 2 * c, M.up2, M.up2.b, M.cat5, 2 * c, B, H2, W2, 2, 0, nullptr, 0, st));
   LDM_TRY(conv3(ctx, M.cat5, 2 * c, M.c5a, M.a5, c, B, H, W, nullptr, 0, st));
   LDM_TRY(conv3(ctx, M.a5, c, M.c5b, M.x6, c, B, H, W, nullptr, 0, st));
   fin.in = M.x6; fin.w = M.out_w; fin.bias = M.out_b; fin.res_ratio = M.res_ratio; fin.x_in = x;
