@@ -12,7 +12,7 @@ Prints ONE JSON line (rank 0).  Besides the base contract the v2 line carries
 
   roofline          the dominant kernel (chain_kernel), CUDA-event timed; `traffic` from the sidecar the profiling
                     script writes (profiles/*chain_traffic.json), never a constant in this file
-  roofline_kernels  every kernel of one traced pass (chain + the 41 decoder launches): {name, what, bound, flop | bytes,
+  roofline_kernels  every kernel of one traced pass (chain + the 38 decoder launches): {name, what, bound, flop | bytes,
                     us, achieved, peak, frac}; tensor-bound ones against the measured bf16 peak, memory-bound ones
                     (norm / gating / LayerNorm passes) as GB/s against the measured HBM copy bandwidth.  Timed with a
                     CUDA event after every launch (ldm_debug_ktrace), not under a profiler
@@ -205,7 +205,7 @@ def run_reference_arm(args, rank):
 # per-kernel records (roofline_kernels)
 # ------------------------------------------------------------------------------------------------------
 def decoder_kernel_table(B):
-    """The 41 launches of one bf16 decode of B latents, in launch order (csrc/decoder.cu: decode_chunk_bf16):
+    """The 38 launches of one bf16 decode of B latents, in launch order (csrc/decoder.cu: decode_chunk_bf16):
     (trace name, what, bound, flop or bytes).  Memory-bound passes: algorithmic bytes = tensors read + written once."""
     t = []
     E = lambda C, H: B * H * H * C      # elements of an NHWC activation
@@ -222,8 +222,8 @@ def decoder_kernel_table(B):
               ("launch_coef_apply_bf16", "res%d.ln1 apply + Swish" % C, "hbm", n * 4),
               ("conv_tc", "res%d.conv2 3x3" % C, "tensor", conv),
               ("launch_norm_coef_bf16", "res%d.ln2 statistics" % C, "hbm", n * 2),
-              ("launch_sa_map_bf16", "res%d channel gate + spatial mean/max map" % C, "hbm", n * 2),
-              ("launch_sa_gate", "res%d sigmoid(conv7x7(map))" % C, "hbm", B * H * H * 12),
+              ("launch_sa_map_gate", "res%d channel gate + spatial mean/max map + sigmoid(conv7x7(map)), one CTA per sample" % C, "hbm",
+               n * 2 + B * H * H * 4),
               ("launch_sa_apply_bf16", "res%d ln2 * CA * SA gate + x, Swish" % C, "hbm", n * 6)]
         no = E(C // 2, 2 * H)
         t += [("conv_tc", "up ConvT(4,2,1) %d->%d @%dx%d" % (C, C // 2, 2 * H, 2 * H), "tensor", 2 * no * 4 * C),

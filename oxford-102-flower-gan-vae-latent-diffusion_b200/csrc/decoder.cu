@@ -29,6 +29,8 @@ int launch_conv_out3(ldm_ctx* ctx, const bf16* in, const float* w, const float* 
 int launch_final_gn_conv3(ldm_ctx* ctx, const bf16* x, const float2* coef, const uint32_t* wf, const float* bias, float* out, int B,
                           int H, int W, cudaStream_t st);
 int launch_final_w_frag(ldm_ctx* ctx, const float* w, uint32_t* wf, cudaStream_t st);
+int launch_sa_map_gate_bf16(ldm_ctx* ctx, const bf16* x, const float2* coef, const float* ca, const float* sa_w, float* gate,
+                            int B, int H, int C, cudaStream_t st, int* done);
 int convt_halo_supported(int H, int W, int Cin, int Cout);
 int launch_convt_halo(ldm_ctx* ctx, const bf16* in, int in_pitch, const ConvLayer& L, const float* bias, bf16* out, int out_pitch,
                       int B, int H, int W, int relu, cudaStream_t st);
@@ -191,8 +193,10 @@ int res_block_bf16(ldm_ctx* ctx, const ResBlockModel& R, int B, const bf16* X, b
   LDM_TRY(launch_norm_coef_bf16_ws(ctx, Y, R.ln2_w, R.ln2_b, coef, B, P, C, 1, ctx->d_part, ctx->d_cnt, st));   // ln2 as (scale, shift)
   // CALayer (v2:64-67): the average pool of an instance-normalised map is its beta, so the channel gate is a
   // per-channel constant computed at pack time (ca_const), the same for every sample
-  LDM_TRY(launch_sa_map_bf16(ctx, Y, coef, R.ca_const, ctx->d_map, B, P, C, st));
-  LDM_TRY(launch_sa_apply_bf16(ctx, Y, coef, R.ca_const, ctx->d_map, R.sa_w, X, OUT, ctx->d_gate, B, H, C, st));
+  int gated = 0;
+  LDM_TRY(launch_sa_map_gate_bf16(ctx, Y, coef, R.ca_const, R.sa_w, ctx->d_gate, B, H, C, st, &gated));      // map + 7x7 gate, one CTA per sample
+  if (!gated) LDM_TRY(launch_sa_map_bf16(ctx, Y, coef, R.ca_const, ctx->d_map, B, P, C, st));
+  LDM_TRY(launch_sa_apply_bf16(ctx, Y, coef, R.ca_const, gated ? nullptr : ctx->d_map, R.sa_w, X, OUT, ctx->d_gate, B, H, C, st));
   return 0;
 }
 

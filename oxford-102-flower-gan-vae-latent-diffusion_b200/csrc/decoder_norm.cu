@@ -408,6 +408,78 @@ sa_map2_kernel(const bf16* __restrict__ x, const float2* __restrict__ coef, cons
   }
 }
 
+// sa_map2 + sa_gate as ONE kernel for maps of up to 32 x 32 pixels: one CTA per sample walks the sample's pixels (the lane
+// layout of sa_map2_kernel, 16 warps, two pixel groups per warp in flight), keeps the [mean, max] map in shared memory and,
+// after a CTA barrier, finishes gate = sigmoid(conv7x7(map)) from it (the tap order of sa_gate_kernel: same bits).  The map
+// never reaches global memory and the separate gate launch (10 - 16 us for 16 k - 262 k pixels) is gone.
+template <int NO>
+__global__ void __launch_bounds__(512, 2)      // two CTAs per SM: all 256 samples of a full batch in one wave
+sa_map_gate_kernel(const bf16* __restrict__ x, const float2* __restrict__ coef, const float* __restrict__ ca,
+                   const float* __restrict__ sa_w, float* __restrict__ gate, int H, int C) {
+  __shared__ float2 smap[1024];
+  __shared__ float w[98];
+  const int HW = H * H, n = blockIdx.x;
+  const int lpp = C / (8 * NO) < 32 ? C / (8 * NO) : 32, ppw = 32 / lpp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % lpp, pj = lane / lpp;
+  if (threadIdx.x < 98) w[threadIdx.x] = sa_w[threadIdx.x];
+  ldm_pdl_wait();
+  float A[NO][8], Bv[NO][8];
+#pragma unroll
+  for (int o = 0; o < NO; ++o) {
+    const int c = (sub + o * lpp) * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float2 k = __ldg(coef + (size_t)n * C + c + e);
+      const float g = __ldg(ca + c + e);
+      A[o][e] = g * k.x; Bv[o][e] = g * k.y;
+    }
+  }
+  const float inv_c = 1.0f / (float)C;
+  const bf16* xs = x + (size_t)n * HW * C;
+  for (int i = warp * 2 * ppw; i < HW; i += 16 * 2 * ppw) {       // HW is a multiple of 2 ppw (checked by the launcher)
+    uint4 u[2][NO];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int o = 0; o < NO; ++o)
+        u[h][o] = __ldg(reinterpret_cast<const uint4*>(xs + (size_t)(i + h * ppw + pj) * C + (sub + o * lpp) * 8));
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float sm = 0.f, m = -INFINITY;
+#pragma unroll
+      for (int o = 0; o < NO; ++o) {
+        float f[8];
+        unpack8(u[h][o], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float z = fmaf(f[e], A[o][e], Bv[o][e]); sm += z; m = fmaxf(m, z); }
+      }
+      for (int o = lpp >> 1; o > 0; o >>= 1) {
+        sm += __shfl_xor_sync(0xffffffffu, sm, o);
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      }
+      if (sub == 0) smap[i + h * ppw + pj] = make_float2(sm * inv_c, m);
+    }
+  }
+  __syncthreads();
+  for (int pix = threadIdx.x; pix < HW; pix += 512) {
+    const int y = pix / H, xx = pix - y * H;
+    float a = 0.f;
+    for (int ky = 0; ky < 7; ++ky) {
+      const int yy = y + ky - 3;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) {
+        const int xq = xx + kx - 3;
+        if (xq < 0 || xq >= H) continue;
+        const float2 v = smap[yy * H + xq];
+        a = fmaf(w[ky * 7 + kx], v.x, a);
+        a = fmaf(w[49 + ky * 7 + kx], v.y, a);
+      }
+    }
+    gate[(size_t)n * HW + pix] = sigmoidf_(a);
+  }
+}
+
 // gate = sigmoid(conv7x7([mean, max] map)) (v2:79-80): one thread per pixel; the map of a sample is a few KiB (L1 / L2)
 __global__ void __launch_bounds__(256)
 sa_gate_kernel(const float* __restrict__ map, const float* __restrict__ sa_w, float* __restrict__ gate, int H, int npix) {
@@ -593,6 +665,21 @@ static int sa_run(int npix, int HW, int ppw) {
   while (run > HW || (run > 2 * ppw && npix / run < 4096)) run >>= 1;
   return run < 2 * ppw ? 2 * ppw : run;
 }
+// map + gate in one launch (sa_map_gate_kernel); returns 1 when it ran, 0 when the shape needs the two-kernel sequence
+int launch_sa_map_gate_bf16(ldm_ctx* ctx, const bf16* x, const float2* coef, const float* ca, const float* sa_w, float* gate,
+                            int B, int H, int C, cudaStream_t st, int* done) {
+  static const bool on = !(getenv("LDM_DEC_FUSE_GATE") && atoi(getenv("LDM_DEC_FUSE_GATE")) == 0);
+  const int HW = H * H, no = C > 256 ? 2 : 1, lpp = C / (8 * no) < 32 ? C / (8 * no) : 32;
+  *done = 0;
+  // one CTA per sample: only with enough samples to occupy the machine (measured: 1.305 -> 1.292 ms per decode at B = 256, bit-identical;
+  // 0.310 -> 0.323 ms at B = 3, where three CTAs would walk the maps alone)
+  if (!on || B < 96 || C % 64 != 0 || C > 512 || HW > 1024 || HW % (2 * (32 / lpp)) != 0) return 0;
+  if (no == 2) LDM_CUDA(launch_maybe_pdl(sa_map_gate_kernel<2>, dim3(B), 512, 0, st, ctx->use_pdl, x, coef, ca, sa_w, gate, H, C));
+  else LDM_CUDA(launch_maybe_pdl(sa_map_gate_kernel<1>, dim3(B), 512, 0, st, ctx->use_pdl, x, coef, ca, sa_w, gate, H, C));
+  LDM_LAUNCHED_AS(ctx, "launch_sa_map_gate");
+  *done = 1;
+  return 0;
+}
 int launch_sa_map_bf16(ldm_ctx* ctx, const bf16* x, const float2* coef, const float* ca, float* map, int B, int HW, int C,
                        cudaStream_t st) {
   LDM_CHECK(C % 64 == 0 && C <= 512 && HW % 4 == 0, "sa_map: C %% 64 == 0, C <= 512 and HW %% 4 == 0 required (C=%d, HW=%d)", C, HW);
@@ -611,8 +698,10 @@ int launch_sa_apply_bf16(ldm_ctx* ctx, const bf16* x, const float2* coef, const 
   const int HW = H * H, npix = B * HW, no = C > 256 ? 2 : 1, lpp = C / (8 * no) < 32 ? C / (8 * no) : 32;
   const int run = sa_run(npix, HW, 32 / lpp), warps = ceil_div(npix, run);
   LDM_CHECK(HW % run == 0, "sa_apply: HW (%d) must be a multiple of the warp run (%d)", HW, run);
-  LDM_CUDA(launch_maybe_pdl(sa_gate_kernel, dim3(ceil_div(npix, 256)), 256, 0, st, ctx->use_pdl, map, sa_w, gate, H, npix));
-  LDM_LAUNCHED_AS(ctx, "launch_sa_gate");
+  if (map) {      // null: the gate is already there (launch_sa_map_gate_bf16)
+    LDM_CUDA(launch_maybe_pdl(sa_gate_kernel, dim3(ceil_div(npix, 256)), 256, 0, st, ctx->use_pdl, map, sa_w, gate, H, npix));
+    LDM_LAUNCHED_AS(ctx, "launch_sa_gate");
+  }
   if (no == 2) LDM_CUDA(launch_maybe_pdl(sa_apply2_kernel<2>, dim3(ceil_div(warps, 8)), 256, 0, st, ctx->use_pdl, x, coef, ca, (const float*)gate, resid, out, HW, C, npix, run));
   else LDM_CUDA(launch_maybe_pdl(sa_apply2_kernel<1>, dim3(ceil_div(warps, 8)), 256, 0, st, ctx->use_pdl, x, coef, ca, (const float*)gate, resid, out, HW, C, npix, run));
   LDM_LAUNCHED(ctx);
