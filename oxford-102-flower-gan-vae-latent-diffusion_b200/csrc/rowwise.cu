@@ -346,6 +346,69 @@ template int launch_stage_mid<float>(ldm_ctx*, const float*, const float*, const
 template int launch_stage_mid<bf16>(ldm_ctx*, const float*, const float*, const float*, const float*, const float*,
                                     const float*, float*, bf16*, int, int, int, cudaStream_t);
 
+// row_ln_big_kernel with 1024 threads: the three passes over the L2-resident row (sum; centred sum of squares; apply) were 32
+// dependent iterations of 256 threads each; here a pass is d / 4096 iterations with four independent 16-byte loads in flight
+// per thread (32 registers: two CTAs per SM, a batch of 256 rows is one wave).  d % 16384 == 0.
+template <typename TOP>
+__global__ void __launch_bounds__(1024, 2)
+row_ln_wide_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ g_, const float* __restrict__ b_,
+                   int act, TOP* __restrict__ out, int ld_out, int d) {
+  __shared__ float red[32];
+  __shared__ float bc;
+  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const float4* ip = reinterpret_cast<const float4*>(in + (size_t)row * ld_in);
+  const int n4 = d >> 2;
+  ldm_pdl_wait();
+  float s = 0.f;
+  for (int q = tid; q < n4; q += 4096) {
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = ip[q + 1024 * j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  }
+  s = warp_sum(s);
+  if (lane == 0) red[wid] = s;
+  __syncthreads();
+  if (wid == 0) { const float t = warp_sum(red[lane]); if (lane == 0) bc = t / (float)d; }
+  __syncthreads();
+  const float mean = bc;
+  float qq = 0.f;
+  for (int q = tid; q < n4; q += 4096) {
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = ip[q + 1024 * j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, e = v[j].w - mean;
+      qq += (a * a + b * b) + (c * c + e * e);
+    }
+  }
+  qq = warp_sum(qq);
+  __syncthreads();
+  if (lane == 0) red[wid] = qq;
+  __syncthreads();
+  if (wid == 0) { const float t = warp_sum(red[lane]); if (lane == 0) bc = 1.0f / sqrtf(t / (float)d + 1e-5f); }
+  __syncthreads();
+  const float rstd = bc;
+  for (int q = tid; q < n4; q += 2048) {
+    float4 v[2], g[2], b[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      v[j] = ip[q + 1024 * j];
+      g[j] = __ldg(reinterpret_cast<const float4*>(g_) + q + 1024 * j);
+      b[j] = __ldg(reinterpret_cast<const float4*>(b_) + q + 1024 * j);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float o0 = (v[j].x - mean) * rstd * g[j].x + b[j].x, o1 = (v[j].y - mean) * rstd * g[j].y + b[j].y;
+      float o2 = (v[j].z - mean) * rstd * g[j].z + b[j].z, o3 = (v[j].w - mean) * rstd * g[j].w + b[j].w;
+      if (act == LDM_ACT_SWISH) { o0 = swishf(o0); o1 = swishf(o1); o2 = swishf(o2); o3 = swishf(o3); }
+      Pack4<TOP>::store(out + (size_t)row * ld_out + (size_t)(q + 1024 * j) * 4, o0, o1, o2, o3);
+    }
+  }
+}
+
 template <typename TOP>
 int launch_row_ln(ldm_ctx* ctx, const float* in, int ld_in, const float* g, const float* b, int act, TOP* out,
                   int ld_out, int M, int d, cudaStream_t st) {
@@ -358,7 +421,11 @@ int launch_row_ln(ldm_ctx* ctx, const float* in, int ld_in, const float* g, cons
       return 0;
     });
   } else {
-    LDM_CUDA(launch_maybe_pdl(row_ln_big_kernel<TOP>, dim3(M), 256, 0, st, ctx->use_pdl, in, ld_in, g, b, act, out, ld_out, d));
+    static const bool reg_rows = !(getenv("LDM_ROW_LN_WIDE") && atoi(getenv("LDM_ROW_LN_WIDE")) == 0);
+    if (reg_rows && d % 16384 == 0)
+      LDM_CUDA(launch_maybe_pdl(row_ln_wide_kernel<TOP>, dim3(M), 1024, 0, st, ctx->use_pdl, in, ld_in, g, b, act, out, ld_out, d));
+    else
+      LDM_CUDA(launch_maybe_pdl(row_ln_big_kernel<TOP>, dim3(M), 256, 0, st, ctx->use_pdl, in, ld_in, g, b, act, out, ld_out, d));
   }
   LDM_LAUNCHED(ctx);
   return 0;
