@@ -13,4 +13,6 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:chai
 echo "chain full rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc -c 2 -f -o gpurun_out/${TAG}_conv_full $CMD > gpurun_out/ncu3.log 2>&1
 echo "conv full rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"final_gn_conv3|convt_halo|sa_map_gate" -c 5 -f -o gpurun_out/${TAG}_dec_full $CMD > gpurun_out/ncu4.log 2>&1
+echo "decoder kernels full rc=$?"
 ls -la gpurun_out/*.ncu-rep
