@@ -73,3 +73,25 @@ def test_v3_loop_kernel_is_bit_stable_over_repetitions():
         assert int(eng.info("launches_per_step")) == 0
         eng.check_device_flags(u3.num_classes)
     assert int(eng.info("tc_error")) == 0
+
+
+def test_full_batch_decoder_kernels_against_the_oracle_and_over_repetitions():
+    """The decoder kernels that only full batches reach (sa_map_gate_kernel: one CTA per sample, B >= 96) next to the ones every
+    batch uses (convt_halo_kernel, final_gn_conv3_kernel, programmatic dependent launches between all of them): rows of a B = 128
+    decode against the CPU restatement, against a small call of the same latents, and bit-stable over repetitions (an early
+    start of a dependent kernel that read its predecessor's output before griddepcontrol.wait would show up here)."""
+    from oracle import philox, restate as R
+    from tests._util import AE_SEED, IMAGE_TOL, make_autoencoder
+    sd = weights.make_autoencoder_state(AE_SEED, "perturbed")
+    ae = make_autoencoder("perturbed", "bf16")
+    z = torch.from_numpy(philox.normal_rows(11, 0, 128, 0))
+    ref = ae.decode(z.cuda())
+    for rep in range(6):
+        assert torch.equal(ae.decode(z.cuda()), ref), rep
+    rows = [0, 63, 64, 127]
+    want = R.decode(sd, z[rows])
+    got = ref[rows].cpu()
+    assert float((got - want).abs().max()) < IMAGE_TOL["bf16"]
+    small = ae.decode(z[rows].cuda()).cpu()                 # two-kernel map / gate sequence, other statistics splits
+    assert float((small - got).abs().max()) < IMAGE_TOL["bf16"]
+    assert float(ref.min()) > 0 and float(ref.max()) < 1
