@@ -624,6 +624,10 @@ static int norm_splits(int blocks, int HW, int pl, int C) {
   while (blocks * s < want && HW / (2 * s) >= 4 * pl && 2 * s * C <= 1024 && s < 16) s *= 2;
   return s;
 }
+static bool norm_wide() {
+  static const bool on = !(getenv("LDM_NORM_WIDE") && atoi(getenv("LDM_NORM_WIDE")) == 0);
+  return on;
+}
 // `part` (B x 1024 float2) and `cnt` (B x 16 ints, zero) enable the pixel splits; without them one CTA walks the whole sample
 int launch_norm_coef_bf16_ws(ldm_ctx* ctx, const bf16* x, const float* gamma, const float* beta, float2* coef, int B, int HW,
                              int C, int group, float2* part, int* cnt, cudaStream_t st) {
@@ -632,6 +636,11 @@ int launch_norm_coef_bf16_ws(ldm_ctx* ctx, const bf16* x, const float* gamma, co
   if (C == 32) {
     const int S = part && cnt ? norm_splits(B, HW, 64, C) : 1;
     LDM_CUDA(launch_maybe_pdl(norm_coef2_kernel<32>, dim3(1, B, S), 256, 0, st, ctx->use_pdl, x, gamma, beta, coef, HW, C, group, part, cnt, S));
+  } else if (C % 256 == 0 && HW <= 256 && B >= 128 && norm_wide()) {
+    // small maps (8 x 8, 16 x 16) of a full batch: 256 channels per CTA - a quarter of the CTAs, each with two to four batches of
+    // loads (decode of 256: 1.281 -> 1.273 ms; of 40: 0.452 -> 0.458, hence the batch condition)
+    const int S = part && cnt ? norm_splits(B * (C / 256), HW, 8, C) : 1;
+    LDM_CUDA(launch_maybe_pdl(norm_coef2_kernel<256>, dim3(C / 256, B, S), 256, 0, st, ctx->use_pdl, x, gamma, beta, coef, HW, C, group, part, cnt, S));
   } else {
     const int S = part && cnt && C / 64 <= 16 ? norm_splits(B * (C / 64), HW, 32, C) : 1;
     LDM_CUDA(launch_maybe_pdl(norm_coef2_kernel<64>, dim3(C / 64, B, S), 256, 0, st, ctx->use_pdl, x, gamma, beta, coef, HW, C, group, part, cnt, S));
