@@ -449,7 +449,7 @@ convt_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint8_t* a_s = smem + kWBytes + 1024;        // one guard KB: tap (-1, -1) of slot 0 reads 128 bytes in front of a tile
   __shared__ __align__(8) uint64_t full_bar[kCtStagesMax], empty_bar[kCtStagesMax], tfull_bar[kTS], tempty_bar[kTS], w_bar;
   __shared__ uint32_t tmem_slot;
-  __shared__ float bias_s[BN];
+  __shared__ __align__(16) float bias_s[BN];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int z = blockIdx.y, pa = z >> 1, pb = z & 1;
@@ -543,30 +543,43 @@ convt_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const uint32_t t_addr = tmem_base + (uint32_t)(s * BN) + ((uint32_t)(q * 32) << 16);
       const size_t op = valid ? ((size_t)n * H2 + (size_t)(2 * y + pa)) * (size_t)W2 + (size_t)(2 * (cx - 1) + pb) : 0;
       bf16* dst = a.out + op * (size_t)a.out_pitch;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        float v[16];
-        tc::tmem_ld16(t_addr + (uint32_t)c0, v);
-        if (valid) {
+      // all column blocks of the accumulator are requested back to back and awaited once; the accumulator stage is handed back
+      // to the MMA issuer before the arithmetic and the stores (the epilogue of a unit, one warp per 32 rows, is as long as the
+      // unit's MMAs: a serial load - wait - finish chain per 16 columns left the tensor core waiting for free stages)
+      uint32_t raw[BN / 16][16];
+#pragma unroll
+      for (int cb = 0; cb < BN / 16; ++cb) tc::tmem_ld16_nowait(t_addr + (uint32_t)(cb * 16), raw[cb]);
+      tc::tmem_ld_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty_bar[s]);
+      if (valid) {
+#pragma unroll
+        for (int cb = 0; cb < BN / 16; ++cb) {
+          float v[16];
           uint32_t pk[8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            v[j] += bias_s[c0 + j];
-            if (a.relu) v[j] = fmaxf(v[j], 0.f);
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(&bias_s[cb * 16 + 4 * q4]);
+            v[4 * q4] = __uint_as_float(raw[cb][4 * q4]) + b4.x;
+            v[4 * q4 + 1] = __uint_as_float(raw[cb][4 * q4 + 1]) + b4.y;
+            v[4 * q4 + 2] = __uint_as_float(raw[cb][4 * q4 + 2]) + b4.z;
+            v[4 * q4 + 3] = __uint_as_float(raw[cb][4 * q4 + 3]) + b4.w;
+          }
+          if (a.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
             pk[j] = *reinterpret_cast<uint32_t*>(&h2);
           }
-          uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+          uint4* d4 = reinterpret_cast<uint4*>(dst + cb * 16);
           d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
       }
-      tc::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&tempty_bar[s]);
     }
   }
   tc::fence_before_sync();
