@@ -17,6 +17,8 @@ LIB = os.path.join(HERE, "libldm_b200.so")
 SOURCES = ["api.cu", "chain.cu", "v3loop.cu", "rowwise.cu", "gemm_f32.cu", "gemm_tc.cu", "conv_tc.cu", "pack.cu", "decoder.cu", "decoder_norm.cu", "pixel.cu", "ublock.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v"]
+if os.environ.get("LDM_CHAIN_PREINIT"):        # chain.cu: additive terms written into the accumulator ahead of the MMAs (A/B builds)
+    NVCC_FLAGS.append("-DLDM_CHAIN_PREINIT=" + os.environ["LDM_CHAIN_PREINIT"])
 if os.environ.get("LDM_CHAIN_TRACE"):          # per-CTA clock stamps inside chain_kernel (tools/chain_sweep.py)
     NVCC_FLAGS.append("-DLDM_CHAIN_TRACE")
 
