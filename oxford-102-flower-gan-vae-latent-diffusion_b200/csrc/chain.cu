@@ -31,6 +31,10 @@
 // SM whatever the grid, DSMEM bulk copies 15.5 B/clk per SM (so operands cannot be broadcast through DSMEM), one
 // tcgen05.mma of M = 128, N <= 128 every 74 clocks whether A comes from shared memory or from TMEM.
 //
+// The additive terms of a tile (bias + time-table row + per-sample terms) do not wait for the contraction: the epilogue warps
+// write them into accumulator 0 of the COMING phase while the hand-over is in flight and that phase's first MMA accumulates
+// (LDM_CHAIN_PREINIT; a monotonic shared-memory counter orders the writes before the MMA thread).
+//
 //   warp 0    : TMA producer of weight tiles (elected thread; per-launch unit plans, no per-slot address arithmetic)
 //   warp 1    : operand producer: waits for the phase hand-over, requests the unit's k-blocks
 //   warp 2    : TMEM allocator + tcgen05.mma issuer
